@@ -1,0 +1,206 @@
+/* ols_b200.h -- C ABI of the B200-native language-feature Gaussian rasterizer + autoencoder.
+ *
+ * This is the drop-in boundary for the hot path of rpng/online_lang_splatting.  Every entry
+ * point replaces one function the reference binds through pybind11 in
+ *   submodules/diff-gaussian-rasterization/ext.cpp:15-21
+ * (the "P/" variant that gaussian_renderer/__init__.py:316-335 really calls), or one torch.nn
+ * call of language/autoencoder/model.py.  Conventions:
+ *
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary;
+ *   - every pointer named d_* is DEVICE memory of the current CUDA device, h_* is HOST memory;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - all functions return OLS_OK (0) or a negative ols_status; the message of the last error on
+ *     the calling thread is returned by ols_last_error();  nothing throws across the ABI;
+ *   - no global mutable state besides the thread-local error string, so several processes,
+ *     devices and streams can use the library concurrently;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     OLS_ERR_CUDA.
+ *
+ * Matrices follow the reference's row-vector convention (transposed world->view, see
+ * utils/camera_utils.py:103-113 and cuda_rasterizer/auxiliary.h:58-77): element (r,c) of the
+ * mathematical matrix is m[c*4+r].  Image tensors are planar CHW float32.
+ */
+#ifndef OLS_B200_H_
+#define OLS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OLS_ABI_VERSION 1
+
+typedef enum ols_status {
+    OLS_OK = 0,
+    OLS_ERR_INVALID = -1,      /* bad argument combination (reference: Python Exception / AT_ERROR)      */
+    OLS_ERR_CUDA = -2,         /* CUDA runtime error or no device                                        */
+    OLS_ERR_WORKSPACE = -3,    /* workspace too small for the fixed part                                 */
+    OLS_ERR_OVERFLOW = -4,     /* instance capacity (R_cap) exceeded; nothing was rendered, see ols_fwd_info */
+    OLS_ERR_UNSUPPORTED = -5   /* feature dimension / tile size not compiled in                          */
+} ols_status;
+
+/* flags for ols_raster_args.flags */
+#define OLS_FLAG_PREFILTERED     (1u << 0)  /* reference: raster_settings.prefiltered                      */
+#define OLS_FLAG_DEBUG           (1u << 1)  /* reference: raster_settings.debug -> sync + check after each kernel */
+#define OLS_FLAG_BITEXACT_BLEND  (1u << 2)  /* accumulate c*alpha*T in the reference's operation order      */
+#define OLS_FLAG_BWD_EXACT       (1u << 3)  /* backward: mathematically exact gradients instead of the
+                                               reference's Q1-Q3 behaviour          */
+
+/* ---------------------------------------------------------------------------------------------
+ * Arguments shared by forward and backward.  Mirrors the positional argument list of
+ * RasterizeLanguageGaussiansCUDA (rasterize_points.h:51-73 / rasterize_points.cu:135-157) plus
+ * GaussianRasterizationSettings (diff_gaussian_rasterization/__init__.py:405-419).
+ * Nullable inputs follow the reference's "empty tensor == not provided" rule.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ols_raster_args {
+    int32_t P;              /* number of Gaussians                                                     */
+    int32_t F;              /* language feature channels (config.h NUM_LANGUAGE_CHANNELS: 15 or 3)       */
+    int32_t sh_degree;      /* active SH degree D                                                      */
+    int32_t M;              /* SH coefficients per Gaussian ((max_degree+1)^2), 0 if d_shs == NULL       */
+    int32_t W, H;           /* image size                                                              */
+    int32_t tile;           /* tile edge in pixels: 15 (config.h of P/) or 16 (D/ and perf mode)         */
+    uint32_t flags;         /* OLS_FLAG_*                                                              */
+    float tanfovx, tanfovy;
+    float scale_modifier;
+    float _pad0;
+    const float* d_bg;              /* [3]                                                             */
+    const float* d_means3D;         /* [P,3]                                                           */
+    const float* d_shs;             /* [P,M,3] or NULL                                                 */
+    const float* d_colors_precomp;  /* [P,3]   or NULL  (exactly one of shs / colors_precomp)          */
+    const float* d_language;        /* [P,F]   (language_precomp)                                      */
+    const float* d_opacities;       /* [P]                                                             */
+    const float* d_scales;          /* [P,3]   or NULL                                                 */
+    const float* d_rotations;       /* [P,4]   or NULL  (r,x,y,z), used as given (not normalised)      */
+    const float* d_cov3D_precomp;   /* [P,6]   or NULL  (exactly one of scale+rot / cov3D_precomp)     */
+    const float* d_viewmatrix;      /* [16]                                                            */
+    const float* d_projmatrix;      /* [16]  full projection                                           */
+    const float* d_projmatrix_raw;  /* [16]  projection only (used by the pose Jacobian in backward)   */
+    const float* d_campos;          /* [3]                                                             */
+    void* d_workspace;              /* ols_lang_workspace_size() bytes, 256-B aligned, kept by the caller
+                                       from forward to backward (reference: geomBuffer+binningBuffer+imgBuffer) */
+    size_t workspace_bytes;
+    int64_t R_cap;                  /* capacity for Gaussian/tile instances the workspace was sized for  */
+} ols_raster_args;
+
+/* Forward outputs.  Reference: the tuple returned at rasterize_points.cu:230-240.  All buffers are
+ * written completely by the call (no pre-zeroing required). */
+typedef struct ols_fwd_out {
+    float* d_color;       /* [3,H,W]                                                                  */
+    float* d_language;    /* [F,H,W]                                                                  */
+    float* d_depth;       /* [1,H,W]                                                                  */
+    float* d_opacity;     /* [1,H,W]                                                                  */
+    int32_t* d_radii;     /* [P]                                                                      */
+    int32_t* d_n_touched; /* [P]                                                                      */
+} ols_fwd_out;
+
+/* Written asynchronously into the first bytes of the workspace; copy it back with
+ * ols_lang_read_info() (one 32-byte D2H) when the host needs R or the overflow flag. */
+typedef struct ols_fwd_info {
+    int64_t R;            /* num_rendered (reference: return value of LanguageRasterizer::forward)      */
+    int32_t overflow;     /* 1 if R > R_cap: binning/sort/blend were skipped, outputs are zero          */
+    int32_t max_tile_len; /* longest per-tile list                                                     */
+    int32_t n_visible;    /* Gaussians with radii > 0                                                  */
+    int32_t _pad[3];
+} ols_fwd_info;
+
+/* Backward.  Reference: RasterizeLanguageGaussiansBackwardCUDA (rasterize_points.h:121-148,
+ * rasterize_points.cu:333-455).  All d_dL_d* outputs are fully written by the call (the library
+ * zero-fills what it accumulates into). */
+typedef struct ols_bwd_args {
+    const float* d_dL_dout_color;     /* [3,H,W]                                                       */
+    const float* d_dL_dout_language;  /* [F,H,W]                                                       */
+    const float* d_dL_dout_depth;     /* [1,H,W]                                                       */
+    const int32_t* d_radii;           /* [P] from forward                                              */
+    float* d_dL_dmeans2D;    /* [P,3]  (NDC units, z = 0)                                              */
+    float* d_dL_dcolors;     /* [P,3]                                                                  */
+    float* d_dL_dlanguage;   /* [P,F]                                                                  */
+    float* d_dL_dopacity;    /* [P,1]                                                                  */
+    float* d_dL_dmeans3D;    /* [P,3]                                                                  */
+    float* d_dL_dcov3D;      /* [P,6]                                                                  */
+    float* d_dL_dsh;         /* [P,M,3] or NULL when M == 0                                            */
+    float* d_dL_dscales;     /* [P,3]                                                                  */
+    float* d_dL_drotations;  /* [P,4]                                                                  */
+    float* d_dL_dtau;        /* [P,6]  per-Gaussian pose gradient (rho | theta); caller sums over P      */
+} ols_bwd_args;
+
+int ols_abi_version(void);
+const char* ols_last_error(void);
+
+/* 1 if a CUDA device is usable from this process, else 0 (never fails). */
+int ols_cuda_available(void);
+
+/* Bytes of workspace needed for a (P, W, H, tile, F) problem with room for R_cap instances.
+ * Replaces the three growable byte tensors + obtain()/required<T>() of
+ * cuda_rasterizer/rasterizer_impl.cu:155-212.  Returns 0 on invalid arguments. */
+size_t ols_lang_workspace_size(int32_t P, int32_t F, int32_t W, int32_t H, int32_t tile, int64_t R_cap);
+
+/* replaces _C.rasterize_language_gaussians (ext.cpp:18).  Asynchronous on `stream`; no host sync. */
+int ols_lang_forward(const ols_raster_args* args, const ols_fwd_out* out, void* stream);
+
+/* D2H copy of the ols_fwd_info header of a workspace (synchronises `stream`). */
+int ols_lang_read_info(const void* d_workspace, ols_fwd_info* h_info, void* stream);
+
+/* replaces _C.rasterize_language_gaussians_backward (ext.cpp:19). */
+int ols_lang_backward(const ols_raster_args* args, const ols_bwd_args* grads, void* stream);
+
+/* replaces _C.mark_visible (ext.cpp:20; checkFrustum, rasterizer_impl.cu:54-66): present[i] = view.z > 0.2 */
+int ols_mark_visible(int32_t P, const float* d_means3D, const float* d_viewmatrix, const float* d_projmatrix,
+                     uint8_t* d_present, void* stream);
+
+/* Views into the workspace for tests / debugging (device pointers; valid after forward).
+ * Reference counterpart: the fromChunk() carving of rasterizer_impl.cu:173-212. */
+typedef struct ols_ws_view {
+    const float* d_records;        /* [P, rec_floats] packed per-Gaussian blend record:
+                                      x, y, conicA, conicB, conicC, opacity, depth, r, g, b, lang[F], 0-pad */
+    int32_t rec_floats;
+    int32_t n_tiles;
+    const float* d_cov3D;          /* [P,6]                                                            */
+    const uint8_t* d_clamped;      /* [P,3]                                                            */
+    const uint32_t* d_tiles_touched; /* [P]                                                            */
+    const uint32_t* d_ranges;      /* [n_tiles,2]                                                      */
+    const uint32_t* d_point_list;  /* [R] sorted Gaussian ids                                          */
+    const uint64_t* d_keys;        /* [R] per tile segment: (depth_bits << 32 | gaussian id), sorted    */
+    const float* d_final_T;        /* [H*W]                                                            */
+    const uint32_t* d_n_contrib;   /* [H*W]                                                            */
+} ols_ws_view;
+int ols_lang_workspace_view(int32_t P, int32_t F, int32_t W, int32_t H, int32_t tile, int64_t R_cap,
+                            const void* d_workspace, ols_ws_view* view);
+
+/* Host-buffer entry point: the same forward, but every input and output lives in HOST memory.
+ * Copies inputs H2D, renders, copies the six outputs D2H, synchronises.  Device scratch is owned
+ * by the library per call.  This is the form a non-torch binding (ctypes / cgo / JNI) would use. */
+typedef struct ols_host_out {
+    float* h_color; float* h_language; float* h_depth; float* h_opacity; int32_t* h_radii; int32_t* h_n_touched;
+} ols_host_out;
+int ols_lang_forward_host(const ols_raster_args* host_args /* all d_* fields hold HOST pointers; workspace ignored */,
+                          const ols_host_out* out, int64_t* num_rendered);
+
+/* ---------------------------------------------------------------------------------------------
+ * Autoencoder (language/autoencoder/model.py:15-62 AutoencoderMLP, :314-354 EncoderDecoderOnline).
+ * A "chain" is Linear -> [ReLU -> Linear]* with eval-mode BatchNorm already folded into the
+ * preceding Linear by the caller, followed by an optional row-wise L2 normalisation.
+ * Weights are row-major [out,in] float32 as torch.nn.Linear stores them.
+ * ------------------------------------------------------------------------------------------- */
+#define OLS_AE_MAX_LAYERS 8
+typedef struct ols_ae_chain {
+    int32_t n_layers;
+    int32_t dims[OLS_AE_MAX_LAYERS + 1];   /* dims[0] = input width, dims[i+1] = output width of layer i */
+    int32_t normalize;                     /* 1: y /= ||y||_2 per row after the last layer               */
+    int32_t _pad;
+    const float* d_weight[OLS_AE_MAX_LAYERS];  /* [dims[i+1], dims[i]]                                  */
+    const float* d_bias[OLS_AE_MAX_LAYERS];    /* [dims[i+1]]                                           */
+} ols_ae_chain;
+
+/* Opaque prepared chain: weights re-laid out for the tensor-core kernel (done once per weight update). */
+typedef struct ols_ae_plan ols_ae_plan;
+int ols_ae_plan_create(const ols_ae_chain* chain, ols_ae_plan** plan, void* stream);
+void ols_ae_plan_destroy(ols_ae_plan* plan);
+/* y[M, dims[n]] = chain(x[M, dims[0]]); replaces AutoencoderMLP.encode / .decode. */
+int ols_ae_forward(const ols_ae_plan* plan, const float* d_x, float* d_y, int64_t M, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OLS_B200_H_ */

@@ -1,0 +1,126 @@
+"""ctypes binding of the C ABI in include/ols_b200.h (libols_b200.so).
+
+PyTorch is used here only as the owner of device memory and streams: every call passes raw
+``data_ptr()`` values and the current CUDA stream handle.  There is no CPU fallback -- if the
+library is missing or no CUDA device is present the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libols_b200.so")
+
+OLS_OK = 0
+OLS_ERR_OVERFLOW = -4
+FLAG_PREFILTERED = 1 << 0
+FLAG_DEBUG = 1 << 1
+FLAG_BITEXACT_BLEND = 1 << 2
+FLAG_BWD_EXACT = 1 << 3
+AE_MAX_LAYERS = 8
+
+# every symbol include/ols_b200.h declares (tests check that the library exports all of them)
+EXPORTED_SYMBOLS = (
+    "ols_abi_version", "ols_last_error", "ols_cuda_available", "ols_lang_workspace_size", "ols_lang_forward",
+    "ols_lang_read_info", "ols_lang_backward", "ols_mark_visible", "ols_lang_workspace_view",
+    "ols_lang_forward_host", "ols_ae_plan_create", "ols_ae_plan_destroy", "ols_ae_forward",
+)
+
+
+class RasterArgs(C.Structure):
+    _fields_ = [("P", C.c_int32), ("F", C.c_int32), ("sh_degree", C.c_int32), ("M", C.c_int32), ("W", C.c_int32),
+                ("H", C.c_int32), ("tile", C.c_int32), ("flags", C.c_uint32), ("tanfovx", C.c_float),
+                ("tanfovy", C.c_float), ("scale_modifier", C.c_float), ("_pad0", C.c_float)] + \
+               [(n, C.c_void_p) for n in ("d_bg", "d_means3D", "d_shs", "d_colors_precomp", "d_language",
+                                          "d_opacities", "d_scales", "d_rotations", "d_cov3D_precomp", "d_viewmatrix",
+                                          "d_projmatrix", "d_projmatrix_raw", "d_campos", "d_workspace")] + \
+               [("workspace_bytes", C.c_size_t), ("R_cap", C.c_int64)]
+
+
+class FwdOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("d_color", "d_language", "d_depth", "d_opacity", "d_radii", "d_n_touched")]
+
+
+class FwdInfo(C.Structure):
+    _fields_ = [("R", C.c_int64), ("overflow", C.c_int32), ("max_tile_len", C.c_int32), ("n_visible", C.c_int32),
+                ("_pad", C.c_int32 * 3)]
+
+
+class BwdArgs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("d_dL_dout_color", "d_dL_dout_language", "d_dL_dout_depth", "d_radii",
+                                          "d_dL_dmeans2D", "d_dL_dcolors", "d_dL_dlanguage", "d_dL_dopacity",
+                                          "d_dL_dmeans3D", "d_dL_dcov3D", "d_dL_dsh", "d_dL_dscales",
+                                          "d_dL_drotations", "d_dL_dtau")]
+
+
+class WsView(C.Structure):
+    _fields_ = [("d_records", C.c_void_p), ("rec_floats", C.c_int32), ("n_tiles", C.c_int32)] + \
+               [(n, C.c_void_p) for n in ("d_cov3D", "d_clamped", "d_tiles_touched", "d_ranges", "d_point_list",
+                                          "d_keys", "d_final_T", "d_n_contrib")]
+
+
+class HostOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("h_color", "h_language", "h_depth", "h_opacity", "h_radii", "h_n_touched")]
+
+
+class AEChain(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("dims", C.c_int32 * (AE_MAX_LAYERS + 1)), ("normalize", C.c_int32),
+                ("_pad", C.c_int32), ("d_weight", C.c_void_p * AE_MAX_LAYERS), ("d_bias", C.c_void_p * AE_MAX_LAYERS)]
+
+
+_LIB: Optional[C.CDLL] = None
+
+
+class OlsError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"ols_b200 error {status}: {msg}")
+        self.status = status
+
+
+def lib() -> C.CDLL:
+    """Loads libols_b200.so (building it first if the sources are newer and nvcc is present)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        _build.build()
+    L = C.CDLL(LIB_PATH)
+    L.ols_abi_version.restype = C.c_int
+    L.ols_last_error.restype = C.c_char_p
+    L.ols_cuda_available.restype = C.c_int
+    L.ols_lang_workspace_size.restype = C.c_size_t
+    L.ols_lang_workspace_size.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64]
+    L.ols_lang_forward.argtypes = [C.POINTER(RasterArgs), C.POINTER(FwdOut), C.c_void_p]
+    L.ols_lang_read_info.argtypes = [C.c_void_p, C.POINTER(FwdInfo), C.c_void_p]
+    L.ols_lang_backward.argtypes = [C.POINTER(RasterArgs), C.POINTER(BwdArgs), C.c_void_p]
+    L.ols_mark_visible.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ols_lang_workspace_view.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
+                                          C.c_void_p, C.POINTER(WsView)]
+    L.ols_lang_forward_host.argtypes = [C.POINTER(RasterArgs), C.POINTER(HostOut), C.POINTER(C.c_int64)]
+    L.ols_ae_plan_create.argtypes = [C.POINTER(AEChain), C.POINTER(C.c_void_p), C.c_void_p]
+    L.ols_ae_plan_destroy.argtypes = [C.c_void_p]
+    L.ols_ae_plan_destroy.restype = None
+    L.ols_ae_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    _LIB = L
+    return L
+
+
+def check(status: int) -> None:
+    if status != OLS_OK:
+        raise OlsError(status, lib().ols_last_error().decode("utf-8", "replace"))
+
+
+def require_cuda() -> None:
+    if not lib().ols_cuda_available():
+        raise OlsError(-2, "no CUDA device: online_lang_splatting_b200 has no CPU path")
+
+
+def ptr(t) -> Optional[int]:
+    """data_ptr of a tensor; None / empty tensors map to NULL exactly like the reference's
+    `torch.Tensor([])` == "not provided" convention (diff_gaussian_rasterization/__init__.py:530-548)."""
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()

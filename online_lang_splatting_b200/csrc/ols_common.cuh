@@ -1,0 +1,94 @@
+// ols_common.cuh -- shared definitions of the B200 rasterizer kernels (workspace layout, helpers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/ols_b200.h"
+
+namespace ols {
+
+// ---- packed per-Gaussian blend record ------------------------------------------------------------
+// floats: 0 x | 1 y | 2 conicA | 3 conicB | 4 conicC | 5 opacity | 6 pth | 7 depth | 8 r | 9 g | 10 b | 11.. lang[F]
+// rounded up to a multiple of 4 floats so a record is a whole number of 16-byte chunks
+// (F=15 -> 28 floats = 112 B, F=3 -> 16 floats = 64 B).  `pth` is a conservative lower bound on the
+// exponent below which alpha < 1/255 is certain, so the blend kernels can skip expf() for far pixels
+// without changing any decision of the reference (forward.cu:446-457).
+constexpr int REC_X = 0, REC_Y = 1, REC_A = 2, REC_B = 3, REC_C = 4, REC_OP = 5, REC_PTH = 6, REC_DEPTH = 7,
+              REC_RGB = 8, REC_LANG = 11;
+__host__ __device__ constexpr int rec_floats(int F) { return ((11 + F) + 3) / 4 * 4; }
+
+struct WsLayout {
+    size_t info, tile_count, tile_cursor, ranges, records, depths, cov3D, clamped, tiles_touched, rect, final_T,
+        n_contrib, keys, point_list, total;
+    int n_tiles, gx, gy, rec;
+};
+
+inline __host__ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Single workspace replacing geomBuffer / binningBuffer / imgBuffer (rasterizer_impl.cu:155-212).
+inline __host__ WsLayout ws_layout(int P, int F, int W, int H, int tile, int64_t R_cap) {
+    WsLayout L;
+    L.gx = (W + tile - 1) / tile;
+    L.gy = (H + tile - 1) / tile;
+    L.n_tiles = L.gx * L.gy;
+    L.rec = rec_floats(F);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
+    const size_t Pz = (size_t)(P > 0 ? P : 1), HW = (size_t)W * H, Rz = (size_t)(R_cap > 0 ? R_cap : 1);
+    L.info = take(256);
+    L.tile_count = take(4 * (size_t)L.n_tiles);
+    L.tile_cursor = take(4 * (size_t)L.n_tiles);
+    L.ranges = take(8 * (size_t)L.n_tiles);
+    L.records = take(4 * (size_t)L.rec * Pz);
+    L.depths = take(4 * Pz);
+    L.cov3D = take(24 * Pz);
+    L.clamped = take(4 * Pz);  // 3 flags packed in the low bytes of a u32
+    L.tiles_touched = take(4 * Pz);
+    L.rect = take(8 * Pz);
+    L.final_T = take(4 * HW);
+    L.n_contrib = take(4 * HW);
+    L.keys = take(8 * Rz);
+    L.point_list = take(4 * Rz);
+    L.total = o;
+    return L;
+}
+
+struct DeviceInfo {  // lives at workspace offset 0; first 32 bytes == ols_fwd_info
+    unsigned long long R;
+    int overflow;
+    int max_tile_len;
+    int n_visible;
+    int pad[3];
+};
+
+// ---- arithmetic helpers: explicit rounding so nvcc cannot re-associate / contract ----------------
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+}  // namespace ols
+
+// error plumbing (ols_api.cu)
+void ols_set_error(const char* fmt, ...);
+#define OLS_CUDA_TRY(expr)                                                                     \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            ols_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return OLS_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+// kernel launchers implemented in ols_forward.cu / ols_backward.cu
+int ols_launch_forward(const ols_raster_args* a, const ols_fwd_out* o, const ols::WsLayout& L, cudaStream_t st);
+int ols_launch_backward(const ols_raster_args* a, const ols_bwd_args* g, const ols::WsLayout& L, cudaStream_t st);

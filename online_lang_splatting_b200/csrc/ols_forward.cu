@@ -1,0 +1,685 @@
+// ols_forward.cu -- forward pass of the language-feature Gaussian rasterizer for sm_100a.
+//
+// Pipeline (all on the caller's stream, no host synchronisation):
+//   k_preprocess   one thread per Gaussian: cull / project / covariance / conic / radius / tile rect,
+//                  packs the blend record, counts instances per tile            (reference: forward.cu:262-371)
+//   k_tile_scan    one CTA: exclusive scan of per-tile counts -> ranges, R        (replaces the InclusiveSum over
+//                  Gaussians + D2H read of rasterizer_impl.cu:451-455)
+//   k_scatter      one thread per Gaussian: writes (depth_bits<<32 | id) into its tiles' buckets
+//                                                                               (reference: duplicateWithKeys :70-111)
+//   k_sort_tiles   one CTA per tile: bitonic sort of the bucket in shared memory  (replaces the global 44-bit
+//                  cub::DeviceRadixSort of :478-483; result order is identical: (tile, depth bits, id) ascending)
+//   k_blend        one CTA per tile: front-to-back alpha blend of RGB + depth + F language channels
+//                                                                               (reference: forward.cu:377-513)
+//
+// Bit-exactness: the per-Gaussian arithmetic mirrors the compiled reference operation by operation
+// (oracle/REF_ARITHMETIC.md), written with explicit-rounding intrinsics so that radii, tile rects,
+// depths and every alpha/T threshold decision are identical to the reference build.
+#include "ols_common.cuh"
+
+#include <cooperative_groups.h>
+#include <math_constants.h>
+#include <cstdio>
+
+namespace ols {
+
+__constant__ float SH_C0 = 0.28209479177387814f;
+__constant__ float SH_C1 = 0.4886025119029199f;
+__constant__ float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                               -1.0925484305920792f, 0.5462742152960396f};
+__constant__ float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                               -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+
+struct PreArgs {
+    int P, F, sh_degree, M, W, H, tile, gx, gy, rec;
+    unsigned flags;
+    float tanfovx, tanfovy, focal_x, focal_y, scale_modifier;
+    const float *means3D, *shs, *colors_precomp, *language, *opacities, *scales, *rotations, *cov3D_precomp;
+    const float *viewmatrix, *projmatrix, *campos;
+    float* records;
+    float* depths;
+    float* cov3D;
+    uint32_t* clamped;
+    uint32_t* tiles_touched;
+    uint2* rect;
+    uint32_t* tile_count;
+    int32_t* radii;
+    DeviceInfo* info;
+};
+
+// m[i]*x + m[4+i]*y + m[8+i]*z + m[12+i] in the compiled reference's order
+__device__ __forceinline__ float xform_row(const float* m, int i, float x, float y, float z) {
+    return fadd(ffma(z, m[8 + i], ffma(x, m[i], fmul(y, m[4 + i]))), m[12 + i]);
+}
+__device__ __forceinline__ float dot3c(float a0, float a1, float a2, float b0, float b1, float b2) {
+    return ffma(a2, b2, ffma(a0, b0, fmul(a1, b1)));
+}
+
+// forward.cu:121-155 (computeCov3D)
+__device__ __forceinline__ void cov3d_from_scale_rot(const float sx0, const float sy0, const float sz0, float mod,
+                                                     const float4 q, float* out) {
+    const float r = q.x, x = q.y, y = q.z, z = q.w;
+    const float sx = fmul(sx0, mod), sy = fmul(sy0, mod), sz = fmul(sz0, mod);
+    const float yy = fmul(y, y), zz = fmul(z, z);
+    const float xx_yy = ffma(x, x, yy);
+    const float R22 = fsub(1.0f, fadd(xx_yy, xx_yy));
+    const float xz = fmul(x, z);
+    const float xz_m_ry = ffma(-r, y, xz), xz_p_ry = ffma(r, y, xz);
+    const float rx = fmul(r, x);
+    const float yz_p_rx = ffma(y, z, rx), yz_m_rx = ffma(y, z, -rx);
+    const float rz = fmul(r, z);
+    const float xy_m_rz = ffma(x, y, -rz), xy_p_rz = ffma(x, y, rz);
+    const float yy_zz = fadd(yy, zz);
+    const float R00 = fsub(1.0f, fadd(yy_zz, yy_zz));
+    const float xx_zz = ffma(x, x, zz);
+    const float R11 = fsub(1.0f, fadd(xx_zz, xx_zz));
+    const float A2 = fadd(xz_m_ry, xz_m_ry), B2 = fadd(yz_p_rx, yz_p_rx), C2 = fadd(xz_p_ry, xz_p_ry);
+    const float D2 = fadd(xy_m_rz, xy_m_rz), E2 = fadd(yz_m_rx, yz_m_rx), G2 = fadd(xy_p_rz, xy_p_rz);
+    // M = S * R as GLM evaluates it: the zero entries of S stay in the products
+    const float zB = fmul(0.0f, B2);
+    const float m22 = ffma(sz, R22, ffma(0.0f, A2, zB));
+    const float m02 = ffma(0.0f, R22, ffma(sx, A2, zB));
+    const float m12 = ffma(0.0f, R22, ffma(0.0f, A2, fmul(sy, B2)));
+    const float z00 = fmul(0.0f, R00);
+    const float m20 = ffma(sz, C2, ffma(0.0f, D2, z00));
+    const float m00 = ffma(0.0f, C2, ffma(0.0f, D2, fmul(sx, R00)));
+    const float m10 = ffma(0.0f, C2, ffma(sy, D2, z00));
+    const float z11 = fmul(0.0f, R11);
+    const float m21 = ffma(sz, E2, ffma(0.0f, G2, z11));
+    const float m01 = ffma(0.0f, E2, ffma(sx, G2, z11));
+    const float m11 = ffma(0.0f, E2, ffma(0.0f, G2, fmul(sy, R11)));
+    out[0] = dot3c(m00, m10, m20, m00, m10, m20);
+    out[1] = dot3c(m00, m10, m20, m01, m11, m21);
+    out[2] = dot3c(m00, m10, m20, m02, m12, m22);
+    out[3] = dot3c(m01, m11, m21, m01, m11, m21);
+    out[4] = dot3c(m01, m11, m21, m02, m12, m22);
+    out[5] = dot3c(m02, m12, m22, m02, m12, m22);
+}
+
+// auxiliary.h:41-44 -- evaluated in double by the reference
+__device__ __forceinline__ float ndc2pix(float v, int S) {
+    return __double2float_rn(__dmul_rn(__fma_rn(__dadd_rn((double)v, 1.0), (double)S, -1.0), 0.5));
+}
+
+// auxiliary.h:46-56
+__device__ __forceinline__ void get_rect(float px, float py, int r, int tile, int gx, int gy, int* mn, int* mx) {
+    const float rf = (float)r, tf = (float)tile;
+    mn[0] = min(gx, max(0, __float2int_rz(fdiv(fsub(px, rf), tf))));
+    mn[1] = min(gy, max(0, __float2int_rz(fdiv(fsub(py, rf), tf))));
+    mx[0] = min(gx, max(0, __float2int_rz(fdiv(fadd(fadd(fadd(px, rf), tf), -1.0f), tf))));
+    mx[1] = min(gy, max(0, __float2int_rz(fdiv(fadd(fadd(fadd(py, rf), tf), -1.0f), tf))));
+}
+
+// forward.cu:23-74 (computeColorFromSH).  Degree 0 (the SLAM configuration) is bit-pinned; higher
+// degrees follow the reference's expression order under nvcc's default contraction.
+__device__ void sh_to_rgb(int deg, int M, const float* sh, float dx, float dy, float dz, float* res) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) res[c] = fmul(SH_C0, sh[c]);
+    if (deg > 0) {
+        const float len = sqrtf(ffma(dz, dz, ffma(dx, dx, fmul(dy, dy))));
+        const float x = dx / len, y = dy / len, z = dz / len;
+#pragma unroll
+        for (int c = 0; c < 3; c++) res[c] = res[c] - SH_C1 * y * sh[3 + c] + SH_C1 * z * sh[6 + c] - SH_C1 * x * sh[9 + c];
+        if (deg > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                res[c] = res[c] + SH_C2[0] * xy * sh[12 + c] + SH_C2[1] * yz * sh[15 + c] +
+                         SH_C2[2] * (2.0f * zz - xx - yy) * sh[18 + c] + SH_C2[3] * xz * sh[21 + c] +
+                         SH_C2[4] * (xx - yy) * sh[24 + c];
+            if (deg > 2) {
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                    res[c] = res[c] + SH_C3[0] * y * (3.0f * xx - yy) * sh[27 + c] + SH_C3[1] * xy * z * sh[30 + c] +
+                             SH_C3[2] * y * (4.0f * zz - xx - yy) * sh[33 + c] +
+                             SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[36 + c] +
+                             SH_C3[4] * x * (4.0f * zz - xx - yy) * sh[39 + c] + SH_C3[5] * z * (xx - yy) * sh[42 + c] +
+                             SH_C3[6] * x * (xx - 3.0f * yy) * sh[45 + c];
+            }
+        }
+    }
+}
+
+constexpr int PRE_THREADS = 256;
+
+// One thread per Gaussian.  Inputs with 3-float rows are staged through shared memory so the global
+// loads are contiguous 16-byte accesses.
+__global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreArgs a) {
+    __shared__ float s_mean[PRE_THREADS * 3];
+    __shared__ float s_scale[PRE_THREADS * 3];
+    __shared__ float s_V[16], s_Pm[16];
+    const int tid = threadIdx.x;
+    const int base = blockIdx.x * PRE_THREADS;
+    const int nloc = min(PRE_THREADS, a.P - base);
+    if (tid < 16) { s_V[tid] = a.viewmatrix[tid]; s_Pm[tid] = a.projmatrix[tid]; }
+    for (int e = tid; e < nloc * 3; e += PRE_THREADS) {
+        s_mean[e] = a.means3D[(size_t)base * 3 + e];
+        if (a.scales) s_scale[e] = a.scales[(size_t)base * 3 + e];
+    }
+    // language rows -> records (coalesced read, near-coalesced write)
+    {
+        const int F = a.F, rec = a.rec;
+        const float* src = a.language + (size_t)base * F;
+        float* dst = a.records + (size_t)base * rec;
+        for (int e = tid; e < nloc * F; e += PRE_THREADS) {
+            const int g = e / F, c = e - g * F;
+            dst[(size_t)g * rec + REC_LANG + c] = src[e];
+        }
+    }
+    __syncthreads();
+    if (tid >= nloc) return;
+    const int i = base + tid;
+    a.radii[i] = 0;
+    a.tiles_touched[i] = 0;
+    const float px3 = s_mean[3 * tid], py3 = s_mean[3 * tid + 1], pz3 = s_mean[3 * tid + 2];
+    const float* V = s_V;
+    const float* Pm = s_Pm;
+    // in_frustum (auxiliary.h:139-164)
+    const float vz = xform_row(V, 2, px3, py3, pz3);
+    if (!(vz > 0.2f)) {
+        if (a.flags & OLS_FLAG_PREFILTERED) {
+            printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+            __trap();
+        }
+        return;
+    }
+    const float hx = xform_row(Pm, 0, px3, py3, pz3);
+    const float hy = xform_row(Pm, 1, px3, py3, pz3);
+    const float hw = xform_row(Pm, 3, px3, py3, pz3);
+    const float pw = __frcp_rn(fadd(hw, 0.0000001f));
+    const float projx = fmul(hx, pw), projy = fmul(hy, pw);
+    float c3[6];
+    if (a.cov3D_precomp) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) c3[k] = a.cov3D_precomp[(size_t)6 * i + k];
+    } else {
+        const float4 q = reinterpret_cast<const float4*>(a.rotations)[i];
+        cov3d_from_scale_rot(s_scale[3 * tid], s_scale[3 * tid + 1], s_scale[3 * tid + 2], a.scale_modifier, q, c3);
+#pragma unroll
+        for (int k = 0; k < 6; k++) a.cov3D[(size_t)6 * i + k] = c3[k];
+    }
+    // computeCov2D (forward.cu:77-116)
+    float ca, cb, cc;
+    {
+        const float tz = vz;
+        const float txr = xform_row(V, 0, px3, py3, pz3);
+        const float tyr = xform_row(V, 1, px3, py3, pz3);
+        const float limx = fmul(a.tanfovx, 1.3f), limy = fmul(a.tanfovy, 1.3f);
+        const float cx = fminf(fmaxf(fdiv(txr, tz), -limx), limx);
+        const float cy = fminf(fmaxf(fdiv(tyr, tz), -limy), limy);
+        const float tz2 = fmul(tz, tz);
+        const float J00 = fdiv(a.focal_x, tz);
+        const float J02 = fdiv(fmul(fmul(tz, -cx), a.focal_x), tz2);
+        const float J11 = fdiv(a.focal_y, tz);
+        const float J12 = fdiv(fmul(fmul(tz, -cy), a.focal_y), tz2);
+        float ta[3], tb[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            ta[k] = ffma(V[4 * k + 2], J02, ffma(V[4 * k], J00, fmul(0.0f, V[4 * k + 1])));
+            tb[k] = ffma(V[4 * k + 2], J12, ffma(0.0f, V[4 * k], fmul(V[4 * k + 1], J11)));
+        }
+        const float ux0 = dot3c(ta[0], ta[1], ta[2], c3[0], c3[1], c3[2]);
+        const float ux1 = dot3c(ta[0], ta[1], ta[2], c3[1], c3[3], c3[4]);
+        const float ux2 = dot3c(ta[0], ta[1], ta[2], c3[2], c3[4], c3[5]);
+        const float uy0 = dot3c(tb[0], tb[1], tb[2], c3[0], c3[1], c3[2]);
+        const float uy1 = dot3c(tb[0], tb[1], tb[2], c3[1], c3[3], c3[4]);
+        const float uy2 = dot3c(tb[0], tb[1], tb[2], c3[2], c3[4], c3[5]);
+        ca = fadd(dot3c(ta[0], ta[1], ta[2], ux0, ux1, ux2), 0.3f);
+        cb = dot3c(ta[0], ta[1], ta[2], uy0, uy1, uy2);
+        cc = fadd(dot3c(tb[0], tb[1], tb[2], uy0, uy1, uy2), 0.3f);
+    }
+    const float det = ffma(ca, cc, -fmul(cb, cb));
+    if (det == 0.0f) return;
+    const float det_inv = __frcp_rn(det);
+    const float mid = fmul(fadd(ca, cc), 0.5f);
+    const float sq = __fsqrt_rn(fmaxf(ffma(mid, mid, -det), 0.1f));
+    const float lam = fmaxf(fadd(mid, sq), fsub(mid, sq));
+    const float my_radius = ceilf(fmul(__fsqrt_rn(lam), 3.0f));
+    const float pix_x = ndc2pix(projx, a.W), pix_y = ndc2pix(projy, a.H);
+    int mn[2], mx[2];
+    const int ri = __float2int_rz(my_radius);
+    get_rect(pix_x, pix_y, ri, a.tile, a.gx, a.gy, mn, mx);
+    const uint32_t tiles = (uint32_t)(mx[0] - mn[0]) * (uint32_t)(mx[1] - mn[1]);
+    if (tiles == 0) return;
+
+    float rgb[3];
+    if (a.colors_precomp) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) rgb[c] = a.colors_precomp[(size_t)3 * i + c];
+    } else {
+        float res[3];
+        sh_to_rgb(a.sh_degree, a.M, a.shs + (size_t)i * a.M * 3, px3 - a.campos[0], py3 - a.campos[1],
+                  pz3 - a.campos[2], res);
+        uint32_t cl = 0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            cl |= (uint32_t)(!(res[c] >= -0.5f)) << (8 * c);  // compiled form of "result < 0 after +0.5"
+            rgb[c] = fmaxf(fadd(res[c], 0.5f), 0.0f);
+        }
+        a.clamped[i] = cl;
+    }
+    const float op = a.opacities[i];
+    // conservative cut: power < pth  =>  op*exp(power) < 1/255 with a wide safety margin
+    const float pth = (op == op) ? (op > 0.0f ? logf(1.0f / (255.0f * op)) - 0.01f : CUDART_INF_F) : -CUDART_INF_F;
+    float4* r4 = reinterpret_cast<float4*>(a.records + (size_t)i * a.rec);
+    r4[0] = make_float4(pix_x, pix_y, fmul(cc, det_inv), fmul(cb, -det_inv));
+    r4[1] = make_float4(fmul(ca, det_inv), op, pth, vz);
+    float* rf = a.records + (size_t)i * a.rec;
+    rf[REC_RGB] = rgb[0];
+    rf[REC_RGB + 1] = rgb[1];
+    rf[REC_RGB + 2] = rgb[2];
+    for (int c = REC_LANG + a.F; c < a.rec; c++) rf[c] = 0.0f;
+    a.depths[i] = vz;
+    a.radii[i] = ri;
+    a.rect[i] = make_uint2((uint32_t)mn[0] | ((uint32_t)mn[1] << 16), (uint32_t)mx[0] | ((uint32_t)mx[1] << 16));
+    a.tiles_touched[i] = tiles;
+    for (int y = mn[1]; y < mx[1]; y++)
+        for (int x = mn[0]; x < mx[0]; x++) atomicAdd(&a.tile_count[y * a.gx + x], 1u);
+}
+
+// One CTA: exclusive scan over tiles.  ranges of empty tiles stay (0,0) like the reference's memset
+// (rasterizer_impl.cu:485).
+constexpr int SCAN_THREADS = 1024;
+__global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(const uint32_t* __restrict__ tile_count,
+                                                          uint32_t* __restrict__ tile_cursor,
+                                                          uint2* __restrict__ ranges, int n_tiles,
+                                                          unsigned long long R_cap, DeviceInfo* info) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    __shared__ uint32_t s_max;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) { s_carry = 0; s_max = 0; }
+    __syncthreads();
+    uint32_t local_max = 0;
+    for (int base = 0; base < n_tiles; base += SCAN_THREADS) {
+        const int t = base + tid;
+        const uint32_t c = t < n_tiles ? tile_count[t] : 0u;
+        local_max = max(local_max, c);
+        uint32_t v = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += n;
+        }
+        if (lane == 31) s_warp[wid] = v;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += n;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t incl = v + (wid ? s_warp[wid - 1] : 0u) + s_carry;
+        if (t < n_tiles) {
+            ranges[t] = c ? make_uint2(incl - c, incl) : make_uint2(0u, 0u);
+            tile_cursor[t] = incl - c;
+        }
+        __syncthreads();
+        if (tid == SCAN_THREADS - 1) s_carry = incl;
+        __syncthreads();
+    }
+    atomicMax(&s_max, local_max);
+    __syncthreads();
+    if (tid == 0) {
+        info->R = s_carry;
+        info->overflow = (unsigned long long)s_carry > R_cap ? 1 : 0;
+        info->max_tile_len = (int)s_max;
+    }
+}
+
+// duplicateWithKeys (rasterizer_impl.cu:70-111), bucketed: the tile id is implicit in the bucket.
+__global__ void __launch_bounds__(256) k_scatter(int P, int gx, const uint32_t* __restrict__ tiles_touched,
+                                                 const uint2* __restrict__ rect, const float* __restrict__ depths,
+                                                 uint32_t* __restrict__ tile_cursor, unsigned long long* __restrict__ keys,
+                                                 const DeviceInfo* __restrict__ info) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P || info->overflow) return;
+    if (tiles_touched[i] == 0) return;
+    const uint2 r = rect[i];
+    const int x0 = r.x & 0xffff, y0 = r.x >> 16, x1 = r.y & 0xffff, y1 = r.y >> 16;
+    const unsigned long long key = ((unsigned long long)__float_as_uint(depths[i]) << 32) | (unsigned)i;
+    for (int y = y0; y < y1; y++)
+        for (int x = x0; x < x1; x++) {
+            const uint32_t slot = atomicAdd(&tile_cursor[y * gx + x], 1u);
+            keys[slot] = key;
+        }
+}
+
+// Per-tile sort.  All comparators are ascending ("mirror" first step per stage), so positions >= n
+// behave as +inf padding without being stored; tiles longer than the shared-memory chunk run the
+// wide strides in global memory and the narrow ones chunk by chunk in shared memory.
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_CHUNK = 4096;  // keys per shared-memory chunk (32 KB)
+
+__device__ __forceinline__ void cmpswap(unsigned long long* s, int a, int b, int n) {
+    if (b < n) {
+        const unsigned long long va = s[a], vb = s[b];
+        if (va > vb) { s[a] = vb; s[b] = va; }
+    }
+}
+__device__ __forceinline__ int pow2_cover(int n) {
+    int span = 1;
+    while (span < n) span <<= 1;
+    return span;
+}
+// mirror step of stage k over `half_pairs` comparator slots: (blk*k + off, blk*k + k-1-off)
+__device__ __forceinline__ void bitonic_mirror(unsigned long long* s, int k, int half_pairs, int n) {
+    const int sh = __ffs(k) - 2;  // log2(k/2)
+    for (int i = threadIdx.x; i < half_pairs; i += SORT_THREADS) {
+        const int blk = i >> sh, off = i & ((k >> 1) - 1);
+        cmpswap(s, (blk << (sh + 1)) + off, (blk << (sh + 1)) + (k - 1 - off), n);
+    }
+    __syncthreads();
+}
+// half-cleaner step with stride j: (a, a|j) for every a with bit j clear
+__device__ __forceinline__ void bitonic_step(unsigned long long* s, int j, int half_pairs, int n) {
+    for (int i = threadIdx.x; i < half_pairs; i += SORT_THREADS) {
+        const int a = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+        cmpswap(s, a, a | j, n);
+    }
+    __syncthreads();
+}
+// complete sort of n <= SORT_CHUNK keys held in shared memory
+__device__ void smem_sort_full(unsigned long long* s, int n) {
+    const int span = pow2_cover(n);
+    for (int k = 2; k <= span; k <<= 1) {
+        bitonic_mirror(s, k, span >> 1, n);
+        for (int j = k >> 2; j > 0; j >>= 1) bitonic_step(s, j, span >> 1, n);
+    }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(unsigned long long* __restrict__ keys,
+                                                            uint32_t* __restrict__ point_list,
+                                                            const uint2* __restrict__ ranges,
+                                                            const DeviceInfo* __restrict__ info) {
+    __shared__ unsigned long long s[SORT_CHUNK];
+    if (info->overflow) return;
+    const uint2 rg = ranges[blockIdx.x];
+    const int n = (int)(rg.y - rg.x);
+    if (n <= 0) return;
+    unsigned long long* g = keys + rg.x;
+    const int tid = threadIdx.x;
+    if (n <= SORT_CHUNK) {
+        for (int i = tid; i < n; i += SORT_THREADS) s[i] = g[i];
+        __syncthreads();
+        smem_sort_full(s, n);
+        for (int i = tid; i < n; i += SORT_THREADS) {
+            const unsigned long long v = s[i];
+            g[i] = v;
+            point_list[rg.x + i] = (uint32_t)v;
+        }
+        return;
+    }
+    // long tile: strides >= SORT_CHUNK run in global memory, the rest chunk by chunk in shared memory
+    const int span = pow2_cover(n);
+    const int n_chunks = (n + SORT_CHUNK - 1) / SORT_CHUNK;
+    for (int c = 0; c < n_chunks; c++) {
+        const int cb = c * SORT_CHUNK, nl = min(SORT_CHUNK, n - cb);
+        for (int i = tid; i < nl; i += SORT_THREADS) s[i] = g[cb + i];
+        __syncthreads();
+        smem_sort_full(s, nl);
+        if (nl < SORT_CHUNK) {  // smem_sort_full stops at pow2_cover(nl); that is a complete sort of the chunk
+        }
+        for (int i = tid; i < nl; i += SORT_THREADS) g[cb + i] = s[i];
+        __syncthreads();
+    }
+    for (int k = SORT_CHUNK * 2; k <= span; k <<= 1) {
+        __threadfence_block();
+        bitonic_mirror(g, k, span >> 1, n);
+        for (int j = k >> 2; j >= SORT_CHUNK; j >>= 1) bitonic_step(g, j, span >> 1, n);
+        for (int c = 0; c < n_chunks; c++) {
+            const int cb = c * SORT_CHUNK, nl = min(SORT_CHUNK, n - cb);
+            for (int i = tid; i < nl; i += SORT_THREADS) s[i] = g[cb + i];
+            __syncthreads();
+            for (int j = SORT_CHUNK >> 1; j > 0; j >>= 1) bitonic_step(s, j, SORT_CHUNK >> 1, nl);
+            for (int i = tid; i < nl; i += SORT_THREADS) g[cb + i] = s[i];
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < n; i += SORT_THREADS) point_list[rg.x + i] = (uint32_t)g[i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Forward blend (forward.cu:377-513).  One CTA of 256 threads per tile, one pixel per thread (threads
+// beyond TILE*TILE only help fetching).  The tile's Gaussian records are streamed global -> shared
+// with cp.async in double-buffered batches; the per-pixel loop reads them as warp-wide broadcasts.
+// ---------------------------------------------------------------------------------------------------
+constexpr int BLEND_THREADS = 256;
+constexpr int BLEND_BATCH = 64;
+
+struct BlendArgs {
+    int W, H, gx;
+    const uint2* ranges;
+    const uint32_t* point_list;
+    const float* records;
+    const float* bg;
+    const DeviceInfo* info;
+    float* final_T;
+    uint32_t* n_contrib;
+    float* out_color;
+    float* out_language;
+    float* out_depth;
+    float* out_opacity;
+    int32_t* n_touched;
+};
+
+template <int TILE, int F, bool BITEXACT>
+__global__ void __launch_bounds__(BLEND_THREADS) k_blend(const BlendArgs a) {
+    constexpr int REC = rec_floats(F);
+    constexpr int R4 = REC / 4;                 // float4 chunks per record
+    constexpr int CHUNKS = BLEND_BATCH * R4;    // 16-byte chunks per batch
+    constexpr int NCH = 3 + F + 1;              // rgb + lang + depth accumulators
+    __shared__ __align__(16) float s_rec[2][BLEND_BATCH * REC];
+    __shared__ uint32_t s_id[2][BLEND_BATCH];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int tile_x = blockIdx.x % a.gx, tile_y = blockIdx.x / a.gx;
+    const int lx = tid % TILE, ly = tid / TILE;
+    const int pxi = tile_x * TILE + lx, pyi = tile_y * TILE + ly;
+    const bool inside = (tid < TILE * TILE) && pxi < a.W && pyi < a.H;
+    const float pfx = (float)pxi, pfy = (float)pyi;
+
+    uint2 rg = a.ranges[blockIdx.x];
+    if (a.info->overflow) rg = make_uint2(0u, 0u);
+    const int total = (int)(rg.y - rg.x);
+    const int n_batches = (total + BLEND_BATCH - 1) / BLEND_BATCH;
+
+    auto issue = [&](int b) {  // cp.async the records of batch b into buffer b&1
+        const int cnt = min(BLEND_BATCH, total - b * BLEND_BATCH);
+        const int buf = b & 1;
+        for (int c = tid; c < CHUNKS; c += BLEND_THREADS) {
+            const int g = c / R4, q = c - g * R4;
+            if (g < cnt) {
+                const uint32_t id = a.point_list[rg.x + b * BLEND_BATCH + g];
+                if (q == 0) s_id[buf][g] = id;
+                cp_async16(&s_rec[buf][g * REC + q * 4], a.records + (size_t)id * REC + q * 4);
+            }
+        }
+        cp_async_commit();
+    };
+
+    float T = 1.0f;
+    float acc[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; c++) acc[c] = 0.0f;
+    uint32_t last_contributor = 0;
+    bool done = !inside;
+
+    if (n_batches > 0) issue(0);
+    for (int b = 0; b < n_batches; b++) {
+        cp_async_wait<0>();
+        // all threads done -> stop (forward.cu:425-427); also publishes batch b and frees buffer (b+1)&1
+        if (__syncthreads_count(done) == BLEND_THREADS) break;
+        if (b + 1 < n_batches) issue(b + 1);
+        if (__all_sync(0xffffffffu, done)) continue;
+        const int cnt = min(BLEND_BATCH, total - b * BLEND_BATCH);
+        const float4* r4 = reinterpret_cast<const float4*>(s_rec[b & 1]);
+        const uint32_t* ids = s_id[b & 1];
+        const uint32_t cbase = (uint32_t)b * BLEND_BATCH;
+        for (int j = 0; j < cnt; j++) {
+            bool touch = false;
+            if (!done) {
+                const float4 g0 = r4[j * R4 + 0];  // x y A B
+                const float4 g1 = r4[j * R4 + 1];  // C op pth depth
+                const float dx = fsub(g0.x, pfx), dy = fsub(g0.y, pfy);
+                const float power =
+                    ffma(ffma(dx, fmul(dx, g0.z), fmul(dy, fmul(dy, g1.x))), -0.5f, -fmul(dy, fmul(dx, g0.w)));
+                if (!(power > 0.0f) && !(power < g1.z)) {
+                    const float alpha = fminf(fmul(g1.y, expf(power)), 0.99f);
+                    if (!(alpha < 1.0f / 255.0f)) {
+                        const float test_T = fmul(T, fsub(1.0f, alpha));
+                        if (test_T < 0.0001f) {
+                            done = true;
+                        } else {
+                            const float4 g2 = r4[j * R4 + 2];  // r g b L0
+                            if (BITEXACT) {
+                                acc[0] = ffma(T, fmul(alpha, g2.x), acc[0]);
+                                acc[1] = ffma(T, fmul(alpha, g2.y), acc[1]);
+                                acc[2] = ffma(T, fmul(alpha, g2.z), acc[2]);
+                                acc[3] = ffma(T, fmul(alpha, g2.w), acc[3]);
+#pragma unroll
+                                for (int q = 3; q < R4; q++) {
+                                    const float4 v = r4[j * R4 + q];
+                                    const int c0 = 4 + (q - 3) * 4;
+                                    if (c0 + 0 < 3 + F) acc[c0 + 0] = ffma(T, fmul(alpha, v.x), acc[c0 + 0]);
+                                    if (c0 + 1 < 3 + F) acc[c0 + 1] = ffma(T, fmul(alpha, v.y), acc[c0 + 1]);
+                                    if (c0 + 2 < 3 + F) acc[c0 + 2] = ffma(T, fmul(alpha, v.z), acc[c0 + 2]);
+                                    if (c0 + 3 < 3 + F) acc[c0 + 3] = ffma(T, fmul(alpha, v.w), acc[c0 + 3]);
+                                }
+                                acc[NCH - 1] = ffma(T, fmul(alpha, g1.w), acc[NCH - 1]);
+                            } else {
+                                const float w = fmul(alpha, T);
+                                acc[0] = ffma(w, g2.x, acc[0]);
+                                acc[1] = ffma(w, g2.y, acc[1]);
+                                acc[2] = ffma(w, g2.z, acc[2]);
+                                acc[3] = ffma(w, g2.w, acc[3]);
+#pragma unroll
+                                for (int q = 3; q < R4; q++) {
+                                    const float4 v = r4[j * R4 + q];
+                                    const int c0 = 4 + (q - 3) * 4;
+                                    if (c0 + 0 < 3 + F) acc[c0 + 0] = ffma(w, v.x, acc[c0 + 0]);
+                                    if (c0 + 1 < 3 + F) acc[c0 + 1] = ffma(w, v.y, acc[c0 + 1]);
+                                    if (c0 + 2 < 3 + F) acc[c0 + 2] = ffma(w, v.z, acc[c0 + 2]);
+                                    if (c0 + 3 < 3 + F) acc[c0 + 3] = ffma(w, v.w, acc[c0 + 3]);
+                                }
+                                acc[NCH - 1] = ffma(w, g1.w, acc[NCH - 1]);
+                            }
+                            touch = test_T > 0.5f;
+                            T = test_T;
+                            last_contributor = cbase + (uint32_t)j + 1u;
+                        }
+                    }
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, touch);
+            if (m != 0u && lane == 0) atomicAdd(&a.n_touched[ids[j]], __popc(m));
+        }
+    }
+    cp_async_wait<0>();
+    if (inside) {
+        const size_t HW = (size_t)a.W * a.H;
+        const size_t pix = (size_t)pyi * a.W + pxi;
+        a.final_T[pix] = T;
+        a.n_contrib[pix] = last_contributor;
+#pragma unroll
+        for (int c = 0; c < 3; c++) a.out_color[c * HW + pix] = ffma(a.bg[c], T, acc[c]);
+#pragma unroll
+        for (int c = 0; c < F; c++) a.out_language[c * HW + pix] = acc[3 + c];
+        a.out_depth[pix] = acc[NCH - 1];
+        a.out_opacity[pix] = fsub(1.0f, T);
+    }
+}
+
+__global__ void k_count_visible(int P, const int32_t* __restrict__ radii, DeviceInfo* info) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool v = i < P && radii[i] > 0;
+    const unsigned m = __ballot_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&info->n_visible, __popc(m));
+}
+
+template <int TILE, int F>
+static int launch_blend(const BlendArgs& ba, int n_tiles, bool bitexact, cudaStream_t st) {
+    if (bitexact)
+        k_blend<TILE, F, true><<<n_tiles, BLEND_THREADS, 0, st>>>(ba);
+    else
+        k_blend<TILE, F, false><<<n_tiles, BLEND_THREADS, 0, st>>>(ba);
+    return 0;
+}
+
+}  // namespace ols
+
+using namespace ols;
+
+int ols_launch_forward(const ols_raster_args* a, const ols_fwd_out* o, const WsLayout& L, cudaStream_t st) {
+    char* ws = (char*)a->d_workspace;
+    DeviceInfo* info = (DeviceInfo*)(ws + L.info);
+    const bool debug = (a->flags & OLS_FLAG_DEBUG) != 0;
+#define OLS_DEBUG_SYNC(name)                                                              \
+    do {                                                                                  \
+        OLS_CUDA_TRY(cudaGetLastError());                                                 \
+        if (debug) {                                                                      \
+            cudaError_t _e = cudaStreamSynchronize(st);                                   \
+            if (_e != cudaSuccess) {                                                      \
+                ols_set_error("kernel %s failed: %s", name, cudaGetErrorString(_e));      \
+                return OLS_ERR_CUDA;                                                      \
+            }                                                                             \
+        }                                                                                 \
+    } while (0)
+
+    // info + tile_count are adjacent at the start of the workspace: one memset clears both
+    OLS_CUDA_TRY(cudaMemsetAsync(ws + L.info, 0, L.tile_cursor - L.info, st));
+    OLS_CUDA_TRY(cudaMemsetAsync(o->d_n_touched, 0, sizeof(int32_t) * (size_t)a->P, st));
+
+    PreArgs p;
+    p.P = a->P; p.F = a->F; p.sh_degree = a->sh_degree; p.M = a->M; p.W = a->W; p.H = a->H; p.tile = a->tile;
+    p.gx = L.gx; p.gy = L.gy; p.rec = L.rec; p.flags = a->flags;
+    p.tanfovx = a->tanfovx; p.tanfovy = a->tanfovy;
+    p.focal_y = a->H / (2.0f * a->tanfovy);  // rasterizer_impl.cu:394-395
+    p.focal_x = a->W / (2.0f * a->tanfovx);
+    p.scale_modifier = a->scale_modifier;
+    p.means3D = a->d_means3D; p.shs = a->d_shs; p.colors_precomp = a->d_colors_precomp; p.language = a->d_language;
+    p.opacities = a->d_opacities; p.scales = a->d_scales; p.rotations = a->d_rotations;
+    p.cov3D_precomp = a->d_cov3D_precomp; p.viewmatrix = a->d_viewmatrix; p.projmatrix = a->d_projmatrix;
+    p.campos = a->d_campos;
+    p.records = (float*)(ws + L.records); p.depths = (float*)(ws + L.depths); p.cov3D = (float*)(ws + L.cov3D);
+    p.clamped = (uint32_t*)(ws + L.clamped); p.tiles_touched = (uint32_t*)(ws + L.tiles_touched);
+    p.rect = (uint2*)(ws + L.rect); p.tile_count = (uint32_t*)(ws + L.tile_count); p.radii = o->d_radii;
+    p.info = info;
+    const int pre_blocks = (a->P + PRE_THREADS - 1) / PRE_THREADS;
+    k_preprocess<<<pre_blocks, PRE_THREADS, 0, st>>>(p);
+    OLS_DEBUG_SYNC("preprocess");
+    k_tile_scan<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)(ws + L.tile_count), (uint32_t*)(ws + L.tile_cursor),
+                                           (uint2*)(ws + L.ranges), L.n_tiles, (unsigned long long)a->R_cap, info);
+    OLS_DEBUG_SYNC("tile_scan");
+    k_count_visible<<<(a->P + 255) / 256, 256, 0, st>>>(a->P, o->d_radii, info);
+    k_scatter<<<(a->P + 255) / 256, 256, 0, st>>>(a->P, L.gx, p.tiles_touched, p.rect, p.depths,
+                                                   (uint32_t*)(ws + L.tile_cursor),
+                                                   (unsigned long long*)(ws + L.keys), info);
+    OLS_DEBUG_SYNC("scatter");
+    k_sort_tiles<<<L.n_tiles, SORT_THREADS, 0, st>>>((unsigned long long*)(ws + L.keys),
+                                                     (uint32_t*)(ws + L.point_list), (const uint2*)(ws + L.ranges), info);
+    OLS_DEBUG_SYNC("sort_tiles");
+
+    BlendArgs ba;
+    ba.W = a->W; ba.H = a->H; ba.gx = L.gx;
+    ba.ranges = (const uint2*)(ws + L.ranges); ba.point_list = (const uint32_t*)(ws + L.point_list);
+    ba.records = (const float*)(ws + L.records); ba.bg = a->d_bg; ba.info = info;
+    ba.final_T = (float*)(ws + L.final_T); ba.n_contrib = (uint32_t*)(ws + L.n_contrib);
+    ba.out_color = o->d_color; ba.out_language = o->d_language; ba.out_depth = o->d_depth;
+    ba.out_opacity = o->d_opacity; ba.n_touched = o->d_n_touched;
+    const bool bitexact = (a->flags & OLS_FLAG_BITEXACT_BLEND) != 0;
+    if (a->tile == 15 && a->F == 15) launch_blend<15, 15>(ba, L.n_tiles, bitexact, st);
+    else if (a->tile == 16 && a->F == 15) launch_blend<16, 15>(ba, L.n_tiles, bitexact, st);
+    else if (a->tile == 15 && a->F == 3) launch_blend<15, 3>(ba, L.n_tiles, bitexact, st);
+    else if (a->tile == 16 && a->F == 3) launch_blend<16, 3>(ba, L.n_tiles, bitexact, st);
+    else {
+        ols_set_error("unsupported (tile=%d, F=%d): compiled variants are tile in {15,16} x F in {3,15}", a->tile, a->F);
+        return OLS_ERR_UNSUPPORTED;
+    }
+    OLS_DEBUG_SYNC("blend");
+    return OLS_OK;
+}

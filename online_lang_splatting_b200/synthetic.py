@@ -149,3 +149,74 @@ def make_clip_maps(B: int, seed: int = 0, C: int = 768, HW: int = 192) -> torch.
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(B * HW * HW, C, generator=g)
     return x / x.norm(dim=1, keepdim=True)
+
+
+class PipelineParams:
+    """The two flags ``render()`` reads from ``pipe`` (configs/rgbd/replicav2/base_config.yaml:97-99)."""
+
+    def __init__(self, compute_cov3D_python: bool = False, convert_SHs_python: bool = False):
+        self.compute_cov3D_python = compute_cov3D_python
+        self.convert_SHs_python = convert_SHs_python
+
+
+class SyntheticGaussianModel:
+    """Stand-in for ``gaussian_splatting/scene/gaussian_model.py:GaussianModel`` exposing exactly the
+    ``get_*`` properties ``render()`` reads.  Parameters are stored *pre-activation*
+    like the reference (:51-57) and activated on access (:67-72, :93-130): exp for scales,
+    sigmoid for opacity, L2-normalise for rotations."""
+
+    def __init__(self, g: Dict[str, torch.Tensor], device="cuda", sh_degree: int = 0, is_language: bool = True,
+                 requires_grad: bool = False):
+        dev = torch.device(device)
+        mk = lambda t: t.to(dev).clone().requires_grad_(requires_grad)
+        self._xyz = mk(g["means3D"])
+        self._scaling = mk(torch.log(g["scales"]))
+        self._rotation = mk(g["rotations"])
+        op = g["opacities"].clamp(1e-6, 1 - 1e-6)
+        self._opacity = mk(torch.log(op / (1 - op)))
+        self._features_dc = mk(g["shs"][:, :1, :])
+        self._features_rest = mk(g["shs"][:, 1:, :])
+        self._language_feature = mk(g["language"])
+        self.active_sh_degree = sh_degree
+        self.max_sh_degree = sh_degree
+        self.is_language = is_language
+
+    def parameters(self):
+        return [self._xyz, self._scaling, self._rotation, self._opacity, self._features_dc, self._features_rest,
+                self._language_feature]
+
+    @property
+    def get_xyz(self):
+        return self._xyz
+
+    @property
+    def get_scaling(self):
+        return torch.exp(self._scaling)
+
+    @property
+    def get_rotation(self):
+        return torch.nn.functional.normalize(self._rotation)
+
+    @property
+    def get_opacity(self):
+        return torch.sigmoid(self._opacity)
+
+    @property
+    def get_features(self):
+        return torch.cat((self._features_dc, self._features_rest), dim=1)
+
+    @property
+    def get_language_features(self):
+        return self._language_feature
+
+    def get_covariance(self, scaling_modifier=1.0):
+        """build_covariance_from_scaling_rotation (gaussian_model.py:59-65): L = R S, Sigma = L L^T, upper 6."""
+        s = self.get_scaling * scaling_modifier
+        q = self.get_rotation
+        r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+        R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                         2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                         2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], -1).view(-1, 3, 3)
+        L = R * s[:, None, :]
+        S = L @ L.transpose(1, 2)
+        return torch.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], -1)

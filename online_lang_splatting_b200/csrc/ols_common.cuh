@@ -18,9 +18,10 @@ constexpr int REC_X = 0, REC_Y = 1, REC_A = 2, REC_B = 3, REC_C = 4, REC_OP = 5,
 __host__ __device__ constexpr int rec_floats(int F) { return ((11 + F) + 3) / 4 * 4; }
 
 struct WsLayout {
-    size_t info, tile_count, tile_cursor, ranges, records, depths, cov3D, clamped, tiles_touched, rect, final_T,
+    size_t info, tile_count, tile_cursor, ranges, cta_hist, records, depths, cov3D, clamped, tiles_touched, rect, final_T,
         n_contrib, keys, point_list, total;
     int n_tiles, gx, gy, rec;
+    int n_ctas, chunk;  // per-Gaussian kernels: n_ctas CTAs, each owning `chunk` consecutive Gaussians
 };
 
 inline __host__ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -39,6 +40,12 @@ inline __host__ WsLayout ws_layout(int P, int F, int W, int H, int tile, int64_t
     L.tile_count = take(4 * (size_t)L.n_tiles);
     L.tile_cursor = take(4 * (size_t)L.n_tiles);
     L.ranges = take(8 * (size_t)L.n_tiles);
+    {
+        const int blocks = (int)((Pz + 255) / 256);
+        L.n_ctas = blocks < 592 ? blocks : 592;  // 4 CTAs per SM on 148 SMs
+        L.chunk = (int)(((Pz + L.n_ctas - 1) / L.n_ctas + 255) / 256 * 256);
+    }
+    L.cta_hist = take(4 * (size_t)L.n_tiles * L.n_ctas);
     L.records = take(4 * (size_t)L.rec * Pz);
     L.depths = take(4 * Pz);
     L.cov3D = take(24 * Pz);

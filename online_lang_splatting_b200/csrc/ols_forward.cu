@@ -42,7 +42,8 @@ struct PreArgs {
     uint32_t* clamped;
     uint32_t* tiles_touched;
     uint2* rect;
-    uint32_t* tile_count;
+    uint32_t* cta_hist;
+    int chunk;
     int32_t* radii;
     DeviceInfo* info;
 };
@@ -142,33 +143,54 @@ __device__ void sh_to_rgb(int deg, int M, const float* sh, float dx, float dy, f
 
 constexpr int PRE_THREADS = 256;
 
-// One thread per Gaussian.  Inputs with 3-float rows are staged through shared memory so the global
-// loads are contiguous 16-byte accesses.
+// Each CTA owns a contiguous chunk of Gaussians (one thread per Gaussian, 256 at a time).  Inputs with
+// 3-float rows are staged through shared memory so the global loads are contiguous; the instances
+// each Gaussian contributes to every tile are counted in a per-CTA shared-memory histogram that is
+// written out once per CTA (cta_hist[cta][tile]) -- no global atomics on hot tile counters.
+__device__ void preprocess_one(const PreArgs& a, int i, int tid, const float* s_mean, const float* s_scale,
+                               const float* V, const float* Pm, uint32_t* s_hist, int& visible);
+
 __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreArgs a) {
+    extern __shared__ uint32_t s_hist[];  // [n_tiles]
     __shared__ float s_mean[PRE_THREADS * 3];
     __shared__ float s_scale[PRE_THREADS * 3];
     __shared__ float s_V[16], s_Pm[16];
     const int tid = threadIdx.x;
-    const int base = blockIdx.x * PRE_THREADS;
-    const int nloc = min(PRE_THREADS, a.P - base);
+    const int n_tiles = a.gx * a.gy;
+    for (int t = tid; t < n_tiles; t += PRE_THREADS) s_hist[t] = 0;
     if (tid < 16) { s_V[tid] = a.viewmatrix[tid]; s_Pm[tid] = a.projmatrix[tid]; }
-    for (int e = tid; e < nloc * 3; e += PRE_THREADS) {
-        s_mean[e] = a.means3D[(size_t)base * 3 + e];
-        if (a.scales) s_scale[e] = a.scales[(size_t)base * 3 + e];
-    }
-    // language rows -> records (coalesced read, near-coalesced write)
-    {
-        const int F = a.F, rec = a.rec;
-        const float* src = a.language + (size_t)base * F;
-        float* dst = a.records + (size_t)base * rec;
-        for (int e = tid; e < nloc * F; e += PRE_THREADS) {
-            const int g = e / F, c = e - g * F;
-            dst[(size_t)g * rec + REC_LANG + c] = src[e];
+    const int chunk_begin = min(a.P, (int)blockIdx.x * a.chunk), chunk_end = min(a.P, chunk_begin + a.chunk);
+    int visible = 0;
+    for (int base = chunk_begin; base < chunk_end; base += PRE_THREADS) {
+        const int nloc = min(PRE_THREADS, chunk_end - base);
+        __syncthreads();  // previous iteration's readers of s_mean/s_scale are done (and s_hist zeroed)
+        for (int e = tid; e < nloc * 3; e += PRE_THREADS) {
+            s_mean[e] = a.means3D[(size_t)base * 3 + e];
+            if (a.scales) s_scale[e] = a.scales[(size_t)base * 3 + e];
         }
+        {   // language rows -> records (coalesced read, near-coalesced write)
+            const int F = a.F, rec = a.rec;
+            const float* src = a.language + (size_t)base * F;
+            float* dst = a.records + (size_t)base * rec;
+            for (int e = tid; e < nloc * F; e += PRE_THREADS) {
+                const int g = e / F, c = e - g * F;
+                dst[(size_t)g * rec + REC_LANG + c] = src[e];
+            }
+        }
+        __syncthreads();
+        if (tid < nloc) preprocess_one(a, base + tid, tid, s_mean, s_scale, s_V, s_Pm, s_hist, visible);
     }
-    __syncthreads();
-    if (tid >= nloc) return;
-    const int i = base + tid;
+    const int nvis = __syncthreads_count(visible);  // also orders the histogram updates before the flush
+    (void)nvis;
+    uint32_t* out = a.cta_hist + (size_t)blockIdx.x * n_tiles;
+    for (int t = tid; t < n_tiles; t += PRE_THREADS) out[t] = s_hist[t];
+    // n_visible: block-reduce the per-thread counts
+    for (int o = 16; o > 0; o >>= 1) visible += __shfl_xor_sync(0xffffffffu, visible, o);
+    if ((tid & 31) == 0 && visible) atomicAdd(&a.info->n_visible, visible);
+}
+
+__device__ void preprocess_one(const PreArgs& a, int i, int tid, const float* s_mean, const float* s_scale,
+                               const float* s_V, const float* s_Pm, uint32_t* s_hist, int& visible) {
     a.radii[i] = 0;
     a.tiles_touched[i] = 0;
     const float px3 = s_mean[3 * tid], py3 = s_mean[3 * tid + 1], pz3 = s_mean[3 * tid + 2];
@@ -273,8 +295,32 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreArgs a) {
     a.radii[i] = ri;
     a.rect[i] = make_uint2((uint32_t)mn[0] | ((uint32_t)mn[1] << 16), (uint32_t)mx[0] | ((uint32_t)mx[1] << 16));
     a.tiles_touched[i] = tiles;
+    visible += 1;
     for (int y = mn[1]; y < mx[1]; y++)
-        for (int x = mn[0]; x < mx[0]; x++) atomicAdd(&a.tile_count[y * a.gx + x], 1u);
+        for (int x = mn[0]; x < mx[0]; x++) atomicAdd(&s_hist[y * a.gx + x], 1u);
+}
+
+// Column scan of cta_hist: afterwards cta_hist[c][t] = instances of tile t emitted by CTAs < c, and
+// tile_count[t] = instances of tile t.  One thread per tile, coalesced across tiles.
+__global__ void __launch_bounds__(128) k_tile_offsets(uint32_t* __restrict__ cta_hist, uint32_t* __restrict__ tile_count,
+                                                      int n_tiles, int n_ctas) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    uint32_t run = 0;
+    int c = 0;
+    for (; c + 8 <= n_ctas; c += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = cta_hist[(size_t)(c + k) * n_tiles + t];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { cta_hist[(size_t)(c + k) * n_tiles + t] = run; run += v[k]; }
+    }
+    for (; c < n_ctas; c++) {
+        const uint32_t v = cta_hist[(size_t)c * n_tiles + t];
+        cta_hist[(size_t)c * n_tiles + t] = run;
+        run += v;
+    }
+    tile_count[t] = run;
 }
 
 // One CTA: exclusive scan over tiles.  ranges of empty tiles stay (0,0) like the reference's memset
@@ -332,21 +378,153 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(const uint32_t* __re
 }
 
 // duplicateWithKeys (rasterizer_impl.cu:70-111), bucketed: the tile id is implicit in the bucket.
-__global__ void __launch_bounds__(256) k_scatter(int P, int gx, const uint32_t* __restrict__ tiles_touched,
-                                                 const uint2* __restrict__ rect, const float* __restrict__ depths,
-                                                 uint32_t* __restrict__ tile_cursor, unsigned long long* __restrict__ keys,
-                                                 const DeviceInfo* __restrict__ info) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P || info->overflow) return;
-    if (tiles_touched[i] == 0) return;
-    const uint2 r = rect[i];
-    const int x0 = r.x & 0xffff, y0 = r.x >> 16, x1 = r.y & 0xffff, y1 = r.y >> 16;
-    const unsigned long long key = ((unsigned long long)__float_as_uint(depths[i]) << 32) | (unsigned)i;
-    for (int y = y0; y < y1; y++)
-        for (int x = x0; x < x1; x++) {
-            const uint32_t slot = atomicAdd(&tile_cursor[y * gx + x], 1u);
-            keys[slot] = key;
+// CTA c handles the same chunk of Gaussians as in k_preprocess; its write cursors (tile start +
+// instances emitted by earlier CTAs) live in shared memory, so slots are handed out by shared-memory
+// atomics only.
+__global__ void __launch_bounds__(PRE_THREADS) k_scatter(int P, int gx, int n_tiles, int chunk,
+                                                         const uint32_t* __restrict__ tiles_touched,
+                                                         const uint2* __restrict__ rect, const float* __restrict__ depths,
+                                                         const uint32_t* __restrict__ cta_hist,
+                                                         const uint32_t* __restrict__ tile_start,
+                                                         unsigned long long* __restrict__ keys,
+                                                         const DeviceInfo* __restrict__ info) {
+    extern __shared__ uint32_t s_cur[];  // [n_tiles]
+    if (info->overflow) return;
+    const int tid = threadIdx.x;
+    const uint32_t* mine = cta_hist + (size_t)blockIdx.x * n_tiles;
+    for (int t = tid; t < n_tiles; t += PRE_THREADS) s_cur[t] = tile_start[t] + mine[t];
+    __syncthreads();
+    const int chunk_begin = min(P, (int)blockIdx.x * chunk), chunk_end = min(P, chunk_begin + chunk);
+    for (int i = chunk_begin + tid; i < chunk_end; i += PRE_THREADS) {
+        if (tiles_touched[i] == 0) continue;
+        const uint2 r = rect[i];
+        const int x0 = r.x & 0xffff, y0 = r.x >> 16, x1 = r.y & 0xffff, y1 = r.y >> 16;
+        const unsigned long long key = ((unsigned long long)__float_as_uint(depths[i]) << 32) | (unsigned)i;
+        for (int y = y0; y < y1; y++)
+            for (int x = x0; x < x1; x++) {
+                const uint32_t slot = atomicAdd(&s_cur[y * gx + x], 1u);
+                keys[slot] = key;
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Per-tile sort, main path: least-significant-digit radix sort of the bucket in shared memory.
+// Keys are (depth_bits << 32 | gaussian id); four stable 8-bit passes over the depth bits, ranks from
+// warp match/ballot primitives and per-warp digit counters, then a neighbour fix-up that orders equal
+// depths by id (the order cub's stable sort gives the reference, since duplicateWithKeys emits ids in
+// ascending order).  Buckets longer than RS_CAP fall through to the bitonic kernel below.
+// ---------------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_CAP = 4096;
+constexpr int RS_ITEMS = RS_CAP / RS_THREADS;  // 16 keys per thread at most
+
+__global__ void __launch_bounds__(RS_THREADS) k_sort_tiles_radix(unsigned long long* __restrict__ keys,
+                                                                uint32_t* __restrict__ point_list,
+                                                                const uint2* __restrict__ ranges,
+                                                                const DeviceInfo* __restrict__ info) {
+    __shared__ unsigned long long s_key[RS_CAP];       // 32 KB
+    __shared__ uint32_t s_cnt[RS_WARPS][256];          // 8 KB  per-warp digit counters / bases
+    __shared__ uint32_t s_scan[RS_WARPS];
+    if (info->overflow) return;
+    const uint2 rg = ranges[blockIdx.x];
+    const int n = (int)(rg.y - rg.x);
+    if (n <= 0 || n > RS_CAP) return;
+    unsigned long long* g = keys + rg.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int items = (n + RS_THREADS - 1) / RS_THREADS;  // rounds per warp (uniform)
+    const int seg = items * 32;                           // keys per warp, contiguous -> stable
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    unsigned long long k[RS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        const int idx = wid * seg + r * 32 + lane;
+        k[r] = (r < items && idx < n) ? g[idx] : ~0ull;  // +inf padding keeps the tail in place
+    }
+    for (int pass = 0; pass < 4; pass++) {
+        const int shift = 32 + 8 * pass;
+        for (int e = tid; e < RS_WARPS * 256; e += RS_THREADS) (&s_cnt[0][0])[e] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < RS_ITEMS; r++) {
+            if (r < items) {
+                const unsigned d = (unsigned)(k[r] >> shift) & 255u;
+                const unsigned peers = __match_any_sync(0xffffffffu, d);
+                if ((peers & lt_mask) == 0) s_cnt[wid][d] += __popc(peers);
+                __syncwarp();
+            }
         }
+        __syncthreads();
+        // exclusive scan in (digit major, warp minor) order; thread d owns digit d
+        uint32_t tot = 0;
+        {
+            uint32_t c[RS_WARPS];
+#pragma unroll
+            for (int w = 0; w < RS_WARPS; w++) { c[w] = s_cnt[w][tid]; }
+#pragma unroll
+            for (int w = 0; w < RS_WARPS; w++) { const uint32_t v = c[w]; c[w] = tot; tot += v; }
+            // all keys share this digit -> the pass is the identity (uniform decision)
+            const uint32_t n_pad = (uint32_t)(items * RS_THREADS - n);
+            const int skip = __syncthreads_or(tot == (uint32_t)n + (tid == 255 ? n_pad : 0u));
+            if (skip) continue;
+            uint32_t incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) s_scan[wid] = incl;
+            __syncthreads();
+            uint32_t base = incl - tot;
+            for (int w = 0; w < wid; w++) base += s_scan[w];
+#pragma unroll
+            for (int w = 0; w < RS_WARPS; w++) s_cnt[w][tid] = base + c[w];
+        }
+        __syncthreads();
+        uint32_t rk[RS_ITEMS];
+#pragma unroll
+        for (int r = 0; r < RS_ITEMS; r++) {
+            if (r < items) {
+                const unsigned d = (unsigned)(k[r] >> shift) & 255u;
+                const unsigned peers = __match_any_sync(0xffffffffu, d);
+                rk[r] = s_cnt[wid][d] + __popc(peers & lt_mask);
+                __syncwarp();
+                if ((peers & lt_mask) == 0) s_cnt[wid][d] += __popc(peers);
+                __syncwarp();
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RS_ITEMS; r++)
+            if (r < items) s_key[rk[r]] = k[r];
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < RS_ITEMS; r++)
+            if (r < items) k[r] = s_key[wid * seg + r * 32 + lane];
+        __syncthreads();
+    }
+    // final order into shared memory, then order runs of equal depth by id (odd-even transposition)
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++)
+        if (r < items) s_key[wid * seg + r * 32 + lane] = k[r];
+    __syncthreads();
+    for (;;) {
+        int swapped = 0;
+        for (int phase = 0; phase < 2; phase++) {
+            for (int i = 2 * tid + phase; i + 1 < n; i += 2 * RS_THREADS) {
+                const unsigned long long x = s_key[i], y = s_key[i + 1];
+                if (x > y) { s_key[i] = y; s_key[i + 1] = x; swapped = 1; }
+            }
+            __syncthreads();
+        }
+        if (!__syncthreads_or(swapped)) break;
+    }
+    for (int i = tid; i < n; i += RS_THREADS) {
+        const unsigned long long v = s_key[i];
+        g[i] = v;
+        point_list[rg.x + i] = (uint32_t)v;
+    }
 }
 
 // Per-tile sort.  All comparators are ascending ("mirror" first step per stage), so positions >= n
@@ -395,12 +573,12 @@ __device__ void smem_sort_full(unsigned long long* s, int n) {
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(unsigned long long* __restrict__ keys,
                                                             uint32_t* __restrict__ point_list,
                                                             const uint2* __restrict__ ranges,
-                                                            const DeviceInfo* __restrict__ info) {
+                                                            const DeviceInfo* __restrict__ info, int min_len) {
     __shared__ unsigned long long s[SORT_CHUNK];
     if (info->overflow) return;
     const uint2 rg = ranges[blockIdx.x];
     const int n = (int)(rg.y - rg.x);
-    if (n <= 0) return;
+    if (n <= min_len) return;
     unsigned long long* g = keys + rg.x;
     const int tid = threadIdx.x;
     if (n <= SORT_CHUNK) {
@@ -422,13 +600,10 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(unsigned long long*
         for (int i = tid; i < nl; i += SORT_THREADS) s[i] = g[cb + i];
         __syncthreads();
         smem_sort_full(s, nl);
-        if (nl < SORT_CHUNK) {  // smem_sort_full stops at pow2_cover(nl); that is a complete sort of the chunk
-        }
         for (int i = tid; i < nl; i += SORT_THREADS) g[cb + i] = s[i];
         __syncthreads();
     }
     for (int k = SORT_CHUNK * 2; k <= span; k <<= 1) {
-        __threadfence_block();
         bitonic_mirror(g, k, span >> 1, n);
         for (int j = k >> 2; j >= SORT_CHUNK; j >>= 1) bitonic_step(g, j, span >> 1, n);
         for (int c = 0; c < n_chunks; c++) {
@@ -594,13 +769,6 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const BlendArgs a) {
     }
 }
 
-__global__ void k_count_visible(int P, const int32_t* __restrict__ radii, DeviceInfo* info) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool v = i < P && radii[i] > 0;
-    const unsigned m = __ballot_sync(0xffffffffu, v);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&info->n_visible, __popc(m));
-}
-
 template <int TILE, int F>
 static int launch_blend(const BlendArgs& ba, int n_tiles, bool bitexact, cudaStream_t st) {
     if (bitexact)
@@ -630,8 +798,7 @@ int ols_launch_forward(const ols_raster_args* a, const ols_fwd_out* o, const WsL
         }                                                                                 \
     } while (0)
 
-    // info + tile_count are adjacent at the start of the workspace: one memset clears both
-    OLS_CUDA_TRY(cudaMemsetAsync(ws + L.info, 0, L.tile_cursor - L.info, st));
+    OLS_CUDA_TRY(cudaMemsetAsync(ws + L.info, 0, 256, st));
     OLS_CUDA_TRY(cudaMemsetAsync(o->d_n_touched, 0, sizeof(int32_t) * (size_t)a->P, st));
 
     PreArgs p;
@@ -647,21 +814,34 @@ int ols_launch_forward(const ols_raster_args* a, const ols_fwd_out* o, const WsL
     p.campos = a->d_campos;
     p.records = (float*)(ws + L.records); p.depths = (float*)(ws + L.depths); p.cov3D = (float*)(ws + L.cov3D);
     p.clamped = (uint32_t*)(ws + L.clamped); p.tiles_touched = (uint32_t*)(ws + L.tiles_touched);
-    p.rect = (uint2*)(ws + L.rect); p.tile_count = (uint32_t*)(ws + L.tile_count); p.radii = o->d_radii;
+    p.rect = (uint2*)(ws + L.rect); p.cta_hist = (uint32_t*)(ws + L.cta_hist); p.chunk = L.chunk; p.radii = o->d_radii;
     p.info = info;
-    const int pre_blocks = (a->P + PRE_THREADS - 1) / PRE_THREADS;
-    k_preprocess<<<pre_blocks, PRE_THREADS, 0, st>>>(p);
+    const size_t hist_smem = sizeof(uint32_t) * (size_t)L.n_tiles;
+    if (hist_smem > 40 * 1024) {
+        if (hist_smem > 200 * 1024) {
+            ols_set_error("image too large: %d tiles exceed the shared-memory tile histogram", L.n_tiles);
+            return OLS_ERR_UNSUPPORTED;
+        }
+        OLS_CUDA_TRY(cudaFuncSetAttribute(k_preprocess, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
+        OLS_CUDA_TRY(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
+    }
+    k_preprocess<<<L.n_ctas, PRE_THREADS, hist_smem, st>>>(p);
     OLS_DEBUG_SYNC("preprocess");
+    k_tile_offsets<<<(L.n_tiles + 127) / 128, 128, 0, st>>>(p.cta_hist, (uint32_t*)(ws + L.tile_count), L.n_tiles, L.n_ctas);
+    OLS_DEBUG_SYNC("tile_offsets");
     k_tile_scan<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)(ws + L.tile_count), (uint32_t*)(ws + L.tile_cursor),
                                            (uint2*)(ws + L.ranges), L.n_tiles, (unsigned long long)a->R_cap, info);
     OLS_DEBUG_SYNC("tile_scan");
-    k_count_visible<<<(a->P + 255) / 256, 256, 0, st>>>(a->P, o->d_radii, info);
-    k_scatter<<<(a->P + 255) / 256, 256, 0, st>>>(a->P, L.gx, p.tiles_touched, p.rect, p.depths,
-                                                   (uint32_t*)(ws + L.tile_cursor),
-                                                   (unsigned long long*)(ws + L.keys), info);
+    k_scatter<<<L.n_ctas, PRE_THREADS, hist_smem, st>>>(a->P, L.gx, L.n_tiles, L.chunk, p.tiles_touched, p.rect, p.depths,
+                                                        p.cta_hist, (const uint32_t*)(ws + L.tile_cursor),
+                                                        (unsigned long long*)(ws + L.keys), info);
     OLS_DEBUG_SYNC("scatter");
-    k_sort_tiles<<<L.n_tiles, SORT_THREADS, 0, st>>>((unsigned long long*)(ws + L.keys),
-                                                     (uint32_t*)(ws + L.point_list), (const uint2*)(ws + L.ranges), info);
+    k_sort_tiles_radix<<<L.n_tiles, RS_THREADS, 0, st>>>((unsigned long long*)(ws + L.keys),
+                                                         (uint32_t*)(ws + L.point_list), (const uint2*)(ws + L.ranges), info);
+    OLS_DEBUG_SYNC("sort_tiles_radix");
+    // buckets longer than the radix kernel's shared-memory capacity (rare): bitonic fallback
+    k_sort_tiles<<<L.n_tiles, SORT_THREADS, 0, st>>>((unsigned long long*)(ws + L.keys), (uint32_t*)(ws + L.point_list),
+                                                     (const uint2*)(ws + L.ranges), info, RS_CAP);
     OLS_DEBUG_SYNC("sort_tiles");
 
     BlendArgs ba;

@@ -47,13 +47,14 @@ class GaussianRasterizationSettings(NamedTuple):
 # and only read the 32-byte info header after everything has been queued.
 _R_HINT: Dict[Tuple, int] = {}
 CHECK_OVERFLOW = True  # set False for fully asynchronous forwards (caller guarantees capacity)
+_SLACK = 65536
 
 
 def _capacity(key, P: int) -> int:
     hint = _R_HINT.get(key)
     if hint is None:
-        return 8 * P + 65536
-    return int(hint * 1.25) + 65536
+        return 8 * P + _SLACK
+    return int(hint * 1.25) + _SLACK
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
@@ -148,7 +149,7 @@ def _forward_native(means3D, sh, colors_precomp, language_precomp, opacities, sc
                 info = N.FwdInfo()
                 N.check(lib.ols_lang_read_info(ws.data_ptr(), C.byref(info), stream))
                 if info.overflow:
-                    cap = int(info.R) + 65536
+                    cap = int(info.R) + _SLACK
                     continue
                 _R_HINT[key] = max(int(info.R), 1)
             break

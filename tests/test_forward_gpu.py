@@ -92,9 +92,13 @@ def test_capacity_overflow_regrows(cuda):
     sc = U.make_scene(P=3000, F=15, W=96, H=64, seed=0, scale=0.3)
     key = (cuda.index if cuda.index is not None else 0, sc["P"], sc["W"], sc["H"], 15)
     dgr._R_HINT[key] = 1  # absurdly small hint -> first attempt overflows on the device, wrapper regrows
-    ours = U.run_ours(sc, cuda)
+    slack, dgr._SLACK = dgr._SLACK, 0
+    try:
+        ours = U.run_ours(sc, cuda)
+    finally:
+        dgr._SLACK = slack
     ora = U.run_oracle(sc)
-    assert ours["R"] == ora["R"] > 70000
+    assert ours["R"] == ora["R"] > 30000
     assert np.array_equal(ours["ws"]["point_list"].astype(np.uint32), ora["point_list"])
 
 
@@ -171,6 +175,6 @@ def test_render_entry_point(cuda):
     sc = U.make_scene(P=4000, F=15, W=W, H=H, seed=3, view=1, scale=0.05)
     ora = U.run_oracle(sc)
     assert np.array_equal(out["radii"].cpu().numpy(), ora["radii"])
-    assert U.rel_err(out["language"].cpu().numpy(), ora["language"]) < 1e-3
+    assert U.rel_err(out["language"].detach().cpu().numpy(), ora["language"]) < 1e-3
     empty = S.SyntheticGaussianModel({k: v[:0] for k, v in g.items()}, device=cuda)
     assert render(cam, empty, S.PipelineParams(), torch.zeros(3, device=cuda)) is None

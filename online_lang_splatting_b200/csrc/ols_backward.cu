@@ -1,6 +1,619 @@
-// placeholder until the backward kernels land
+// ols_backward.cu -- backward pass of the language-feature Gaussian rasterizer for sm_100a.
+//
+//   k_blend_bwd       one CTA per tile, one pixel per thread, back-to-front over the tile's sorted list
+//                     (reference: language_render_cuda, backward.cu:932-1201).  Per-pixel gradients of a
+//                     Gaussian are summed over the warp with a register butterfly (31 shuffles for all
+//                     25 values at F=15), accumulated per batch in shared memory and flushed with one
+//                     global atomic per (tile, Gaussian, value) into a packed gradient record.
+//   k_geometry_bwd    one thread per Gaussian: conic -> cov2D -> cov3D/mean/pose gradients, projection,
+//                     depth, SH, scale/rotation (reference: computeCov2DCUDA backward.cu:150-346 and
+//                     language_preprocessCUDA :541-682, fused; the packed record is unpacked here).
+//
+// Two gradient modes ("parity policy"):
+//   compat  reproduces the reference build's behaviour: Q1 language gradient from the tile's first pixel
+//           only, Q2 language recurrence also advanced by non-contributing Gaussians the block visits,
+//           Q3 the lossy 225-thread tree reduction (lane mask) at 15x15 tiles;
+//   exact   the mathematically correct gradient (validated against finite differences and the oracle).
+//
+// The per-pixel recurrence of the reference (accum_rec[ch], last_color[ch]) only enters dL/dalpha through
+// sum_ch (c_ch - accum_rec_ch) * dL/dpix_ch.  Both modes carry that sum as two scalars
+//   A <- last_alpha * D_last + (1 - last_alpha) * A,   D = sum_ch c_ch * dL/dpix_ch
+// which is algebraically identical and keeps the per-thread state at ~25 registers instead of ~60.
 #include "ols_common.cuh"
-int ols_launch_backward(const ols_raster_args*, const ols_bwd_args*, const ols::WsLayout&, cudaStream_t) {
-    ols_set_error("backward not built yet");
-    return OLS_ERR_UNSUPPORTED;
+
+namespace ols {
+
+constexpr int BWD_THREADS = 256;
+constexpr int BWD_BATCH = 32;
+
+__host__ __device__ constexpr int grad_floats(int F) { return ((10 + F) + 3) / 4 * 4; }
+// packed gradient record: 0 dmean2D.x | 1 dmean2D.y | 2 dconic.x | 3 dconic.y | 4 dconic.w | 5 dopacity |
+//                         6 ddepth | 7..9 dcolor | 10.. dlanguage[F]
+constexpr int GR_MX = 0, GR_MY = 1, GR_CX = 2, GR_CY = 3, GR_CW = 4, GR_OP = 5, GR_DEPTH = 6, GR_RGB = 7, GR_LANG = 10;
+
+struct BwdBlendArgs {
+    int W, H, gx;
+    const uint2* ranges;
+    const uint32_t* point_list;
+    const float* records;
+    const float* bg;
+    const DeviceInfo* info;
+    const float* final_T;
+    const uint32_t* n_contrib;
+    const float* dL_dcolor;
+    const float* dL_dlanguage;
+    const float* dL_ddepth;
+    float* gacc;             // [P, grad_floats(F)] zero-initialised
+    uint32_t lane_ok[8];     // Q3 lane mask (compat); all ones otherwise
+};
+
+// Sum NV per-lane values over the 32 lanes of a warp; afterwards v[0] of lane L holds the total of
+// value index (L * NV / 32).  NV/2 + NV/4 + ... shuffles instead of 5 * NV.
+template <int NV>
+__device__ __forceinline__ void warp_multi_reduce(float (&v)[NV], int lane) {
+    static_assert(NV == 32 || NV == 16, "NV must be 16 or 32");
+    int off = 16;
+#pragma unroll
+    for (int n = NV / 2; n >= 1; n >>= 1) {
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n; i++) {
+            const float send = hi ? v[i] : v[i + n];
+            const float keep = hi ? v[i + n] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+        off >>= 1;
+    }
+    if (NV == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+template <int TILE, int F, bool COMPAT>
+__global__ void __launch_bounds__(BWD_THREADS) k_blend_bwd(const BwdBlendArgs a) {
+    constexpr int REC = rec_floats(F);
+    constexpr int R4 = REC / 4;
+    constexpr int GR = grad_floats(F);
+    constexpr int NCH = 3 + F;  // rgb + language
+    __shared__ __align__(16) float s_rec[BWD_BATCH * REC];
+    __shared__ uint32_t s_id[BWD_BATCH];
+    __shared__ float s_acc[BWD_BATCH * GR];
+    __shared__ uint32_t s_maxc;
+    __shared__ uint32_t s_mask;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int tile_x = blockIdx.x % a.gx, tile_y = blockIdx.x / a.gx;
+    const int lx = tid % TILE, ly = tid / TILE;
+    const int pxi = tile_x * TILE + lx, pyi = tile_y * TILE + ly;
+    const bool inside = (tid < TILE * TILE) && pxi < a.W && pyi < a.H;
+    const float pfx = (float)pxi, pfy = (float)pyi;
+    const size_t HW = (size_t)a.W * a.H;
+    const size_t pix = inside ? (size_t)pyi * a.W + pxi : 0;
+
+    uint2 rg = a.ranges[blockIdx.x];
+    if (a.info->overflow) rg = make_uint2(0u, 0u);
+    const uint32_t last_contributor = inside ? a.n_contrib[pix] : 0u;
+    if (tid == 0) { s_maxc = 0; s_mask = 0; }
+    for (int e = tid; e < BWD_BATCH * GR; e += BWD_THREADS) s_acc[e] = 0.0f;
+    __syncthreads();
+    {
+        const uint32_t m = __reduce_max_sync(0xffffffffu, last_contributor);
+        if (lane == 0 && m) atomicMax(&s_maxc, m);
+    }
+    __syncthreads();
+    // entries at positions >= max n_contrib are skipped by every pixel of the tile in both modes
+    const int total = min((int)s_maxc, (int)(rg.y - rg.x));
+    if (total == 0) return;
+
+    const float T_final = inside ? a.final_T[pix] : 0.0f;
+    float T = T_final;
+    float g[NCH];
+    float gd = 0.0f;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) g[c] = 0.0f;
+    if (inside) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) g[c] = a.dL_dcolor[c * HW + pix];
+#pragma unroll
+        for (int c = 0; c < F; c++) g[3 + c] = a.dL_dlanguage[c * HW + pix];
+        gd = a.dL_ddepth[pix];
+    }
+    const float bg_dot = a.bg[0] * g[0] + a.bg[1] * g[1] + a.bg[2] * g[2];
+    const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
+    const bool lane_ok = COMPAT ? ((a.lane_ok[tid >> 5] >> lane) & 1u) != 0 : true;
+
+    float last_alpha = 0.0f;
+    float A_c = 0.0f, Dl_c = 0.0f;  // rgb + depth part of sum_ch accum_rec*g and of last_color*g
+    float A_f = 0.0f, Dl_f = 0.0f;  // language part (separate because of Q2 in compat mode)
+
+    const int n_batches = (total + BWD_BATCH - 1) / BWD_BATCH;
+    for (int b = n_batches - 1; b >= 0; b--) {
+        const int base = b * BWD_BATCH;
+        const int cnt = min(BWD_BATCH, total - base);
+        __syncthreads();  // previous batch fully consumed / flushed
+        for (int c = tid; c < BWD_BATCH * R4; c += BWD_THREADS) {
+            const int gi = c / R4, q = c - gi * R4;
+            if (gi < cnt) {
+                const uint32_t id = a.point_list[rg.x + base + gi];
+                if (q == 0) s_id[gi] = id;
+                cp_async16(&s_rec[gi * REC + q * 4], a.records + (size_t)id * REC + q * 4);
+            }
+        }
+        if (COMPAT && tid == 0) s_mask = 0;
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        const float4* r4 = reinterpret_cast<const float4*>(s_rec);
+
+        // which Gaussians of the batch does this pixel contribute to (same decisions as the forward)
+        uint32_t mymask = 0;
+        if (inside) {
+            for (int j = 0; j < cnt; j++) {
+                if ((uint32_t)(base + j) >= last_contributor) break;
+                const float4 g0 = r4[j * R4 + 0];
+                const float4 g1 = r4[j * R4 + 1];
+                const float dx = fsub(g0.x, pfx), dy = fsub(g0.y, pfy);
+                const float power =
+                    ffma(ffma(dx, fmul(dx, g0.z), fmul(dy, fmul(dy, g1.x))), -0.5f, -fmul(dy, fmul(dx, g0.w)));
+                if (power > 0.0f || power < g1.z) continue;
+                const float alpha = fminf(0.99f, fmul(g1.y, expf(power)));
+                if (alpha < 1.0f / 255.0f) continue;
+                mymask |= 1u << j;
+            }
+        }
+        uint32_t visit;  // Gaussians somebody in the block (compat) / warp (exact) contributes to
+        if (COMPAT) {
+            const uint32_t wm = __reduce_or_sync(0xffffffffu, mymask);
+            if (lane == 0 && wm) atomicOr(&s_mask, wm);
+            __syncthreads();
+            visit = s_mask;
+        } else {
+            visit = __reduce_or_sync(0xffffffffu, mymask);
+        }
+
+        while (visit) {
+            const int j = 31 - __clz(visit);  // back to front
+            visit &= ~(1u << j);
+            const bool contrib = (mymask >> j) & 1u;
+            const float4 g0 = r4[j * R4 + 0];  // x y A B
+            const float4 g1 = r4[j * R4 + 1];  // C op pth depth
+            constexpr int NV = COMPAT ? 16 : 32;
+            float v[NV];
+#pragma unroll
+            for (int i = 0; i < NV; i++) v[i] = 0.0f;
+            float D_f = 0.0f, D_c = 0.0f;
+            if (inside && (COMPAT || contrib)) {
+                // D = sum_ch c_ch * dL/dpix_ch over rgb / language (and depth below)
+                const float4 c0 = r4[j * R4 + 2];  // r g b L0
+                D_c = c0.x * g[0] + c0.y * g[1] + c0.z * g[2] + g1.w * gd;
+                D_f = c0.w * g[3];
+#pragma unroll
+                for (int q = 3; q < R4; q++) {
+                    const float4 c = r4[j * R4 + q];
+                    const int k0 = 4 + (q - 3) * 4;
+                    if (k0 + 0 < NCH) D_f = fmaf(c.x, g[k0 + 0], D_f);
+                    if (k0 + 1 < NCH) D_f = fmaf(c.y, g[k0 + 1], D_f);
+                    if (k0 + 2 < NCH) D_f = fmaf(c.z, g[k0 + 2], D_f);
+                    if (k0 + 3 < NCH) D_f = fmaf(c.w, g[k0 + 3], D_f);
+                }
+                if (COMPAT) {  // Q2: recurrence advances for every pixel of a visited Gaussian
+                    A_f = last_alpha * Dl_f + (1.0f - last_alpha) * A_f;
+                    Dl_f = D_f;
+                }
+            }
+            float w = 0.0f;
+            if (contrib) {
+                const float dx = fsub(g0.x, pfx), dy = fsub(g0.y, pfy);
+                const float power =
+                    ffma(ffma(dx, fmul(dx, g0.z), fmul(dy, fmul(dy, g1.x))), -0.5f, -fmul(dy, fmul(dx, g0.w)));
+                const float G = expf(power);
+                const float alpha = fminf(0.99f, fmul(g1.y, G));
+                T = T / (1.0f - alpha);
+                w = alpha * T;
+                A_c = last_alpha * Dl_c + (1.0f - last_alpha) * A_c;
+                Dl_c = D_c;
+                if (!COMPAT) {
+                    A_f = last_alpha * Dl_f + (1.0f - last_alpha) * A_f;
+                    Dl_f = D_f;
+                }
+                float dL_dalpha = ((D_c - A_c) + (D_f - A_f)) * T;
+                last_alpha = alpha;
+                dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot;
+                const float dL_dG = g1.y * dL_dalpha;
+                const float gdx = G * dx, gdy = G * dy;
+                const float dG_ddelx = -gdx * g0.z - gdy * g0.w;
+                const float dG_ddely = -gdy * g1.x - gdx * g0.w;
+                if (lane_ok) {
+                    v[GR_MX] = dL_dG * dG_ddelx * ddelx_dx;
+                    v[GR_MY] = dL_dG * dG_ddely * ddely_dy;
+                    v[GR_CX] = -0.5f * gdx * dx * dL_dG;
+                    v[GR_CY] = -0.5f * gdx * dy * dL_dG;
+                    v[GR_CW] = -0.5f * gdy * dy * dL_dG;
+                    v[GR_OP] = G * dL_dalpha;
+                    v[GR_DEPTH] = w * gd;
+                    v[GR_RGB + 0] = w * g[0];
+                    v[GR_RGB + 1] = w * g[1];
+                    v[GR_RGB + 2] = w * g[2];
+                    if (!COMPAT) {
+#pragma unroll
+                        for (int c = 0; c < F; c++) v[GR_LANG + c] = w * g[3 + c];
+                    }
+                }
+            }
+            if (COMPAT) {
+                // Q1: only the tile's first thread contributes its own pixel's language gradient
+                if (tid == 0 && contrib) {
+#pragma unroll
+                    for (int c = 0; c < F; c++) s_acc[j * GR + GR_LANG + c] += w * g[3 + c];
+                }
+                if (__any_sync(0xffffffffu, contrib && lane_ok)) {
+                    warp_multi_reduce<NV>(v, lane);
+                    const int vi = lane >> 1;
+                    if ((lane & 1) == 0 && vi < 10 && v[0] != 0.0f) atomicAdd(&s_acc[j * GR + vi], v[0]);
+                }
+            } else {
+                warp_multi_reduce<NV>(v, lane);
+                if (lane < 10 + F && v[0] != 0.0f) atomicAdd(&s_acc[j * GR + lane], v[0]);
+            }
+        }
+        __syncthreads();
+        // flush the batch: one global atomic per (Gaussian, value) that received something
+        for (int e = tid; e < cnt * GR; e += BWD_THREADS) {
+            const float val = s_acc[e];
+            if (val != 0.0f) {
+                const int gi = e / GR, vi = e - gi * GR;
+                atomicAdd(&a.gacc[(size_t)s_id[gi] * GR + vi], val);
+                s_acc[e] = 0.0f;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct GeomBwdArgs {
+    int P, F, sh_degree, M, W, H, gr;
+    float tanfovx, tanfovy, focal_x, focal_y, scale_modifier;
+    const float *means3D, *shs, *scales, *rotations, *cov3D, *viewmatrix, *projmatrix, *projmatrix_raw, *campos;
+    const uint32_t* clamped;
+    const int32_t* radii;
+    const float* gacc;
+    bool colors_precomp;
+    float *dL_dmeans2D, *dL_dcolors, *dL_dlanguage, *dL_dopacity, *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales,
+        *dL_drots, *dL_dtau;
+};
+
+__constant__ float B_SH_C0 = 0.28209479177387814f;
+__constant__ float B_SH_C1 = 0.4886025119029199f;
+__constant__ float B_SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                 -1.0925484305920792f, 0.5462742152960396f};
+__constant__ float B_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                                 -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+
+__global__ void __launch_bounds__(256) k_geometry_bwd(const GeomBwdArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.P) return;
+    const int F = a.F, M = a.M;
+    const float* gr = a.gacc + (size_t)i * a.gr;
+    float dmean[3] = {0, 0, 0}, dcov[6] = {0, 0, 0, 0, 0, 0}, dtau[6] = {0, 0, 0, 0, 0, 0};
+    float dsc[3] = {0, 0, 0}, dq[4] = {0, 0, 0, 0};
+    const bool vis = a.radii[i] > 0;
+    // unpack what the blend pass accumulated (zero for invisible Gaussians)
+    const float g2x = gr[GR_MX], g2y = gr[GR_MY];
+    a.dL_dmeans2D[3 * (size_t)i] = g2x;
+    a.dL_dmeans2D[3 * (size_t)i + 1] = g2y;
+    a.dL_dmeans2D[3 * (size_t)i + 2] = 0.0f;
+    a.dL_dopacity[i] = gr[GR_OP];
+    float dcol[3];
+    for (int c = 0; c < 3; c++) { dcol[c] = gr[GR_RGB + c]; a.dL_dcolors[3 * (size_t)i + c] = dcol[c]; }
+    for (int c = 0; c < F; c++) a.dL_dlanguage[(size_t)F * i + c] = gr[GR_LANG + c];
+    if (a.dL_dsh)
+        for (int k = 0; k < 3 * M; k++) a.dL_dsh[(size_t)3 * M * i + k] = 0.0f;
+
+    if (vis) {
+        const float* V = a.viewmatrix;
+        const float* Pm = a.projmatrix;
+        const float* Praw = a.projmatrix_raw;
+        const float* c3 = a.cov3D + 6 * (size_t)i;
+        const float mp[3] = {a.means3D[3 * (size_t)i], a.means3D[3 * (size_t)i + 1], a.means3D[3 * (size_t)i + 2]};
+        const float fx = a.focal_x, fy = a.focal_y;
+        // ---- computeCov2DCUDA (backward.cu:150-346)
+        const float dcx = gr[GR_CX], dcy = gr[GR_CY], dcz = gr[GR_CW];
+        float t[3] = {V[0] * mp[0] + V[4] * mp[1] + V[8] * mp[2] + V[12], V[1] * mp[0] + V[5] * mp[1] + V[9] * mp[2] + V[13],
+                      V[2] * mp[0] + V[6] * mp[1] + V[10] * mp[2] + V[14]};
+        const float limx = 1.3f * a.tanfovx, limy = 1.3f * a.tanfovy;
+        const float txtz = t[0] / t[2], tytz = t[1] / t[2];
+        t[0] = fminf(limx, fmaxf(-limx, txtz)) * t[2];
+        t[1] = fminf(limy, fmaxf(-limy, tytz)) * t[2];
+        const float xgm = (txtz < -limx || txtz > limx) ? 0.0f : 1.0f;
+        const float ygm = (tytz < -limy || tytz > limy) ? 0.0f : 1.0f;
+        // column-major like GLM: X[c][r]
+        const float J[3][3] = {{fx / t[2], 0, -(fx * t[0]) / (t[2] * t[2])}, {0, fy / t[2], -(fy * t[1]) / (t[2] * t[2])}, {0, 0, 0}};
+        const float Wm[3][3] = {{V[0], V[4], V[8]}, {V[1], V[5], V[9]}, {V[2], V[6], V[10]}};
+        const float Vrk[3][3] = {{c3[0], c3[1], c3[2]}, {c3[1], c3[3], c3[4]}, {c3[2], c3[4], c3[5]}};
+        float Tm[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int r = 0; r < 3; r++) Tm[c][r] = Wm[0][r] * J[c][0] + Wm[1][r] * J[c][1] + Wm[2][r] * J[c][2];
+        float TV[2][3];  // TV[i][q] = sum_p Tm[i][p] * Vrk[p][q]
+#pragma unroll
+        for (int ii = 0; ii < 2; ii++)
+#pragma unroll
+            for (int q = 0; q < 3; q++) TV[ii][q] = Tm[ii][0] * Vrk[0][q] + Tm[ii][1] * Vrk[1][q] + Tm[ii][2] * Vrk[2][q];
+        const float ca = TV[0][0] * Tm[0][0] + TV[0][1] * Tm[0][1] + TV[0][2] * Tm[0][2] + 0.3f;
+        const float cb = TV[0][0] * Tm[1][0] + TV[0][1] * Tm[1][1] + TV[0][2] * Tm[1][2];
+        const float cc = TV[1][0] * Tm[1][0] + TV[1][1] * Tm[1][1] + TV[1][2] * Tm[1][2] + 0.3f;
+        const float denom = ca * cc - cb * cb;
+        float dL_da = 0, dL_db = 0, dL_dc = 0;
+        const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+        if (denom2inv != 0) {
+            dL_da = denom2inv * (-cc * cc * dcx + 2 * cb * cc * dcy + (denom - ca * cc) * dcz);
+            dL_dc = denom2inv * (-ca * ca * dcz + 2 * ca * cb * dcy + (denom - ca * cc) * dcx);
+            dL_db = denom2inv * 2 * (cb * cc * dcx - (denom + 2 * cb * cb) * dcy + ca * cb * dcz);
+            dcov[0] = (Tm[0][0] * Tm[0][0] * dL_da + Tm[0][0] * Tm[1][0] * dL_db + Tm[1][0] * Tm[1][0] * dL_dc);
+            dcov[3] = (Tm[0][1] * Tm[0][1] * dL_da + Tm[0][1] * Tm[1][1] * dL_db + Tm[1][1] * Tm[1][1] * dL_dc);
+            dcov[5] = (Tm[0][2] * Tm[0][2] * dL_da + Tm[0][2] * Tm[1][2] * dL_db + Tm[1][2] * Tm[1][2] * dL_dc);
+            dcov[1] = 2 * Tm[0][0] * Tm[0][1] * dL_da + (Tm[0][0] * Tm[1][1] + Tm[0][1] * Tm[1][0]) * dL_db + 2 * Tm[1][0] * Tm[1][1] * dL_dc;
+            dcov[2] = 2 * Tm[0][0] * Tm[0][2] * dL_da + (Tm[0][0] * Tm[1][2] + Tm[0][2] * Tm[1][0]) * dL_db + 2 * Tm[1][0] * Tm[1][2] * dL_dc;
+            dcov[4] = 2 * Tm[0][2] * Tm[0][1] * dL_da + (Tm[0][1] * Tm[1][2] + Tm[0][2] * Tm[1][1]) * dL_db + 2 * Tm[1][1] * Tm[1][2] * dL_dc;
+        }
+        // TV[r][k] equals the reference's (T[r] . Vrk[k]) because Vrk is symmetric
+        const float dT00 = 2 * TV[0][0] * dL_da + TV[1][0] * dL_db, dT01 = 2 * TV[0][1] * dL_da + TV[1][1] * dL_db,
+                    dT02 = 2 * TV[0][2] * dL_da + TV[1][2] * dL_db;
+        const float dT10 = 2 * TV[1][0] * dL_dc + TV[0][0] * dL_db, dT11 = 2 * TV[1][1] * dL_dc + TV[0][1] * dL_db,
+                    dT12 = 2 * TV[1][2] * dL_dc + TV[0][2] * dL_db;
+        const float dJ00 = Wm[0][0] * dT00 + Wm[0][1] * dT01 + Wm[0][2] * dT02;
+        const float dJ02 = Wm[2][0] * dT00 + Wm[2][1] * dT01 + Wm[2][2] * dT02;
+        const float dJ11 = Wm[1][0] * dT10 + Wm[1][1] * dT11 + Wm[1][2] * dT12;
+        const float dJ12 = Wm[2][0] * dT10 + Wm[2][1] * dT11 + Wm[2][2] * dT12;
+        const float tz = 1.f / t[2], tz2 = tz * tz, tz3 = tz2 * tz;
+        const float dtx = xgm * -fx * tz2 * dJ02;
+        const float dty = ygm * -fy * tz2 * dJ12;
+        const float dtz = -fx * tz2 * dJ00 - fy * tz2 * dJ11 + (2 * fx * t[0]) * tz3 * dJ02 + (2 * fy * t[1]) * tz3 * dJ12;
+        {   // pose: dpC/drho = I, dpC/dtheta = -skew(t)
+            const float th[3][3] = {{0, -t[2], t[1]}, {t[2], 0, -t[0]}, {-t[1], t[0], 0}};
+            const float d3[3] = {dtx, dty, dtz};
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                dtau[k] += d3[k];
+                dtau[k + 3] += dtx * th[k][0] + dty * th[k][1] + dtz * th[k][2];
+            }
+        }
+        dmean[0] = V[0] * dtx + V[1] * dty + V[2] * dtz;
+        dmean[1] = V[4] * dtx + V[5] * dty + V[6] * dtz;
+        dmean[2] = V[8] * dtx + V[9] * dty + V[10] * dtz;
+        {   // dL/dW through T = W * J, folded onto the rotation's so(3) tangent
+            const float dW00 = J[0][0] * dT00, dW01 = J[0][0] * dT01, dW02 = J[0][0] * dT02;
+            const float dW10 = J[1][1] * dT10, dW11 = J[1][1] * dT11, dW12 = J[1][1] * dT12;
+            const float dW20 = J[0][2] * dT00 + J[1][2] * dT10, dW21 = J[0][2] * dT01 + J[1][2] * dT11,
+                        dW22 = J[0][2] * dT02 + J[1][2] * dT12;
+            const float c1[3] = {V[0], V[1], V[2]}, c2[3] = {V[4], V[5], V[6]}, c3_[3] = {V[8], V[9], V[10]};
+            const float w1[3] = {dW00, dW10, dW20}, w2[3] = {dW01, dW11, dW21}, w3[3] = {dW02, dW12, dW22};
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                float acc = 0.0f;
+                const float* cs[3] = {c1, c2, c3_};
+                const float* ws[3] = {w1, w2, w3};
+#pragma unroll
+                for (int m = 0; m < 3; m++) {
+                    const float* vv = cs[m];
+                    const float S[3][3] = {{0, -vv[2], vv[1]}, {vv[2], 0, -vv[0]}, {-vv[1], vv[0], 0}};
+                    acc += ws[m][0] * S[k][0] + ws[m][1] * S[k][1] + ws[m][2] * S[k][2];
+                }
+                dtau[3 + k] += acc;
+            }
+        }
+        // ---- language_preprocessCUDA (backward.cu:541-682)
+        const float hxw = Pm[0] * mp[0] + Pm[4] * mp[1] + Pm[8] * mp[2] + Pm[12];
+        const float hyw = Pm[1] * mp[0] + Pm[5] * mp[1] + Pm[9] * mp[2] + Pm[13];
+        const float hww = Pm[3] * mp[0] + Pm[7] * mp[1] + Pm[11] * mp[2] + Pm[15];
+        const float m_w = 1.0f / (hww + 0.0000001f);
+        const float mul1 = hxw * m_w * m_w, mul2 = hyw * m_w * m_w;
+        dmean[0] += (Pm[0] * m_w - Pm[3] * mul1) * g2x + (Pm[1] * m_w - Pm[3] * mul2) * g2y;
+        dmean[1] += (Pm[4] * m_w - Pm[7] * mul1) * g2x + (Pm[5] * m_w - Pm[7] * mul2) * g2y;
+        dmean[2] += (Pm[8] * m_w - Pm[11] * mul1) * g2x + (Pm[9] * m_w - Pm[11] * mul2) * g2y;
+        {
+            const float alpha = 1.0f * m_w, beta = -hxw * m_w * m_w, gamma = -hyw * m_w * m_w;
+            const float pa = Praw[0], pb = Praw[5], pe = Praw[11];
+            const float pC[3] = {V[0] * mp[0] + V[4] * mp[1] + V[8] * mp[2] + V[12], V[1] * mp[0] + V[5] * mp[1] + V[9] * mp[2] + V[13],
+                                 V[2] * mp[0] + V[6] * mp[1] + V[10] * mp[2] + V[14]};
+            const float d1[3] = {alpha * pa, 0.f, beta * pe}, d2[3] = {0.f, alpha * pb, gamma * pe};
+            const float th[3][3] = {{0, -pC[2], pC[1]}, {pC[2], 0, -pC[0]}, {-pC[1], pC[0], 0}};
+            const float dz = gr[GR_DEPTH];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                dtau[k] += g2x * d1[k] + g2y * d2[k];
+                const float t1 = th[k][0] * d1[0] + th[k][1] * d1[1] + th[k][2] * d1[2];
+                const float t2 = th[k][0] * d2[0] + th[k][1] * d2[1] + th[k][2] * d2[2];
+                dtau[3 + k] += g2x * t1 + g2y * t2;
+            }
+            dmean[0] += dz * V[2]; dmean[1] += dz * V[6]; dmean[2] += dz * V[10];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                dtau[k] += dz * (k == 2 ? 1.0f : 0.0f);
+                dtau[3 + k] += dz * th[k][2];
+            }
+        }
+        if (a.shs && !a.colors_precomp) {  // computeColorFromSH backward (backward.cu:21-145)
+            const float* sh = a.shs + (size_t)i * M * 3;
+            float* dsh = a.dL_dsh + (size_t)i * M * 3;
+            const int deg = a.sh_degree;
+            const float dir0[3] = {mp[0] - a.campos[0], mp[1] - a.campos[1], mp[2] - a.campos[2]};
+            const float len = sqrtf(dir0[0] * dir0[0] + dir0[1] * dir0[1] + dir0[2] * dir0[2]);
+            const float x = dir0[0] / len, y = dir0[1] / len, z = dir0[2] / len;
+            const uint32_t cl = a.clamped[i];
+            float dRGB[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) dRGB[c] = dcol[c] * (((cl >> (8 * c)) & 0xffu) ? 0.f : 1.f);
+            float dx_[3] = {0, 0, 0}, dy_[3] = {0, 0, 0}, dz_[3] = {0, 0, 0};
+            for (int c = 0; c < 3; c++) dsh[c] = B_SH_C0 * dRGB[c];
+            if (deg > 0) {
+                for (int c = 0; c < 3; c++) {
+                    dsh[3 + c] = -B_SH_C1 * y * dRGB[c]; dsh[6 + c] = B_SH_C1 * z * dRGB[c]; dsh[9 + c] = -B_SH_C1 * x * dRGB[c];
+                    dx_[c] = -B_SH_C1 * sh[9 + c]; dy_[c] = -B_SH_C1 * sh[3 + c]; dz_[c] = B_SH_C1 * sh[6 + c];
+                }
+                if (deg > 1) {
+                    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                    for (int c = 0; c < 3; c++) {
+                        dsh[12 + c] = B_SH_C2[0] * xy * dRGB[c]; dsh[15 + c] = B_SH_C2[1] * yz * dRGB[c];
+                        dsh[18 + c] = B_SH_C2[2] * (2.f * zz - xx - yy) * dRGB[c]; dsh[21 + c] = B_SH_C2[3] * xz * dRGB[c];
+                        dsh[24 + c] = B_SH_C2[4] * (xx - yy) * dRGB[c];
+                        dx_[c] += B_SH_C2[0] * y * sh[12 + c] + B_SH_C2[2] * 2.f * -x * sh[18 + c] + B_SH_C2[3] * z * sh[21 + c] + B_SH_C2[4] * 2.f * x * sh[24 + c];
+                        dy_[c] += B_SH_C2[0] * x * sh[12 + c] + B_SH_C2[1] * z * sh[15 + c] + B_SH_C2[2] * 2.f * -y * sh[18 + c] + B_SH_C2[4] * 2.f * -y * sh[24 + c];
+                        dz_[c] += B_SH_C2[1] * y * sh[15 + c] + B_SH_C2[2] * 2.f * 2.f * z * sh[18 + c] + B_SH_C2[3] * x * sh[21 + c];
+                    }
+                    if (deg > 2) {
+                        for (int c = 0; c < 3; c++) {
+                            dsh[27 + c] = B_SH_C3[0] * y * (3.f * xx - yy) * dRGB[c]; dsh[30 + c] = B_SH_C3[1] * xy * z * dRGB[c];
+                            dsh[33 + c] = B_SH_C3[2] * y * (4.f * zz - xx - yy) * dRGB[c];
+                            dsh[36 + c] = B_SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy) * dRGB[c];
+                            dsh[39 + c] = B_SH_C3[4] * x * (4.f * zz - xx - yy) * dRGB[c]; dsh[42 + c] = B_SH_C3[5] * z * (xx - yy) * dRGB[c];
+                            dsh[45 + c] = B_SH_C3[6] * x * (xx - 3.f * yy) * dRGB[c];
+                            dx_[c] += (B_SH_C3[0] * sh[27 + c] * 3.f * 2.f * xy + B_SH_C3[1] * sh[30 + c] * yz + B_SH_C3[2] * sh[33 + c] * -2.f * xy +
+                                       B_SH_C3[3] * sh[36 + c] * -3.f * 2.f * xz + B_SH_C3[4] * sh[39 + c] * (-3.f * xx + 4.f * zz - yy) +
+                                       B_SH_C3[5] * sh[42 + c] * 2.f * xz + B_SH_C3[6] * sh[45 + c] * 3.f * (xx - yy));
+                            dy_[c] += (B_SH_C3[0] * sh[27 + c] * 3.f * (xx - yy) + B_SH_C3[1] * sh[30 + c] * xz + B_SH_C3[2] * sh[33 + c] * (-3.f * yy + 4.f * zz - xx) +
+                                       B_SH_C3[3] * sh[36 + c] * -3.f * 2.f * yz + B_SH_C3[4] * sh[39 + c] * -2.f * xy + B_SH_C3[5] * sh[42 + c] * -2.f * yz +
+                                       B_SH_C3[6] * sh[45 + c] * -3.f * 2.f * xy);
+                            dz_[c] += (B_SH_C3[1] * sh[30 + c] * xy + B_SH_C3[2] * sh[33 + c] * 4.f * 2.f * yz + B_SH_C3[3] * sh[36 + c] * 3.f * (2.f * zz - xx - yy) +
+                                       B_SH_C3[4] * sh[39 + c] * 4.f * 2.f * xz + B_SH_C3[5] * sh[42 + c] * (xx - yy));
+                        }
+                    }
+                }
+            }
+            const float ddir[3] = {dx_[0] * dRGB[0] + dx_[1] * dRGB[1] + dx_[2] * dRGB[2], dy_[0] * dRGB[0] + dy_[1] * dRGB[1] + dy_[2] * dRGB[2],
+                                   dz_[0] * dRGB[0] + dz_[1] * dRGB[1] + dz_[2] * dRGB[2]};
+            const float sum2 = dir0[0] * dir0[0] + dir0[1] * dir0[1] + dir0[2] * dir0[2];
+            const float inv32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+            const float dm[3] = {((+sum2 - dir0[0] * dir0[0]) * ddir[0] - dir0[1] * dir0[0] * ddir[1] - dir0[2] * dir0[0] * ddir[2]) * inv32,
+                                 (-dir0[0] * dir0[1] * ddir[0] + (sum2 - dir0[1] * dir0[1]) * ddir[1] - dir0[2] * dir0[1] * ddir[2]) * inv32,
+                                 (-dir0[0] * dir0[2] * ddir[0] - dir0[1] * dir0[2] * ddir[1] + (sum2 - dir0[2] * dir0[2]) * ddir[2]) * inv32};
+#pragma unroll
+            for (int k = 0; k < 3; k++) { dmean[k] += dm[k]; dtau[k] += -dm[k]; }
+        }
+        if (a.scales) {  // computeCov3D backward (backward.cu:350-413); no quaternion-normalisation Jacobian (:412)
+            const float4 q = reinterpret_cast<const float4*>(a.rotations)[i];
+            const float* sc = a.scales + 3 * (size_t)i;
+            const float r = q.x, x = q.y, y = q.z, z = q.w;
+            const float Rm[3][3] = {{1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
+                                    {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
+                                    {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};
+            const float sv[3] = {a.scale_modifier * sc[0], a.scale_modifier * sc[1], a.scale_modifier * sc[2]};
+            float Mm[3][3];
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int rr = 0; rr < 3; rr++) Mm[c][rr] = sv[rr] * Rm[c][rr];
+            const float dS[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]}, {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]}, {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
+            float dMt[3][3];  // transpose of dL_dM = 2 * M * dL_dSigma
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int rr = 0; rr < 3; rr++) dMt[rr][c] = 2.0f * (Mm[0][rr] * dS[c][0] + Mm[1][rr] * dS[c][1] + Mm[2][rr] * dS[c][2]);
+#pragma unroll
+            for (int k = 0; k < 3; k++) dsc[k] = Rm[0][k] * dMt[k][0] + Rm[1][k] * dMt[k][1] + Rm[2][k] * dMt[k][2];
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+#pragma unroll
+                for (int rr = 0; rr < 3; rr++) dMt[k][rr] *= sv[k];
+            dq[0] = 2 * z * (dMt[0][1] - dMt[1][0]) + 2 * y * (dMt[2][0] - dMt[0][2]) + 2 * x * (dMt[1][2] - dMt[2][1]);
+            dq[1] = 2 * y * (dMt[1][0] + dMt[0][1]) + 2 * z * (dMt[2][0] + dMt[0][2]) + 2 * r * (dMt[1][2] - dMt[2][1]) - 4 * x * (dMt[2][2] + dMt[1][1]);
+            dq[2] = 2 * x * (dMt[1][0] + dMt[0][1]) + 2 * r * (dMt[2][0] - dMt[0][2]) + 2 * z * (dMt[1][2] + dMt[2][1]) - 4 * y * (dMt[2][2] + dMt[0][0]);
+            dq[3] = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) - 4 * z * (dMt[1][1] + dMt[0][0]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) a.dL_dmeans3D[3 * (size_t)i + k] = dmean[k];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { a.dL_dcov3D[6 * (size_t)i + k] = dcov[k]; a.dL_dtau[6 * (size_t)i + k] = dtau[k]; }
+#pragma unroll
+    for (int k = 0; k < 3; k++) a.dL_dscales[3 * (size_t)i + k] = dsc[k];
+#pragma unroll
+    for (int k = 0; k < 4; k++) a.dL_drots[4 * (size_t)i + k] = dq[k];
+}
+
+template <int TILE, int F>
+static void launch_blend_bwd(const BwdBlendArgs& ba, int n_tiles, bool exact, cudaStream_t st) {
+    if (exact)
+        k_blend_bwd<TILE, F, false><<<n_tiles, BWD_THREADS, 0, st>>>(ba);
+    else
+        k_blend_bwd<TILE, F, true><<<n_tiles, BWD_THREADS, 0, st>>>(ba);
+}
+
+}  // namespace ols
+
+using namespace ols;
+
+size_t ols_bwd_scratch_bytes(int P, int F) { return sizeof(float) * (size_t)grad_floats(F) * (size_t)(P > 0 ? P : 1); }
+
+int ols_launch_backward(const ols_raster_args* a, const ols_bwd_args* g, const WsLayout& L, cudaStream_t st) {
+    char* ws = (char*)a->d_workspace;
+    const bool debug = (a->flags & OLS_FLAG_DEBUG) != 0;
+    const bool exact = (a->flags & OLS_FLAG_BWD_EXACT) != 0;
+    float* gacc = (float*)(ws + L.gacc);
+    OLS_CUDA_TRY(cudaMemsetAsync(gacc, 0, ols_bwd_scratch_bytes(a->P, a->F), st));
+
+    BwdBlendArgs ba;
+    ba.W = a->W; ba.H = a->H; ba.gx = L.gx;
+    ba.ranges = (const uint2*)(ws + L.ranges); ba.point_list = (const uint32_t*)(ws + L.point_list);
+    ba.records = (const float*)(ws + L.records); ba.bg = a->d_bg; ba.info = (const DeviceInfo*)(ws + L.info);
+    ba.final_T = (const float*)(ws + L.final_T); ba.n_contrib = (const uint32_t*)(ws + L.n_contrib);
+    ba.dL_dcolor = g->d_dL_dout_color; ba.dL_dlanguage = g->d_dL_dout_language; ba.dL_ddepth = g->d_dL_dout_depth;
+    ba.gacc = gacc;
+    {   // Q3: lanes of an n-thread block that reach data[0] in the reference's tree reduction
+        // (render_cuda_reduce_sum, backward.cu:684-702: i = n/2, n/4, ... with integer division)
+        const int n = a->tile * a->tile;
+        bool reach[256];
+        for (int k = 0; k < 256; k++) reach[k] = false;
+        if (exact) {
+            for (int k = 0; k < 256; k++) reach[k] = true;
+        } else {
+            // walk the reduction backwards: lane l reaches 0 iff repeatedly folding (l -> l - i when i <= l < 2i) ends at 0
+            for (int l = 0; l < n; l++) {
+                int pos = l;
+                bool ok = true;
+                for (int i = n / 2; i > 0; i /= 2) {
+                    if (pos >= i) {
+                        if (pos < 2 * i) pos -= i; else { ok = false; break; }
+                    }
+                }
+                reach[l] = ok && pos == 0;
+            }
+        }
+        for (int w = 0; w < 8; w++) {
+            uint32_t m = 0;
+            for (int b = 0; b < 32; b++) m |= (uint32_t)reach[w * 32 + b] << b;
+            ba.lane_ok[w] = m;
+        }
+    }
+    if (a->tile == 15 && a->F == 15) launch_blend_bwd<15, 15>(ba, L.n_tiles, exact, st);
+    else if (a->tile == 16 && a->F == 15) launch_blend_bwd<16, 15>(ba, L.n_tiles, exact, st);
+    else if (a->tile == 15 && a->F == 3) launch_blend_bwd<15, 3>(ba, L.n_tiles, exact, st);
+    else if (a->tile == 16 && a->F == 3) launch_blend_bwd<16, 3>(ba, L.n_tiles, exact, st);
+    else { ols_set_error("unsupported (tile=%d, F=%d)", a->tile, a->F); return OLS_ERR_UNSUPPORTED; }
+    OLS_CUDA_TRY(cudaGetLastError());
+    if (debug) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { ols_set_error("kernel blend_bwd failed: %s", cudaGetErrorString(e)); return OLS_ERR_CUDA; }
+    }
+
+    GeomBwdArgs ga;
+    ga.P = a->P; ga.F = a->F; ga.sh_degree = a->sh_degree; ga.M = a->M; ga.W = a->W; ga.H = a->H; ga.gr = grad_floats(a->F);
+    ga.tanfovx = a->tanfovx; ga.tanfovy = a->tanfovy;
+    ga.focal_y = a->H / (2.0f * a->tanfovy); ga.focal_x = a->W / (2.0f * a->tanfovx);
+    ga.scale_modifier = a->scale_modifier;
+    ga.means3D = a->d_means3D; ga.shs = a->d_shs; ga.scales = a->d_scales; ga.rotations = a->d_rotations;
+    ga.cov3D = a->d_cov3D_precomp ? a->d_cov3D_precomp : (const float*)(ws + L.cov3D);
+    ga.viewmatrix = a->d_viewmatrix; ga.projmatrix = a->d_projmatrix; ga.projmatrix_raw = a->d_projmatrix_raw;
+    ga.campos = a->d_campos; ga.clamped = (const uint32_t*)(ws + L.clamped); ga.radii = g->d_radii; ga.gacc = gacc;
+    ga.colors_precomp = a->d_colors_precomp != nullptr;
+    ga.dL_dmeans2D = g->d_dL_dmeans2D; ga.dL_dcolors = g->d_dL_dcolors; ga.dL_dlanguage = g->d_dL_dlanguage;
+    ga.dL_dopacity = g->d_dL_dopacity; ga.dL_dmeans3D = g->d_dL_dmeans3D; ga.dL_dcov3D = g->d_dL_dcov3D;
+    ga.dL_dsh = (a->d_shs && a->M > 0) ? g->d_dL_dsh : nullptr; ga.dL_dscales = g->d_dL_dscales;
+    ga.dL_drots = g->d_dL_drotations; ga.dL_dtau = g->d_dL_dtau;
+    k_geometry_bwd<<<(a->P + 255) / 256, 256, 0, st>>>(ga);
+    OLS_CUDA_TRY(cudaGetLastError());
+    if (debug) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { ols_set_error("kernel geometry_bwd failed: %s", cudaGetErrorString(e)); return OLS_ERR_CUDA; }
+    }
+    return OLS_OK;
 }

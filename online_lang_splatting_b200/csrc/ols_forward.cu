@@ -301,26 +301,54 @@ __device__ void preprocess_one(const PreArgs& a, int i, int tid, const float* s_
 }
 
 // Column scan of cta_hist: afterwards cta_hist[c][t] = instances of tile t emitted by CTAs < c, and
-// tile_count[t] = instances of tile t.  One thread per tile, coalesced across tiles.
-__global__ void __launch_bounds__(128) k_tile_offsets(uint32_t* __restrict__ cta_hist, uint32_t* __restrict__ tile_count,
-                                                      int n_tiles, int n_ctas) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_tiles) return;
-    uint32_t run = 0;
-    int c = 0;
-    for (; c + 8 <= n_ctas; c += 8) {
+// tile_count[t] = instances of tile t.  A CTA handles 32 tiles; its 8 warps split the CTA axis, each lane
+// owns one tile (128-byte coalesced rows), partial sums are combined through shared memory.
+constexpr int TO_WARPS = 8;
+__global__ void __launch_bounds__(32 * TO_WARPS) k_tile_offsets(uint32_t* __restrict__ cta_hist,
+                                                               uint32_t* __restrict__ tile_count, int n_tiles,
+                                                               int n_ctas) {
+    __shared__ uint32_t s_part[TO_WARPS][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int t = blockIdx.x * 32 + lane;
+    const bool ok = t < n_tiles;
+    const int seg = (n_ctas + TO_WARPS - 1) / TO_WARPS;
+    const int c0 = min(n_ctas, w * seg), c1 = min(n_ctas, c0 + seg);
+    uint32_t sum = 0;
+    if (ok) {
+        int c = c0;
+        for (; c + 8 <= c1; c += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = cta_hist[(size_t)(c + k) * n_tiles + t];
+#pragma unroll
+            for (int k = 0; k < 8; k++) sum += v[k];
+        }
+        for (; c < c1; c++) sum += cta_hist[(size_t)c * n_tiles + t];
+    }
+    s_part[w][lane] = sum;
+    __syncthreads();
+    uint32_t run = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < TO_WARPS; k++) {
+        const uint32_t v = s_part[k][lane];
+        if (k < w) run += v;
+        total += v;
+    }
+    if (!ok) return;
+    int c = c0;
+    for (; c + 8 <= c1; c += 8) {
         uint32_t v[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) v[k] = cta_hist[(size_t)(c + k) * n_tiles + t];
 #pragma unroll
         for (int k = 0; k < 8; k++) { cta_hist[(size_t)(c + k) * n_tiles + t] = run; run += v[k]; }
     }
-    for (; c < n_ctas; c++) {
+    for (; c < c1; c++) {
         const uint32_t v = cta_hist[(size_t)c * n_tiles + t];
         cta_hist[(size_t)c * n_tiles + t] = run;
         run += v;
     }
-    tile_count[t] = run;
+    if (w == 0) tile_count[t] = total;
 }
 
 // One CTA: exclusive scan over tiles.  ranges of empty tiles stay (0,0) like the reference's memset
@@ -438,21 +466,46 @@ __global__ void __launch_bounds__(RS_THREADS) k_sort_tiles_radix(unsigned long l
     const unsigned lt_mask = (1u << lane) - 1u;
 
     unsigned long long k[RS_ITEMS];
+    uint32_t dmin = 0xffffffffu, dmax = 0u;
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; r++) {
         const int idx = wid * seg + r * 32 + lane;
-        k[r] = (r < items && idx < n) ? g[idx] : ~0ull;  // +inf padding keeps the tail in place
+        const bool real = r < items && idx < n;
+        k[r] = real ? g[idx] : ~0ull;  // +inf padding keeps the tail in place
+        if (real) { dmin = min(dmin, (uint32_t)(k[r] >> 32)); dmax = max(dmax, (uint32_t)(k[r] >> 32)); }
     }
-    for (int pass = 0; pass < 4; pass++) {
-        const int shift = 32 + 8 * pass;
+    // digits are taken from (depth_bits - tile minimum): only the bytes that differ inside the tile are sorted
+    dmin = __reduce_min_sync(0xffffffffu, dmin);
+    dmax = __reduce_max_sync(0xffffffffu, dmax);
+    if (tid == 0) { s_scan[0] = 0xffffffffu; s_scan[1] = 0u; }
+    __syncthreads();
+    if (lane == 0) { atomicMin(&s_scan[0], dmin); atomicMax(&s_scan[1], dmax); }
+    __syncthreads();
+    dmin = s_scan[0];
+    const uint32_t spread = s_scan[1] - dmin;
+    const int n_pass = spread == 0 ? 0 : (32 - __clz(spread) + 7) / 8;
+    __syncthreads();
+    for (int pass = 0; pass < n_pass; pass++) {
+        const int shift = 8 * pass;
         for (int e = tid; e < RS_WARPS * 256; e += RS_THREADS) (&s_cnt[0][0])[e] = 0;
         __syncthreads();
+        uint32_t rk[RS_ITEMS];  // sweep 1: (digit | rank among warp peers << 8 | leader << 16); sweep 2: final rank
 #pragma unroll
         for (int r = 0; r < RS_ITEMS; r++) {
             if (r < items) {
-                const unsigned d = (unsigned)(k[r] >> shift) & 255u;
-                const unsigned peers = __match_any_sync(0xffffffffu, d);
-                if ((peers & lt_mask) == 0) s_cnt[wid][d] += __popc(peers);
+                const bool pad = k[r] == ~0ull;
+                const unsigned d = pad ? 255u : ((((uint32_t)(k[r] >> 32) - dmin) >> shift) & 255u);
+                unsigned peers = 0xffffffffu;  // lanes holding the same digit (8 ballots; no MATCH instruction)
+#pragma unroll
+                for (int bit = 0; bit < 8; bit++) {
+                    const bool on = (d >> bit) & 1u;
+                    const unsigned m = __ballot_sync(0xffffffffu, on);
+                    peers &= on ? m : ~m;
+                }
+                const unsigned below = __popc(peers & lt_mask);
+                const bool leader = below == 0;
+                if (leader) s_cnt[wid][d] += __popc(peers);
+                rk[r] = d | (below << 8) | ((leader ? __popc(peers) : 0u) << 16);
                 __syncwarp();
             }
         }
@@ -465,7 +518,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_sort_tiles_radix(unsigned long l
             for (int w = 0; w < RS_WARPS; w++) { c[w] = s_cnt[w][tid]; }
 #pragma unroll
             for (int w = 0; w < RS_WARPS; w++) { const uint32_t v = c[w]; c[w] = tot; tot += v; }
-            // all keys share this digit -> the pass is the identity (uniform decision)
+            // all real keys share this digit -> the pass is the identity (uniform decision)
             const uint32_t n_pad = (uint32_t)(items * RS_THREADS - n);
             const int skip = __syncthreads_or(tot == (uint32_t)n + (tid == 255 ? n_pad : 0u));
             if (skip) continue;
@@ -483,15 +536,13 @@ __global__ void __launch_bounds__(RS_THREADS) k_sort_tiles_radix(unsigned long l
             for (int w = 0; w < RS_WARPS; w++) s_cnt[w][tid] = base + c[w];
         }
         __syncthreads();
-        uint32_t rk[RS_ITEMS];
 #pragma unroll
         for (int r = 0; r < RS_ITEMS; r++) {
             if (r < items) {
-                const unsigned d = (unsigned)(k[r] >> shift) & 255u;
-                const unsigned peers = __match_any_sync(0xffffffffu, d);
-                rk[r] = s_cnt[wid][d] + __popc(peers & lt_mask);
+                const unsigned d = rk[r] & 255u, below = (rk[r] >> 8) & 255u, cnt = rk[r] >> 16;
+                rk[r] = s_cnt[wid][d] + below;
                 __syncwarp();
-                if ((peers & lt_mask) == 0) s_cnt[wid][d] += __popc(peers);
+                if (cnt) s_cnt[wid][d] += cnt;
                 __syncwarp();
             }
         }
@@ -827,7 +878,7 @@ int ols_launch_forward(const ols_raster_args* a, const ols_fwd_out* o, const WsL
     }
     k_preprocess<<<L.n_ctas, PRE_THREADS, hist_smem, st>>>(p);
     OLS_DEBUG_SYNC("preprocess");
-    k_tile_offsets<<<(L.n_tiles + 127) / 128, 128, 0, st>>>(p.cta_hist, (uint32_t*)(ws + L.tile_count), L.n_tiles, L.n_ctas);
+    k_tile_offsets<<<(L.n_tiles + 31) / 32, 32 * TO_WARPS, 0, st>>>(p.cta_hist, (uint32_t*)(ws + L.tile_count), L.n_tiles, L.n_ctas);
     OLS_DEBUG_SYNC("tile_offsets");
     k_tile_scan<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)(ws + L.tile_count), (uint32_t*)(ws + L.tile_cursor),
                                            (uint2*)(ws + L.ranges), L.n_tiles, (unsigned long long)a->R_cap, info);

@@ -1,0 +1,177 @@
+"""Drop-in for the reference's language autoencoders (language/autoencoder/model.py):
+
+* ``AutoencoderMLP``       (:15-62)   768 -> code -> 768 per-pixel MLP, BatchNorm in the encoder
+* ``EncoderDecoderOnline`` (:314-354) the online 32 -> 24 -> 15 -> 24 -> 32 code compressor
+
+Same constructor arguments, same sub-module names and indices (``encoder.0`` ... so reference
+``state_dict``s load unchanged), same ``encode`` / ``decode`` / ``forward`` semantics.
+
+Inference (``torch.no_grad()`` / eval mode, CUDA tensors) runs the whole layer chain as ONE fused
+tcgen05 kernel through the C ABI (``ols_ae_forward``): eval-mode BatchNorm is folded into the
+preceding Linear here, on the host side.  Calls that need autograd (the online autoencoder's Adam
+step, utils/slam_backend.py:266-323) run the same module graph through torch so gradients exist;
+CPU tensors are rejected -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _native as N
+
+
+class _FusedChain:
+    """Owns an ``ols_ae_plan`` for a list of (weight, bias) pairs and rebuilds it when they change."""
+
+    def __init__(self):
+        self._plan: Optional[int] = None
+        self._key = None
+        self._keep = None
+
+    def _destroy(self):
+        if self._plan is not None:
+            N.lib().ols_ae_plan_destroy(self._plan)
+            self._plan = None
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass
+
+    def run(self, layers: Sequence[Tuple[torch.Tensor, Optional[torch.Tensor]]], version_key, normalize: bool,
+            x: torch.Tensor) -> torch.Tensor:
+        N.require_cuda()
+        if not x.is_cuda:
+            raise RuntimeError("autoencoder input must be a CUDA tensor: the fused kernel has no CPU path")
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, x.shape[-1])
+        if x2.dtype != torch.float32:
+            x2 = x2.float()
+        x2 = x2.contiguous()
+        dev = x2.device
+        key = (version_key, dev.index, normalize)
+        lib = N.lib()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            if self._plan is None or self._key != key:
+                self._destroy()
+                ws = [w.detach().to(dev, torch.float32).contiguous() for w, _ in layers]
+                bs = [None if b is None else b.detach().to(dev, torch.float32).contiguous() for _, b in layers]
+                chain = N.AEChain(n_layers=len(ws), normalize=int(normalize))
+                chain.dims[0] = ws[0].shape[1]
+                for i, w in enumerate(ws):
+                    chain.dims[i + 1] = w.shape[0]
+                    chain.d_weight[i] = w.data_ptr()
+                    chain.d_bias[i] = 0 if bs[i] is None else bs[i].data_ptr()
+                plan = C.c_void_p()
+                N.check(lib.ols_ae_plan_create(C.byref(chain), C.byref(plan), stream))
+                self._plan, self._key, self._keep = plan, key, (ws, bs)
+            if x2.shape[1] != self._keep[0][0].shape[1]:
+                raise RuntimeError(f"expected input width {self._keep[0][0].shape[1]}, got {x2.shape[1]}")
+            y = torch.empty((x2.shape[0], self._keep[0][-1].shape[0]), dtype=torch.float32, device=dev)
+            N.check(lib.ols_ae_forward(self._plan, x2.data_ptr(), y.data_ptr(), x2.shape[0], stream))
+        return y.reshape(*lead, y.shape[-1])
+
+
+def _fold(modules: Sequence[nn.Module]) -> List[Tuple[torch.Tensor, Optional[torch.Tensor]]]:
+    """Linear [-> BatchNorm1d(eval)] [-> ReLU] ... -> list of (W, b) with the BatchNorm folded in."""
+    out: List[Tuple[torch.Tensor, Optional[torch.Tensor]]] = []
+    for m in modules:
+        if isinstance(m, nn.Linear):
+            out.append((m.weight.detach(), None if m.bias is None else m.bias.detach()))
+        elif isinstance(m, nn.BatchNorm1d):
+            W, b = out[-1]
+            inv = torch.rsqrt(m.running_var.detach() + m.eps)
+            g = inv if m.weight is None else m.weight.detach() * inv
+            b0 = torch.zeros_like(m.running_mean) if b is None else b
+            beta = torch.zeros_like(m.running_mean) if m.bias is None else m.bias.detach()
+            out[-1] = (W * g[:, None], (b0 - m.running_mean.detach()) * g + beta)
+        elif isinstance(m, nn.ReLU):
+            continue
+        else:
+            raise RuntimeError(f"unsupported module in autoencoder chain: {type(m).__name__}")
+    return out
+
+
+def _version(modules: Sequence[nn.Module]):
+    v = []
+    for m in modules:
+        for t in list(m.parameters(recurse=False)) + list(m.buffers(recurse=False)):
+            v.append((t.data_ptr(), t._version))
+    return tuple(v)
+
+
+class _ChainMixin:
+    def _run(self, which: str, modules, x: torch.Tensor) -> torch.Tensor:
+        needs_graph = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for m in modules for p in m.parameters()))
+        bn_training = any(isinstance(m, nn.BatchNorm1d) and m.training for m in modules)
+        if needs_graph or bn_training:
+            if not x.is_cuda:
+                raise RuntimeError("autoencoder input must be a CUDA tensor")
+            for m in modules:  # the reference's own graph (model.py:52-62), for autograd / batch statistics
+                x = m(x)
+            return x / x.norm(dim=-1, keepdim=True)
+        fused = self.__dict__.setdefault("_fused_" + which, _FusedChain())
+        return fused.run(_fold(modules), _version(modules), True, x)
+
+
+class AutoencoderMLP(nn.Module, _ChainMixin):
+    def __init__(self, encoder_hidden_dims, decoder_hidden_dims, clip_dim=768):
+        super().__init__()
+        encoder_layers = []
+        for i in range(len(encoder_hidden_dims)):
+            if i == 0:
+                encoder_layers.append(nn.Linear(clip_dim, encoder_hidden_dims[i]))
+            else:
+                encoder_layers.append(nn.BatchNorm1d(encoder_hidden_dims[i - 1]))
+                encoder_layers.append(nn.ReLU())
+                encoder_layers.append(nn.Linear(encoder_hidden_dims[i - 1], encoder_hidden_dims[i]))
+        self.encoder = nn.ModuleList(encoder_layers)
+        decoder_layers = []
+        for i in range(len(decoder_hidden_dims)):
+            if i == 0:
+                decoder_layers.append(nn.Linear(encoder_hidden_dims[-1], decoder_hidden_dims[i]))
+            else:
+                decoder_layers.append(nn.ReLU())
+                decoder_layers.append(nn.Linear(decoder_hidden_dims[i - 1], decoder_hidden_dims[i]))
+        self.decoder = nn.ModuleList(decoder_layers)
+
+    def forward(self, x):
+        return self.decode(self.encode(x))
+
+    def encode(self, x):
+        return self._run("enc", list(self.encoder), x)
+
+    def decode(self, x):
+        return self._run("dec", list(self.decoder), x)
+
+
+class EncoderDecoderOnline(nn.Module, _ChainMixin):
+    def __init__(self, method="mlp", input_dim=32, compressed_dim=15):
+        super().__init__()
+        if method != "mlp":
+            # the reference's 'pca' branch (sklearn IncrementalPCA on the host) is documented as worse and unused
+            raise NotImplementedError("only method='mlp' is provided (model.py:317)")
+        self.method = method
+        self.encoder = nn.Sequential(nn.Linear(input_dim, 24), nn.ReLU(), nn.Linear(24, 15))
+        self.decoder = nn.Sequential(nn.Linear(15, 24), nn.ReLU(), nn.Linear(24, input_dim))
+
+    def encode(self, x):
+        return self._run("enc", list(self.encoder), x)
+
+    def decode(self, x):
+        return self._run("dec", list(self.decoder), x)
+
+    def forward(self, x):
+        return self.decode(self.encode(x))
+
+
+def reference_chain(modules: Sequence[nn.Module], x: torch.Tensor) -> torch.Tensor:
+    """The reference's arithmetic in plain torch (used by tests and the CPU baseline only)."""
+    for m in modules:
+        x = m(x)
+    return x / x.norm(dim=-1, keepdim=True)

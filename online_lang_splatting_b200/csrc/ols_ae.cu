@@ -1,7 +1,542 @@
-// placeholder until the autoencoder kernels land
+// ols_ae.cu -- the per-frame language autoencoder as ONE fused tensor-core kernel for sm_100a.
+//
+// Reference: language/autoencoder/model.py:15-62 (AutoencoderMLP.encode / .decode) and :314-354
+// (EncoderDecoderOnline): y = normalize( L_n( relu( ... relu( L_1(x) ) ... ) ) ), applied to the
+// [H*W, 768] flattened CLIP map (utils/slam_backend.py:392-395,557-559).  Eval-mode BatchNorm is an
+// affine map and is folded into the preceding Linear by the caller.
+//
+// Design (B200-first, not a translation of the torch module):
+//   * persistent kernel, one CTA per SM, a CTA owns 128-row tiles of the activation matrix;
+//   * the whole layer chain runs inside the kernel: the 128 x N_l fp32 accumulator of a layer lives in
+//     TMEM (tcgen05.mma, M = 128), the epilogue warps read it back (tcgen05.ld), add bias, apply ReLU,
+//     convert to bf16 and write it into shared memory in the 128-byte-swizzled K-major layout the next
+//     layer's tcgen05.mma reads as its A operand -- activations never touch HBM between layers, so the
+//     algorithmic HBM traffic is x in, y out (+ the weights once, they stay L2 resident);
+//   * layer 0 multiplies the fp32 input directly (kind::tf32, x tiles arrive by TMA, no conversion
+//     pass); the inner layers run kind::f16 on bf16 with fp32 accumulation;
+//   * weights are streamed through a TMA ring of K-slabs (128 bytes of K per row), one elected thread
+//     issues TMA, one elected thread issues MMA, four warps run the epilogue; mbarriers only.
+//   * the final row-wise L2 normalisation is fused into the last epilogue (one thread owns one row).
 #include "ols_common.cuh"
-extern "C" {
-int ols_ae_plan_create(const ols_ae_chain*, ols_ae_plan**, void*) { ols_set_error("AE not built yet"); return OLS_ERR_UNSUPPORTED; }
-void ols_ae_plan_destroy(ols_ae_plan*) {}
-int ols_ae_forward(const ols_ae_plan*, const float*, float*, int64_t, void*) { ols_set_error("AE not built yet"); return OLS_ERR_UNSUPPORTED; }
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cstring>
+#include <vector>
+
+namespace ols {
+
+constexpr int AE_M = 128;             // rows per tile (UMMA M)
+constexpr int AE_THREADS = 192;       // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int AE_SLAB_BYTES = 128;    // bytes of K per row in one slab (SWIZZLE_128B)
+constexpr int AE_BLOCK_MAX = 384;     // max rows of a weight slab resident in one ring stage
+constexpr int AE_CHUNK_MAX = 256;     // max N of one tcgen05.mma
+constexpr int AE_TMEM_COLS = 512;
+constexpr int AE_MAX_BLOCKS = 4;
+
+struct AeLayer {
+    int K, N;            // padded: K multiple of the slab width, N multiple of 16
+    int n_slabs;         // K / (elements per 128-byte slab)
+    int block_n;         // rows of the weight slab streamed per stage (<= AE_BLOCK_MAX)
+    int chunk_n;         // N of one MMA instruction (block_n or block_n / 2)
+    int n_blocks;        // N / block_n
+    int blocks_per_pass; // N-blocks accumulated in TMEM before the epilogue runs (pass width <= 512 columns)
+    int relu;
+    int tf32;            // 1: A and B are fp32 (kind::tf32, 32 elements per slab); 0: bf16 (64 per slab)
+    const float* bias;   // [N] zero padded
+};
+
+struct AeParams {
+    CUtensorMap tmap_x;
+    CUtensorMap tmap_w[OLS_AE_MAX_LAYERS];
+    AeLayer layer[OLS_AE_MAX_LAYERS];
+    int n_layers;
+    int manual_x;    // 1: layer-0 input is loaded by the epilogue warps (row stride not TMA compatible)
+    int K0_real;     // real input width
+    int out_real;    // real output width
+    int normalize;
+    int n_stages, stage_bytes, act_bytes;
+    const float* x;
+    float* y;
+    long long M;
+    int n_tiles;
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T ; both operands K-major, 128-byte swizzle
+template <bool TF32>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    if (TF32)
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+            "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+            : "memory");
+    else
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+            "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+            : "memory");
+}
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fffu);  // start address
+    d |= (uint64_t)1 << 16;                   // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;         // stride byte offset
+    d |= (uint64_t)1 << 46;                   // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, K-major A and B, M = 128
+__device__ __forceinline__ uint32_t make_idesc(bool tf32, int n) {
+    const uint32_t fmt = tf32 ? 2u : 1u;  // 2 = TF32, 1 = BF16
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(AE_M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// byte offset of 16-byte chunk j of row r inside a [rows x 128 B] SWIZZLE_128B slab
+__device__ __forceinline__ uint32_t sw128(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(AE_THREADS, 1) k_ae_chain(const __grid_constant__ AeParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* ring = smem;                                          // n_stages * stage_bytes
+    uint8_t* act = smem + (size_t)p.n_stages * p.stage_bytes;      // act_bytes: [K-slab][128 rows][128 B]
+    uint64_t* bars = (uint64_t*)(act + p.act_bytes);
+    uint64_t* full = bars;                   // [n_stages] TMA -> MMA
+    uint64_t* empty = bars + 8;              // [n_stages] MMA -> TMA
+    uint64_t* mma_done = bars + 16;          // MMA -> epilogue (accumulator pass complete)
+    uint64_t* epi_done = bars + 17;          // epilogue -> MMA (TMEM drained, next A operand in smem)
+    uint32_t* tmem_slot = (uint32_t*)(bars + 18);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.n_stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(mma_done, 1);
+        mbar_init(epi_done, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(AE_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_x) : "memory");
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                for (int l = 0; l < p.n_layers; l++) {
+                    const AeLayer& L = p.layer[l];
+                    const int slab_elems = L.tf32 ? 32 : 64;
+                    const bool load_x = (l == 0) && !p.manual_x;
+                    for (int b = 0; b < L.n_blocks; b++) {
+                        for (int s = 0; s < L.n_slabs; s++) {
+                            mbar_wait(&empty[stage], phase ^ 1);
+                            uint8_t* st = ring + (size_t)stage * p.stage_bytes;
+                            const uint32_t bytes = (uint32_t)L.block_n * AE_SLAB_BYTES + (load_x ? AE_M * AE_SLAB_BYTES : 0);
+                            mbar_expect_tx(&full[stage], bytes);
+                            uint8_t* bdst = st;
+                            if (load_x) {
+                                tma_load_2d(st, &p.tmap_x, &full[stage], s * slab_elems, tile * AE_M);
+                                bdst = st + AE_M * AE_SLAB_BYTES;
+                            }
+                            for (int c = 0; c < L.block_n; c += L.chunk_n)
+                                tma_load_2d(bdst + (size_t)c * AE_SLAB_BYTES, &p.tmap_w[l], &full[stage], s * slab_elems,
+                                            b * L.block_n + c);
+                            if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        int stage = 0;
+        uint32_t phase = 0, epi_phase = 0;
+        int tiles_done = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, tiles_done++) {
+            for (int l = 0; l < p.n_layers; l++) {
+                const AeLayer& L = p.layer[l];
+                const bool a_from_ring = (l == 0) && !p.manual_x;
+                const uint32_t idesc = make_idesc(L.tf32 != 0, L.chunk_n);
+                for (int b = 0; b < L.n_blocks; b++) {
+                    const int in_pass = b % L.blocks_per_pass;
+                    if (in_pass == 0) {
+                        // the previous accumulator pass must be drained (and, for l > 0, the A operand written)
+                        if (l == 0 && b == 0) {
+                            if (tiles_done > 0) { mbar_wait(epi_done, epi_phase); epi_phase ^= 1; }  // last pass of the previous tile
+                            if (p.manual_x) { mbar_wait(epi_done, epi_phase); epi_phase ^= 1; }       // hand-written A operand
+                        } else {
+                            mbar_wait(epi_done, epi_phase);
+                            epi_phase ^= 1;
+                        }
+                        tcgen05_fence_after();
+                    }
+                    for (int s = 0; s < L.n_slabs; s++) {
+                        mbar_wait(&full[stage], phase);
+                        tcgen05_fence_after();
+                        if (lane == 0) {
+                            uint8_t* st = ring + (size_t)stage * p.stage_bytes;
+                            const uint32_t a_addr = a_from_ring ? smem_u32(st) : smem_u32(act + (size_t)s * AE_M * AE_SLAB_BYTES);
+                            const uint32_t b_addr = smem_u32(st) + (a_from_ring ? AE_M * AE_SLAB_BYTES : 0);
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {  // 4 x 32 bytes of K per slab
+                                const uint64_t ad = make_sdesc(a_addr + k * 32);
+                                for (int c = 0; c < L.block_n; c += L.chunk_n) {
+                                    const uint64_t bd = make_sdesc(b_addr + (uint32_t)c * AE_SLAB_BYTES + k * 32);
+                                    const uint32_t d = tmem_base + (uint32_t)(in_pass * L.block_n + c);
+                                    if (L.tf32) umma<true>(d, ad, bd, idesc, (s | k) ? 1u : 0u);
+                                    else umma<false>(d, ad, bd, idesc, (s | k) ? 1u : 0u);
+                                }
+                            }
+                            umma_commit(&empty[stage]);  // frees the ring slot when these MMAs have read it
+                        }
+                        __syncwarp();
+                        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+                    }
+                    if (in_pass == L.blocks_per_pass - 1 || b == L.n_blocks - 1) {
+                        if (lane == 0) umma_commit(mma_done);
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue warps (one thread = one row = one TMEM lane) =====================
+        const int quad = warp & 3;                 // TMEM lanes [32*quad, 32*quad + 32) are accessible to this warp
+        const int row = quad * 32 + lane;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+        uint32_t done_phase = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const long long grow = (long long)tile * AE_M + row;
+            if (p.manual_x) {
+                // layer-0 A operand written by hand: fp32, zero padded to the slab width
+                const AeLayer& L0 = p.layer[0];
+                for (int s = 0; s < L0.n_slabs; s++) {
+                    for (int j = 0; j < 8; j++) {
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        float* vv = &v.x;
+                        for (int e = 0; e < 4; e++) {
+                            const int col = s * 32 + j * 4 + e;
+                            if (col < p.K0_real && grow < p.M) vv[e] = p.x[grow * p.K0_real + col];
+                        }
+                        *(float4*)(act + (size_t)s * AE_M * AE_SLAB_BYTES + sw128(row, j)) = v;
+                    }
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(epi_done);
+            }
+            for (int l = 0; l < p.n_layers; l++) {
+                const AeLayer& L = p.layer[l];
+                const bool last = l == p.n_layers - 1;
+                const int pass_w = L.block_n * L.blocks_per_pass;
+                float sumsq = 0.0f;
+                for (int n0 = 0; n0 < L.N; n0 += pass_w) {
+                    const int w = min(pass_w, L.N - n0);
+                    mbar_wait(mma_done, done_phase);
+                    done_phase ^= 1;
+                    tcgen05_fence_after();
+                    for (int c = 0; c < w; c += 32) {
+                        uint32_t r[32];
+                        const int nc = min(32, w - c);
+                        if (nc == 32) tmem_ld32(t_lane + (uint32_t)c, r);
+                        else {
+                            tmem_ld16(t_lane + (uint32_t)c, r);
+#pragma unroll
+                            for (int i = 16; i < 32; i++) r[i] = 0u;
+                        }
+                        tmem_ld_wait();
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 32; i++) {
+                            const int col = n0 + c + i;
+                            float f = __uint_as_float(r[i]) + (i < nc ? __ldg(L.bias + col) : 0.0f);
+                            if (L.relu) f = fmaxf(f, 0.0f);
+                            v[i] = f;
+                        }
+                        if (!last) {
+                            // next layer's A operand: bf16, K-major, 128-byte swizzle; column col -> slab col/64
+                            const int col0 = n0 + c;
+                            uint8_t* slab = act + (size_t)(col0 >> 6) * AE_M * AE_SLAB_BYTES;
+                            const int j0 = (col0 & 63) >> 3;  // first 16-byte chunk (8 bf16) inside the slab row
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                uint4 pk;
+                                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[q * 8 + 0], v[q * 8 + 1]);
+                                __nv_bfloat162 h1 = __floats2bfloat162_rn(v[q * 8 + 2], v[q * 8 + 3]);
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[q * 8 + 4], v[q * 8 + 5]);
+                                __nv_bfloat162 h3 = __floats2bfloat162_rn(v[q * 8 + 6], v[q * 8 + 7]);
+                                pk.x = *(uint32_t*)&h0; pk.y = *(uint32_t*)&h1; pk.z = *(uint32_t*)&h2; pk.w = *(uint32_t*)&h3;
+                                if (q * 8 < nc) *(uint4*)(slab + sw128(row, j0 + q)) = pk;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; i++) {
+                                const int col = n0 + c + i;
+                                if (i < nc && col < p.out_real) {
+                                    sumsq = fmaf(v[i], v[i], sumsq);
+                                    if (grow < p.M) p.y[grow * p.out_real + col] = v[i];
+                                }
+                            }
+                        }
+                    }
+                    if (!last) {
+                        // zero the K padding of the next layer's A operand (its K may exceed this layer's N)
+                        const AeLayer& Ln = p.layer[l + 1];
+                        for (int col0 = L.N; col0 < Ln.K; col0 += 8)
+                            *(uint4*)(act + (size_t)(col0 >> 6) * AE_M * AE_SLAB_BYTES + sw128(row, (col0 & 63) >> 3)) =
+                                make_uint4(0u, 0u, 0u, 0u);
+                    }
+                    tcgen05_fence_before();
+                    if (!last) fence_proxy_async_smem();
+                    mbar_arrive(epi_done);
+                }
+                if (last && p.normalize && grow < p.M) {
+                    // x / ||x||_2 (model.py:55,61) -- the un-normalised row was just written by this thread
+                    const float inv = 1.0f / sqrtf(sumsq);
+                    float* yr = p.y + grow * p.out_real;
+                    for (int col = 0; col < p.out_real; col++) yr[col] *= inv;
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(AE_TMEM_COLS));
+    }
+}
+
+// weight re-layout: pad [N,K] fp32 -> [N_pad,K_pad] fp32 (layer 0) or bf16 (inner layers), zero filled
+__global__ void k_ae_pack_weight(const float* __restrict__ w, int N, int K, void* __restrict__ out, int N_pad, int K_pad,
+                                 int to_bf16) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)N_pad * K_pad) return;
+    const int n = (int)(i / K_pad), k = (int)(i % K_pad);
+    const float v = (n < N && k < K) ? w[(size_t)n * K + k] : 0.0f;
+    if (to_bf16) ((__nv_bfloat16*)out)[i] = __float2bfloat16_rn(v);
+    else ((float*)out)[i] = v;
+}
+__global__ void k_ae_pack_bias(const float* __restrict__ b, int N, float* __restrict__ out, int N_pad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N_pad) out[i] = (i < N && b) ? b[i] : 0.0f;
+}
+
+}  // namespace ols
+
+using namespace ols;
+
+struct ols_ae_plan {
+    AeParams p;
+    std::vector<void*> owned;
+    int device;
+    int sm_count;
+    size_t smem_bytes;
+};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)ptr;
+    }
+    return fn;
+}
+
+// 2-D row-major tensor [rows, cols] with a [box_rows, 128 bytes] box, 128-byte swizzle
+static int make_map(CUtensorMap* map, const void* base, bool bf16, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { ols_set_error("cuTensorMapEncodeTiled not available"); return OLS_ERR_CUDA; }
+    const uint32_t esz = bf16 ? 2 : 4;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * esz};
+    cuuint32_t box[2] = {AE_SLAB_BYTES / esz, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ols_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return OLS_ERR_CUDA; }
+    return OLS_OK;
+}
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+extern "C" {
+
+int ols_ae_plan_create(const ols_ae_chain* chain, ols_ae_plan** out_plan, void* stream) {
+    if (!chain || !out_plan) { ols_set_error("null argument"); return OLS_ERR_INVALID; }
+    if (chain->n_layers < 1 || chain->n_layers > OLS_AE_MAX_LAYERS) { ols_set_error("n_layers out of range"); return OLS_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    ols_ae_plan* plan = new ols_ae_plan();
+    AeParams& p = plan->p;
+    memset(&p, 0, sizeof(p));
+    auto fail = [&](int rc) { ols_ae_plan_destroy(plan); return rc; };
+    if (cudaGetDevice(&plan->device) != cudaSuccess) { ols_set_error("no CUDA device"); return fail(OLS_ERR_CUDA); }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, plan->device) != cudaSuccess) { ols_set_error("cudaGetDeviceProperties failed"); return fail(OLS_ERR_CUDA); }
+    plan->sm_count = prop.multiProcessorCount;
+    p.n_layers = chain->n_layers;
+    p.K0_real = chain->dims[0];
+    p.out_real = chain->dims[chain->n_layers];
+    p.normalize = chain->normalize;
+    p.manual_x = (chain->dims[0] % 32 != 0) ? 1 : 0;  // TMA needs 16-byte row strides; keep whole slabs too
+    int stage_bytes = 0, act_cols_bytes = 0;
+    for (int l = 0; l < chain->n_layers; l++) {
+        const int K = chain->dims[l], N = chain->dims[l + 1];
+        if (K <= 0 || N <= 0 || !chain->d_weight[l]) { ols_set_error("bad layer %d", l); return fail(OLS_ERR_INVALID); }
+        AeLayer& L = p.layer[l];
+        L.tf32 = l == 0;
+        const int slab = L.tf32 ? 32 : 64;
+        // K of layer l must equal the padded N of layer l-1 (the activation the epilogue wrote)
+        L.K = round_up(K, slab);
+        L.N = round_up(N, 16);
+        L.n_slabs = L.K / slab;
+        // split N into equal blocks of at most AE_BLOCK_MAX rows, each a multiple of 16
+        int nb = (L.N + AE_BLOCK_MAX - 1) / AE_BLOCK_MAX;
+        while ((L.N % nb) != 0 || ((L.N / nb) % 16) != 0) nb++;
+        L.n_blocks = nb;
+        L.block_n = L.N / nb;
+        L.chunk_n = L.block_n;
+        if (L.chunk_n > AE_CHUNK_MAX) {
+            if ((L.block_n / 2) % 16 != 0) { ols_set_error("layer %d: cannot split N=%d", l, L.N); return fail(OLS_ERR_UNSUPPORTED); }
+            L.chunk_n = L.block_n / 2;
+        }
+        if (L.n_blocks > AE_MAX_BLOCKS) { ols_set_error("layer %d too wide (N=%d)", l, N); return fail(OLS_ERR_UNSUPPORTED); }
+        L.blocks_per_pass = AE_TMEM_COLS / L.block_n;
+        if (L.blocks_per_pass > L.n_blocks) L.blocks_per_pass = L.n_blocks;
+        const bool last = l == chain->n_layers - 1;
+        if (!last && L.blocks_per_pass != L.n_blocks) { ols_set_error("hidden layer %d wider than 512", l); return fail(OLS_ERR_UNSUPPORTED); }
+        L.relu = last ? 0 : 1;
+        const int sb = L.block_n * AE_SLAB_BYTES + ((l == 0 && !p.manual_x) ? AE_M * AE_SLAB_BYTES : 0);
+        if (sb > stage_bytes) stage_bytes = sb;
+        if (l > 0 || p.manual_x) { const int ab = L.n_slabs * AE_M * AE_SLAB_BYTES; if (ab > act_cols_bytes) act_cols_bytes = ab; }
+        // packed weights and bias
+        void* wbuf = nullptr; float* bbuf = nullptr;
+        const size_t wbytes = (size_t)L.N * L.K * (L.tf32 ? 4 : 2);
+        if (cudaMalloc(&wbuf, wbytes) != cudaSuccess || cudaMalloc((void**)&bbuf, sizeof(float) * L.N) != cudaSuccess) {
+            if (wbuf) cudaFree(wbuf);
+            ols_set_error("out of device memory"); return fail(OLS_ERR_CUDA);
+        }
+        plan->owned.push_back(wbuf); plan->owned.push_back(bbuf);
+        const size_t tot = (size_t)L.N * L.K;
+        k_ae_pack_weight<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(chain->d_weight[l], N, K, wbuf, L.N, L.K, L.tf32 ? 0 : 1);
+        k_ae_pack_bias<<<(L.N + 255) / 256, 256, 0, st>>>(chain->d_bias[l], N, bbuf, L.N);
+        L.bias = bbuf;
+        int rc = make_map(&p.tmap_w[l], wbuf, !L.tf32, (uint64_t)L.N, (uint64_t)L.K, (uint32_t)L.chunk_n);
+        if (rc != OLS_OK) return fail(rc);
+    }
+    for (int l = 1; l < chain->n_layers; l++) {
+        if (p.layer[l].K < p.layer[l - 1].N) { ols_set_error("internal: K/N padding mismatch at layer %d", l); return fail(OLS_ERR_INVALID); }
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { ols_set_error("weight packing failed"); return fail(OLS_ERR_CUDA); }
+    stage_bytes = round_up(stage_bytes, 1024);
+    const int act_bytes = round_up(act_cols_bytes > 0 ? act_cols_bytes : 1024, 1024);
+    const int budget = 227 * 1024 - 1024 /*alignment*/ - 256 /*barriers*/ - act_bytes;
+    int n_stages = budget / stage_bytes;
+    if (n_stages > 8) n_stages = 8;
+    if (n_stages < 2) { ols_set_error("layer chain does not fit shared memory (stage %d B, act %d B)", stage_bytes, act_bytes); return fail(OLS_ERR_UNSUPPORTED); }
+    p.n_stages = n_stages; p.stage_bytes = stage_bytes; p.act_bytes = act_bytes;
+    plan->smem_bytes = (size_t)n_stages * stage_bytes + act_bytes + 256 + 1024;
+    if (cudaFuncSetAttribute(k_ae_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess) {
+        ols_set_error("cannot reserve %zu bytes of shared memory", plan->smem_bytes); return fail(OLS_ERR_CUDA);
+    }
+    *out_plan = plan;
+    return OLS_OK;
+}
+
+void ols_ae_plan_destroy(ols_ae_plan* plan) {
+    if (!plan) return;
+    for (void* q : plan->owned) cudaFree(q);
+    delete plan;
+}
+
+int ols_ae_forward(const ols_ae_plan* plan, const float* d_x, float* d_y, int64_t M, void* stream) {
+    if (!plan || !d_x || !d_y || M < 0) { ols_set_error("bad arguments"); return OLS_ERR_INVALID; }
+    if (M == 0) return OLS_OK;
+    AeParams p = plan->p;
+    p.x = d_x; p.y = d_y; p.M = M;
+    p.n_tiles = (int)((M + AE_M - 1) / AE_M);
+    if (!p.manual_x) {
+        if (((uintptr_t)d_x & 15) != 0) { ols_set_error("x must be 16-byte aligned"); return OLS_ERR_INVALID; }
+        int rc = make_map(&p.tmap_x, d_x, false, (uint64_t)M, (uint64_t)p.K0_real, AE_M);
+        if (rc != OLS_OK) return rc;
+    }
+    const int grid = p.n_tiles < plan->sm_count ? p.n_tiles : plan->sm_count;
+    k_ae_chain<<<grid, AE_THREADS, plan->smem_bytes, (cudaStream_t)stream>>>(p);
+    OLS_CUDA_TRY(cudaGetLastError());
+    return OLS_OK;
+}
+
+}  // extern "C"

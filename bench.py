@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native language-splatting hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json metric / configs[2] shape): 1,000,000 Gaussians, 15-dim language features,
+960x540, 8 synthetic keyframes per GPU and step.  For every keyframe a step does what a mapping
+iteration of the reference does on the hot path (utils/slam_backend.py:510-670): encode the frame's
+192x192x768 CLIP map with the autoencoder, render (forward), and back-propagate (backward) into the
+Gaussian gradient buffer; with N > 1 the flat gradient buffer is all-reduced over NCCL once per step.
+
+  value    frames/s with every input resident in HBM, kernels called back to back (CUDA events)
+  e2e      frames/s through the public API (render() + AutoencoderMLP.encode + torch loss glue) with the
+           per-frame inputs (CLIP map, ground-truth RGB-D, camera) copied from pinned host memory and the
+           loss + the 15-dim code map read back every step
+  roofline the forward blend kernel named by the metric: algorithmic bytes / its mean launch
+           time measured with CUDA events recorded inside the library over the timed region
+  cpu_baseline / --impl reference: the CPU restatement of the reference (oracle/) + the reference AE on
+           torch-CPU, one keyframe, all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "lang-splat render+AE FPS @1M Gaussians/15-dim/960×540; blend HBM GB/s vs peak"
+ENC_DIMS = [384, 192, 96, 48, 24, 15]
+DEC_DIMS = [24, 48, 96, 192, 384, 384, 768]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gaussians", type=int, default=1_000_000)
+    ap.add_argument("--keyframes", type=int, default=8, help="keyframes per GPU per step")
+    ap.add_argument("--width", type=int, default=960)
+    ap.add_argument("--height", type=int, default=540)
+    ap.add_argument("--tile", type=int, default=15, help="15 = the reference build's tile geometry")
+    ap.add_argument("--backward-mode", default="compat", choices=["compat", "exact"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for i, n in enumerate(names):
+                if len(r) > 5 + i and r[5 + i].lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_frame_seconds(args, keyframes: int = 1):
+    """One keyframe of the same workload on the host: oracle forward+backward + reference AE encode on torch-CPU."""
+    import torch
+    from online_lang_splatting_b200 import synthetic as S
+    from online_lang_splatting_b200 import autoencoder as AE
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _util as U
+    from oracle import oracle as O
+    cores = O.num_threads()
+    torch.set_num_threads(max(cores, 1))
+    sc = U.make_scene(P=args.gaussians, F=15, W=args.width, H=args.height, seed=0, scale=0.01)
+    grads = U.loss_weights(15, args.width, args.height, seed=1)
+    torch.manual_seed(0)
+    ae = AE.AutoencoderMLP(ENC_DIMS, DEC_DIMS).eval()
+    x = S.make_clip_maps(1, seed=0)
+    t0 = time.perf_counter()
+    for _ in range(keyframes):
+        with torch.no_grad():
+            AE.reference_chain(list(ae.encoder), x)
+        U.run_oracle(sc, tile=args.tile, grads=grads, compat=(args.backward_mode == "compat"))
+    dt = (time.perf_counter() - t0) / keyframes
+    return dt, cores
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sec = []
+    if args.warmup > 0:
+        cpu_frame_seconds(args)
+    for _ in range(max(1, min(args.steps, 3))):
+        dt, cores = cpu_frame_seconds(args)
+        sec.append(dt)
+    dt = sum(sec) / len(sec)
+    fps = 1.0 / dt
+    sample = (f"{len(sec)} keyframe(s) of the same workload (P={args.gaussians}, F=15, {args.width}x{args.height}): CPU "
+              f"restatement of the reference rasterizer forward+backward (oracle/ols_oracle.cpp, OpenMP) + reference "
+              f"AutoencoderMLP.encode on torch-CPU; the reference ships no CPU render path (SURVEY 0.4)")
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": len(sec), "warmup": 1 if args.warmup else 0, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    gpu_ref = compiled_reference_ms(args)
+    if gpu_ref is not None:
+        line["gpu_reference_cuda"] = gpu_ref
+    print(json.dumps(line), flush=True)
+
+
+def compiled_reference_ms(args):
+    """Context only: the reference's own CUDA (oracle/_ref/ref_P_C.so, sm_100 build) on the same scene."""
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return None
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import _util as U
+        mod = U.ref_module("ref_P_C")
+        if mod is None:
+            return None
+        dev = torch.device("cuda:0")
+        sc = U.make_scene(P=args.gaussians, F=15, W=args.width, H=args.height, seed=0, scale=0.01)
+        grads = [g.to(dev) for g in U.loss_weights(15, args.width, args.height, seed=1)]
+        d = lambda t: t.to(dev).contiguous()
+        e = torch.Tensor([])
+        a = (d(sc["bg"]), d(sc["means3D"]), e, d(sc["language"]), d(sc["opacities"]), d(sc["scales"]), d(sc["rotations"]),
+             1.0, e, d(sc["viewmatrix"]), d(sc["projmatrix"]), d(sc["projmatrix_raw"]), sc["tanfovx"], sc["tanfovy"],
+             args.height, args.width, d(sc["shs"]), 0, d(sc["campos"]), False, False)
+        tf = tb = 0.0
+        n = 5
+        for it in range(n + 2):
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            R, color, language, radii, geom, binning, img, depth, opacity, n_touched = mod.rasterize_language_gaussians(*a)
+            e1.record()
+            b = (a[0], a[1], radii, e, a[3], a[5], a[6], 1.0, e, a[9], a[10], a[11], a[12], a[13], grads[0], grads[1],
+                 grads[2], a[16], 0, a[18], geom, R, binning, img, False)
+            mod.rasterize_language_gaussians_backward(*b)
+            e2.record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                tf += e0.elapsed_time(e1)
+                tb += e1.elapsed_time(e2)
+        return {"forward_ms": tf / n, "backward_ms": tb / n, "R": int(R),
+                "note": "reference P/ CUDA (15x15 tiles, F=15) rebuilt for sm_100, one view, rasterizer only"}
+    except Exception as ex:  # context only -- never fail the arm
+        return {"error": str(ex)[:200]}
+
+
+def workload_config(args):
+    return {"workload": f"{args.gaussians} Gaussians, 15-dim language features, {args.width}x{args.height}, "
+                        f"{args.keyframes} keyframes per GPU per step: AE encode of a 192x192x768 CLIP map + render "
+                        f"forward + backward per keyframe, NCCL all-reduce of the flat gradient buffer per step (N>1)",
+            "gaussians": args.gaussians, "feature_dim": 15, "width": args.width, "height": args.height,
+            "keyframes_per_gpu": args.keyframes, "tile": args.tile, "backward_mode": args.backward_mode,
+            "autoencoder": "768-384-192-96-48-24-15 (1-stage, BN folded)", "parallelism": f"frames x{args.gpus}",
+            "l2_policy": "per-step inputs (8 CLIP maps = 906 MB + 112 MB records) exceed the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from online_lang_splatting_b200 import _native as N
+    from online_lang_splatting_b200 import autoencoder as AE
+    from online_lang_splatting_b200 import diff_gaussian_rasterization as dgr
+    from online_lang_splatting_b200 import synthetic as S
+    from online_lang_splatting_b200.gaussian_renderer import render
+    import online_lang_splatting_b200.gaussian_renderer as GR
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    N.require_cuda()
+
+    P, W, H, KF = args.gaussians, args.width, args.height, args.keyframes
+    GR.TILE_SIZE, GR.BACKWARD_MODE = args.tile, args.backward_mode
+    g = S.make_gaussians(P, 15, W, H, seed=0, scale_px_sigma=0.01)
+    pc = S.SyntheticGaussianModel(g, device=dev, requires_grad=True)
+    pipe = S.PipelineParams()
+    bg = torch.zeros(3, device=dev)
+    cams = [S.make_camera(W, H, view=rank * KF + k, seed=0, device=str(dev)) for k in range(KF)]
+    torch.manual_seed(0)
+    ae = AE.AutoencoderMLP(ENC_DIMS, DEC_DIMS).eval().to(dev)
+    for p_ in ae.parameters():
+        p_.requires_grad_(False)
+
+    # per-keyframe inputs: device-resident copies (value) and pinned host copies (e2e)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    clip_dev, clip_host, gt_host = [], [], []
+    for k in range(KF):
+        x = torch.randn(192 * 192, 768, device=dev, generator=gen)
+        x = x / x.norm(dim=-1, keepdim=True)
+        clip_dev.append(x)
+        if not args.no_e2e:
+            clip_host.append(x.cpu().pin_memory())
+            gt_host.append((torch.rand(3, H, W).pin_memory(), (torch.rand(1, H, W) * 5).pin_memory()))
+    wc, wl, wd = (torch.randn(s, device=dev, generator=gen) for s in ((3, H, W), (15, H, W), (1, H, W)))
+
+    # flat gradient buffer [xyz 3 | f_dc 3 | opacity 1 | scaling 3 | rotation 4 | language 15] x P  
+    flat = torch.zeros(29 * P, device=dev)
+    o = 0
+    views = {}
+    for name, shape in (("means3D", (P, 3)), ("sh", (P, 1, 3)), ("opacity", (P, 1)), ("scales", (P, 3)),
+                        ("rotations", (P, 4)), ("language", (P, 15))):
+        n = math.prod(shape)
+        views[name] = flat[o:o + n].view(shape)
+        o += n
+    scratch = {n_: torch.empty(s_, device=dev) for n_, s_ in (("means2D", (P, 3)), ("colors", (P, 3)), ("cov3D", (P, 6)),
+                                                             ("tau", (P, 6)))}
+    out_bufs = dict(views, **scratch)
+    rs_list = []
+    with torch.no_grad():
+        act = {"means3D": pc.get_xyz.detach(), "shs": pc.get_features.detach().contiguous(),
+               "language": pc.get_language_features.detach(), "opacities": pc.get_opacity.detach(),
+               "scales": pc.get_scaling.detach(), "rotations": pc.get_rotation.detach()}
+    for cam in cams:
+        rs_list.append(dgr.GaussianRasterizationSettings(
+            image_height=H, image_width=W, tanfovx=math.tan(cam.FoVx * 0.5), tanfovy=math.tan(cam.FoVy * 0.5), bg=bg,
+            scale_modifier=1.0, viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform,
+            projmatrix_raw=cam.projection_matrix, sh_degree=0, campos=cam.camera_center, prefiltered=False, debug=False,
+            tile_size=args.tile, backward_mode=args.backward_mode))
+    empty = torch.Tensor([])
+    Rs = []
+
+    def step_resident():
+        flat.zero_()
+        for k in range(KF):
+            with torch.no_grad():
+                ae.encode(clip_dev[k])
+            R, color, language, radii, depth, opacity, n_touched, st = dgr._forward_native(
+                act["means3D"], act["shs"], empty, act["language"], act["opacities"], act["scales"], act["rotations"],
+                empty, rs_list[k])
+            dgr._backward_native(st, radii, wc, wl, wd, out=out_bufs, accumulate=True)
+            if R >= 0:
+                Rs.append(R)
+        if world > 1:
+            dist.all_reduce(flat)
+
+    code_host = [torch.empty(192 * 192, 15).pin_memory() for _ in range(KF)] if not args.no_e2e else []
+    params = pc.parameters()
+
+    def step_e2e():
+        total = torch.zeros((), device=dev)
+        for k in range(KF):
+            x = clip_host[k].to(dev, non_blocking=True)
+            gt_rgb = gt_host[k][0].to(dev, non_blocking=True)
+            gt_d = gt_host[k][1].to(dev, non_blocking=True)
+            with torch.no_grad():
+                code = ae.encode(x)                                  # [36864, 15] -> gt_lang_feat (slam_backend.py:557-576)
+            code_host[k].copy_(code, non_blocking=True)              # the reference keeps it on the CPU (:576)
+            gt_lang = torch.nn.functional.interpolate(code.view(192, 192, 15).permute(2, 0, 1)[None], size=(H, W),
+                                                      mode="bilinear", align_corners=False)[0]
+            out = render(cams[k], pc, pipe, bg)
+            loss = (out["render"] - gt_rgb).abs().mean() + (out["depth"] - gt_d).abs().mean() + \
+                   (out["language"] - gt_lang).abs().mean()
+            loss.backward()
+            total = total + loss.detach()
+        if world > 1:
+            for p_ in params:
+                if p_.grad is not None:
+                    dist.all_reduce(p_.grad)
+        val = float(total.item())                                     # D2H read of the step's result
+        for p_ in params:
+            p_.grad = None
+        return val
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, with_marks=False):
+        barrier()
+        if with_marks:
+            N.timing_begin(steps * KF * 16 + 64)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        marks = N.timing_end() if with_marks else None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, marks
+
+    # ---- value: device-resident ----
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+    dgr.CHECK_OVERFLOW = False  # capacity is established by the warm-up; the timed region is fully asynchronous
+    Rs.clear()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, marks = timed(step_resident, args.steps, with_marks=True)
+    clocks = sampler.stop() if rank == 0 else None
+    dgr.CHECK_OVERFLOW = True
+    step_resident()  # one checked step: proves no instance-capacity overflow happened with this capacity
+    R_mean = sum(Rs) / max(len(Rs), 1)
+    frames = world * KF * args.steps
+    value = frames / (ms * 1e-3)
+
+    # ---- e2e: public API + host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            step_e2e()
+        ms_e, _ = timed(step_e2e, args.steps)
+        h2d = KF * (192 * 192 * 768 * 4 + 3 * H * W * 4 + H * W * 4)
+        d2h = KF * (192 * 192 * 15 * 4) + 4
+        e2e = {"value": frames / (ms_e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": ms_e / args.steps,
+               "api": "gaussian_renderer.render() + AutoencoderMLP.encode() + torch L1 loss glue, loss.backward()"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the blend kernel (algorithmic bytes: SURVEY 8d) ----
+    peak, peak_src = peaks()
+    HW = W * H
+    per_kernel = {}
+    alg = {"blend_fwd": 104 * R_mean + 88 * HW + 4 * P, "blend_bwd": 104 * R_mean + 84 * HW + 216 * P,
+           "preprocess": 131 * P, "binning": 20 * P + 12 * R_mean + 8 * P, "sort": 24 * R_mean,
+           "geometry_bwd": 230 * P, "ae": 192 * 192 * (768 * 4 + 15 * 4)}
+    for tag, (tot, cnt) in (marks or {}).items():
+        if cnt:
+            avg_ms = tot / cnt
+            per_kernel[tag] = {"ms_per_launch": avg_ms, "launches": cnt,
+                               "algorithmic_GBps": alg.get(tag, 0) / (avg_ms * 1e-3) / 1e9 if tag in alg else None}
+    bf = per_kernel.get("blend_fwd", {"ms_per_launch": float("nan"), "algorithmic_GBps": float("nan")})
+    roofline = {"kernel": "k_blend (forward alpha-blend, the kernel the metric names)", "bound": "hbm",
+                "achieved": bf["algorithmic_GBps"], "peak": peak, "unit": "GB/s",
+                "frac": (bf["algorithmic_GBps"] or 0.0) / peak, "traffic": traffic_from_profiles(),
+                "peak_source": peak_src, "ms_per_launch": bf["ms_per_launch"],
+                "algorithmic_bytes_per_launch": alg["blend_fwd"], "R_mean": R_mean,
+                "note": "algorithmic bytes = 104*R + 88*H*W + 4*P (SURVEY 8d); the kernel stops at per-pixel saturation, "
+                        "so most of the R list is never read -- see DESIGN.md for the ncu dram traffic"}
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        dt, cores = cpu_frame_seconds(args)
+        cpu = {"value": 1.0 / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": "1 keyframe of the same workload: oracle forward+backward (OpenMP, all cores) + reference AE "
+                         "encode on torch-CPU"}
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+            "roofline": roofline, "kernels": per_kernel, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": args.steps * KF * 10, "clocks": clocks}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def traffic_from_profiles():
+    """dram bytes per launch of k_blend from the committed ncu --set full capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "blend_fwd_dram_bytes.json")) as f:
+            return json.load(f)["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+if __name__ == "__main__":
+    main()

@@ -47,6 +47,9 @@ typedef enum ols_status {
 #define OLS_FLAG_BITEXACT_BLEND  (1u << 2)  /* accumulate c*alpha*T in the reference's operation order      */
 #define OLS_FLAG_BWD_EXACT       (1u << 3)  /* backward: mathematically exact gradients instead of the
                                                reference's Q1-Q3 behaviour          */
+#define OLS_FLAG_BWD_ACCUMULATE  (1u << 4)  /* backward: add into dL_dmeans3D/sh/opacity/scales/rotations/
+                                               language/cov3D instead of overwriting (sums the views of a
+                                               mapping iteration, utils/slam_backend.py:510-670)            */
 
 /* ---------------------------------------------------------------------------------------------
  * Arguments shared by forward and backward.  Mirrors the positional argument list of
@@ -176,6 +179,16 @@ typedef struct ols_host_out {
 } ols_host_out;
 int ols_lang_forward_host(const ols_raster_args* host_args /* all d_* fields hold HOST pointers; workspace ignored */,
                           const ols_host_out* out, int64_t* num_rendered);
+
+/* Per-kernel device timing (CUDA events recorded between the kernels of every call while enabled).
+ * ols_timing_begin() allocates `max_marks` events and enables recording on the calling thread;
+ * ols_timing_end() synchronises, sums the elapsed milliseconds per tag, reports how many intervals
+ * each tag saw, and disables recording.  The reference has no counterpart. */
+#define OLS_TIMING_TAGS 8
+enum { OLS_T_PREPROCESS = 0, OLS_T_BINNING = 1, OLS_T_SORT = 2, OLS_T_BLEND_FWD = 3, OLS_T_BLEND_BWD = 4,
+       OLS_T_GEOMETRY_BWD = 5, OLS_T_AE = 6, OLS_T_OTHER = 7 };
+int ols_timing_begin(int32_t max_marks);
+int ols_timing_end(float* ms_per_tag /* [OLS_TIMING_TAGS] */, int32_t* count_per_tag /* [OLS_TIMING_TAGS] */);
 
 /* ---------------------------------------------------------------------------------------------
  * Autoencoder (language/autoencoder/model.py:15-62 AutoencoderMLP, :314-354 EncoderDecoderOnline).

@@ -19,13 +19,15 @@ FLAG_PREFILTERED = 1 << 0
 FLAG_DEBUG = 1 << 1
 FLAG_BITEXACT_BLEND = 1 << 2
 FLAG_BWD_EXACT = 1 << 3
+FLAG_BWD_ACCUMULATE = 1 << 4
+TIMING_TAGS = ("preprocess", "binning", "sort", "blend_fwd", "blend_bwd", "geometry_bwd", "ae", "other")
 AE_MAX_LAYERS = 8
 
 # every symbol include/ols_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = (
     "ols_abi_version", "ols_last_error", "ols_cuda_available", "ols_lang_workspace_size", "ols_lang_forward",
     "ols_lang_read_info", "ols_lang_backward", "ols_mark_visible", "ols_lang_workspace_view",
-    "ols_lang_forward_host", "ols_ae_plan_create", "ols_ae_plan_destroy", "ols_ae_forward",
+    "ols_lang_forward_host", "ols_timing_begin", "ols_timing_end", "ols_ae_plan_create", "ols_ae_plan_destroy", "ols_ae_forward",
 )
 
 
@@ -100,6 +102,8 @@ def lib() -> C.CDLL:
     L.ols_lang_workspace_view.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                                           C.c_void_p, C.POINTER(WsView)]
     L.ols_lang_forward_host.argtypes = [C.POINTER(RasterArgs), C.POINTER(HostOut), C.POINTER(C.c_int64)]
+    L.ols_timing_begin.argtypes = [C.c_int32]
+    L.ols_timing_end.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int32)]
     L.ols_ae_plan_create.argtypes = [C.POINTER(AEChain), C.POINTER(C.c_void_p), C.c_void_p]
     L.ols_ae_plan_destroy.argtypes = [C.c_void_p]
     L.ols_ae_plan_destroy.restype = None
@@ -124,3 +128,15 @@ def ptr(t) -> Optional[int]:
     if t is None or t.numel() == 0:
         return None
     return t.data_ptr()
+
+
+def timing_begin(max_marks: int = 8192) -> None:
+    check(lib().ols_timing_begin(int(max_marks)))
+
+
+def timing_end():
+    """-> {tag: (total_ms, intervals)} for the calls made since timing_begin() on this thread."""
+    ms = (C.c_float * len(TIMING_TAGS))()
+    cnt = (C.c_int32 * len(TIMING_TAGS))()
+    check(lib().ols_timing_end(ms, cnt))
+    return {t: (float(ms[i]), int(cnt[i])) for i, t in enumerate(TIMING_TAGS)}

@@ -534,8 +534,10 @@ int ols_ae_forward(const ols_ae_plan* plan, const float* d_x, float* d_y, int64_
         if (rc != OLS_OK) return rc;
     }
     const int grid = p.n_tiles < plan->sm_count ? p.n_tiles : plan->sm_count;
+    ols_timing_mark(-1, (cudaStream_t)stream);
     k_ae_chain<<<grid, AE_THREADS, plan->smem_bytes, (cudaStream_t)stream>>>(p);
     OLS_CUDA_TRY(cudaGetLastError());
+    ols_timing_mark(OLS_T_AE, (cudaStream_t)stream);
     return OLS_OK;
 }
 

@@ -18,6 +18,22 @@ void ols_set_error(const char* fmt, ...) {
 
 using namespace ols;
 
+// ---- per-kernel timing -----------------------------------------------------------------------------
+struct TimingState {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> tag;
+    int used = 0;
+};
+static thread_local TimingState g_timing;
+
+void ols_timing_mark(int tag, cudaStream_t st) {
+    TimingState& t = g_timing;
+    if (!t.on || t.used >= (int)t.ev.size()) return;
+    if (cudaEventRecord(t.ev[t.used], st) != cudaSuccess) { cudaGetLastError(); return; }
+    t.tag[t.used++] = tag;
+}
+
 namespace ols {
 __global__ void k_check_frustum(int P, const float* __restrict__ means, const float* __restrict__ V,
                                 uint8_t* __restrict__ present) {
@@ -122,6 +138,38 @@ int ols_lang_backward(const ols_raster_args* a, const ols_bwd_args* g, void* str
     if (a->M > 0 && a->d_shs && !g->d_dL_dsh) { ols_set_error("d_dL_dsh is null but SHs were given"); return OLS_ERR_INVALID; }
     if (!a->d_projmatrix_raw) { ols_set_error("projmatrix_raw is required by backward"); return OLS_ERR_INVALID; }
     return ols_launch_backward(a, g, L, (cudaStream_t)stream);
+}
+
+int ols_timing_begin(int32_t max_marks) {
+    TimingState& t = g_timing;
+    if (max_marks <= 0) { ols_set_error("max_marks must be positive"); return OLS_ERR_INVALID; }
+    while ((int)t.ev.size() < max_marks) {
+        cudaEvent_t e;
+        OLS_CUDA_TRY(cudaEventCreate(&e));
+        t.ev.push_back(e);
+    }
+    t.tag.assign(t.ev.size(), -1);
+    t.used = 0;
+    t.on = true;
+    return OLS_OK;
+}
+
+int ols_timing_end(float* ms_per_tag, int32_t* count_per_tag) {
+    TimingState& t = g_timing;
+    t.on = false;
+    if (!ms_per_tag || !count_per_tag) { ols_set_error("null pointer"); return OLS_ERR_INVALID; }
+    for (int i = 0; i < OLS_TIMING_TAGS; i++) { ms_per_tag[i] = 0.0f; count_per_tag[i] = 0; }
+    if (t.used > 0) OLS_CUDA_TRY(cudaEventSynchronize(t.ev[t.used - 1]));
+    for (int i = 1; i < t.used; i++) {
+        const int tag = t.tag[i];
+        if (tag < 0 || tag >= OLS_TIMING_TAGS) continue;
+        float ms = 0.0f;
+        OLS_CUDA_TRY(cudaEventElapsedTime(&ms, t.ev[i - 1], t.ev[i]));
+        ms_per_tag[tag] += ms;
+        count_per_tag[tag] += 1;
+    }
+    t.used = 0;
+    return OLS_OK;
 }
 
 int ols_mark_visible(int32_t P, const float* d_means3D, const float* d_viewmatrix, const float* d_projmatrix,

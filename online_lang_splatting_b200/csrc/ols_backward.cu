@@ -276,6 +276,7 @@ struct GeomBwdArgs {
     const int32_t* radii;
     const float* gacc;
     bool colors_precomp;
+    bool accumulate;  // += into the parameter gradients (means3D, sh, opacity, scales, rotations, language, cov3D)
     float *dL_dmeans2D, *dL_dcolors, *dL_dlanguage, *dL_dopacity, *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales,
         *dL_drots, *dL_dtau;
 };
@@ -300,11 +301,15 @@ __global__ void __launch_bounds__(256) k_geometry_bwd(const GeomBwdArgs a) {
     a.dL_dmeans2D[3 * (size_t)i] = g2x;
     a.dL_dmeans2D[3 * (size_t)i + 1] = g2y;
     a.dL_dmeans2D[3 * (size_t)i + 2] = 0.0f;
-    a.dL_dopacity[i] = gr[GR_OP];
+    const bool acc = a.accumulate;
+    a.dL_dopacity[i] = (acc ? a.dL_dopacity[i] : 0.0f) + gr[GR_OP];
     float dcol[3];
-    for (int c = 0; c < 3; c++) { dcol[c] = gr[GR_RGB + c]; a.dL_dcolors[3 * (size_t)i + c] = dcol[c]; }
-    for (int c = 0; c < F; c++) a.dL_dlanguage[(size_t)F * i + c] = gr[GR_LANG + c];
-    if (a.dL_dsh)
+    for (int c = 0; c < 3; c++) {
+        dcol[c] = gr[GR_RGB + c];
+        a.dL_dcolors[3 * (size_t)i + c] = (acc ? a.dL_dcolors[3 * (size_t)i + c] : 0.0f) + dcol[c];
+    }
+    for (int c = 0; c < F; c++) a.dL_dlanguage[(size_t)F * i + c] = (acc ? a.dL_dlanguage[(size_t)F * i + c] : 0.0f) + gr[GR_LANG + c];
+    if (a.dL_dsh && !acc)
         for (int k = 0; k < 3 * M; k++) a.dL_dsh[(size_t)3 * M * i + k] = 0.0f;
 
     if (vis) {
@@ -434,7 +439,7 @@ __global__ void __launch_bounds__(256) k_geometry_bwd(const GeomBwdArgs a) {
         }
         if (a.shs && !a.colors_precomp) {  // computeColorFromSH backward (backward.cu:21-145)
             const float* sh = a.shs + (size_t)i * M * 3;
-            float* dsh = a.dL_dsh + (size_t)i * M * 3;
+            float* dsh = a.dL_dsh + (size_t)i * M * 3;  // zeroed above unless accumulating: always add
             const int deg = a.sh_degree;
             const float dir0[3] = {mp[0] - a.campos[0], mp[1] - a.campos[1], mp[2] - a.campos[2]};
             const float len = sqrtf(dir0[0] * dir0[0] + dir0[1] * dir0[1] + dir0[2] * dir0[2]);
@@ -444,29 +449,29 @@ __global__ void __launch_bounds__(256) k_geometry_bwd(const GeomBwdArgs a) {
 #pragma unroll
             for (int c = 0; c < 3; c++) dRGB[c] = dcol[c] * (((cl >> (8 * c)) & 0xffu) ? 0.f : 1.f);
             float dx_[3] = {0, 0, 0}, dy_[3] = {0, 0, 0}, dz_[3] = {0, 0, 0};
-            for (int c = 0; c < 3; c++) dsh[c] = B_SH_C0 * dRGB[c];
+            for (int c = 0; c < 3; c++) dsh[c] += B_SH_C0 * dRGB[c];
             if (deg > 0) {
                 for (int c = 0; c < 3; c++) {
-                    dsh[3 + c] = -B_SH_C1 * y * dRGB[c]; dsh[6 + c] = B_SH_C1 * z * dRGB[c]; dsh[9 + c] = -B_SH_C1 * x * dRGB[c];
+                    dsh[3 + c] += -B_SH_C1 * y * dRGB[c]; dsh[6 + c] += B_SH_C1 * z * dRGB[c]; dsh[9 + c] += -B_SH_C1 * x * dRGB[c];
                     dx_[c] = -B_SH_C1 * sh[9 + c]; dy_[c] = -B_SH_C1 * sh[3 + c]; dz_[c] = B_SH_C1 * sh[6 + c];
                 }
                 if (deg > 1) {
                     const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
                     for (int c = 0; c < 3; c++) {
-                        dsh[12 + c] = B_SH_C2[0] * xy * dRGB[c]; dsh[15 + c] = B_SH_C2[1] * yz * dRGB[c];
-                        dsh[18 + c] = B_SH_C2[2] * (2.f * zz - xx - yy) * dRGB[c]; dsh[21 + c] = B_SH_C2[3] * xz * dRGB[c];
-                        dsh[24 + c] = B_SH_C2[4] * (xx - yy) * dRGB[c];
+                        dsh[12 + c] += B_SH_C2[0] * xy * dRGB[c]; dsh[15 + c] += B_SH_C2[1] * yz * dRGB[c];
+                        dsh[18 + c] += B_SH_C2[2] * (2.f * zz - xx - yy) * dRGB[c]; dsh[21 + c] += B_SH_C2[3] * xz * dRGB[c];
+                        dsh[24 + c] += B_SH_C2[4] * (xx - yy) * dRGB[c];
                         dx_[c] += B_SH_C2[0] * y * sh[12 + c] + B_SH_C2[2] * 2.f * -x * sh[18 + c] + B_SH_C2[3] * z * sh[21 + c] + B_SH_C2[4] * 2.f * x * sh[24 + c];
                         dy_[c] += B_SH_C2[0] * x * sh[12 + c] + B_SH_C2[1] * z * sh[15 + c] + B_SH_C2[2] * 2.f * -y * sh[18 + c] + B_SH_C2[4] * 2.f * -y * sh[24 + c];
                         dz_[c] += B_SH_C2[1] * y * sh[15 + c] + B_SH_C2[2] * 2.f * 2.f * z * sh[18 + c] + B_SH_C2[3] * x * sh[21 + c];
                     }
                     if (deg > 2) {
                         for (int c = 0; c < 3; c++) {
-                            dsh[27 + c] = B_SH_C3[0] * y * (3.f * xx - yy) * dRGB[c]; dsh[30 + c] = B_SH_C3[1] * xy * z * dRGB[c];
-                            dsh[33 + c] = B_SH_C3[2] * y * (4.f * zz - xx - yy) * dRGB[c];
-                            dsh[36 + c] = B_SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy) * dRGB[c];
-                            dsh[39 + c] = B_SH_C3[4] * x * (4.f * zz - xx - yy) * dRGB[c]; dsh[42 + c] = B_SH_C3[5] * z * (xx - yy) * dRGB[c];
-                            dsh[45 + c] = B_SH_C3[6] * x * (xx - 3.f * yy) * dRGB[c];
+                            dsh[27 + c] += B_SH_C3[0] * y * (3.f * xx - yy) * dRGB[c]; dsh[30 + c] += B_SH_C3[1] * xy * z * dRGB[c];
+                            dsh[33 + c] += B_SH_C3[2] * y * (4.f * zz - xx - yy) * dRGB[c];
+                            dsh[36 + c] += B_SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy) * dRGB[c];
+                            dsh[39 + c] += B_SH_C3[4] * x * (4.f * zz - xx - yy) * dRGB[c]; dsh[42 + c] += B_SH_C3[5] * z * (xx - yy) * dRGB[c];
+                            dsh[45 + c] += B_SH_C3[6] * x * (xx - 3.f * yy) * dRGB[c];
                             dx_[c] += (B_SH_C3[0] * sh[27 + c] * 3.f * 2.f * xy + B_SH_C3[1] * sh[30 + c] * yz + B_SH_C3[2] * sh[33 + c] * -2.f * xy +
                                        B_SH_C3[3] * sh[36 + c] * -3.f * 2.f * xz + B_SH_C3[4] * sh[39 + c] * (-3.f * xx + 4.f * zz - yy) +
                                        B_SH_C3[5] * sh[42 + c] * 2.f * xz + B_SH_C3[6] * sh[45 + c] * 3.f * (xx - yy));
@@ -521,13 +526,16 @@ __global__ void __launch_bounds__(256) k_geometry_bwd(const GeomBwdArgs a) {
         }
     }
 #pragma unroll
-    for (int k = 0; k < 3; k++) a.dL_dmeans3D[3 * (size_t)i + k] = dmean[k];
+    for (int k = 0; k < 3; k++) a.dL_dmeans3D[3 * (size_t)i + k] = (acc ? a.dL_dmeans3D[3 * (size_t)i + k] : 0.0f) + dmean[k];
 #pragma unroll
-    for (int k = 0; k < 6; k++) { a.dL_dcov3D[6 * (size_t)i + k] = dcov[k]; a.dL_dtau[6 * (size_t)i + k] = dtau[k]; }
+    for (int k = 0; k < 6; k++) {
+        a.dL_dcov3D[6 * (size_t)i + k] = (acc ? a.dL_dcov3D[6 * (size_t)i + k] : 0.0f) + dcov[k];
+        a.dL_dtau[6 * (size_t)i + k] = dtau[k];  // per-view pose gradient: never accumulated
+    }
 #pragma unroll
-    for (int k = 0; k < 3; k++) a.dL_dscales[3 * (size_t)i + k] = dsc[k];
+    for (int k = 0; k < 3; k++) a.dL_dscales[3 * (size_t)i + k] = (acc ? a.dL_dscales[3 * (size_t)i + k] : 0.0f) + dsc[k];
 #pragma unroll
-    for (int k = 0; k < 4; k++) a.dL_drots[4 * (size_t)i + k] = dq[k];
+    for (int k = 0; k < 4; k++) a.dL_drots[4 * (size_t)i + k] = (acc ? a.dL_drots[4 * (size_t)i + k] : 0.0f) + dq[k];
 }
 
 template <int TILE, int F>
@@ -550,6 +558,7 @@ int ols_launch_backward(const ols_raster_args* a, const ols_bwd_args* g, const W
     const bool exact = (a->flags & OLS_FLAG_BWD_EXACT) != 0;
     float* gacc = (float*)(ws + L.gacc);
     OLS_CUDA_TRY(cudaMemsetAsync(gacc, 0, ols_bwd_scratch_bytes(a->P, a->F), st));
+    ols_timing_mark(-1, st);
 
     BwdBlendArgs ba;
     ba.W = a->W; ba.H = a->H; ba.gx = L.gx;
@@ -595,7 +604,9 @@ int ols_launch_backward(const ols_raster_args* a, const ols_bwd_args* g, const W
         if (e != cudaSuccess) { ols_set_error("kernel blend_bwd failed: %s", cudaGetErrorString(e)); return OLS_ERR_CUDA; }
     }
 
+    ols_timing_mark(OLS_T_BLEND_BWD, st);
     GeomBwdArgs ga;
+    ga.accumulate = (a->flags & OLS_FLAG_BWD_ACCUMULATE) != 0;
     ga.P = a->P; ga.F = a->F; ga.sh_degree = a->sh_degree; ga.M = a->M; ga.W = a->W; ga.H = a->H; ga.gr = grad_floats(a->F);
     ga.tanfovx = a->tanfovx; ga.tanfovy = a->tanfovy;
     ga.focal_y = a->H / (2.0f * a->tanfovy); ga.focal_x = a->W / (2.0f * a->tanfovx);
@@ -615,5 +626,6 @@ int ols_launch_backward(const ols_raster_args* a, const ols_bwd_args* g, const W
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { ols_set_error("kernel geometry_bwd failed: %s", cudaGetErrorString(e)); return OLS_ERR_CUDA; }
     }
+    ols_timing_mark(OLS_T_GEOMETRY_BWD, st);
     return OLS_OK;
 }

@@ -97,6 +97,9 @@ void ols_set_error(const char* fmt, ...);
         }                                                                                      \
     } while (0)
 
+// timing marks (ols_api.cu): tag < 0 starts a sequence, tag >= 0 closes the interval since the previous mark
+void ols_timing_mark(int tag, cudaStream_t st);
+
 // kernel launchers implemented in ols_forward.cu / ols_backward.cu
 int ols_launch_forward(const ols_raster_args* a, const ols_fwd_out* o, const ols::WsLayout& L, cudaStream_t st);
 int ols_launch_backward(const ols_raster_args* a, const ols_bwd_args* g, const ols::WsLayout& L, cudaStream_t st);

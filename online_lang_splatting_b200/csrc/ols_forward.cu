@@ -876,8 +876,10 @@ int ols_launch_forward(const ols_raster_args* a, const ols_fwd_out* o, const WsL
         OLS_CUDA_TRY(cudaFuncSetAttribute(k_preprocess, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
         OLS_CUDA_TRY(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
     }
+    ols_timing_mark(-1, st);
     k_preprocess<<<L.n_ctas, PRE_THREADS, hist_smem, st>>>(p);
     OLS_DEBUG_SYNC("preprocess");
+    ols_timing_mark(OLS_T_PREPROCESS, st);
     k_tile_offsets<<<(L.n_tiles + 31) / 32, 32 * TO_WARPS, 0, st>>>(p.cta_hist, (uint32_t*)(ws + L.tile_count), L.n_tiles, L.n_ctas);
     OLS_DEBUG_SYNC("tile_offsets");
     k_tile_scan<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)(ws + L.tile_count), (uint32_t*)(ws + L.tile_cursor),
@@ -887,6 +889,7 @@ int ols_launch_forward(const ols_raster_args* a, const ols_fwd_out* o, const WsL
                                                         p.cta_hist, (const uint32_t*)(ws + L.tile_cursor),
                                                         (unsigned long long*)(ws + L.keys), info);
     OLS_DEBUG_SYNC("scatter");
+    ols_timing_mark(OLS_T_BINNING, st);
     k_sort_tiles_radix<<<L.n_tiles, RS_THREADS, 0, st>>>((unsigned long long*)(ws + L.keys),
                                                          (uint32_t*)(ws + L.point_list), (const uint2*)(ws + L.ranges), info);
     OLS_DEBUG_SYNC("sort_tiles_radix");
@@ -894,6 +897,7 @@ int ols_launch_forward(const ols_raster_args* a, const ols_fwd_out* o, const WsL
     k_sort_tiles<<<L.n_tiles, SORT_THREADS, 0, st>>>((unsigned long long*)(ws + L.keys), (uint32_t*)(ws + L.point_list),
                                                      (const uint2*)(ws + L.ranges), info, RS_CAP);
     OLS_DEBUG_SYNC("sort_tiles");
+    ols_timing_mark(OLS_T_SORT, st);
 
     BlendArgs ba;
     ba.W = a->W; ba.H = a->H; ba.gx = L.gx;
@@ -912,5 +916,6 @@ int ols_launch_forward(const ols_raster_args* a, const ols_fwd_out* o, const WsL
         return OLS_ERR_UNSUPPORTED;
     }
     OLS_DEBUG_SYNC("blend");
+    ols_timing_mark(OLS_T_BLEND_FWD, st);
     return OLS_OK;
 }

@@ -162,14 +162,25 @@ def _forward_native(means3D, sh, colors_precomp, language_precomp, opacities, sc
     return st.R, color, language, radii, depth, opacity, n_touched, st
 
 
-def _backward_native(st: _Ctx, radii, grad_color, grad_language, grad_depth):
+GRAD_SHAPES = lambda P, F, M: {"means2D": (P, 3), "colors": (P, 3), "language": (P, F), "opacity": (P, 1),
+                                "means3D": (P, 3), "cov3D": (P, 6), "sh": (P, M, 3), "scales": (P, 3),
+                                "rotations": (P, 4), "tau": (P, 6)}
+
+
+def _backward_native(st: _Ctx, radii, grad_color, grad_language, grad_depth, out=None, accumulate=False):
+    """Calls ols_lang_backward.  ``out`` may hold preallocated (contiguous fp32) gradient tensors keyed like
+    GRAD_SHAPES -- e.g. views into one flat buffer that is all-reduced across ranks; with
+    ``accumulate=True`` the parameter gradients are added to what ``out`` already holds."""
     k = st.keep
     a = st.args
     dev = k["means3D"].device
     P, F, M = a.P, a.F, a.M
-    z = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
-    g = {"means2D": z(P, 3), "colors": z(P, 3), "language": z(P, F), "opacity": z(P, 1), "means3D": z(P, 3),
-         "cov3D": z(P, 6), "sh": z(P, M, 3), "scales": z(P, 3), "rotations": z(P, 4), "tau": z(P, 6)}
+    g = {}
+    for name, shape in GRAD_SHAPES(P, F, M).items():
+        t = None if out is None else out.get(name)
+        if t is None:
+            t = (torch.zeros if accumulate else torch.empty)(shape, dtype=torch.float32, device=dev)
+        g[name] = t
     gc, gl, gd = _f32c(grad_color), _f32c(grad_language), _f32c(grad_depth)
     b = N.BwdArgs(d_dL_dout_color=gc.data_ptr(), d_dL_dout_language=gl.data_ptr(), d_dL_dout_depth=gd.data_ptr(),
                   d_radii=radii.data_ptr(), d_dL_dmeans2D=g["means2D"].data_ptr(), d_dL_dcolors=g["colors"].data_ptr(),
@@ -177,9 +188,15 @@ def _backward_native(st: _Ctx, radii, grad_color, grad_language, grad_depth):
                   d_dL_dmeans3D=g["means3D"].data_ptr(), d_dL_dcov3D=g["cov3D"].data_ptr(),
                   d_dL_dsh=N.ptr(g["sh"]), d_dL_dscales=g["scales"].data_ptr(),
                   d_dL_drotations=g["rotations"].data_ptr(), d_dL_dtau=g["tau"].data_ptr())
-    with torch.cuda.device(dev):
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        N.check(N.lib().ols_lang_backward(C.byref(a), C.byref(b), stream))
+    flags = a.flags
+    if accumulate:
+        a.flags = flags | N.FLAG_BWD_ACCUMULATE
+    try:
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            N.check(N.lib().ols_lang_backward(C.byref(a), C.byref(b), stream))
+    finally:
+        a.flags = flags
     return g
 
 

@@ -8,7 +8,7 @@ import pytest
 
 import _util as U
 
-GOLDEN = sorted(glob.glob(os.path.join(U.GOLDEN_DIR, "*.npz")))
+GOLDEN = sorted(glob.glob(os.path.join(U.GOLDEN_DIR, "p15_*.npz")))
 
 
 def _l2rel(a, b):

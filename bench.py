@@ -256,17 +256,12 @@ def main():
     wc, wl, wd = (torch.randn(s, device=dev, generator=gen) for s in ((3, H, W), (15, H, W), (1, H, W)))
 
     # flat gradient buffer [xyz 3 | f_dc 3 | opacity 1 | scaling 3 | rotation 4 | language 15] x P  
-    flat = torch.zeros(29 * P, device=dev)
-    o = 0
-    views = {}
-    for name, shape in (("means3D", (P, 3)), ("sh", (P, 1, 3)), ("opacity", (P, 1)), ("scales", (P, 3)),
-                        ("rotations", (P, 4)), ("language", (P, 15))):
-        n = math.prod(shape)
-        views[name] = flat[o:o + n].view(shape)
-        o += n
+    from online_lang_splatting_b200.sharding import FlatGradBuffer
+    fbuf = FlatGradBuffer(P, 15, 1, device=dev)
+    flat = fbuf.flat
     scratch = {n_: torch.empty(s_, device=dev) for n_, s_ in (("means2D", (P, 3)), ("colors", (P, 3)), ("cov3D", (P, 6)),
                                                              ("tau", (P, 6)))}
-    out_bufs = dict(views, **scratch)
+    out_bufs = fbuf.backward_outputs(scratch)
     rs_list = []
     with torch.no_grad():
         act = {"means3D": pc.get_xyz.detach(), "shs": pc.get_features.detach().contiguous(),
@@ -292,18 +287,34 @@ def main():
             dgr._backward_native(st, radii, wc, wl, wd, out=out_bufs, accumulate=True)
             if R >= 0:
                 Rs.append(R)
-        if world > 1:
-            dist.all_reduce(flat)
+        fbuf.all_reduce()
 
     code_host = [torch.empty(192 * 192, 15).pin_memory() for _ in range(KF)] if not args.no_e2e else []
     params = pc.parameters()
 
-    def step_e2e():
-        total = torch.zeros((), device=dev)
-        for k in range(KF):
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def prefetch(k):
+        """H2D of keyframe k's inputs from pinned memory on the copy stream (overlaps the previous keyframe's kernels)."""
+        with torch.cuda.stream(copy_stream):
             x = clip_host[k].to(dev, non_blocking=True)
             gt_rgb = gt_host[k][0].to(dev, non_blocking=True)
             gt_d = gt_host[k][1].to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return x, gt_rgb, gt_d, ev
+
+    def step_e2e():
+        total = torch.zeros((), device=dev)
+        cur_stream = torch.cuda.current_stream(dev)
+        nxt = prefetch(0)
+        for k in range(KF):
+            x, gt_rgb, gt_d, ev = nxt
+            if k + 1 < KF:
+                nxt = prefetch(k + 1)
+            cur_stream.wait_event(ev)
+            for t in (x, gt_rgb, gt_d):
+                t.record_stream(cur_stream)
             with torch.no_grad():
                 code = ae.encode(x)                                  # [36864, 15] -> gt_lang_feat (slam_backend.py:557-576)
             code_host[k].copy_(code, non_blocking=True)              # the reference keeps it on the CPU (:576)

@@ -288,29 +288,32 @@ __constant__ float B_SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31
 __constant__ float B_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
                                  -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
 
+template <int F>
 __global__ void __launch_bounds__(256) k_geometry_bwd(const GeomBwdArgs a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.P) return;
-    const int F = a.F, M = a.M;
-    const float* gr = a.gacc + (size_t)i * a.gr;
+    const int M = a.M;
+    constexpr int GRF = grad_floats(F);
+    // the whole packed gradient record in registers: GRF/4 independent 16-byte loads
+    float gr[GRF];
+    {
+        const float4* src = reinterpret_cast<const float4*>(a.gacc + (size_t)i * GRF);
+#pragma unroll
+        for (int q = 0; q < GRF / 4; q++) {
+            const float4 v = src[q];
+            gr[4 * q] = v.x; gr[4 * q + 1] = v.y; gr[4 * q + 2] = v.z; gr[4 * q + 3] = v.w;
+        }
+    }
     float dmean[3] = {0, 0, 0}, dcov[6] = {0, 0, 0, 0, 0, 0}, dtau[6] = {0, 0, 0, 0, 0, 0};
     float dsc[3] = {0, 0, 0}, dq[4] = {0, 0, 0, 0};
     const bool vis = a.radii[i] > 0;
-    // unpack what the blend pass accumulated (zero for invisible Gaussians)
+    // unpack what the blend pass accumulated (zero for invisible Gaussians); all stores happen at the end
     const float g2x = gr[GR_MX], g2y = gr[GR_MY];
-    a.dL_dmeans2D[3 * (size_t)i] = g2x;
-    a.dL_dmeans2D[3 * (size_t)i + 1] = g2y;
-    a.dL_dmeans2D[3 * (size_t)i + 2] = 0.0f;
     const bool acc = a.accumulate;
-    a.dL_dopacity[i] = (acc ? a.dL_dopacity[i] : 0.0f) + gr[GR_OP];
-    float dcol[3];
-    for (int c = 0; c < 3; c++) {
-        dcol[c] = gr[GR_RGB + c];
-        a.dL_dcolors[3 * (size_t)i + c] = (acc ? a.dL_dcolors[3 * (size_t)i + c] : 0.0f) + dcol[c];
-    }
-    for (int c = 0; c < F; c++) a.dL_dlanguage[(size_t)F * i + c] = (acc ? a.dL_dlanguage[(size_t)F * i + c] : 0.0f) + gr[GR_LANG + c];
-    if (a.dL_dsh && !acc)
-        for (int k = 0; k < 3 * M; k++) a.dL_dsh[(size_t)3 * M * i + k] = 0.0f;
+    float dcol[3] = {gr[GR_RGB], gr[GR_RGB + 1], gr[GR_RGB + 2]};
+    float dsh0[3] = {0, 0, 0};
+    if (a.dL_dsh && !acc && M > 1)
+        for (int k = 3; k < 3 * M; k++) a.dL_dsh[(size_t)3 * M * i + k] = 0.0f;
 
     if (vis) {
         const float* V = a.viewmatrix;
@@ -449,7 +452,7 @@ __global__ void __launch_bounds__(256) k_geometry_bwd(const GeomBwdArgs a) {
 #pragma unroll
             for (int c = 0; c < 3; c++) dRGB[c] = dcol[c] * (((cl >> (8 * c)) & 0xffu) ? 0.f : 1.f);
             float dx_[3] = {0, 0, 0}, dy_[3] = {0, 0, 0}, dz_[3] = {0, 0, 0};
-            for (int c = 0; c < 3; c++) dsh[c] += B_SH_C0 * dRGB[c];
+            for (int c = 0; c < 3; c++) dsh0[c] = B_SH_C0 * dRGB[c];
             if (deg > 0) {
                 for (int c = 0; c < 3; c++) {
                     dsh[3 + c] += -B_SH_C1 * y * dRGB[c]; dsh[6 + c] += B_SH_C1 * z * dRGB[c]; dsh[9 + c] += -B_SH_C1 * x * dRGB[c];
@@ -525,17 +528,56 @@ __global__ void __launch_bounds__(256) k_geometry_bwd(const GeomBwdArgs a) {
             dq[3] = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) - 4 * z * (dMt[1][1] + dMt[0][0]);
         }
     }
+    // ---- outputs: when accumulating, fetch every old value first (independent loads), then store ----
+    float o_mean[3], o_cov[6], o_sc[3], o_q[4], o_op, o_col[3], o_lang[F], o_sh[3];
+    float* p_mean = a.dL_dmeans3D + 3 * (size_t)i;
+    float* p_cov = a.dL_dcov3D + 6 * (size_t)i;
+    float* p_sc = a.dL_dscales + 3 * (size_t)i;
+    float* p_q = a.dL_drots + 4 * (size_t)i;
+    float* p_col = a.dL_dcolors + 3 * (size_t)i;
+    float* p_lang = a.dL_dlanguage + (size_t)F * i;
+    float* p_sh = a.dL_dsh ? a.dL_dsh + (size_t)3 * M * i : nullptr;
+    if (acc) {
 #pragma unroll
-    for (int k = 0; k < 3; k++) a.dL_dmeans3D[3 * (size_t)i + k] = (acc ? a.dL_dmeans3D[3 * (size_t)i + k] : 0.0f) + dmean[k];
+        for (int k = 0; k < 3; k++) { o_mean[k] = p_mean[k]; o_sc[k] = p_sc[k]; o_col[k] = p_col[k]; o_sh[k] = p_sh ? p_sh[k] : 0.0f; }
+#pragma unroll
+        for (int k = 0; k < 6; k++) o_cov[k] = p_cov[k];
+#pragma unroll
+        for (int k = 0; k < 4; k++) o_q[k] = p_q[k];
+#pragma unroll
+        for (int k = 0; k < F; k++) o_lang[k] = p_lang[k];
+        o_op = a.dL_dopacity[i];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { o_mean[k] = 0; o_sc[k] = 0; o_col[k] = 0; o_sh[k] = 0; }
+#pragma unroll
+        for (int k = 0; k < 6; k++) o_cov[k] = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) o_q[k] = 0;
+#pragma unroll
+        for (int k = 0; k < F; k++) o_lang[k] = 0;
+        o_op = 0;
+    }
+    a.dL_dmeans2D[3 * (size_t)i] = g2x;
+    a.dL_dmeans2D[3 * (size_t)i + 1] = g2y;
+    a.dL_dmeans2D[3 * (size_t)i + 2] = 0.0f;
+    a.dL_dopacity[i] = o_op + gr[GR_OP];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        p_mean[k] = o_mean[k] + dmean[k];
+        p_sc[k] = o_sc[k] + dsc[k];
+        p_col[k] = o_col[k] + dcol[k];
+        if (p_sh) p_sh[k] = o_sh[k] + dsh0[k];
+    }
 #pragma unroll
     for (int k = 0; k < 6; k++) {
-        a.dL_dcov3D[6 * (size_t)i + k] = (acc ? a.dL_dcov3D[6 * (size_t)i + k] : 0.0f) + dcov[k];
+        p_cov[k] = o_cov[k] + dcov[k];
         a.dL_dtau[6 * (size_t)i + k] = dtau[k];  // per-view pose gradient: never accumulated
     }
 #pragma unroll
-    for (int k = 0; k < 3; k++) a.dL_dscales[3 * (size_t)i + k] = (acc ? a.dL_dscales[3 * (size_t)i + k] : 0.0f) + dsc[k];
+    for (int k = 0; k < 4; k++) p_q[k] = o_q[k] + dq[k];
 #pragma unroll
-    for (int k = 0; k < 4; k++) a.dL_drots[4 * (size_t)i + k] = (acc ? a.dL_drots[4 * (size_t)i + k] : 0.0f) + dq[k];
+    for (int k = 0; k < F; k++) p_lang[k] = o_lang[k] + gr[GR_LANG + k];
 }
 
 template <int TILE, int F>
@@ -620,7 +662,8 @@ int ols_launch_backward(const ols_raster_args* a, const ols_bwd_args* g, const W
     ga.dL_dopacity = g->d_dL_dopacity; ga.dL_dmeans3D = g->d_dL_dmeans3D; ga.dL_dcov3D = g->d_dL_dcov3D;
     ga.dL_dsh = (a->d_shs && a->M > 0) ? g->d_dL_dsh : nullptr; ga.dL_dscales = g->d_dL_dscales;
     ga.dL_drots = g->d_dL_drotations; ga.dL_dtau = g->d_dL_dtau;
-    k_geometry_bwd<<<(a->P + 255) / 256, 256, 0, st>>>(ga);
+    if (a->F == 15) k_geometry_bwd<15><<<(a->P + 255) / 256, 256, 0, st>>>(ga);
+    else k_geometry_bwd<3><<<(a->P + 255) / 256, 256, 0, st>>>(ga);
     OLS_CUDA_TRY(cudaGetLastError());
     if (debug) {
         cudaError_t e = cudaStreamSynchronize(st);

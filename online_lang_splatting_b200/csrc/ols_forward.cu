@@ -168,13 +168,26 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreArgs a) {
             s_mean[e] = a.means3D[(size_t)base * 3 + e];
             if (a.scales) s_scale[e] = a.scales[(size_t)base * 3 + e];
         }
-        {   // language rows -> records (coalesced read, near-coalesced write)
+        {   // language rows -> records: coalesced reads issued as one batch (up to 16 per thread), then the stores
             const int F = a.F, rec = a.rec;
-            const float* src = a.language + (size_t)base * F;
-            float* dst = a.records + (size_t)base * rec;
-            for (int e = tid; e < nloc * F; e += PRE_THREADS) {
-                const int g = e / F, c = e - g * F;
-                dst[(size_t)g * rec + REC_LANG + c] = src[e];
+            const float* __restrict__ src = a.language + (size_t)base * F;
+            float* __restrict__ dst = a.records + (size_t)base * rec;
+            const int n_el = nloc * F;
+            for (int e0 = 0; e0 < n_el; e0 += 16 * PRE_THREADS) {
+                float tmp[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    const int e = e0 + k * PRE_THREADS + tid;
+                    tmp[k] = e < n_el ? __ldg(src + e) : 0.0f;
+                }
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    const int e = e0 + k * PRE_THREADS + tid;
+                    if (e < n_el) {
+                        const int g = e / F, c = e - g * F;
+                        dst[(size_t)g * rec + REC_LANG + c] = tmp[k];
+                    }
+                }
             }
         }
         __syncthreads();

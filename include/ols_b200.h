@@ -156,7 +156,8 @@ int ols_mark_visible(int32_t P, const float* d_means3D, const float* d_viewmatri
  * Reference counterpart: the fromChunk() carving of rasterizer_impl.cu:173-212. */
 typedef struct ols_ws_view {
     const float* d_records;        /* [P, rec_floats] packed per-Gaussian blend record:
-                                      x, y, conicA, conicB, conicC, opacity, depth, r, g, b, lang[F], 0-pad */
+                                      x, y, conicA, conicB, conicC, opacity, pth, depth, r, g, b, lang[F], 0-pad,
+                                      ex, ey (last two floats: conservative half-extents of alpha >= 1/255) */
     int32_t rec_floats;
     int32_t n_tiles;
     const float* d_cov3D;          /* [P,6]                                                            */

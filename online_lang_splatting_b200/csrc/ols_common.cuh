@@ -12,10 +12,13 @@ namespace ols {
 // rounded up to a multiple of 4 floats so a record is a whole number of 16-byte chunks
 // (F=15 -> 28 floats = 112 B, F=3 -> 16 floats = 64 B).  `pth` is a conservative lower bound on the
 // exponent below which alpha < 1/255 is certain, so the blend kernels can skip expf() for far pixels
-// without changing any decision of the reference (forward.cu:446-457).
+// without changing any decision of the reference (forward.cu:446-457).  The last two floats of the
+// record (rec_ext(F), +1) hold conservative half-extents (ex, ey) of the region where alpha >= 1/255 is
+// possible; the blend kernels use them to reject a Gaussian for a whole warp's pixel block at once.
 constexpr int REC_X = 0, REC_Y = 1, REC_A = 2, REC_B = 3, REC_C = 4, REC_OP = 5, REC_PTH = 6, REC_DEPTH = 7,
               REC_RGB = 8, REC_LANG = 11;
-__host__ __device__ constexpr int rec_floats(int F) { return ((11 + F) + 3) / 4 * 4; }
+__host__ __device__ constexpr int rec_floats(int F) { return ((13 + F) + 3) / 4 * 4; }
+__host__ __device__ constexpr int rec_ext(int F) { return rec_floats(F) - 2; }
 
 struct WsLayout {
     size_t info, tile_count, tile_cursor, ranges, cta_hist, records, depths, cov3D, clamped, tiles_touched, rect, final_T,

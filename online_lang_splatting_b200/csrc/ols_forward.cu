@@ -297,13 +297,30 @@ __device__ void preprocess_one(const PreArgs& a, int i, int tid, const float* s_
     // conservative cut: power < pth  =>  op*exp(power) < 1/255 with a wide safety margin
     const float pth = (op == op) ? (op > 0.0f ? logf(1.0f / (255.0f * op)) - 0.01f : CUDART_INF_F) : -CUDART_INF_F;
     float4* r4 = reinterpret_cast<float4*>(a.records + (size_t)i * a.rec);
-    r4[0] = make_float4(pix_x, pix_y, fmul(cc, det_inv), fmul(cb, -det_inv));
-    r4[1] = make_float4(fmul(ca, det_inv), op, pth, vz);
+    const float conA = fmul(cc, det_inv), conB = fmul(cb, -det_inv), conC = fmul(ca, det_inv);
+    r4[0] = make_float4(pix_x, pix_y, conA, conB);
+    r4[1] = make_float4(conC, op, pth, vz);
     float* rf = a.records + (size_t)i * a.rec;
     rf[REC_RGB] = rgb[0];
     rf[REC_RGB + 1] = rgb[1];
     rf[REC_RGB + 2] = rgb[2];
-    for (int c = REC_LANG + a.F; c < a.rec; c++) rf[c] = 0.0f;
+    for (int c = REC_LANG + a.F; c < a.rec - 2; c++) rf[c] = 0.0f;
+    {   // half-extents of {power >= pth_c} for the conic as stored: |dx| <= sqrt(-2 pth_c C / (AC - B^2)), same for y.
+        // pth_c widens pth by more than the rounding error of the float evaluation of `power` when the
+        // form is reasonably conditioned; otherwise (or for NaNs) the extents are infinite = never rejected.
+        const double A = (double)conA, B = (double)conB, Cc = (double)conC;
+        const double detc = A * Cc - B * B, tr = A + Cc;
+        float ex = CUDART_INF_F, ey = CUDART_INF_F;
+        if (pth > 0.0f) {
+            ex = ey = -CUDART_INF_F;  // opacity below 1/255: no pixel can pass
+        } else if (pth > -CUDART_INF_F && A > 0.0 && Cc > 0.0 && detc > 0.0 && tr * tr < 1000.0 * detc) {
+            const double k = -2.0 * (1.002 * (double)pth - 0.02) / detc;
+            ex = (float)(sqrt(k * Cc) * 1.0001 + 0.01);
+            ey = (float)(sqrt(k * A) * 1.0001 + 0.01);
+        }
+        rf[a.rec - 2] = ex;
+        rf[a.rec - 1] = ey;
+    }
     a.depths[i] = vz;
     a.radii[i] = ri;
     a.rect[i] = make_uint2((uint32_t)mn[0] | ((uint32_t)mn[1] << 16), (uint32_t)mx[0] | ((uint32_t)mx[1] << 16));
@@ -683,9 +700,13 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(unsigned long long*
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Forward blend (forward.cu:377-513).  One CTA of 256 threads per tile, one pixel per thread (threads
-// beyond TILE*TILE only help fetching).  The tile's Gaussian records are streamed global -> shared
-// with cp.async in double-buffered batches; the per-pixel loop reads them as warp-wide broadcasts.
+// Forward blend (forward.cu:377-513).  One CTA of 256 threads per tile; each of the 8 warps owns an
+// 8x4 pixel block of the tile (2 x 4 blocks cover 16x16; lanes beyond TILE only help fetching).  The
+// tile's Gaussian records are streamed global -> shared with cp.async in double-buffered batches.
+// Every warp first tests 32 records at a time -- one per lane -- against its own pixel block using the
+// record's conservative half-extents (a Gaussian that cannot reach alpha >= 1/255 anywhere in the block
+// is skipped by every pixel of the reference as well), ballots, and then runs the per-pixel evaluation
+// only for the surviving records.  The channel accumulators are updated with packed FFMA2.
 // ---------------------------------------------------------------------------------------------------
 constexpr int BLEND_THREADS = 256;
 constexpr int BLEND_BATCH = 64;
@@ -706,21 +727,48 @@ struct BlendArgs {
     int32_t* n_touched;
 };
 
+typedef unsigned long long f32x2;  // two floats in one 64-bit register pair (lo = first)
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {  // per-component fma.rn
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {  // per-component mul.rn
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 template <int TILE, int F, bool BITEXACT>
 __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const BlendArgs a) {
+    static_assert(TILE <= 16 && (3 + F) % 2 == 0, "8 warps of 8x4 pixels cover at most 16x16; channel pairs");
     constexpr int REC = rec_floats(F);
     constexpr int R4 = REC / 4;                 // float4 chunks per record
     constexpr int CHUNKS = BLEND_BATCH * R4;    // 16-byte chunks per batch
-    constexpr int NCH = 3 + F + 1;              // rgb + lang + depth accumulators
+    constexpr int NPAIR = (3 + F) / 2;          // (r,g) (b,L0) (L1,L2) ... as stored from REC_RGB on
+    constexpr int EXT = rec_ext(F);
     __shared__ __align__(16) float s_rec[2][BLEND_BATCH * REC];
     __shared__ uint32_t s_id[2][BLEND_BATCH];
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int tile_x = blockIdx.x % a.gx, tile_y = blockIdx.x / a.gx;
-    const int lx = tid % TILE, ly = tid / TILE;
+    const int bx0 = (wid & 1) * 8, by0 = (wid >> 1) * 4;
+    const int lx = bx0 + (lane & 7), ly = by0 + (lane >> 3);
     const int pxi = tile_x * TILE + lx, pyi = tile_y * TILE + ly;
-    const bool inside = (tid < TILE * TILE) && pxi < a.W && pyi < a.H;
+    const bool inside = lx < TILE && ly < TILE && pxi < a.W && pyi < a.H;
     const float pfx = (float)pxi, pfy = (float)pyi;
+    // this warp's pixel rectangle, clipped to the tile and the image
+    const float fx0 = (float)(tile_x * TILE + bx0), fy0 = (float)(tile_y * TILE + by0);
+    const float fx1 = (float)min(min(tile_x * TILE + bx0 + 7, tile_x * TILE + TILE - 1), a.W - 1);
+    const float fy1 = (float)min(min(tile_y * TILE + by0 + 3, tile_y * TILE + TILE - 1), a.H - 1);
 
     uint2 rg = a.ranges[blockIdx.x];
     if (a.info->overflow) rg = make_uint2(0u, 0u);
@@ -742,9 +790,10 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const BlendArgs a) {
     };
 
     float T = 1.0f;
-    float acc[NCH];
+    f32x2 acc2[NPAIR];
 #pragma unroll
-    for (int c = 0; c < NCH; c++) acc[c] = 0.0f;
+    for (int c = 0; c < NPAIR; c++) acc2[c] = 0ull;
+    float acc_d = 0.0f;
     uint32_t last_contributor = 0;
     bool done = !inside;
 
@@ -754,81 +803,86 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const BlendArgs a) {
         // all threads done -> stop (forward.cu:425-427); also publishes batch b and frees buffer (b+1)&1
         if (__syncthreads_count(done) == BLEND_THREADS) break;
         if (b + 1 < n_batches) issue(b + 1);
-        if (__all_sync(0xffffffffu, done)) continue;
         const int cnt = min(BLEND_BATCH, total - b * BLEND_BATCH);
-        const float4* r4 = reinterpret_cast<const float4*>(s_rec[b & 1]);
+        const float* rec = s_rec[b & 1];
         const uint32_t* ids = s_id[b & 1];
         const uint32_t cbase = (uint32_t)b * BLEND_BATCH;
-        for (int j = 0; j < cnt; j++) {
-            bool touch = false;
-            if (!done) {
-                const float4 g0 = r4[j * R4 + 0];  // x y A B
-                const float4 g1 = r4[j * R4 + 1];  // C op pth depth
-                const float dx = fsub(g0.x, pfx), dy = fsub(g0.y, pfy);
-                const float power =
-                    ffma(ffma(dx, fmul(dx, g0.z), fmul(dy, fmul(dy, g1.x))), -0.5f, -fmul(dy, fmul(dx, g0.w)));
-                if (!(power > 0.0f) && !(power < g1.z)) {
-                    const float alpha = fminf(fmul(g1.y, expf(power)), 0.99f);
-                    if (!(alpha < 1.0f / 255.0f)) {
-                        const float test_T = fmul(T, fsub(1.0f, alpha));
-                        if (test_T < 0.0001f) {
-                            done = true;
-                        } else {
-                            const float4 g2 = r4[j * R4 + 2];  // r g b L0
-                            if (BITEXACT) {
-                                acc[0] = ffma(T, fmul(alpha, g2.x), acc[0]);
-                                acc[1] = ffma(T, fmul(alpha, g2.y), acc[1]);
-                                acc[2] = ffma(T, fmul(alpha, g2.z), acc[2]);
-                                acc[3] = ffma(T, fmul(alpha, g2.w), acc[3]);
-#pragma unroll
-                                for (int q = 3; q < R4; q++) {
-                                    const float4 v = r4[j * R4 + q];
-                                    const int c0 = 4 + (q - 3) * 4;
-                                    if (c0 + 0 < 3 + F) acc[c0 + 0] = ffma(T, fmul(alpha, v.x), acc[c0 + 0]);
-                                    if (c0 + 1 < 3 + F) acc[c0 + 1] = ffma(T, fmul(alpha, v.y), acc[c0 + 1]);
-                                    if (c0 + 2 < 3 + F) acc[c0 + 2] = ffma(T, fmul(alpha, v.z), acc[c0 + 2]);
-                                    if (c0 + 3 < 3 + F) acc[c0 + 3] = ffma(T, fmul(alpha, v.w), acc[c0 + 3]);
-                                }
-                                acc[NCH - 1] = ffma(T, fmul(alpha, g1.w), acc[NCH - 1]);
+#pragma unroll 1
+        for (int half = 0; half < BLEND_BATCH / 32; half++) {
+            if (__all_sync(0xffffffffu, done)) break;
+            const int e = half * 32 + lane;
+            bool hit = false;
+            if (e < cnt) {
+                const float2 c = *reinterpret_cast<const float2*>(rec + e * REC + REC_X);
+                const float2 h = *reinterpret_cast<const float2*>(rec + e * REC + EXT);
+                hit = (c.x + h.x >= fx0) && (c.x - h.x <= fx1) && (c.y + h.y >= fy0) && (c.y - h.y <= fy1);
+            }
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            while (m) {
+                const int j = half * 32 + __ffs(m) - 1;
+                m &= m - 1;
+                const float* rj = rec + j * REC;
+                bool touch = false;
+                if (!done) {
+                    const float4 g0 = *reinterpret_cast<const float4*>(rj);      // x y A B
+                    const float4 g1 = *reinterpret_cast<const float4*>(rj + 4);  // C op pth depth
+                    const float dx = fsub(g0.x, pfx), dy = fsub(g0.y, pfy);
+                    const float power =
+                        ffma(ffma(dx, fmul(dx, g0.z), fmul(dy, fmul(dy, g1.x))), -0.5f, -fmul(dy, fmul(dx, g0.w)));
+                    if (!(power > 0.0f) && !(power < g1.z)) {
+                        const float alpha = fminf(fmul(g1.y, expf(power)), 0.99f);
+                        if (!(alpha < 1.0f / 255.0f)) {
+                            const float test_T = fmul(T, fsub(1.0f, alpha));
+                            if (test_T < 0.0001f) {
+                                done = true;
                             } else {
-                                const float w = fmul(alpha, T);
-                                acc[0] = ffma(w, g2.x, acc[0]);
-                                acc[1] = ffma(w, g2.y, acc[1]);
-                                acc[2] = ffma(w, g2.z, acc[2]);
-                                acc[3] = ffma(w, g2.w, acc[3]);
+                                f32x2 v[NPAIR];
 #pragma unroll
-                                for (int q = 3; q < R4; q++) {
-                                    const float4 v = r4[j * R4 + q];
-                                    const int c0 = 4 + (q - 3) * 4;
-                                    if (c0 + 0 < 3 + F) acc[c0 + 0] = ffma(w, v.x, acc[c0 + 0]);
-                                    if (c0 + 1 < 3 + F) acc[c0 + 1] = ffma(w, v.y, acc[c0 + 1]);
-                                    if (c0 + 2 < 3 + F) acc[c0 + 2] = ffma(w, v.z, acc[c0 + 2]);
-                                    if (c0 + 3 < 3 + F) acc[c0 + 3] = ffma(w, v.w, acc[c0 + 3]);
+                                for (int p = 0; p + 1 < NPAIR; p += 2) {
+                                    const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(rj + REC_RGB + 2 * p);
+                                    v[p] = t.x;
+                                    v[p + 1] = t.y;
                                 }
-                                acc[NCH - 1] = ffma(w, g1.w, acc[NCH - 1]);
+                                if (NPAIR & 1)
+                                    v[NPAIR - 1] = *reinterpret_cast<const f32x2*>(rj + REC_RGB + 2 * (NPAIR - 1));
+                                if (BITEXACT) {  // acc = fma(T, alpha * c, acc) like the compiled reference
+                                    const f32x2 a2 = pack2(alpha, alpha), T2 = pack2(T, T);
+#pragma unroll
+                                    for (int p = 0; p < NPAIR; p++) acc2[p] = ffma2(T2, fmul2(a2, v[p]), acc2[p]);
+                                    acc_d = ffma(T, fmul(alpha, g1.w), acc_d);
+                                } else {
+                                    const float w = fmul(alpha, T);
+                                    const f32x2 w2 = pack2(w, w);
+#pragma unroll
+                                    for (int p = 0; p < NPAIR; p++) acc2[p] = ffma2(w2, v[p], acc2[p]);
+                                    acc_d = ffma(w, g1.w, acc_d);
+                                }
+                                touch = test_T > 0.5f;
+                                T = test_T;
+                                last_contributor = cbase + (uint32_t)j + 1u;
                             }
-                            touch = test_T > 0.5f;
-                            T = test_T;
-                            last_contributor = cbase + (uint32_t)j + 1u;
                         }
                     }
                 }
+                const unsigned tm = __ballot_sync(0xffffffffu, touch);
+                if (tm != 0u && lane == 0) atomicAdd(&a.n_touched[ids[j]], __popc(tm));
             }
-            const unsigned m = __ballot_sync(0xffffffffu, touch);
-            if (m != 0u && lane == 0) atomicAdd(&a.n_touched[ids[j]], __popc(m));
         }
     }
     cp_async_wait<0>();
     if (inside) {
         const size_t HW = (size_t)a.W * a.H;
         const size_t pix = (size_t)pyi * a.W + pxi;
+        float acc[2 * NPAIR];
+#pragma unroll
+        for (int p = 0; p < NPAIR; p++) unpack2(acc2[p], acc[2 * p], acc[2 * p + 1]);
         a.final_T[pix] = T;
         a.n_contrib[pix] = last_contributor;
 #pragma unroll
         for (int c = 0; c < 3; c++) a.out_color[c * HW + pix] = ffma(a.bg[c], T, acc[c]);
 #pragma unroll
         for (int c = 0; c < F; c++) a.out_language[c * HW + pix] = acc[3 + c];
-        a.out_depth[pix] = acc[NCH - 1];
+        a.out_depth[pix] = acc_d;
         a.out_opacity[pix] = fsub(1.0f, T);
     }
 }

@@ -26,6 +26,8 @@ for tile in (15, 16):
         torch.cuda.synchronize()
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         tf = tb = 0.0
+        from online_lang_splatting_b200 import _native as N
+        N.timing_begin(iters * 16 + 64)
         for _ in range(iters):
             e0.record()
             R, color, language, radii, depth, opacity, n_touched, st = dgr._forward_native(*args)
@@ -33,7 +35,9 @@ for tile in (15, 16):
             dgr._backward_native(st, radii, grads[0], grads[1], grads[2])
             e2.record(); torch.cuda.synchronize()
             tf += e0.elapsed_time(e1); tb += e1.elapsed_time(e2)
-        print(f"P={P} tile={tile} mode={mode} R={R} fwd_ms={tf/iters:.3f} bwd_ms={tb/iters:.3f}", flush=True)
+        marks = N.timing_end()
+        print(f"P={P} tile={tile} mode={mode} R={R} fwd_ms={tf/iters:.3f} bwd_ms={tb/iters:.3f}  " +
+              " ".join(f"{k}={v[0]/max(v[1],1):.3f}" for k, v in marks.items() if v[1]), flush=True)
 if os.environ.get("OLS_SKIP_REF"):
     sys.exit(0)
 mod = U.ref_module("ref_P_C")

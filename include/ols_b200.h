@@ -181,6 +181,71 @@ typedef struct ols_host_out {
 int ols_lang_forward_host(const ols_raster_args* host_args /* all d_* fields hold HOST pointers; workspace ignored */,
                           const ols_host_out* out, int64_t* num_rendered);
 
+/* ---------------------------------------------------------------------------------------------
+ * Disentangled variant ("D/": submodules/diff-gaussian-rasterization-disentangle-optim).  Every
+ * Gaussian carries a second footprint (opacities_lang, scales_lang, rotations_lang) used only by
+ * the language pass; colour + depth and language are binned, sorted and blended independently.
+ * Entry points replace the pybind functions of D/ext.cpp:15-21 whose signatures are
+ * D/rasterize_points.h:51-80 (forward, 25 positional arguments, 15 returns) and :128-162
+ * (backward, 32 arguments, 14 returns).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ols_dis_args {
+    ols_raster_args base;               /* colour footprint + everything shared; base.d_workspace holds
+                                           ols_dis_workspace_size() bytes; base.R_cap = colour-list capacity */
+    const float* d_opacities_lang;      /* [P]                                                           */
+    const float* d_scales_lang;         /* [P,3] or NULL                                                 */
+    const float* d_rotations_lang;      /* [P,4] or NULL                                                 */
+    const float* d_cov3D_precomp_lang;  /* [P,6] or NULL (exactly one of scale+rot / cov3D, as for colour) */
+    int64_t R_cap_lang;                 /* language-list capacity                                        */
+} ols_dis_args;
+
+/* Forward outputs: the tensors returned at D/rasterize_points.cu:251-265. */
+typedef struct ols_dis_fwd_out {
+    float* d_color;            /* [3,H,W] */
+    float* d_language;         /* [F,H,W] */
+    float* d_depth;            /* [1,H,W] */
+    float* d_opacity;          /* [1,H,W] */
+    float* d_opacity_lang;     /* [1,H,W] */
+    int32_t* d_radii;          /* [P] */
+    int32_t* d_radii_lang;     /* [P] */
+    int32_t* d_n_touched;      /* [P] */
+    int32_t* d_n_touched_lang; /* [P] */
+} ols_dis_fwd_out;
+
+/* Backward: the 14 tensors returned at D/rasterize_points.cu:499-515.  Language gradients reach
+ * language, opacity_lang, scales_lang and rotations_lang only (D/backward.cu:1074,1117). */
+typedef struct ols_dis_bwd_args {
+    const float* d_dL_dout_color;     /* [3,H,W] */
+    const float* d_dL_dout_language;  /* [F,H,W] */
+    const float* d_dL_dout_depth;     /* [1,H,W] */
+    const int32_t* d_radii;           /* [P] from forward */
+    const int32_t* d_radii_lang;      /* [P] from forward */
+    float* d_dL_dmeans2D;         /* [P,3] */
+    float* d_dL_dcolors;          /* [P,3] */
+    float* d_dL_dlanguage;        /* [P,F] */
+    float* d_dL_dopacity;         /* [P,1] */
+    float* d_dL_dopacity_lang;    /* [P,1] */
+    float* d_dL_dmeans3D;         /* [P,3] */
+    float* d_dL_dcov3D;           /* [P,6] */
+    float* d_dL_dcov3D_lang;      /* [P,6] */
+    float* d_dL_dsh;              /* [P,M,3] or NULL when M == 0 */
+    float* d_dL_dscales;          /* [P,3] */
+    float* d_dL_dscales_lang;     /* [P,3] */
+    float* d_dL_drotations;       /* [P,4] */
+    float* d_dL_drotations_lang;  /* [P,4] */
+    float* d_dL_dtau;             /* [P,6] */
+} ols_dis_bwd_args;
+
+size_t ols_dis_workspace_size(int32_t P, int32_t F, int32_t W, int32_t H, int32_t tile, int64_t R_cap, int64_t R_cap_lang);
+/* replaces D/'s _C.rasterize_language_gaussians; asynchronous, no host sync */
+int ols_dis_forward(const ols_dis_args* args, const ols_dis_fwd_out* out, void* stream);
+/* both info headers (colour list, language list) in one call; synchronises `stream` */
+int ols_dis_read_info(const ols_dis_args* args, ols_fwd_info* h_info_color, ols_fwd_info* h_info_lang, void* stream);
+/* replaces D/'s _C.rasterize_language_gaussians_backward */
+int ols_dis_backward(const ols_dis_args* args, const ols_dis_bwd_args* grads, void* stream);
+/* workspace views of the two lists (tests / debugging) */
+int ols_dis_workspace_view(const ols_dis_args* args, ols_ws_view* view_color, ols_ws_view* view_lang);
+
 /* Per-kernel device timing (CUDA events recorded between the kernels of every call while enabled).
  * ols_timing_begin() allocates `max_marks` events and enables recording on the calling thread;
  * ols_timing_end() synchronises, sums the elapsed milliseconds per tag, reports how many intervals

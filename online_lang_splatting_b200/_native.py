@@ -28,6 +28,7 @@ EXPORTED_SYMBOLS = (
     "ols_abi_version", "ols_last_error", "ols_cuda_available", "ols_lang_workspace_size", "ols_lang_forward",
     "ols_lang_read_info", "ols_lang_backward", "ols_mark_visible", "ols_lang_workspace_view",
     "ols_lang_forward_host", "ols_timing_begin", "ols_timing_end", "ols_ae_plan_create", "ols_ae_plan_destroy", "ols_ae_forward",
+    "ols_dis_workspace_size", "ols_dis_forward", "ols_dis_read_info", "ols_dis_backward", "ols_dis_workspace_view",
 )
 
 
@@ -55,6 +56,26 @@ class BwdArgs(C.Structure):
                                           "d_dL_dmeans2D", "d_dL_dcolors", "d_dL_dlanguage", "d_dL_dopacity",
                                           "d_dL_dmeans3D", "d_dL_dcov3D", "d_dL_dsh", "d_dL_dscales",
                                           "d_dL_drotations", "d_dL_dtau")]
+
+
+class DisArgs(C.Structure):
+    """ols_dis_args: the disentangled (D/) rasterizer's arguments = ols_raster_args + the language footprint."""
+    _fields_ = [("base", RasterArgs)] + \
+               [(n, C.c_void_p) for n in ("d_opacities_lang", "d_scales_lang", "d_rotations_lang", "d_cov3D_precomp_lang")] + \
+               [("R_cap_lang", C.c_int64)]
+
+
+class DisFwdOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("d_color", "d_language", "d_depth", "d_opacity", "d_opacity_lang", "d_radii",
+                                          "d_radii_lang", "d_n_touched", "d_n_touched_lang")]
+
+
+class DisBwdArgs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("d_dL_dout_color", "d_dL_dout_language", "d_dL_dout_depth", "d_radii",
+                                          "d_radii_lang", "d_dL_dmeans2D", "d_dL_dcolors", "d_dL_dlanguage",
+                                          "d_dL_dopacity", "d_dL_dopacity_lang", "d_dL_dmeans3D", "d_dL_dcov3D",
+                                          "d_dL_dcov3D_lang", "d_dL_dsh", "d_dL_dscales", "d_dL_dscales_lang",
+                                          "d_dL_drotations", "d_dL_drotations_lang", "d_dL_dtau")]
 
 
 class WsView(C.Structure):
@@ -102,6 +123,12 @@ def lib() -> C.CDLL:
     L.ols_lang_workspace_view.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                                           C.c_void_p, C.POINTER(WsView)]
     L.ols_lang_forward_host.argtypes = [C.POINTER(RasterArgs), C.POINTER(HostOut), C.POINTER(C.c_int64)]
+    L.ols_dis_workspace_size.restype = C.c_size_t
+    L.ols_dis_workspace_size.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64]
+    L.ols_dis_forward.argtypes = [C.POINTER(DisArgs), C.POINTER(DisFwdOut), C.c_void_p]
+    L.ols_dis_read_info.argtypes = [C.POINTER(DisArgs), C.POINTER(FwdInfo), C.POINTER(FwdInfo), C.c_void_p]
+    L.ols_dis_backward.argtypes = [C.POINTER(DisArgs), C.POINTER(DisBwdArgs), C.c_void_p]
+    L.ols_dis_workspace_view.argtypes = [C.POINTER(DisArgs), C.POINTER(WsView), C.POINTER(WsView)]
     L.ols_timing_begin.argtypes = [C.c_int32]
     L.ols_timing_end.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int32)]
     L.ols_ae_plan_create.argtypes = [C.POINTER(AEChain), C.POINTER(C.c_void_p), C.c_void_p]

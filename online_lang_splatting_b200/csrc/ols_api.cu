@@ -46,7 +46,7 @@ __global__ void k_check_frustum(int P, const float* __restrict__ means, const fl
 }
 }  // namespace ols
 
-static int validate(const ols_raster_args* a, WsLayout* L) {
+static int validate(const ols_raster_args* a, WsLayout* L, bool check_workspace = true) {
     if (!a) { ols_set_error("null args"); return OLS_ERR_INVALID; }
     if (a->P < 0 || a->W <= 0 || a->H <= 0) { ols_set_error("bad sizes P=%d W=%d H=%d", a->P, a->W, a->H); return OLS_ERR_INVALID; }
     if (!((a->tile == 15 || a->tile == 16) && (a->F == 3 || a->F == 15))) {
@@ -78,6 +78,7 @@ static int validate(const ols_raster_args* a, WsLayout* L) {
         return OLS_ERR_INVALID;
     }
     *L = ws_layout(a->P, a->F, a->W, a->H, a->tile, a->R_cap);
+    if (!check_workspace) return OLS_OK;
     if (!a->d_workspace || a->workspace_bytes < L->total) {
         ols_set_error("workspace too small: have %zu need %zu bytes", a->workspace_bytes, L->total);
         return OLS_ERR_WORKSPACE;
@@ -169,6 +170,111 @@ int ols_timing_end(float* ms_per_tag, int32_t* count_per_tag) {
         count_per_tag[tag] += 1;
     }
     t.used = 0;
+    return OLS_OK;
+}
+
+// ---- disentangled variant ---------------------------------------------------------------------------
+struct DisLayout { WsLayout c, l; size_t lang_base, total; };
+static DisLayout dis_layout(int P, int F, int W, int H, int tile, int64_t R_cap, int64_t R_cap_lang) {
+    DisLayout D;
+    D.c = ws_layout(P, 0, W, H, tile, R_cap, 3);        // colour + depth list
+    D.l = ws_layout(P, F, W, H, tile, R_cap_lang, 0);   // language list
+    D.lang_base = align_up(D.c.total, 256);
+    D.total = D.lang_base + D.l.total;
+    return D;
+}
+
+static int validate_dis(const ols_dis_args* d, DisLayout* D) {
+    if (!d) { ols_set_error("null args"); return OLS_ERR_INVALID; }
+    WsLayout tmp;
+    int rc = validate(&d->base, &tmp, false);
+    if (rc != OLS_OK) return rc;
+    const ols_raster_args* a = &d->base;
+    // reference: D/diff_gaussian_rasterization/__init__.py:600-605
+    const bool sr = d->d_scales_lang != nullptr && d->d_rotations_lang != nullptr;
+    const bool any_sr = d->d_scales_lang != nullptr || d->d_rotations_lang != nullptr;
+    if ((!sr && d->d_cov3D_precomp_lang == nullptr) || (any_sr && d->d_cov3D_precomp_lang != nullptr)) {
+        ols_set_error("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance for language!");
+        return OLS_ERR_INVALID;
+    }
+    if (!d->d_opacities_lang) { ols_set_error("opacities_lang is required"); return OLS_ERR_INVALID; }
+    if (d->R_cap_lang < 0) { ols_set_error("bad R_cap_lang"); return OLS_ERR_INVALID; }
+    *D = dis_layout(a->P, a->F, a->W, a->H, a->tile, a->R_cap, d->R_cap_lang);
+    if (!a->d_workspace || a->workspace_bytes < D->total) {
+        ols_set_error("workspace too small: have %zu need %zu bytes", a->workspace_bytes, D->total);
+        return OLS_ERR_WORKSPACE;
+    }
+    if (((uintptr_t)a->d_workspace & 255) != 0) { ols_set_error("workspace must be 256-byte aligned"); return OLS_ERR_INVALID; }
+    return OLS_OK;
+}
+
+static void fill_view(ols_ws_view* v, const char* ws, const WsLayout& L) {
+    v->d_records = (const float*)(ws + L.records);
+    v->rec_floats = L.rec;
+    v->n_tiles = L.n_tiles;
+    v->d_cov3D = (const float*)(ws + L.cov3D);
+    v->d_clamped = (const uint8_t*)(ws + L.clamped);
+    v->d_tiles_touched = (const uint32_t*)(ws + L.tiles_touched);
+    v->d_ranges = (const uint32_t*)(ws + L.ranges);
+    v->d_point_list = (const uint32_t*)(ws + L.point_list);
+    v->d_keys = (const uint64_t*)(ws + L.keys);
+    v->d_final_T = (const float*)(ws + L.final_T);
+    v->d_n_contrib = (const uint32_t*)(ws + L.n_contrib);
+}
+
+size_t ols_dis_workspace_size(int32_t P, int32_t F, int32_t W, int32_t H, int32_t tile, int64_t R_cap, int64_t R_cap_lang) {
+    if (P < 0 || F <= 0 || W <= 0 || H <= 0 || tile <= 0 || R_cap < 0 || R_cap_lang < 0) return 0;
+    return dis_layout(P, F, W, H, tile, R_cap, R_cap_lang).total;
+}
+
+int ols_dis_forward(const ols_dis_args* d, const ols_dis_fwd_out* o, void* stream) {
+    DisLayout D;
+    int rc = validate_dis(d, &D);
+    if (rc != OLS_OK) return rc;
+    if (!o || !o->d_color || !o->d_language || !o->d_depth || !o->d_opacity || !o->d_opacity_lang || !o->d_radii ||
+        !o->d_radii_lang || !o->d_n_touched || !o->d_n_touched_lang) {
+        ols_set_error("null output pointer");
+        return OLS_ERR_INVALID;
+    }
+    if (d->base.P == 0) { ols_set_error("P == 0: nothing to render"); return OLS_ERR_INVALID; }
+    return ols_launch_forward_dis(d, o, D.c, D.l, D.lang_base, (cudaStream_t)stream);
+}
+
+int ols_dis_read_info(const ols_dis_args* d, ols_fwd_info* h_c, ols_fwd_info* h_l, void* stream) {
+    if (!d || !h_c || !h_l || !d->base.d_workspace) { ols_set_error("null pointer"); return OLS_ERR_INVALID; }
+    const ols_raster_args* a = &d->base;
+    const DisLayout D = dis_layout(a->P, a->F, a->W, a->H, a->tile, a->R_cap, d->R_cap_lang);
+    const char* ws = (const char*)a->d_workspace;
+    OLS_CUDA_TRY(cudaMemcpyAsync(h_c, ws + D.c.info, sizeof(ols_fwd_info), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    OLS_CUDA_TRY(cudaMemcpyAsync(h_l, ws + D.lang_base + D.l.info, sizeof(ols_fwd_info), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    OLS_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return OLS_OK;
+}
+
+int ols_dis_backward(const ols_dis_args* d, const ols_dis_bwd_args* g, void* stream) {
+    DisLayout D;
+    int rc = validate_dis(d, &D);
+    if (rc != OLS_OK) return rc;
+    if (!g || !g->d_dL_dout_color || !g->d_dL_dout_language || !g->d_dL_dout_depth || !g->d_radii || !g->d_radii_lang ||
+        !g->d_dL_dmeans2D || !g->d_dL_dcolors || !g->d_dL_dlanguage || !g->d_dL_dopacity || !g->d_dL_dopacity_lang ||
+        !g->d_dL_dmeans3D || !g->d_dL_dcov3D || !g->d_dL_dcov3D_lang || !g->d_dL_dscales || !g->d_dL_dscales_lang ||
+        !g->d_dL_drotations || !g->d_dL_drotations_lang || !g->d_dL_dtau) {
+        ols_set_error("null gradient pointer");
+        return OLS_ERR_INVALID;
+    }
+    const ols_raster_args* a = &d->base;
+    if (a->M > 0 && a->d_shs && !g->d_dL_dsh) { ols_set_error("d_dL_dsh is null but SHs were given"); return OLS_ERR_INVALID; }
+    if (!a->d_projmatrix_raw) { ols_set_error("projmatrix_raw is required by backward"); return OLS_ERR_INVALID; }
+    if (a->flags & OLS_FLAG_BWD_ACCUMULATE) { ols_set_error("accumulate is not supported by the disentangled backward"); return OLS_ERR_UNSUPPORTED; }
+    return ols_launch_backward_dis(d, g, D.c, D.l, D.lang_base, (cudaStream_t)stream);
+}
+
+int ols_dis_workspace_view(const ols_dis_args* d, ols_ws_view* vc, ols_ws_view* vl) {
+    if (!d || !vc || !vl || !d->base.d_workspace) { ols_set_error("bad arguments"); return OLS_ERR_INVALID; }
+    const ols_raster_args* a = &d->base;
+    const DisLayout D = dis_layout(a->P, a->F, a->W, a->H, a->tile, a->R_cap, d->R_cap_lang);
+    fill_view(vc, (const char*)a->d_workspace, D.c);
+    fill_view(vl, (const char*)a->d_workspace + D.lang_base, D.l);
     return OLS_OK;
 }
 

@@ -67,37 +67,46 @@ __device__ __forceinline__ void warp_multi_reduce(float (&v)[NV], int lane) {
     if (NV == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-template <int TILE, int F, bool COMPAT>
+// NCOL = 3: colour + depth channels take part (joint pass of P/, colour pass of D/); NCOL = 0: the
+// language-only pass of D/ (no mean2D gradient, no background term: D/backward.cu:1318-1427).
+// Thread -> pixel mapping: warp w owns the 8x4 pixel block ((w & 1) * 8, (w >> 1) * 4) of the tile, as in
+// the forward; a Gaussian whose conservative extents miss the block is never evaluated by that warp.
+template <int TILE, int NCOL, int F, bool COMPAT>
 __global__ void __launch_bounds__(BWD_THREADS) k_blend_bwd(const BwdBlendArgs a) {
-    constexpr int REC = rec_floats(F);
+    static_assert(TILE <= 16 && BWD_BATCH == 32, "8 warps of 8x4 pixels; one ballot per batch");
+    constexpr int NCH = NCOL + F;
+    constexpr int REC = rec_floats_nch(NCH);
     constexpr int R4 = REC / 4;
+    constexpr int EXT = REC - 2;
     constexpr int GR = grad_floats(F);
-    constexpr int NCH = 3 + F;  // rgb + language
+    constexpr int NQ = (NCH + 3) / 4;  // float4 chunks holding the channels
     __shared__ __align__(16) float s_rec[BWD_BATCH * REC];
     __shared__ uint32_t s_id[BWD_BATCH];
     __shared__ float s_acc[BWD_BATCH * GR];
     __shared__ uint32_t s_maxc;
     __shared__ uint32_t s_mask;
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int tile_x = blockIdx.x % a.gx, tile_y = blockIdx.x / a.gx;
-    const int lx = tid % TILE, ly = tid / TILE;
+    const int bx0 = (wid & 1) * 8, by0 = (wid >> 1) * 4;
+    const int lx = bx0 + (lane & 7), ly = by0 + (lane >> 3);
     const int pxi = tile_x * TILE + lx, pyi = tile_y * TILE + ly;
-    const bool inside = (tid < TILE * TILE) && pxi < a.W && pyi < a.H;
+    const bool inside = lx < TILE && ly < TILE && pxi < a.W && pyi < a.H;
     const float pfx = (float)pxi, pfy = (float)pyi;
     const size_t HW = (size_t)a.W * a.H;
     const size_t pix = inside ? (size_t)pyi * a.W + pxi : 0;
+    const float fx0 = (float)(tile_x * TILE + bx0), fy0 = (float)(tile_y * TILE + by0);
+    const float fx1 = (float)min(min(tile_x * TILE + bx0 + 7, tile_x * TILE + TILE - 1), a.W - 1);
+    const float fy1 = (float)min(min(tile_y * TILE + by0 + 3, tile_y * TILE + TILE - 1), a.H - 1);
 
     uint2 rg = a.ranges[blockIdx.x];
     if (a.info->overflow) rg = make_uint2(0u, 0u);
     const uint32_t last_contributor = inside ? a.n_contrib[pix] : 0u;
+    const uint32_t warp_maxc = __reduce_max_sync(0xffffffffu, last_contributor);
     if (tid == 0) { s_maxc = 0; s_mask = 0; }
     for (int e = tid; e < BWD_BATCH * GR; e += BWD_THREADS) s_acc[e] = 0.0f;
     __syncthreads();
-    {
-        const uint32_t m = __reduce_max_sync(0xffffffffu, last_contributor);
-        if (lane == 0 && m) atomicMax(&s_maxc, m);
-    }
+    if (lane == 0 && warp_maxc) atomicMax(&s_maxc, warp_maxc);
     __syncthreads();
     // entries at positions >= max n_contrib are skipped by every pixel of the tile in both modes
     const int total = min((int)s_maxc, (int)(rg.y - rg.x));
@@ -105,20 +114,23 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_bwd(const BwdBlendArgs a)
 
     const float T_final = inside ? a.final_T[pix] : 0.0f;
     float T = T_final;
-    float g[NCH];
+    float g[NCH > 0 ? NCH : 1];
     float gd = 0.0f;
 #pragma unroll
     for (int c = 0; c < NCH; c++) g[c] = 0.0f;
     if (inside) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) g[c] = a.dL_dcolor[c * HW + pix];
+        for (int c = 0; c < NCOL; c++) g[c] = a.dL_dcolor[c * HW + pix];
 #pragma unroll
-        for (int c = 0; c < F; c++) g[3 + c] = a.dL_dlanguage[c * HW + pix];
-        gd = a.dL_ddepth[pix];
+        for (int c = 0; c < F; c++) g[NCOL + c] = a.dL_dlanguage[c * HW + pix];
+        if (NCOL) gd = a.dL_ddepth[pix];
     }
-    const float bg_dot = a.bg[0] * g[0] + a.bg[1] * g[1] + a.bg[2] * g[2];
+    float bg_dot = 0.0f;
+    if (NCOL) bg_dot = a.bg[0] * g[0] + a.bg[1] * g[1] + a.bg[2] * g[2];
     const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
-    const bool lane_ok = COMPAT ? ((a.lane_ok[tid >> 5] >> lane) & 1u) != 0 : true;
+    // Q3: the lane mask is indexed by the reference's thread rank ly * TILE + lx
+    const int ref_rank = ly * TILE + lx;
+    const bool lane_ok = COMPAT ? (inside && ((a.lane_ok[(ref_rank >> 5) & 7] >> (ref_rank & 31)) & 1u) != 0) : true;
 
     float last_alpha = 0.0f;
     float A_c = 0.0f, Dl_c = 0.0f;  // rgb + depth part of sum_ch accum_rec*g and of last_color*g
@@ -143,20 +155,31 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_bwd(const BwdBlendArgs a)
         __syncthreads();
         const float4* r4 = reinterpret_cast<const float4*>(s_rec);
 
-        // which Gaussians of the batch does this pixel contribute to (same decisions as the forward)
+        // entries this warp's pixel block can reach at all (one entry per lane), then, per pixel, which of
+        // those it contributes to (same decisions as the forward)
+        unsigned cand;
+        {
+            bool hit = false;
+            if (lane < cnt && (uint32_t)(base + lane) < warp_maxc) {
+                const float2 c = *reinterpret_cast<const float2*>(s_rec + lane * REC + REC_X);
+                const float2 h = *reinterpret_cast<const float2*>(s_rec + lane * REC + EXT);
+                hit = (c.x + h.x >= fx0) && (c.x - h.x <= fx1) && (c.y + h.y >= fy0) && (c.y - h.y <= fy1);
+            }
+            cand = __ballot_sync(0xffffffffu, hit);
+        }
         uint32_t mymask = 0;
-        if (inside) {
-            for (int j = 0; j < cnt; j++) {
-                if ((uint32_t)(base + j) >= last_contributor) break;
+        for (unsigned m = cand; m; m &= m - 1) {
+            const int j = __ffs(m) - 1;
+            if (inside && (uint32_t)(base + j) < last_contributor) {
                 const float4 g0 = r4[j * R4 + 0];
                 const float4 g1 = r4[j * R4 + 1];
                 const float dx = fsub(g0.x, pfx), dy = fsub(g0.y, pfy);
                 const float power =
                     ffma(ffma(dx, fmul(dx, g0.z), fmul(dy, fmul(dy, g1.x))), -0.5f, -fmul(dy, fmul(dx, g0.w)));
-                if (power > 0.0f || power < g1.z) continue;
-                const float alpha = fminf(0.99f, fmul(g1.y, expf(power)));
-                if (alpha < 1.0f / 255.0f) continue;
-                mymask |= 1u << j;
+                if (!(power > 0.0f) && !(power < g1.z)) {
+                    const float alpha = fminf(0.99f, fmul(g1.y, expf(power)));
+                    if (!(alpha < 1.0f / 255.0f)) mymask |= 1u << j;
+                }
             }
         }
         uint32_t visit;  // Gaussians somebody in the block (compat) / warp (exact) contributes to
@@ -180,21 +203,21 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_bwd(const BwdBlendArgs a)
 #pragma unroll
             for (int i = 0; i < NV; i++) v[i] = 0.0f;
             float D_f = 0.0f, D_c = 0.0f;
-            if (inside && (COMPAT || contrib)) {
-                // D = sum_ch c_ch * dL/dpix_ch over rgb / language (and depth below)
-                const float4 c0 = r4[j * R4 + 2];  // r g b L0
-                D_c = c0.x * g[0] + c0.y * g[1] + c0.z * g[2] + g1.w * gd;
-                D_f = c0.w * g[3];
+            if (inside && ((COMPAT && F > 0) || contrib)) {
+                // D = sum_ch c_ch * dL/dpix_ch over rgb (+ depth) / language
 #pragma unroll
-                for (int q = 3; q < R4; q++) {
-                    const float4 c = r4[j * R4 + q];
-                    const int k0 = 4 + (q - 3) * 4;
-                    if (k0 + 0 < NCH) D_f = fmaf(c.x, g[k0 + 0], D_f);
-                    if (k0 + 1 < NCH) D_f = fmaf(c.y, g[k0 + 1], D_f);
-                    if (k0 + 2 < NCH) D_f = fmaf(c.z, g[k0 + 2], D_f);
-                    if (k0 + 3 < NCH) D_f = fmaf(c.w, g[k0 + 3], D_f);
+                for (int q = 0; q < NQ; q++) {
+                    const float4 c = r4[j * R4 + 2 + q];
+                    const float cv[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int k = 4 * q + e;
+                        if (k < NCOL) D_c = fmaf(cv[e], g[k], D_c);
+                        else if (k < NCH) D_f = fmaf(cv[e], g[k], D_f);
+                    }
                 }
-                if (COMPAT) {  // Q2: recurrence advances for every pixel of a visited Gaussian
+                if (NCOL) D_c = fmaf(g1.w, gd, D_c);
+                if (COMPAT && F > 0) {  // Q2: recurrence advances for every pixel of a visited Gaussian
                     A_f = last_alpha * Dl_f + (1.0f - last_alpha) * A_f;
                     Dl_f = D_f;
                 }
@@ -208,41 +231,45 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_bwd(const BwdBlendArgs a)
                 const float alpha = fminf(0.99f, fmul(g1.y, G));
                 T = T / (1.0f - alpha);
                 w = alpha * T;
-                A_c = last_alpha * Dl_c + (1.0f - last_alpha) * A_c;
-                Dl_c = D_c;
-                if (!COMPAT) {
+                if (NCOL) {
+                    A_c = last_alpha * Dl_c + (1.0f - last_alpha) * A_c;
+                    Dl_c = D_c;
+                }
+                if (!COMPAT && F > 0) {
                     A_f = last_alpha * Dl_f + (1.0f - last_alpha) * A_f;
                     Dl_f = D_f;
                 }
                 float dL_dalpha = ((D_c - A_c) + (D_f - A_f)) * T;
                 last_alpha = alpha;
-                dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot;
+                if (NCOL) dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot;
                 const float dL_dG = g1.y * dL_dalpha;
                 const float gdx = G * dx, gdy = G * dy;
-                const float dG_ddelx = -gdx * g0.z - gdy * g0.w;
-                const float dG_ddely = -gdy * g1.x - gdx * g0.w;
                 if (lane_ok) {
-                    v[GR_MX] = dL_dG * dG_ddelx * ddelx_dx;
-                    v[GR_MY] = dL_dG * dG_ddely * ddely_dy;
+                    if (NCOL) {  // D/ drops the mean gradient of the language footprint (D/backward.cu:1074,1117)
+                        const float dG_ddelx = -gdx * g0.z - gdy * g0.w;
+                        const float dG_ddely = -gdy * g1.x - gdx * g0.w;
+                        v[GR_MX] = dL_dG * dG_ddelx * ddelx_dx;
+                        v[GR_MY] = dL_dG * dG_ddely * ddely_dy;
+                        v[GR_DEPTH] = w * gd;
+                        v[GR_RGB + 0] = w * g[0];
+                        v[GR_RGB + 1] = w * g[1];
+                        v[GR_RGB + 2] = w * g[2];
+                    }
                     v[GR_CX] = -0.5f * gdx * dx * dL_dG;
                     v[GR_CY] = -0.5f * gdx * dy * dL_dG;
                     v[GR_CW] = -0.5f * gdy * dy * dL_dG;
                     v[GR_OP] = G * dL_dalpha;
-                    v[GR_DEPTH] = w * gd;
-                    v[GR_RGB + 0] = w * g[0];
-                    v[GR_RGB + 1] = w * g[1];
-                    v[GR_RGB + 2] = w * g[2];
                     if (!COMPAT) {
 #pragma unroll
-                        for (int c = 0; c < F; c++) v[GR_LANG + c] = w * g[3 + c];
+                        for (int c = 0; c < F; c++) v[GR_LANG + c] = w * g[NCOL + c];
                     }
                 }
             }
             if (COMPAT) {
                 // Q1: only the tile's first thread contributes its own pixel's language gradient
-                if (tid == 0 && contrib) {
+                if (F > 0 && tid == 0 && contrib) {
 #pragma unroll
-                    for (int c = 0; c < F; c++) s_acc[j * GR + GR_LANG + c] += w * g[3 + c];
+                    for (int c = 0; c < F; c++) s_acc[j * GR + GR_LANG + c] += w * g[NCOL + c];
                 }
                 if (__any_sync(0xffffffffu, contrib && lane_ok)) {
                     warp_multi_reduce<NV>(v, lane);
@@ -250,8 +277,10 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_bwd(const BwdBlendArgs a)
                     if ((lane & 1) == 0 && vi < 10 && v[0] != 0.0f) atomicAdd(&s_acc[j * GR + vi], v[0]);
                 }
             } else {
-                warp_multi_reduce<NV>(v, lane);
-                if (lane < 10 + F && v[0] != 0.0f) atomicAdd(&s_acc[j * GR + lane], v[0]);
+                if (__any_sync(0xffffffffu, contrib)) {
+                    warp_multi_reduce<NV>(v, lane);
+                    if (lane < 10 + F && v[0] != 0.0f) atomicAdd(&s_acc[j * GR + lane], v[0]);
+                }
             }
         }
         __syncthreads();
@@ -268,17 +297,21 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_bwd(const BwdBlendArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------------
-struct GeomBwdArgs {
+struct GeomCommon {
     int P, F, sh_degree, M, W, H, gr;
     float tanfovx, tanfovy, focal_x, focal_y, scale_modifier;
-    const float *means3D, *shs, *scales, *rotations, *cov3D, *viewmatrix, *projmatrix, *projmatrix_raw, *campos;
+    const float *means3D, *shs, *viewmatrix, *projmatrix, *projmatrix_raw, *campos;
     const uint32_t* clamped;
-    const int32_t* radii;
     const float* gacc;
     bool colors_precomp;
     bool accumulate;  // += into the parameter gradients (means3D, sh, opacity, scales, rotations, language, cov3D)
-    float *dL_dmeans2D, *dL_dcolors, *dL_dlanguage, *dL_dopacity, *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales,
-        *dL_drots, *dL_dtau;
+    float* dL_dsh;
+};
+
+struct GeomBwdArgs : GeomCommon {
+    const float *scales, *rotations, *cov3D;
+    const int32_t* radii;
+    float *dL_dmeans2D, *dL_dcolors, *dL_dlanguage, *dL_dopacity, *dL_dmeans3D, *dL_dcov3D, *dL_dscales, *dL_drots, *dL_dtau;
 };
 
 __constant__ float B_SH_C0 = 0.28209479177387814f;
@@ -287,6 +320,234 @@ __constant__ float B_SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31
                                  -1.0925484305920792f, 0.5462742152960396f};
 __constant__ float B_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
                                  -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+
+// computeCov2DCUDA (backward.cu:150-346): conic gradient -> dL/dcov3D (written), dL/dmean3D (assigned) and the
+// pose gradient (accumulated).  D/'s computeCov2DCUDA_no_tau (D/backward.cu:354-446) is the same arithmetic
+// keeping only dL/dcov3D: callers simply drop the other two results.
+__device__ __forceinline__ void geom_cov2d_bwd(const GeomCommon& a, const float* V, const float* mp, const float* c3,
+                                       float dcx, float dcy, float dcz, float* dcov, float* dmean, float* dtau) {
+    const float fx = a.focal_x, fy = a.focal_y;
+    // ---- computeCov2DCUDA (backward.cu:150-346)
+    float t[3] = {V[0] * mp[0] + V[4] * mp[1] + V[8] * mp[2] + V[12], V[1] * mp[0] + V[5] * mp[1] + V[9] * mp[2] + V[13],
+                  V[2] * mp[0] + V[6] * mp[1] + V[10] * mp[2] + V[14]};
+    const float limx = 1.3f * a.tanfovx, limy = 1.3f * a.tanfovy;
+    const float txtz = t[0] / t[2], tytz = t[1] / t[2];
+    t[0] = fminf(limx, fmaxf(-limx, txtz)) * t[2];
+    t[1] = fminf(limy, fmaxf(-limy, tytz)) * t[2];
+    const float xgm = (txtz < -limx || txtz > limx) ? 0.0f : 1.0f;
+    const float ygm = (tytz < -limy || tytz > limy) ? 0.0f : 1.0f;
+    // column-major like GLM: X[c][r]
+    const float J[3][3] = {{fx / t[2], 0, -(fx * t[0]) / (t[2] * t[2])}, {0, fy / t[2], -(fy * t[1]) / (t[2] * t[2])}, {0, 0, 0}};
+    const float Wm[3][3] = {{V[0], V[4], V[8]}, {V[1], V[5], V[9]}, {V[2], V[6], V[10]}};
+    const float Vrk[3][3] = {{c3[0], c3[1], c3[2]}, {c3[1], c3[3], c3[4]}, {c3[2], c3[4], c3[5]}};
+    float Tm[3][3];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) Tm[c][r] = Wm[0][r] * J[c][0] + Wm[1][r] * J[c][1] + Wm[2][r] * J[c][2];
+    float TV[2][3];  // TV[i][q] = sum_p Tm[i][p] * Vrk[p][q]
+#pragma unroll
+    for (int ii = 0; ii < 2; ii++)
+#pragma unroll
+        for (int q = 0; q < 3; q++) TV[ii][q] = Tm[ii][0] * Vrk[0][q] + Tm[ii][1] * Vrk[1][q] + Tm[ii][2] * Vrk[2][q];
+    const float ca = TV[0][0] * Tm[0][0] + TV[0][1] * Tm[0][1] + TV[0][2] * Tm[0][2] + 0.3f;
+    const float cb = TV[0][0] * Tm[1][0] + TV[0][1] * Tm[1][1] + TV[0][2] * Tm[1][2];
+    const float cc = TV[1][0] * Tm[1][0] + TV[1][1] * Tm[1][1] + TV[1][2] * Tm[1][2] + 0.3f;
+    const float denom = ca * cc - cb * cb;
+    float dL_da = 0, dL_db = 0, dL_dc = 0;
+    const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+    if (denom2inv != 0) {
+        dL_da = denom2inv * (-cc * cc * dcx + 2 * cb * cc * dcy + (denom - ca * cc) * dcz);
+        dL_dc = denom2inv * (-ca * ca * dcz + 2 * ca * cb * dcy + (denom - ca * cc) * dcx);
+        dL_db = denom2inv * 2 * (cb * cc * dcx - (denom + 2 * cb * cb) * dcy + ca * cb * dcz);
+        dcov[0] = (Tm[0][0] * Tm[0][0] * dL_da + Tm[0][0] * Tm[1][0] * dL_db + Tm[1][0] * Tm[1][0] * dL_dc);
+        dcov[3] = (Tm[0][1] * Tm[0][1] * dL_da + Tm[0][1] * Tm[1][1] * dL_db + Tm[1][1] * Tm[1][1] * dL_dc);
+        dcov[5] = (Tm[0][2] * Tm[0][2] * dL_da + Tm[0][2] * Tm[1][2] * dL_db + Tm[1][2] * Tm[1][2] * dL_dc);
+        dcov[1] = 2 * Tm[0][0] * Tm[0][1] * dL_da + (Tm[0][0] * Tm[1][1] + Tm[0][1] * Tm[1][0]) * dL_db + 2 * Tm[1][0] * Tm[1][1] * dL_dc;
+        dcov[2] = 2 * Tm[0][0] * Tm[0][2] * dL_da + (Tm[0][0] * Tm[1][2] + Tm[0][2] * Tm[1][0]) * dL_db + 2 * Tm[1][0] * Tm[1][2] * dL_dc;
+        dcov[4] = 2 * Tm[0][2] * Tm[0][1] * dL_da + (Tm[0][1] * Tm[1][2] + Tm[0][2] * Tm[1][1]) * dL_db + 2 * Tm[1][1] * Tm[1][2] * dL_dc;
+    }
+    // TV[r][k] equals the reference's (T[r] . Vrk[k]) because Vrk is symmetric
+    const float dT00 = 2 * TV[0][0] * dL_da + TV[1][0] * dL_db, dT01 = 2 * TV[0][1] * dL_da + TV[1][1] * dL_db,
+                dT02 = 2 * TV[0][2] * dL_da + TV[1][2] * dL_db;
+    const float dT10 = 2 * TV[1][0] * dL_dc + TV[0][0] * dL_db, dT11 = 2 * TV[1][1] * dL_dc + TV[0][1] * dL_db,
+                dT12 = 2 * TV[1][2] * dL_dc + TV[0][2] * dL_db;
+    const float dJ00 = Wm[0][0] * dT00 + Wm[0][1] * dT01 + Wm[0][2] * dT02;
+    const float dJ02 = Wm[2][0] * dT00 + Wm[2][1] * dT01 + Wm[2][2] * dT02;
+    const float dJ11 = Wm[1][0] * dT10 + Wm[1][1] * dT11 + Wm[1][2] * dT12;
+    const float dJ12 = Wm[2][0] * dT10 + Wm[2][1] * dT11 + Wm[2][2] * dT12;
+    const float tz = 1.f / t[2], tz2 = tz * tz, tz3 = tz2 * tz;
+    const float dtx = xgm * -fx * tz2 * dJ02;
+    const float dty = ygm * -fy * tz2 * dJ12;
+    const float dtz = -fx * tz2 * dJ00 - fy * tz2 * dJ11 + (2 * fx * t[0]) * tz3 * dJ02 + (2 * fy * t[1]) * tz3 * dJ12;
+    {   // pose: dpC/drho = I, dpC/dtheta = -skew(t)
+        const float th[3][3] = {{0, -t[2], t[1]}, {t[2], 0, -t[0]}, {-t[1], t[0], 0}};
+        const float d3[3] = {dtx, dty, dtz};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            dtau[k] += d3[k];
+            dtau[k + 3] += dtx * th[k][0] + dty * th[k][1] + dtz * th[k][2];
+        }
+    }
+    dmean[0] = V[0] * dtx + V[1] * dty + V[2] * dtz;
+    dmean[1] = V[4] * dtx + V[5] * dty + V[6] * dtz;
+    dmean[2] = V[8] * dtx + V[9] * dty + V[10] * dtz;
+    {   // dL/dW through T = W * J, folded onto the rotation's so(3) tangent
+        const float dW00 = J[0][0] * dT00, dW01 = J[0][0] * dT01, dW02 = J[0][0] * dT02;
+        const float dW10 = J[1][1] * dT10, dW11 = J[1][1] * dT11, dW12 = J[1][1] * dT12;
+        const float dW20 = J[0][2] * dT00 + J[1][2] * dT10, dW21 = J[0][2] * dT01 + J[1][2] * dT11,
+                    dW22 = J[0][2] * dT02 + J[1][2] * dT12;
+        const float c1[3] = {V[0], V[1], V[2]}, c2[3] = {V[4], V[5], V[6]}, c3_[3] = {V[8], V[9], V[10]};
+        const float w1[3] = {dW00, dW10, dW20}, w2[3] = {dW01, dW11, dW21}, w3[3] = {dW02, dW12, dW22};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            float acc = 0.0f;
+            const float* cs[3] = {c1, c2, c3_};
+            const float* ws[3] = {w1, w2, w3};
+#pragma unroll
+            for (int m = 0; m < 3; m++) {
+                const float* vv = cs[m];
+                const float S[3][3] = {{0, -vv[2], vv[1]}, {vv[2], 0, -vv[0]}, {-vv[1], vv[0], 0}};
+                acc += ws[m][0] * S[k][0] + ws[m][1] * S[k][1] + ws[m][2] * S[k][2];
+            }
+            dtau[3 + k] += acc;
+        }
+    }
+}
+
+// language_preprocessCUDA (backward.cu:541-682): projection and depth paths of the mean / pose gradient
+__device__ __forceinline__ void geom_proj_bwd(const float* V, const float* Pm, const float* Praw, const float* mp,
+                                      float g2x, float g2y, float dzv, float* dmean, float* dtau) {
+    // ---- language_preprocessCUDA (backward.cu:541-682)
+    const float hxw = Pm[0] * mp[0] + Pm[4] * mp[1] + Pm[8] * mp[2] + Pm[12];
+    const float hyw = Pm[1] * mp[0] + Pm[5] * mp[1] + Pm[9] * mp[2] + Pm[13];
+    const float hww = Pm[3] * mp[0] + Pm[7] * mp[1] + Pm[11] * mp[2] + Pm[15];
+    const float m_w = 1.0f / (hww + 0.0000001f);
+    const float mul1 = hxw * m_w * m_w, mul2 = hyw * m_w * m_w;
+    dmean[0] += (Pm[0] * m_w - Pm[3] * mul1) * g2x + (Pm[1] * m_w - Pm[3] * mul2) * g2y;
+    dmean[1] += (Pm[4] * m_w - Pm[7] * mul1) * g2x + (Pm[5] * m_w - Pm[7] * mul2) * g2y;
+    dmean[2] += (Pm[8] * m_w - Pm[11] * mul1) * g2x + (Pm[9] * m_w - Pm[11] * mul2) * g2y;
+    {
+        const float alpha = 1.0f * m_w, beta = -hxw * m_w * m_w, gamma = -hyw * m_w * m_w;
+        const float pa = Praw[0], pb = Praw[5], pe = Praw[11];
+        const float pC[3] = {V[0] * mp[0] + V[4] * mp[1] + V[8] * mp[2] + V[12], V[1] * mp[0] + V[5] * mp[1] + V[9] * mp[2] + V[13],
+                             V[2] * mp[0] + V[6] * mp[1] + V[10] * mp[2] + V[14]};
+        const float d1[3] = {alpha * pa, 0.f, beta * pe}, d2[3] = {0.f, alpha * pb, gamma * pe};
+        const float th[3][3] = {{0, -pC[2], pC[1]}, {pC[2], 0, -pC[0]}, {-pC[1], pC[0], 0}};
+        const float dz = dzv;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            dtau[k] += g2x * d1[k] + g2y * d2[k];
+            const float t1 = th[k][0] * d1[0] + th[k][1] * d1[1] + th[k][2] * d1[2];
+            const float t2 = th[k][0] * d2[0] + th[k][1] * d2[1] + th[k][2] * d2[2];
+            dtau[3 + k] += g2x * t1 + g2y * t2;
+        }
+        dmean[0] += dz * V[2]; dmean[1] += dz * V[6]; dmean[2] += dz * V[10];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            dtau[k] += dz * (k == 2 ? 1.0f : 0.0f);
+            dtau[3 + k] += dz * th[k][2];
+        }
+    }
+}
+
+// computeColorFromSH backward (backward.cu:21-145)
+__device__ __forceinline__ void geom_sh_bwd(const GeomCommon& a, int i, const float* mp, const float* dcol, float* dsh0,
+                                    float* dmean, float* dtau) {
+    const int M = a.M;
+    if (a.shs && !a.colors_precomp) {  // computeColorFromSH backward (backward.cu:21-145)
+        const float* sh = a.shs + (size_t)i * M * 3;
+        float* dsh = a.dL_dsh + (size_t)i * M * 3;  // zeroed above unless accumulating: always add
+        const int deg = a.sh_degree;
+        const float dir0[3] = {mp[0] - a.campos[0], mp[1] - a.campos[1], mp[2] - a.campos[2]};
+        const float len = sqrtf(dir0[0] * dir0[0] + dir0[1] * dir0[1] + dir0[2] * dir0[2]);
+        const float x = dir0[0] / len, y = dir0[1] / len, z = dir0[2] / len;
+        const uint32_t cl = a.clamped[i];
+        float dRGB[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) dRGB[c] = dcol[c] * (((cl >> (8 * c)) & 0xffu) ? 0.f : 1.f);
+        float dx_[3] = {0, 0, 0}, dy_[3] = {0, 0, 0}, dz_[3] = {0, 0, 0};
+        for (int c = 0; c < 3; c++) dsh0[c] = B_SH_C0 * dRGB[c];
+        if (deg > 0) {
+            for (int c = 0; c < 3; c++) {
+                dsh[3 + c] += -B_SH_C1 * y * dRGB[c]; dsh[6 + c] += B_SH_C1 * z * dRGB[c]; dsh[9 + c] += -B_SH_C1 * x * dRGB[c];
+                dx_[c] = -B_SH_C1 * sh[9 + c]; dy_[c] = -B_SH_C1 * sh[3 + c]; dz_[c] = B_SH_C1 * sh[6 + c];
+            }
+            if (deg > 1) {
+                const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                for (int c = 0; c < 3; c++) {
+                    dsh[12 + c] += B_SH_C2[0] * xy * dRGB[c]; dsh[15 + c] += B_SH_C2[1] * yz * dRGB[c];
+                    dsh[18 + c] += B_SH_C2[2] * (2.f * zz - xx - yy) * dRGB[c]; dsh[21 + c] += B_SH_C2[3] * xz * dRGB[c];
+                    dsh[24 + c] += B_SH_C2[4] * (xx - yy) * dRGB[c];
+                    dx_[c] += B_SH_C2[0] * y * sh[12 + c] + B_SH_C2[2] * 2.f * -x * sh[18 + c] + B_SH_C2[3] * z * sh[21 + c] + B_SH_C2[4] * 2.f * x * sh[24 + c];
+                    dy_[c] += B_SH_C2[0] * x * sh[12 + c] + B_SH_C2[1] * z * sh[15 + c] + B_SH_C2[2] * 2.f * -y * sh[18 + c] + B_SH_C2[4] * 2.f * -y * sh[24 + c];
+                    dz_[c] += B_SH_C2[1] * y * sh[15 + c] + B_SH_C2[2] * 2.f * 2.f * z * sh[18 + c] + B_SH_C2[3] * x * sh[21 + c];
+                }
+                if (deg > 2) {
+                    for (int c = 0; c < 3; c++) {
+                        dsh[27 + c] += B_SH_C3[0] * y * (3.f * xx - yy) * dRGB[c]; dsh[30 + c] += B_SH_C3[1] * xy * z * dRGB[c];
+                        dsh[33 + c] += B_SH_C3[2] * y * (4.f * zz - xx - yy) * dRGB[c];
+                        dsh[36 + c] += B_SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy) * dRGB[c];
+                        dsh[39 + c] += B_SH_C3[4] * x * (4.f * zz - xx - yy) * dRGB[c]; dsh[42 + c] += B_SH_C3[5] * z * (xx - yy) * dRGB[c];
+                        dsh[45 + c] += B_SH_C3[6] * x * (xx - 3.f * yy) * dRGB[c];
+                        dx_[c] += (B_SH_C3[0] * sh[27 + c] * 3.f * 2.f * xy + B_SH_C3[1] * sh[30 + c] * yz + B_SH_C3[2] * sh[33 + c] * -2.f * xy +
+                                   B_SH_C3[3] * sh[36 + c] * -3.f * 2.f * xz + B_SH_C3[4] * sh[39 + c] * (-3.f * xx + 4.f * zz - yy) +
+                                   B_SH_C3[5] * sh[42 + c] * 2.f * xz + B_SH_C3[6] * sh[45 + c] * 3.f * (xx - yy));
+                        dy_[c] += (B_SH_C3[0] * sh[27 + c] * 3.f * (xx - yy) + B_SH_C3[1] * sh[30 + c] * xz + B_SH_C3[2] * sh[33 + c] * (-3.f * yy + 4.f * zz - xx) +
+                                   B_SH_C3[3] * sh[36 + c] * -3.f * 2.f * yz + B_SH_C3[4] * sh[39 + c] * -2.f * xy + B_SH_C3[5] * sh[42 + c] * -2.f * yz +
+                                   B_SH_C3[6] * sh[45 + c] * -3.f * 2.f * xy);
+                        dz_[c] += (B_SH_C3[1] * sh[30 + c] * xy + B_SH_C3[2] * sh[33 + c] * 4.f * 2.f * yz + B_SH_C3[3] * sh[36 + c] * 3.f * (2.f * zz - xx - yy) +
+                                   B_SH_C3[4] * sh[39 + c] * 4.f * 2.f * xz + B_SH_C3[5] * sh[42 + c] * (xx - yy));
+                    }
+                }
+            }
+        }
+        const float ddir[3] = {dx_[0] * dRGB[0] + dx_[1] * dRGB[1] + dx_[2] * dRGB[2], dy_[0] * dRGB[0] + dy_[1] * dRGB[1] + dy_[2] * dRGB[2],
+                               dz_[0] * dRGB[0] + dz_[1] * dRGB[1] + dz_[2] * dRGB[2]};
+        const float sum2 = dir0[0] * dir0[0] + dir0[1] * dir0[1] + dir0[2] * dir0[2];
+        const float inv32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+        const float dm[3] = {((+sum2 - dir0[0] * dir0[0]) * ddir[0] - dir0[1] * dir0[0] * ddir[1] - dir0[2] * dir0[0] * ddir[2]) * inv32,
+                             (-dir0[0] * dir0[1] * ddir[0] + (sum2 - dir0[1] * dir0[1]) * ddir[1] - dir0[2] * dir0[1] * ddir[2]) * inv32,
+                             (-dir0[0] * dir0[2] * ddir[0] - dir0[1] * dir0[2] * ddir[1] + (sum2 - dir0[2] * dir0[2]) * ddir[2]) * inv32};
+#pragma unroll
+        for (int k = 0; k < 3; k++) { dmean[k] += dm[k]; dtau[k] += -dm[k]; }
+    }
+}
+
+// computeCov3D backward (backward.cu:350-413); no quaternion-normalisation Jacobian (:412)
+__device__ __forceinline__ void geom_cov3d_bwd(const float* scales, const float* rotations, float scale_modifier_, int i,
+                                       const float* dcov, float* dsc, float* dq) {
+    if (scales) {  // computeCov3D backward (backward.cu:350-413); no quaternion-normalisation Jacobian (:412)
+        const float4 q = reinterpret_cast<const float4*>(rotations)[i];
+        const float* sc = scales + 3 * (size_t)i;
+        const float r = q.x, x = q.y, y = q.z, z = q.w;
+        const float Rm[3][3] = {{1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
+                                {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
+                                {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};
+        const float sv[3] = {scale_modifier_ * sc[0], scale_modifier_ * sc[1], scale_modifier_ * sc[2]};
+        float Mm[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int rr = 0; rr < 3; rr++) Mm[c][rr] = sv[rr] * Rm[c][rr];
+        const float dS[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]}, {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]}, {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
+        float dMt[3][3];  // transpose of dL_dM = 2 * M * dL_dSigma
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int rr = 0; rr < 3; rr++) dMt[rr][c] = 2.0f * (Mm[0][rr] * dS[c][0] + Mm[1][rr] * dS[c][1] + Mm[2][rr] * dS[c][2]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) dsc[k] = Rm[0][k] * dMt[k][0] + Rm[1][k] * dMt[k][1] + Rm[2][k] * dMt[k][2];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+            for (int rr = 0; rr < 3; rr++) dMt[k][rr] *= sv[k];
+        dq[0] = 2 * z * (dMt[0][1] - dMt[1][0]) + 2 * y * (dMt[2][0] - dMt[0][2]) + 2 * x * (dMt[1][2] - dMt[2][1]);
+        dq[1] = 2 * y * (dMt[1][0] + dMt[0][1]) + 2 * z * (dMt[2][0] + dMt[0][2]) + 2 * r * (dMt[1][2] - dMt[2][1]) - 4 * x * (dMt[2][2] + dMt[1][1]);
+        dq[2] = 2 * x * (dMt[1][0] + dMt[0][1]) + 2 * r * (dMt[2][0] - dMt[0][2]) + 2 * z * (dMt[1][2] + dMt[2][1]) - 4 * y * (dMt[2][2] + dMt[0][0]);
+        dq[3] = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) - 4 * z * (dMt[1][1] + dMt[0][0]);
+    }
+}
 
 template <int F>
 __global__ void __launch_bounds__(256) k_geometry_bwd(const GeomBwdArgs a) {
@@ -317,216 +578,12 @@ __global__ void __launch_bounds__(256) k_geometry_bwd(const GeomBwdArgs a) {
 
     if (vis) {
         const float* V = a.viewmatrix;
-        const float* Pm = a.projmatrix;
-        const float* Praw = a.projmatrix_raw;
         const float* c3 = a.cov3D + 6 * (size_t)i;
         const float mp[3] = {a.means3D[3 * (size_t)i], a.means3D[3 * (size_t)i + 1], a.means3D[3 * (size_t)i + 2]};
-        const float fx = a.focal_x, fy = a.focal_y;
-        // ---- computeCov2DCUDA (backward.cu:150-346)
-        const float dcx = gr[GR_CX], dcy = gr[GR_CY], dcz = gr[GR_CW];
-        float t[3] = {V[0] * mp[0] + V[4] * mp[1] + V[8] * mp[2] + V[12], V[1] * mp[0] + V[5] * mp[1] + V[9] * mp[2] + V[13],
-                      V[2] * mp[0] + V[6] * mp[1] + V[10] * mp[2] + V[14]};
-        const float limx = 1.3f * a.tanfovx, limy = 1.3f * a.tanfovy;
-        const float txtz = t[0] / t[2], tytz = t[1] / t[2];
-        t[0] = fminf(limx, fmaxf(-limx, txtz)) * t[2];
-        t[1] = fminf(limy, fmaxf(-limy, tytz)) * t[2];
-        const float xgm = (txtz < -limx || txtz > limx) ? 0.0f : 1.0f;
-        const float ygm = (tytz < -limy || tytz > limy) ? 0.0f : 1.0f;
-        // column-major like GLM: X[c][r]
-        const float J[3][3] = {{fx / t[2], 0, -(fx * t[0]) / (t[2] * t[2])}, {0, fy / t[2], -(fy * t[1]) / (t[2] * t[2])}, {0, 0, 0}};
-        const float Wm[3][3] = {{V[0], V[4], V[8]}, {V[1], V[5], V[9]}, {V[2], V[6], V[10]}};
-        const float Vrk[3][3] = {{c3[0], c3[1], c3[2]}, {c3[1], c3[3], c3[4]}, {c3[2], c3[4], c3[5]}};
-        float Tm[3][3];
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-#pragma unroll
-            for (int r = 0; r < 3; r++) Tm[c][r] = Wm[0][r] * J[c][0] + Wm[1][r] * J[c][1] + Wm[2][r] * J[c][2];
-        float TV[2][3];  // TV[i][q] = sum_p Tm[i][p] * Vrk[p][q]
-#pragma unroll
-        for (int ii = 0; ii < 2; ii++)
-#pragma unroll
-            for (int q = 0; q < 3; q++) TV[ii][q] = Tm[ii][0] * Vrk[0][q] + Tm[ii][1] * Vrk[1][q] + Tm[ii][2] * Vrk[2][q];
-        const float ca = TV[0][0] * Tm[0][0] + TV[0][1] * Tm[0][1] + TV[0][2] * Tm[0][2] + 0.3f;
-        const float cb = TV[0][0] * Tm[1][0] + TV[0][1] * Tm[1][1] + TV[0][2] * Tm[1][2];
-        const float cc = TV[1][0] * Tm[1][0] + TV[1][1] * Tm[1][1] + TV[1][2] * Tm[1][2] + 0.3f;
-        const float denom = ca * cc - cb * cb;
-        float dL_da = 0, dL_db = 0, dL_dc = 0;
-        const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
-        if (denom2inv != 0) {
-            dL_da = denom2inv * (-cc * cc * dcx + 2 * cb * cc * dcy + (denom - ca * cc) * dcz);
-            dL_dc = denom2inv * (-ca * ca * dcz + 2 * ca * cb * dcy + (denom - ca * cc) * dcx);
-            dL_db = denom2inv * 2 * (cb * cc * dcx - (denom + 2 * cb * cb) * dcy + ca * cb * dcz);
-            dcov[0] = (Tm[0][0] * Tm[0][0] * dL_da + Tm[0][0] * Tm[1][0] * dL_db + Tm[1][0] * Tm[1][0] * dL_dc);
-            dcov[3] = (Tm[0][1] * Tm[0][1] * dL_da + Tm[0][1] * Tm[1][1] * dL_db + Tm[1][1] * Tm[1][1] * dL_dc);
-            dcov[5] = (Tm[0][2] * Tm[0][2] * dL_da + Tm[0][2] * Tm[1][2] * dL_db + Tm[1][2] * Tm[1][2] * dL_dc);
-            dcov[1] = 2 * Tm[0][0] * Tm[0][1] * dL_da + (Tm[0][0] * Tm[1][1] + Tm[0][1] * Tm[1][0]) * dL_db + 2 * Tm[1][0] * Tm[1][1] * dL_dc;
-            dcov[2] = 2 * Tm[0][0] * Tm[0][2] * dL_da + (Tm[0][0] * Tm[1][2] + Tm[0][2] * Tm[1][0]) * dL_db + 2 * Tm[1][0] * Tm[1][2] * dL_dc;
-            dcov[4] = 2 * Tm[0][2] * Tm[0][1] * dL_da + (Tm[0][1] * Tm[1][2] + Tm[0][2] * Tm[1][1]) * dL_db + 2 * Tm[1][1] * Tm[1][2] * dL_dc;
-        }
-        // TV[r][k] equals the reference's (T[r] . Vrk[k]) because Vrk is symmetric
-        const float dT00 = 2 * TV[0][0] * dL_da + TV[1][0] * dL_db, dT01 = 2 * TV[0][1] * dL_da + TV[1][1] * dL_db,
-                    dT02 = 2 * TV[0][2] * dL_da + TV[1][2] * dL_db;
-        const float dT10 = 2 * TV[1][0] * dL_dc + TV[0][0] * dL_db, dT11 = 2 * TV[1][1] * dL_dc + TV[0][1] * dL_db,
-                    dT12 = 2 * TV[1][2] * dL_dc + TV[0][2] * dL_db;
-        const float dJ00 = Wm[0][0] * dT00 + Wm[0][1] * dT01 + Wm[0][2] * dT02;
-        const float dJ02 = Wm[2][0] * dT00 + Wm[2][1] * dT01 + Wm[2][2] * dT02;
-        const float dJ11 = Wm[1][0] * dT10 + Wm[1][1] * dT11 + Wm[1][2] * dT12;
-        const float dJ12 = Wm[2][0] * dT10 + Wm[2][1] * dT11 + Wm[2][2] * dT12;
-        const float tz = 1.f / t[2], tz2 = tz * tz, tz3 = tz2 * tz;
-        const float dtx = xgm * -fx * tz2 * dJ02;
-        const float dty = ygm * -fy * tz2 * dJ12;
-        const float dtz = -fx * tz2 * dJ00 - fy * tz2 * dJ11 + (2 * fx * t[0]) * tz3 * dJ02 + (2 * fy * t[1]) * tz3 * dJ12;
-        {   // pose: dpC/drho = I, dpC/dtheta = -skew(t)
-            const float th[3][3] = {{0, -t[2], t[1]}, {t[2], 0, -t[0]}, {-t[1], t[0], 0}};
-            const float d3[3] = {dtx, dty, dtz};
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                dtau[k] += d3[k];
-                dtau[k + 3] += dtx * th[k][0] + dty * th[k][1] + dtz * th[k][2];
-            }
-        }
-        dmean[0] = V[0] * dtx + V[1] * dty + V[2] * dtz;
-        dmean[1] = V[4] * dtx + V[5] * dty + V[6] * dtz;
-        dmean[2] = V[8] * dtx + V[9] * dty + V[10] * dtz;
-        {   // dL/dW through T = W * J, folded onto the rotation's so(3) tangent
-            const float dW00 = J[0][0] * dT00, dW01 = J[0][0] * dT01, dW02 = J[0][0] * dT02;
-            const float dW10 = J[1][1] * dT10, dW11 = J[1][1] * dT11, dW12 = J[1][1] * dT12;
-            const float dW20 = J[0][2] * dT00 + J[1][2] * dT10, dW21 = J[0][2] * dT01 + J[1][2] * dT11,
-                        dW22 = J[0][2] * dT02 + J[1][2] * dT12;
-            const float c1[3] = {V[0], V[1], V[2]}, c2[3] = {V[4], V[5], V[6]}, c3_[3] = {V[8], V[9], V[10]};
-            const float w1[3] = {dW00, dW10, dW20}, w2[3] = {dW01, dW11, dW21}, w3[3] = {dW02, dW12, dW22};
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                float acc = 0.0f;
-                const float* cs[3] = {c1, c2, c3_};
-                const float* ws[3] = {w1, w2, w3};
-#pragma unroll
-                for (int m = 0; m < 3; m++) {
-                    const float* vv = cs[m];
-                    const float S[3][3] = {{0, -vv[2], vv[1]}, {vv[2], 0, -vv[0]}, {-vv[1], vv[0], 0}};
-                    acc += ws[m][0] * S[k][0] + ws[m][1] * S[k][1] + ws[m][2] * S[k][2];
-                }
-                dtau[3 + k] += acc;
-            }
-        }
-        // ---- language_preprocessCUDA (backward.cu:541-682)
-        const float hxw = Pm[0] * mp[0] + Pm[4] * mp[1] + Pm[8] * mp[2] + Pm[12];
-        const float hyw = Pm[1] * mp[0] + Pm[5] * mp[1] + Pm[9] * mp[2] + Pm[13];
-        const float hww = Pm[3] * mp[0] + Pm[7] * mp[1] + Pm[11] * mp[2] + Pm[15];
-        const float m_w = 1.0f / (hww + 0.0000001f);
-        const float mul1 = hxw * m_w * m_w, mul2 = hyw * m_w * m_w;
-        dmean[0] += (Pm[0] * m_w - Pm[3] * mul1) * g2x + (Pm[1] * m_w - Pm[3] * mul2) * g2y;
-        dmean[1] += (Pm[4] * m_w - Pm[7] * mul1) * g2x + (Pm[5] * m_w - Pm[7] * mul2) * g2y;
-        dmean[2] += (Pm[8] * m_w - Pm[11] * mul1) * g2x + (Pm[9] * m_w - Pm[11] * mul2) * g2y;
-        {
-            const float alpha = 1.0f * m_w, beta = -hxw * m_w * m_w, gamma = -hyw * m_w * m_w;
-            const float pa = Praw[0], pb = Praw[5], pe = Praw[11];
-            const float pC[3] = {V[0] * mp[0] + V[4] * mp[1] + V[8] * mp[2] + V[12], V[1] * mp[0] + V[5] * mp[1] + V[9] * mp[2] + V[13],
-                                 V[2] * mp[0] + V[6] * mp[1] + V[10] * mp[2] + V[14]};
-            const float d1[3] = {alpha * pa, 0.f, beta * pe}, d2[3] = {0.f, alpha * pb, gamma * pe};
-            const float th[3][3] = {{0, -pC[2], pC[1]}, {pC[2], 0, -pC[0]}, {-pC[1], pC[0], 0}};
-            const float dz = gr[GR_DEPTH];
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                dtau[k] += g2x * d1[k] + g2y * d2[k];
-                const float t1 = th[k][0] * d1[0] + th[k][1] * d1[1] + th[k][2] * d1[2];
-                const float t2 = th[k][0] * d2[0] + th[k][1] * d2[1] + th[k][2] * d2[2];
-                dtau[3 + k] += g2x * t1 + g2y * t2;
-            }
-            dmean[0] += dz * V[2]; dmean[1] += dz * V[6]; dmean[2] += dz * V[10];
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                dtau[k] += dz * (k == 2 ? 1.0f : 0.0f);
-                dtau[3 + k] += dz * th[k][2];
-            }
-        }
-        if (a.shs && !a.colors_precomp) {  // computeColorFromSH backward (backward.cu:21-145)
-            const float* sh = a.shs + (size_t)i * M * 3;
-            float* dsh = a.dL_dsh + (size_t)i * M * 3;  // zeroed above unless accumulating: always add
-            const int deg = a.sh_degree;
-            const float dir0[3] = {mp[0] - a.campos[0], mp[1] - a.campos[1], mp[2] - a.campos[2]};
-            const float len = sqrtf(dir0[0] * dir0[0] + dir0[1] * dir0[1] + dir0[2] * dir0[2]);
-            const float x = dir0[0] / len, y = dir0[1] / len, z = dir0[2] / len;
-            const uint32_t cl = a.clamped[i];
-            float dRGB[3];
-#pragma unroll
-            for (int c = 0; c < 3; c++) dRGB[c] = dcol[c] * (((cl >> (8 * c)) & 0xffu) ? 0.f : 1.f);
-            float dx_[3] = {0, 0, 0}, dy_[3] = {0, 0, 0}, dz_[3] = {0, 0, 0};
-            for (int c = 0; c < 3; c++) dsh0[c] = B_SH_C0 * dRGB[c];
-            if (deg > 0) {
-                for (int c = 0; c < 3; c++) {
-                    dsh[3 + c] += -B_SH_C1 * y * dRGB[c]; dsh[6 + c] += B_SH_C1 * z * dRGB[c]; dsh[9 + c] += -B_SH_C1 * x * dRGB[c];
-                    dx_[c] = -B_SH_C1 * sh[9 + c]; dy_[c] = -B_SH_C1 * sh[3 + c]; dz_[c] = B_SH_C1 * sh[6 + c];
-                }
-                if (deg > 1) {
-                    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-                    for (int c = 0; c < 3; c++) {
-                        dsh[12 + c] += B_SH_C2[0] * xy * dRGB[c]; dsh[15 + c] += B_SH_C2[1] * yz * dRGB[c];
-                        dsh[18 + c] += B_SH_C2[2] * (2.f * zz - xx - yy) * dRGB[c]; dsh[21 + c] += B_SH_C2[3] * xz * dRGB[c];
-                        dsh[24 + c] += B_SH_C2[4] * (xx - yy) * dRGB[c];
-                        dx_[c] += B_SH_C2[0] * y * sh[12 + c] + B_SH_C2[2] * 2.f * -x * sh[18 + c] + B_SH_C2[3] * z * sh[21 + c] + B_SH_C2[4] * 2.f * x * sh[24 + c];
-                        dy_[c] += B_SH_C2[0] * x * sh[12 + c] + B_SH_C2[1] * z * sh[15 + c] + B_SH_C2[2] * 2.f * -y * sh[18 + c] + B_SH_C2[4] * 2.f * -y * sh[24 + c];
-                        dz_[c] += B_SH_C2[1] * y * sh[15 + c] + B_SH_C2[2] * 2.f * 2.f * z * sh[18 + c] + B_SH_C2[3] * x * sh[21 + c];
-                    }
-                    if (deg > 2) {
-                        for (int c = 0; c < 3; c++) {
-                            dsh[27 + c] += B_SH_C3[0] * y * (3.f * xx - yy) * dRGB[c]; dsh[30 + c] += B_SH_C3[1] * xy * z * dRGB[c];
-                            dsh[33 + c] += B_SH_C3[2] * y * (4.f * zz - xx - yy) * dRGB[c];
-                            dsh[36 + c] += B_SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy) * dRGB[c];
-                            dsh[39 + c] += B_SH_C3[4] * x * (4.f * zz - xx - yy) * dRGB[c]; dsh[42 + c] += B_SH_C3[5] * z * (xx - yy) * dRGB[c];
-                            dsh[45 + c] += B_SH_C3[6] * x * (xx - 3.f * yy) * dRGB[c];
-                            dx_[c] += (B_SH_C3[0] * sh[27 + c] * 3.f * 2.f * xy + B_SH_C3[1] * sh[30 + c] * yz + B_SH_C3[2] * sh[33 + c] * -2.f * xy +
-                                       B_SH_C3[3] * sh[36 + c] * -3.f * 2.f * xz + B_SH_C3[4] * sh[39 + c] * (-3.f * xx + 4.f * zz - yy) +
-                                       B_SH_C3[5] * sh[42 + c] * 2.f * xz + B_SH_C3[6] * sh[45 + c] * 3.f * (xx - yy));
-                            dy_[c] += (B_SH_C3[0] * sh[27 + c] * 3.f * (xx - yy) + B_SH_C3[1] * sh[30 + c] * xz + B_SH_C3[2] * sh[33 + c] * (-3.f * yy + 4.f * zz - xx) +
-                                       B_SH_C3[3] * sh[36 + c] * -3.f * 2.f * yz + B_SH_C3[4] * sh[39 + c] * -2.f * xy + B_SH_C3[5] * sh[42 + c] * -2.f * yz +
-                                       B_SH_C3[6] * sh[45 + c] * -3.f * 2.f * xy);
-                            dz_[c] += (B_SH_C3[1] * sh[30 + c] * xy + B_SH_C3[2] * sh[33 + c] * 4.f * 2.f * yz + B_SH_C3[3] * sh[36 + c] * 3.f * (2.f * zz - xx - yy) +
-                                       B_SH_C3[4] * sh[39 + c] * 4.f * 2.f * xz + B_SH_C3[5] * sh[42 + c] * (xx - yy));
-                        }
-                    }
-                }
-            }
-            const float ddir[3] = {dx_[0] * dRGB[0] + dx_[1] * dRGB[1] + dx_[2] * dRGB[2], dy_[0] * dRGB[0] + dy_[1] * dRGB[1] + dy_[2] * dRGB[2],
-                                   dz_[0] * dRGB[0] + dz_[1] * dRGB[1] + dz_[2] * dRGB[2]};
-            const float sum2 = dir0[0] * dir0[0] + dir0[1] * dir0[1] + dir0[2] * dir0[2];
-            const float inv32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
-            const float dm[3] = {((+sum2 - dir0[0] * dir0[0]) * ddir[0] - dir0[1] * dir0[0] * ddir[1] - dir0[2] * dir0[0] * ddir[2]) * inv32,
-                                 (-dir0[0] * dir0[1] * ddir[0] + (sum2 - dir0[1] * dir0[1]) * ddir[1] - dir0[2] * dir0[1] * ddir[2]) * inv32,
-                                 (-dir0[0] * dir0[2] * ddir[0] - dir0[1] * dir0[2] * ddir[1] + (sum2 - dir0[2] * dir0[2]) * ddir[2]) * inv32};
-#pragma unroll
-            for (int k = 0; k < 3; k++) { dmean[k] += dm[k]; dtau[k] += -dm[k]; }
-        }
-        if (a.scales) {  // computeCov3D backward (backward.cu:350-413); no quaternion-normalisation Jacobian (:412)
-            const float4 q = reinterpret_cast<const float4*>(a.rotations)[i];
-            const float* sc = a.scales + 3 * (size_t)i;
-            const float r = q.x, x = q.y, y = q.z, z = q.w;
-            const float Rm[3][3] = {{1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
-                                    {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
-                                    {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};
-            const float sv[3] = {a.scale_modifier * sc[0], a.scale_modifier * sc[1], a.scale_modifier * sc[2]};
-            float Mm[3][3];
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-#pragma unroll
-                for (int rr = 0; rr < 3; rr++) Mm[c][rr] = sv[rr] * Rm[c][rr];
-            const float dS[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]}, {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]}, {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
-            float dMt[3][3];  // transpose of dL_dM = 2 * M * dL_dSigma
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-#pragma unroll
-                for (int rr = 0; rr < 3; rr++) dMt[rr][c] = 2.0f * (Mm[0][rr] * dS[c][0] + Mm[1][rr] * dS[c][1] + Mm[2][rr] * dS[c][2]);
-#pragma unroll
-            for (int k = 0; k < 3; k++) dsc[k] = Rm[0][k] * dMt[k][0] + Rm[1][k] * dMt[k][1] + Rm[2][k] * dMt[k][2];
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-#pragma unroll
-                for (int rr = 0; rr < 3; rr++) dMt[k][rr] *= sv[k];
-            dq[0] = 2 * z * (dMt[0][1] - dMt[1][0]) + 2 * y * (dMt[2][0] - dMt[0][2]) + 2 * x * (dMt[1][2] - dMt[2][1]);
-            dq[1] = 2 * y * (dMt[1][0] + dMt[0][1]) + 2 * z * (dMt[2][0] + dMt[0][2]) + 2 * r * (dMt[1][2] - dMt[2][1]) - 4 * x * (dMt[2][2] + dMt[1][1]);
-            dq[2] = 2 * x * (dMt[1][0] + dMt[0][1]) + 2 * r * (dMt[2][0] - dMt[0][2]) + 2 * z * (dMt[1][2] + dMt[2][1]) - 4 * y * (dMt[2][2] + dMt[0][0]);
-            dq[3] = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) - 4 * z * (dMt[1][1] + dMt[0][0]);
-        }
+        geom_cov2d_bwd(a, V, mp, c3, gr[GR_CX], gr[GR_CY], gr[GR_CW], dcov, dmean, dtau);
+        geom_proj_bwd(V, a.projmatrix, a.projmatrix_raw, mp, g2x, g2y, gr[GR_DEPTH], dmean, dtau);
+        geom_sh_bwd(a, i, mp, dcol, dsh0, dmean, dtau);
+        geom_cov3d_bwd(a.scales, a.rotations, a.scale_modifier, i, dcov, dsc, dq);
     }
     // ---- outputs: when accumulating, fetch every old value first (independent loads), then store ----
     float o_mean[3], o_cov[6], o_sc[3], o_q[4], o_op, o_col[3], o_lang[F], o_sh[3];
@@ -580,12 +637,99 @@ __global__ void __launch_bounds__(256) k_geometry_bwd(const GeomBwdArgs a) {
     for (int k = 0; k < F; k++) p_lang[k] = o_lang[k] + gr[GR_LANG + k];
 }
 
-template <int TILE, int F>
+// ---------------------------------------------------------------------------------------------------
+// Disentangled variant: one thread per Gaussian, both footprints.  Reference order of operations
+// (D/backward.cu:1504-1618): computeCov2DCUDA for radii > 0, computeCov2DCUDA_no_tau for radii_lang > 0,
+// then language_preprocessCUDA -- which returns early unless BOTH radii are positive (:676-677), so in
+// compat mode the projection / depth / SH / scale / rotation gradients of either footprint only exist for
+// Gaussians visible in both lists.  Exact mode gates every term by the footprint it belongs to.
+struct GeomDisArgs : GeomCommon {
+    const float *scales, *rotations, *cov3D, *scales_lang, *rotations_lang, *cov3D_lang;
+    const int32_t *radii, *radii_lang;
+    const float* gacc_lang;
+    bool exact;
+    float *dL_dmeans2D, *dL_dcolors, *dL_dlanguage, *dL_dopacity, *dL_dopacity_lang, *dL_dmeans3D, *dL_dcov3D,
+        *dL_dcov3D_lang, *dL_dscales, *dL_dscales_lang, *dL_drots, *dL_drots_lang, *dL_dtau;
+};
+
+template <int F>
+__global__ void __launch_bounds__(256) k_geometry_bwd_dis(const GeomDisArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.P) return;
+    const int M = a.M;
+    constexpr int GRC = grad_floats(0), GRL = grad_floats(F);
+    float gc[GRC], gl[GRL];
+    {
+        const float4* src = reinterpret_cast<const float4*>(a.gacc + (size_t)i * GRC);
+#pragma unroll
+        for (int q = 0; q < GRC / 4; q++) {
+            const float4 v = src[q];
+            gc[4 * q] = v.x; gc[4 * q + 1] = v.y; gc[4 * q + 2] = v.z; gc[4 * q + 3] = v.w;
+        }
+        const float4* srl = reinterpret_cast<const float4*>(a.gacc_lang + (size_t)i * GRL);
+#pragma unroll
+        for (int q = 0; q < GRL / 4; q++) {
+            const float4 v = srl[q];
+            gl[4 * q] = v.x; gl[4 * q + 1] = v.y; gl[4 * q + 2] = v.z; gl[4 * q + 3] = v.w;
+        }
+    }
+    float dmean[3] = {0, 0, 0}, dcov[6] = {0, 0, 0, 0, 0, 0}, dcovl[6] = {0, 0, 0, 0, 0, 0}, dtau[6] = {0, 0, 0, 0, 0, 0};
+    float dsc[3] = {0, 0, 0}, dq[4] = {0, 0, 0, 0}, dscl[3] = {0, 0, 0}, dql[4] = {0, 0, 0, 0};
+    float dcol[3] = {gc[GR_RGB], gc[GR_RGB + 1], gc[GR_RGB + 2]};
+    float dsh0[3] = {0, 0, 0};
+    const bool vis_c = a.radii[i] > 0, vis_l = a.radii_lang[i] > 0;
+    const float g2x = gc[GR_MX], g2y = gc[GR_MY];
+    if (a.dL_dsh && M > 1)
+        for (int k = 3; k < 3 * M; k++) a.dL_dsh[(size_t)3 * M * i + k] = 0.0f;
+    const float* V = a.viewmatrix;
+    const float mp[3] = {a.means3D[3 * (size_t)i], a.means3D[3 * (size_t)i + 1], a.means3D[3 * (size_t)i + 2]};
+    if (vis_c) geom_cov2d_bwd(a, V, mp, a.cov3D + 6 * (size_t)i, gc[GR_CX], gc[GR_CY], gc[GR_CW], dcov, dmean, dtau);
+    if (vis_l) {
+        float dm_unused[3] = {0, 0, 0}, dt_unused[6] = {0, 0, 0, 0, 0, 0};
+        geom_cov2d_bwd(a, V, mp, a.cov3D_lang + 6 * (size_t)i, gl[GR_CX], gl[GR_CY], gl[GR_CW], dcovl, dm_unused, dt_unused);
+    }
+    const bool both = vis_c && vis_l;
+    if (a.exact ? vis_c : both) {
+        geom_proj_bwd(V, a.projmatrix, a.projmatrix_raw, mp, g2x, g2y, gc[GR_DEPTH], dmean, dtau);
+        geom_sh_bwd(a, i, mp, dcol, dsh0, dmean, dtau);
+        geom_cov3d_bwd(a.scales, a.rotations, a.scale_modifier, i, dcov, dsc, dq);
+    }
+    if (a.exact ? vis_l : both) geom_cov3d_bwd(a.scales_lang, a.rotations_lang, a.scale_modifier, i, dcovl, dscl, dql);
+
+    a.dL_dmeans2D[3 * (size_t)i] = g2x;
+    a.dL_dmeans2D[3 * (size_t)i + 1] = g2y;
+    a.dL_dmeans2D[3 * (size_t)i + 2] = 0.0f;
+    a.dL_dopacity[i] = gc[GR_OP];
+    a.dL_dopacity_lang[i] = gl[GR_OP];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        a.dL_dmeans3D[3 * (size_t)i + k] = dmean[k];
+        a.dL_dscales[3 * (size_t)i + k] = dsc[k];
+        a.dL_dscales_lang[3 * (size_t)i + k] = dscl[k];
+        a.dL_dcolors[3 * (size_t)i + k] = dcol[k];
+        if (a.dL_dsh) a.dL_dsh[(size_t)3 * M * i + k] = dsh0[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        a.dL_dcov3D[6 * (size_t)i + k] = dcov[k];
+        a.dL_dcov3D_lang[6 * (size_t)i + k] = dcovl[k];
+        a.dL_dtau[6 * (size_t)i + k] = dtau[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        a.dL_drots[4 * (size_t)i + k] = dq[k];
+        a.dL_drots_lang[4 * (size_t)i + k] = dql[k];
+    }
+#pragma unroll
+    for (int k = 0; k < F; k++) a.dL_dlanguage[(size_t)F * i + k] = gl[GR_LANG + k];
+}
+
+template <int TILE, int NCOL, int F>
 static void launch_blend_bwd(const BwdBlendArgs& ba, int n_tiles, bool exact, cudaStream_t st) {
     if (exact)
-        k_blend_bwd<TILE, F, false><<<n_tiles, BWD_THREADS, 0, st>>>(ba);
+        k_blend_bwd<TILE, NCOL, F, false><<<n_tiles, BWD_THREADS, 0, st>>>(ba);
     else
-        k_blend_bwd<TILE, F, true><<<n_tiles, BWD_THREADS, 0, st>>>(ba);
+        k_blend_bwd<TILE, NCOL, F, true><<<n_tiles, BWD_THREADS, 0, st>>>(ba);
 }
 
 }  // namespace ols
@@ -594,80 +738,141 @@ using namespace ols;
 
 size_t ols_bwd_scratch_bytes(int P, int F) { return sizeof(float) * (size_t)grad_floats(F) * (size_t)(P > 0 ? P : 1); }
 
-int ols_launch_backward(const ols_raster_args* a, const ols_bwd_args* g, const WsLayout& L, cudaStream_t st) {
-    char* ws = (char*)a->d_workspace;
-    const bool debug = (a->flags & OLS_FLAG_DEBUG) != 0;
-    const bool exact = (a->flags & OLS_FLAG_BWD_EXACT) != 0;
-    float* gacc = (float*)(ws + L.gacc);
-    OLS_CUDA_TRY(cudaMemsetAsync(gacc, 0, ols_bwd_scratch_bytes(a->P, a->F), st));
-    ols_timing_mark(-1, st);
-
-    BwdBlendArgs ba;
-    ba.W = a->W; ba.H = a->H; ba.gx = L.gx;
-    ba.ranges = (const uint2*)(ws + L.ranges); ba.point_list = (const uint32_t*)(ws + L.point_list);
-    ba.records = (const float*)(ws + L.records); ba.bg = a->d_bg; ba.info = (const DeviceInfo*)(ws + L.info);
-    ba.final_T = (const float*)(ws + L.final_T); ba.n_contrib = (const uint32_t*)(ws + L.n_contrib);
-    ba.dL_dcolor = g->d_dL_dout_color; ba.dL_dlanguage = g->d_dL_dout_language; ba.dL_ddepth = g->d_dL_dout_depth;
-    ba.gacc = gacc;
-    {   // Q3: lanes of an n-thread block that reach data[0] in the reference's tree reduction
-        // (render_cuda_reduce_sum, backward.cu:684-702: i = n/2, n/4, ... with integer division)
-        const int n = a->tile * a->tile;
-        bool reach[256];
-        for (int k = 0; k < 256; k++) reach[k] = false;
-        if (exact) {
-            for (int k = 0; k < 256; k++) reach[k] = true;
-        } else {
-            // walk the reduction backwards: lane l reaches 0 iff repeatedly folding (l -> l - i when i <= l < 2i) ends at 0
-            for (int l = 0; l < n; l++) {
-                int pos = l;
-                bool ok = true;
-                for (int i = n / 2; i > 0; i /= 2) {
-                    if (pos >= i) {
-                        if (pos < 2 * i) pos -= i; else { ok = false; break; }
-                    }
+// Q3: lanes of an n-thread block that reach data[0] in the reference's tree reduction
+// (render_cuda_reduce_sum, backward.cu:684-702: i = n/2, n/4, ... with integer division)
+static void reduce_lane_mask(int n, bool exact, uint32_t* mask8) {
+    bool reach[256];
+    for (int k = 0; k < 256; k++) reach[k] = exact;
+    if (!exact) {
+        // walk the reduction backwards: lane l reaches 0 iff repeatedly folding (l -> l - i when i <= l < 2i) ends at 0
+        for (int l = 0; l < n; l++) {
+            int pos = l;
+            bool ok = true;
+            for (int i = n / 2; i > 0; i /= 2) {
+                if (pos >= i) {
+                    if (pos < 2 * i) pos -= i; else { ok = false; break; }
                 }
-                reach[l] = ok && pos == 0;
             }
-        }
-        for (int w = 0; w < 8; w++) {
-            uint32_t m = 0;
-            for (int b = 0; b < 32; b++) m |= (uint32_t)reach[w * 32 + b] << b;
-            ba.lane_ok[w] = m;
+            reach[l] = ok && pos == 0;
         }
     }
-    if (a->tile == 15 && a->F == 15) launch_blend_bwd<15, 15>(ba, L.n_tiles, exact, st);
-    else if (a->tile == 16 && a->F == 15) launch_blend_bwd<16, 15>(ba, L.n_tiles, exact, st);
-    else if (a->tile == 15 && a->F == 3) launch_blend_bwd<15, 3>(ba, L.n_tiles, exact, st);
-    else if (a->tile == 16 && a->F == 3) launch_blend_bwd<16, 3>(ba, L.n_tiles, exact, st);
-    else { ols_set_error("unsupported (tile=%d, F=%d)", a->tile, a->F); return OLS_ERR_UNSUPPORTED; }
+    for (int w = 0; w < 8; w++) {
+        uint32_t m = 0;
+        for (int b = 0; b < 32; b++) m |= (uint32_t)reach[w * 32 + b] << b;
+        mask8[w] = m;
+    }
+}
+
+// backward blend of one pass (its own sorted list, records, final_T, n_contrib and gradient scratch)
+static int run_blend_bwd(int W, int H, int tile, int ncol, int F, unsigned flags, char* ws, const WsLayout& L, const float* d_bg,
+                         const float* dL_dcolor, const float* dL_dlanguage, const float* dL_ddepth, cudaStream_t st) {
+    const bool exact = (flags & OLS_FLAG_BWD_EXACT) != 0;
+    float* gacc = (float*)(ws + L.gacc);
+    BwdBlendArgs ba;
+    ba.W = W; ba.H = H; ba.gx = L.gx;
+    ba.ranges = (const uint2*)(ws + L.ranges); ba.point_list = (const uint32_t*)(ws + L.point_list);
+    ba.records = (const float*)(ws + L.records); ba.bg = d_bg; ba.info = (const DeviceInfo*)(ws + L.info);
+    ba.final_T = (const float*)(ws + L.final_T); ba.n_contrib = (const uint32_t*)(ws + L.n_contrib);
+    ba.dL_dcolor = dL_dcolor; ba.dL_dlanguage = dL_dlanguage; ba.dL_ddepth = dL_ddepth;
+    ba.gacc = gacc;
+    reduce_lane_mask(tile * tile, exact, ba.lane_ok);
+    const int key = tile * 10000 + ncol * 100 + F;
+    switch (key) {
+        case 150315: launch_blend_bwd<15, 3, 15>(ba, L.n_tiles, exact, st); break;
+        case 160315: launch_blend_bwd<16, 3, 15>(ba, L.n_tiles, exact, st); break;
+        case 150303: launch_blend_bwd<15, 3, 3>(ba, L.n_tiles, exact, st); break;
+        case 160303: launch_blend_bwd<16, 3, 3>(ba, L.n_tiles, exact, st); break;
+        case 150300: launch_blend_bwd<15, 3, 0>(ba, L.n_tiles, exact, st); break;
+        case 160300: launch_blend_bwd<16, 3, 0>(ba, L.n_tiles, exact, st); break;
+        case 150003: launch_blend_bwd<15, 0, 3>(ba, L.n_tiles, exact, st); break;
+        case 160003: launch_blend_bwd<16, 0, 3>(ba, L.n_tiles, exact, st); break;
+        case 150015: launch_blend_bwd<15, 0, 15>(ba, L.n_tiles, exact, st); break;
+        case 160015: launch_blend_bwd<16, 0, 15>(ba, L.n_tiles, exact, st); break;
+        default: ols_set_error("unsupported (tile=%d, F=%d)", tile, F); return OLS_ERR_UNSUPPORTED;
+    }
     OLS_CUDA_TRY(cudaGetLastError());
-    if (debug) {
+    if (flags & OLS_FLAG_DEBUG) {
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { ols_set_error("kernel blend_bwd failed: %s", cudaGetErrorString(e)); return OLS_ERR_CUDA; }
     }
+    return OLS_OK;
+}
 
-    ols_timing_mark(OLS_T_BLEND_BWD, st);
-    GeomBwdArgs ga;
+static void fill_geom_common(GeomCommon& ga, const ols_raster_args* a, const char* ws, const WsLayout& L, float* dL_dsh) {
     ga.accumulate = (a->flags & OLS_FLAG_BWD_ACCUMULATE) != 0;
     ga.P = a->P; ga.F = a->F; ga.sh_degree = a->sh_degree; ga.M = a->M; ga.W = a->W; ga.H = a->H; ga.gr = grad_floats(a->F);
     ga.tanfovx = a->tanfovx; ga.tanfovy = a->tanfovy;
     ga.focal_y = a->H / (2.0f * a->tanfovy); ga.focal_x = a->W / (2.0f * a->tanfovx);
     ga.scale_modifier = a->scale_modifier;
-    ga.means3D = a->d_means3D; ga.shs = a->d_shs; ga.scales = a->d_scales; ga.rotations = a->d_rotations;
-    ga.cov3D = a->d_cov3D_precomp ? a->d_cov3D_precomp : (const float*)(ws + L.cov3D);
+    ga.means3D = a->d_means3D; ga.shs = a->d_shs;
     ga.viewmatrix = a->d_viewmatrix; ga.projmatrix = a->d_projmatrix; ga.projmatrix_raw = a->d_projmatrix_raw;
-    ga.campos = a->d_campos; ga.clamped = (const uint32_t*)(ws + L.clamped); ga.radii = g->d_radii; ga.gacc = gacc;
+    ga.campos = a->d_campos; ga.clamped = (const uint32_t*)(ws + L.clamped); ga.gacc = (const float*)(ws + L.gacc);
     ga.colors_precomp = a->d_colors_precomp != nullptr;
+    ga.dL_dsh = (a->d_shs && a->M > 0) ? dL_dsh : nullptr;
+}
+
+int ols_launch_backward(const ols_raster_args* a, const ols_bwd_args* g, const WsLayout& L, cudaStream_t st) {
+    char* ws = (char*)a->d_workspace;
+    const bool debug = (a->flags & OLS_FLAG_DEBUG) != 0;
+    OLS_CUDA_TRY(cudaMemsetAsync(ws + L.gacc, 0, ols_bwd_scratch_bytes(a->P, a->F), st));
+    ols_timing_mark(-1, st);
+    int rc = run_blend_bwd(a->W, a->H, a->tile, 3, a->F, a->flags, ws, L, a->d_bg, g->d_dL_dout_color, g->d_dL_dout_language,
+                           g->d_dL_dout_depth, st);
+    if (rc != OLS_OK) return rc;
+    ols_timing_mark(OLS_T_BLEND_BWD, st);
+    GeomBwdArgs ga;
+    fill_geom_common(ga, a, ws, L, g->d_dL_dsh);
+    ga.scales = a->d_scales; ga.rotations = a->d_rotations;
+    ga.cov3D = a->d_cov3D_precomp ? a->d_cov3D_precomp : (const float*)(ws + L.cov3D);
+    ga.radii = g->d_radii;
     ga.dL_dmeans2D = g->d_dL_dmeans2D; ga.dL_dcolors = g->d_dL_dcolors; ga.dL_dlanguage = g->d_dL_dlanguage;
     ga.dL_dopacity = g->d_dL_dopacity; ga.dL_dmeans3D = g->d_dL_dmeans3D; ga.dL_dcov3D = g->d_dL_dcov3D;
-    ga.dL_dsh = (a->d_shs && a->M > 0) ? g->d_dL_dsh : nullptr; ga.dL_dscales = g->d_dL_dscales;
-    ga.dL_drots = g->d_dL_drotations; ga.dL_dtau = g->d_dL_dtau;
+    ga.dL_dscales = g->d_dL_dscales; ga.dL_drots = g->d_dL_drotations; ga.dL_dtau = g->d_dL_dtau;
     if (a->F == 15) k_geometry_bwd<15><<<(a->P + 255) / 256, 256, 0, st>>>(ga);
     else k_geometry_bwd<3><<<(a->P + 255) / 256, 256, 0, st>>>(ga);
     OLS_CUDA_TRY(cudaGetLastError());
     if (debug) {
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { ols_set_error("kernel geometry_bwd failed: %s", cudaGetErrorString(e)); return OLS_ERR_CUDA; }
+    }
+    ols_timing_mark(OLS_T_GEOMETRY_BWD, st);
+    return OLS_OK;
+}
+
+int ols_launch_backward_dis(const ols_dis_args* d, const ols_dis_bwd_args* g, const WsLayout& Lc, const WsLayout& Ll,
+                            size_t lang_base, cudaStream_t st) {
+    const ols_raster_args* a = &d->base;
+    char* wc = (char*)a->d_workspace;
+    char* wl = wc + lang_base;
+    const bool debug = (a->flags & OLS_FLAG_DEBUG) != 0;
+    OLS_CUDA_TRY(cudaMemsetAsync(wc + Lc.gacc, 0, ols_bwd_scratch_bytes(a->P, 0), st));
+    OLS_CUDA_TRY(cudaMemsetAsync(wl + Ll.gacc, 0, ols_bwd_scratch_bytes(a->P, a->F), st));
+    ols_timing_mark(-1, st);
+    int rc = run_blend_bwd(a->W, a->H, a->tile, 3, 0, a->flags, wc, Lc, a->d_bg, g->d_dL_dout_color, nullptr, g->d_dL_dout_depth, st);
+    if (rc != OLS_OK) return rc;
+    rc = run_blend_bwd(a->W, a->H, a->tile, 0, a->F, a->flags, wl, Ll, a->d_bg, nullptr, g->d_dL_dout_language, nullptr, st);
+    if (rc != OLS_OK) return rc;
+    ols_timing_mark(OLS_T_BLEND_BWD, st);
+    GeomDisArgs ga;
+    fill_geom_common(ga, a, wc, Lc, g->d_dL_dsh);
+    ga.exact = (a->flags & OLS_FLAG_BWD_EXACT) != 0;
+    ga.scales = a->d_scales; ga.rotations = a->d_rotations;
+    ga.cov3D = a->d_cov3D_precomp ? a->d_cov3D_precomp : (const float*)(wc + Lc.cov3D);
+    ga.scales_lang = d->d_scales_lang; ga.rotations_lang = d->d_rotations_lang;
+    ga.cov3D_lang = d->d_cov3D_precomp_lang ? d->d_cov3D_precomp_lang : (const float*)(wl + Ll.cov3D);
+    ga.radii = g->d_radii; ga.radii_lang = g->d_radii_lang;
+    ga.gacc_lang = (const float*)(wl + Ll.gacc);
+    ga.dL_dmeans2D = g->d_dL_dmeans2D; ga.dL_dcolors = g->d_dL_dcolors; ga.dL_dlanguage = g->d_dL_dlanguage;
+    ga.dL_dopacity = g->d_dL_dopacity; ga.dL_dopacity_lang = g->d_dL_dopacity_lang; ga.dL_dmeans3D = g->d_dL_dmeans3D;
+    ga.dL_dcov3D = g->d_dL_dcov3D; ga.dL_dcov3D_lang = g->d_dL_dcov3D_lang;
+    ga.dL_dscales = g->d_dL_dscales; ga.dL_dscales_lang = g->d_dL_dscales_lang;
+    ga.dL_drots = g->d_dL_drotations; ga.dL_drots_lang = g->d_dL_drotations_lang; ga.dL_dtau = g->d_dL_dtau;
+    if (a->F == 15) k_geometry_bwd_dis<15><<<(a->P + 255) / 256, 256, 0, st>>>(ga);
+    else k_geometry_bwd_dis<3><<<(a->P + 255) / 256, 256, 0, st>>>(ga);
+    OLS_CUDA_TRY(cudaGetLastError());
+    if (debug) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { ols_set_error("kernel geometry_bwd_dis failed: %s", cudaGetErrorString(e)); return OLS_ERR_CUDA; }
     }
     ols_timing_mark(OLS_T_GEOMETRY_BWD, st);
     return OLS_OK;

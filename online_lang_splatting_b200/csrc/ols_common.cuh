@@ -8,17 +8,19 @@
 namespace ols {
 
 // ---- packed per-Gaussian blend record ------------------------------------------------------------
-// floats: 0 x | 1 y | 2 conicA | 3 conicB | 4 conicC | 5 opacity | 6 pth | 7 depth | 8 r | 9 g | 10 b | 11.. lang[F]
-// rounded up to a multiple of 4 floats so a record is a whole number of 16-byte chunks
-// (F=15 -> 28 floats = 112 B, F=3 -> 16 floats = 64 B).  `pth` is a conservative lower bound on the
-// exponent below which alpha < 1/255 is certain, so the blend kernels can skip expf() for far pixels
-// without changing any decision of the reference (forward.cu:446-457).  The last two floats of the
-// record (rec_ext(F), +1) hold conservative half-extents (ex, ey) of the region where alpha >= 1/255 is
-// possible; the blend kernels use them to reject a Gaussian for a whole warp's pixel block at once.
+// floats: 0 x | 1 y | 2 conicA | 3 conicB | 4 conicC | 5 opacity | 6 pth | 7 depth | 8.. channels[NCH] | 0-pad | ex | ey
+// rounded up to a multiple of 4 floats so a record is a whole number of 16-byte chunks.  The channels
+// are what one blending pass accumulates: rgb + lang[F] for the joint pass of P/ (NCH = 3 + F; F=15 ->
+// 28 floats = 112 B, F=3 -> 16 floats), rgb only (NCH = 3) or lang[F] only (NCH = F) for the two passes
+// of the disentangled variant D/.  `pth` is a conservative lower bound on the exponent below which
+// alpha < 1/255 is certain, so the blend kernels can skip expf() for far pixels without changing any
+// decision of the reference (forward.cu:446-457).  The last two floats hold conservative half-extents
+// (ex, ey) of the region where alpha >= 1/255 is possible; the blend kernels use them to reject a
+// Gaussian for a whole warp's pixel block at once.
 constexpr int REC_X = 0, REC_Y = 1, REC_A = 2, REC_B = 3, REC_C = 4, REC_OP = 5, REC_PTH = 6, REC_DEPTH = 7,
-              REC_RGB = 8, REC_LANG = 11;
-__host__ __device__ constexpr int rec_floats(int F) { return ((13 + F) + 3) / 4 * 4; }
-__host__ __device__ constexpr int rec_ext(int F) { return rec_floats(F) - 2; }
+              REC_CH = 8;
+__host__ __device__ constexpr int rec_floats_nch(int nch) { return ((10 + nch) + 3) / 4 * 4; }
+__host__ __device__ constexpr int rec_floats(int F) { return rec_floats_nch(3 + F); }  // joint pass
 
 struct WsLayout {
     size_t info, tile_count, tile_cursor, ranges, cta_hist, records, depths, cov3D, clamped, tiles_touched, rect, final_T,
@@ -30,12 +32,13 @@ struct WsLayout {
 inline __host__ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Single workspace replacing geomBuffer / binningBuffer / imgBuffer (rasterizer_impl.cu:155-212).
-inline __host__ WsLayout ws_layout(int P, int F, int W, int H, int tile, int64_t R_cap) {
+// `ncol` = 3 for passes that blend colour (joint / colour-only), 0 for the language-only pass of D/.
+inline __host__ WsLayout ws_layout(int P, int F, int W, int H, int tile, int64_t R_cap, int ncol = 3) {
     WsLayout L;
     L.gx = (W + tile - 1) / tile;
     L.gy = (H + tile - 1) / tile;
     L.n_tiles = L.gx * L.gy;
-    L.rec = rec_floats(F);
+    L.rec = rec_floats_nch(ncol + F);
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
     const size_t Pz = (size_t)(P > 0 ? P : 1), HW = (size_t)W * H, Rz = (size_t)(R_cap > 0 ? R_cap : 1);
@@ -106,3 +109,7 @@ void ols_timing_mark(int tag, cudaStream_t st);
 // kernel launchers implemented in ols_forward.cu / ols_backward.cu
 int ols_launch_forward(const ols_raster_args* a, const ols_fwd_out* o, const ols::WsLayout& L, cudaStream_t st);
 int ols_launch_backward(const ols_raster_args* a, const ols_bwd_args* g, const ols::WsLayout& L, cudaStream_t st);
+int ols_launch_forward_dis(const ols_dis_args* d, const ols_dis_fwd_out* o, const ols::WsLayout& Lc, const ols::WsLayout& Ll,
+                           size_t lang_base, cudaStream_t st);
+int ols_launch_backward_dis(const ols_dis_args* d, const ols_dis_bwd_args* g, const ols::WsLayout& Lc, const ols::WsLayout& Ll,
+                            size_t lang_base, cudaStream_t st);

@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreArgs a) {
                     const int e = e0 + k * PRE_THREADS + tid;
                     if (e < n_el) {
                         const int g = e / F, c = e - g * F;
-                        dst[(size_t)g * rec + REC_LANG + c] = tmp[k];
+                        dst[(size_t)g * rec + REC_CH + 3 + c] = tmp[k];
                     }
                 }
             }
@@ -200,6 +200,86 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreArgs a) {
     // n_visible: block-reduce the per-thread counts
     for (int o = 16; o > 0; o >>= 1) visible += __shfl_xor_sync(0xffffffffu, visible, o);
     if ((tid & 31) == 0 && visible) atomicAdd(&a.info->n_visible, visible);
+}
+
+// ---- pieces of the per-Gaussian preprocess shared by the joint (P/) and the disentangled (D/) kernels ----
+
+// computeCov2D (forward.cu:77-116): cov2D (a, b, c) with the 0.3 dilation already added to a and c
+__device__ __forceinline__ void cov2d_from_cov3d(const float* V, float px3, float py3, float pz3, float vz,
+                                                 float tanfovx, float tanfovy, float focal_x, float focal_y,
+                                                 const float* c3, float& ca, float& cb, float& cc) {
+    const float tz = vz;
+    const float txr = xform_row(V, 0, px3, py3, pz3);
+    const float tyr = xform_row(V, 1, px3, py3, pz3);
+    const float limx = fmul(tanfovx, 1.3f), limy = fmul(tanfovy, 1.3f);
+    const float cx = fminf(fmaxf(fdiv(txr, tz), -limx), limx);
+    const float cy = fminf(fmaxf(fdiv(tyr, tz), -limy), limy);
+    const float tz2 = fmul(tz, tz);
+    const float J00 = fdiv(focal_x, tz);
+    const float J02 = fdiv(fmul(fmul(tz, -cx), focal_x), tz2);
+    const float J11 = fdiv(focal_y, tz);
+    const float J12 = fdiv(fmul(fmul(tz, -cy), focal_y), tz2);
+    float ta[3], tb[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        ta[k] = ffma(V[4 * k + 2], J02, ffma(V[4 * k], J00, fmul(0.0f, V[4 * k + 1])));
+        tb[k] = ffma(V[4 * k + 2], J12, ffma(0.0f, V[4 * k], fmul(V[4 * k + 1], J11)));
+    }
+    const float ux0 = dot3c(ta[0], ta[1], ta[2], c3[0], c3[1], c3[2]);
+    const float ux1 = dot3c(ta[0], ta[1], ta[2], c3[1], c3[3], c3[4]);
+    const float ux2 = dot3c(ta[0], ta[1], ta[2], c3[2], c3[4], c3[5]);
+    const float uy0 = dot3c(tb[0], tb[1], tb[2], c3[0], c3[1], c3[2]);
+    const float uy1 = dot3c(tb[0], tb[1], tb[2], c3[1], c3[3], c3[4]);
+    const float uy2 = dot3c(tb[0], tb[1], tb[2], c3[2], c3[4], c3[5]);
+    ca = fadd(dot3c(ta[0], ta[1], ta[2], ux0, ux1, ux2), 0.3f);
+    cb = dot3c(ta[0], ta[1], ta[2], uy0, uy1, uy2);
+    cc = fadd(dot3c(tb[0], tb[1], tb[2], uy0, uy1, uy2), 0.3f);
+}
+
+// forward.cu:344-347: radius = ceil(3 * sqrt(larger eigenvalue))
+__device__ __forceinline__ float splat_radius(float ca, float cc, float det) {
+    const float mid = fmul(fadd(ca, cc), 0.5f);
+    const float sq = __fsqrt_rn(fmaxf(ffma(mid, mid, -det), 0.1f));
+    const float lam = fmaxf(fadd(mid, sq), fsub(mid, sq));
+    return ceilf(fmul(__fsqrt_rn(lam), 3.0f));
+}
+
+// SH -> rgb with the clamp flags (forward.cu:23-74,  +0.5 and max(.,0) at :66-73)
+__device__ __forceinline__ uint32_t rgb_from_sh(int deg, int M, const float* sh, float dx, float dy, float dz, float* rgb) {
+    float res[3];
+    sh_to_rgb(deg, M, sh, dx, dy, dz, res);
+    uint32_t cl = 0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        cl |= (uint32_t)(!(res[c] >= -0.5f)) << (8 * c);  // compiled form of "result < 0 after +0.5"
+        rgb[c] = fmaxf(fadd(res[c], 0.5f), 0.0f);
+    }
+    return cl;
+}
+
+// Header (x y A B | C op pth depth) and the trailing half-extents (ex, ey) of a blend record.
+__device__ __forceinline__ void write_record_frame(float* rf, int rec, float pix_x, float pix_y, float conA, float conB,
+                                                   float conC, float op, float depth) {
+    // conservative cut: power < pth  =>  op*exp(power) < 1/255 with a wide safety margin
+    const float pth = (op == op) ? (op > 0.0f ? logf(1.0f / (255.0f * op)) - 0.01f : CUDART_INF_F) : -CUDART_INF_F;
+    float4* r4 = reinterpret_cast<float4*>(rf);
+    r4[0] = make_float4(pix_x, pix_y, conA, conB);
+    r4[1] = make_float4(conC, op, pth, depth);
+    // half-extents of {power >= pth_c} for the conic as stored: |dx| <= sqrt(-2 pth_c C / (AC - B^2)), same for y.
+    // pth_c widens pth by more than the rounding error of the float evaluation of `power` when the
+    // form is reasonably conditioned; otherwise (or for NaNs) the extents are infinite = never rejected.
+    const double A = (double)conA, B = (double)conB, Cc = (double)conC;
+    const double detc = A * Cc - B * B, tr = A + Cc;
+    float ex = CUDART_INF_F, ey = CUDART_INF_F;
+    if (pth > 0.0f) {
+        ex = ey = -CUDART_INF_F;  // opacity below 1/255: no pixel can pass
+    } else if (pth > -CUDART_INF_F && A > 0.0 && Cc > 0.0 && detc > 0.0 && tr * tr < 1000.0 * detc) {
+        const double k = -2.0 * (1.002 * (double)pth - 0.02) / detc;
+        ex = (float)(sqrt(k * Cc) * 1.0001 + 0.01);
+        ey = (float)(sqrt(k * A) * 1.0001 + 0.01);
+    }
+    rf[rec - 2] = ex;
+    rf[rec - 1] = ey;
 }
 
 __device__ void preprocess_one(const PreArgs& a, int i, int tid, const float* s_mean, const float* s_scale,
@@ -233,43 +313,12 @@ __device__ void preprocess_one(const PreArgs& a, int i, int tid, const float* s_
 #pragma unroll
         for (int k = 0; k < 6; k++) a.cov3D[(size_t)6 * i + k] = c3[k];
     }
-    // computeCov2D (forward.cu:77-116)
     float ca, cb, cc;
-    {
-        const float tz = vz;
-        const float txr = xform_row(V, 0, px3, py3, pz3);
-        const float tyr = xform_row(V, 1, px3, py3, pz3);
-        const float limx = fmul(a.tanfovx, 1.3f), limy = fmul(a.tanfovy, 1.3f);
-        const float cx = fminf(fmaxf(fdiv(txr, tz), -limx), limx);
-        const float cy = fminf(fmaxf(fdiv(tyr, tz), -limy), limy);
-        const float tz2 = fmul(tz, tz);
-        const float J00 = fdiv(a.focal_x, tz);
-        const float J02 = fdiv(fmul(fmul(tz, -cx), a.focal_x), tz2);
-        const float J11 = fdiv(a.focal_y, tz);
-        const float J12 = fdiv(fmul(fmul(tz, -cy), a.focal_y), tz2);
-        float ta[3], tb[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            ta[k] = ffma(V[4 * k + 2], J02, ffma(V[4 * k], J00, fmul(0.0f, V[4 * k + 1])));
-            tb[k] = ffma(V[4 * k + 2], J12, ffma(0.0f, V[4 * k], fmul(V[4 * k + 1], J11)));
-        }
-        const float ux0 = dot3c(ta[0], ta[1], ta[2], c3[0], c3[1], c3[2]);
-        const float ux1 = dot3c(ta[0], ta[1], ta[2], c3[1], c3[3], c3[4]);
-        const float ux2 = dot3c(ta[0], ta[1], ta[2], c3[2], c3[4], c3[5]);
-        const float uy0 = dot3c(tb[0], tb[1], tb[2], c3[0], c3[1], c3[2]);
-        const float uy1 = dot3c(tb[0], tb[1], tb[2], c3[1], c3[3], c3[4]);
-        const float uy2 = dot3c(tb[0], tb[1], tb[2], c3[2], c3[4], c3[5]);
-        ca = fadd(dot3c(ta[0], ta[1], ta[2], ux0, ux1, ux2), 0.3f);
-        cb = dot3c(ta[0], ta[1], ta[2], uy0, uy1, uy2);
-        cc = fadd(dot3c(tb[0], tb[1], tb[2], uy0, uy1, uy2), 0.3f);
-    }
+    cov2d_from_cov3d(V, px3, py3, pz3, vz, a.tanfovx, a.tanfovy, a.focal_x, a.focal_y, c3, ca, cb, cc);
     const float det = ffma(ca, cc, -fmul(cb, cb));
     if (det == 0.0f) return;
     const float det_inv = __frcp_rn(det);
-    const float mid = fmul(fadd(ca, cc), 0.5f);
-    const float sq = __fsqrt_rn(fmaxf(ffma(mid, mid, -det), 0.1f));
-    const float lam = fmaxf(fadd(mid, sq), fsub(mid, sq));
-    const float my_radius = ceilf(fmul(__fsqrt_rn(lam), 3.0f));
+    const float my_radius = splat_radius(ca, cc, det);
     const float pix_x = ndc2pix(projx, a.W), pix_y = ndc2pix(projy, a.H);
     int mn[2], mx[2];
     const int ri = __float2int_rz(my_radius);
@@ -282,45 +331,15 @@ __device__ void preprocess_one(const PreArgs& a, int i, int tid, const float* s_
 #pragma unroll
         for (int c = 0; c < 3; c++) rgb[c] = a.colors_precomp[(size_t)3 * i + c];
     } else {
-        float res[3];
-        sh_to_rgb(a.sh_degree, a.M, a.shs + (size_t)i * a.M * 3, px3 - a.campos[0], py3 - a.campos[1],
-                  pz3 - a.campos[2], res);
-        uint32_t cl = 0;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            cl |= (uint32_t)(!(res[c] >= -0.5f)) << (8 * c);  // compiled form of "result < 0 after +0.5"
-            rgb[c] = fmaxf(fadd(res[c], 0.5f), 0.0f);
-        }
-        a.clamped[i] = cl;
+        a.clamped[i] = rgb_from_sh(a.sh_degree, a.M, a.shs + (size_t)i * a.M * 3, px3 - a.campos[0], py3 - a.campos[1],
+                                   pz3 - a.campos[2], rgb);
     }
-    const float op = a.opacities[i];
-    // conservative cut: power < pth  =>  op*exp(power) < 1/255 with a wide safety margin
-    const float pth = (op == op) ? (op > 0.0f ? logf(1.0f / (255.0f * op)) - 0.01f : CUDART_INF_F) : -CUDART_INF_F;
-    float4* r4 = reinterpret_cast<float4*>(a.records + (size_t)i * a.rec);
-    const float conA = fmul(cc, det_inv), conB = fmul(cb, -det_inv), conC = fmul(ca, det_inv);
-    r4[0] = make_float4(pix_x, pix_y, conA, conB);
-    r4[1] = make_float4(conC, op, pth, vz);
     float* rf = a.records + (size_t)i * a.rec;
-    rf[REC_RGB] = rgb[0];
-    rf[REC_RGB + 1] = rgb[1];
-    rf[REC_RGB + 2] = rgb[2];
-    for (int c = REC_LANG + a.F; c < a.rec - 2; c++) rf[c] = 0.0f;
-    {   // half-extents of {power >= pth_c} for the conic as stored: |dx| <= sqrt(-2 pth_c C / (AC - B^2)), same for y.
-        // pth_c widens pth by more than the rounding error of the float evaluation of `power` when the
-        // form is reasonably conditioned; otherwise (or for NaNs) the extents are infinite = never rejected.
-        const double A = (double)conA, B = (double)conB, Cc = (double)conC;
-        const double detc = A * Cc - B * B, tr = A + Cc;
-        float ex = CUDART_INF_F, ey = CUDART_INF_F;
-        if (pth > 0.0f) {
-            ex = ey = -CUDART_INF_F;  // opacity below 1/255: no pixel can pass
-        } else if (pth > -CUDART_INF_F && A > 0.0 && Cc > 0.0 && detc > 0.0 && tr * tr < 1000.0 * detc) {
-            const double k = -2.0 * (1.002 * (double)pth - 0.02) / detc;
-            ex = (float)(sqrt(k * Cc) * 1.0001 + 0.01);
-            ey = (float)(sqrt(k * A) * 1.0001 + 0.01);
-        }
-        rf[a.rec - 2] = ex;
-        rf[a.rec - 1] = ey;
-    }
+    rf[REC_CH] = rgb[0];
+    rf[REC_CH + 1] = rgb[1];
+    rf[REC_CH + 2] = rgb[2];
+    for (int c = REC_CH + 3 + a.F; c < a.rec - 2; c++) rf[c] = 0.0f;
+    write_record_frame(rf, a.rec, pix_x, pix_y, fmul(cc, det_inv), fmul(cb, -det_inv), fmul(ca, det_inv), a.opacities[i], vz);
     a.depths[i] = vz;
     a.radii[i] = ri;
     a.rect[i] = make_uint2((uint32_t)mn[0] | ((uint32_t)mn[1] << 16), (uint32_t)mx[0] | ((uint32_t)mx[1] << 16));
@@ -328,6 +347,147 @@ __device__ void preprocess_one(const PreArgs& a, int i, int tid, const float* s_
     visible += 1;
     for (int y = mn[1]; y < mx[1]; y++)
         for (int x = mn[0]; x < mx[0]; x++) atomicAdd(&s_hist[y * a.gx + x], 1u);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Disentangled variant (D/: submodules/diff-gaussian-rasterization-disentangle-optim).  One Gaussian has
+// two screen-space footprints -- (scales, rotations, opacities) for colour + depth and (scales_lang,
+// rotations_lang, opacities_lang) for the language features -- sharing the projected mean and the depth
+// (D/cuda_rasterizer/forward.cu:262-430).  The kernel fills one blend record, rect and tile histogram
+// per footprint; binning, sorting and blending then run once per footprint with the kernels below.
+// ---------------------------------------------------------------------------------------------------
+struct PreDisArgs {
+    int P, F, sh_degree, M, W, H, tile, gx, gy, rec_c, rec_l, chunk;
+    unsigned flags;
+    float tanfovx, tanfovy, focal_x, focal_y, scale_modifier;
+    const float *means3D, *shs, *colors_precomp, *language;
+    const float *opacities, *scales, *rotations, *cov3D_precomp;
+    const float *opacities_lang, *scales_lang, *rotations_lang, *cov3D_precomp_lang;
+    const float *viewmatrix, *projmatrix, *campos;
+    float *records_c, *records_l, *depths, *cov3D, *cov3D_lang;
+    uint32_t *clamped, *tiles_touched_c, *tiles_touched_l, *cta_hist_c, *cta_hist_l;
+    uint2 *rect_c, *rect_l;
+    int32_t *radii, *radii_lang;
+    DeviceInfo *info_c, *info_l;
+};
+
+__global__ void __launch_bounds__(PRE_THREADS) k_preprocess_dis(const PreDisArgs a) {
+    extern __shared__ uint32_t s_hist2[];  // [2][n_tiles]
+    __shared__ float s_V[16], s_Pm[16];
+    const int tid = threadIdx.x;
+    const int n_tiles = a.gx * a.gy;
+    uint32_t* hist_c = s_hist2;
+    uint32_t* hist_l = s_hist2 + n_tiles;
+    for (int t = tid; t < 2 * n_tiles; t += PRE_THREADS) s_hist2[t] = 0;
+    if (tid < 16) { s_V[tid] = a.viewmatrix[tid]; s_Pm[tid] = a.projmatrix[tid]; }
+    __syncthreads();
+    const float* V = s_V;
+    const float* Pm = s_Pm;
+    const int chunk_begin = min(a.P, (int)blockIdx.x * a.chunk), chunk_end = min(a.P, chunk_begin + a.chunk);
+    int vis_c = 0, vis_l = 0;
+    for (int i = chunk_begin + tid; i < chunk_end; i += PRE_THREADS) {
+        a.radii[i] = 0;
+        a.radii_lang[i] = 0;
+        a.tiles_touched_c[i] = 0;
+        a.tiles_touched_l[i] = 0;
+        float* rc = a.records_c + (size_t)i * a.rec_c;
+        float* rl = a.records_l + (size_t)i * a.rec_l;
+        // language channels of the record are written for every Gaussian (only listed ones are read)
+        for (int c = 0; c < a.F; c++) rl[REC_CH + c] = a.language[(size_t)i * a.F + c];
+        for (int c = REC_CH + a.F; c < a.rec_l - 2; c++) rl[c] = 0.0f;
+        const float px3 = a.means3D[3 * (size_t)i], py3 = a.means3D[3 * (size_t)i + 1], pz3 = a.means3D[3 * (size_t)i + 2];
+        const float vz = xform_row(V, 2, px3, py3, pz3);
+        if (!(vz > 0.2f)) {
+            if (a.flags & OLS_FLAG_PREFILTERED) {
+                printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+                __trap();
+            }
+            continue;
+        }
+        const float hx = xform_row(Pm, 0, px3, py3, pz3);
+        const float hy = xform_row(Pm, 1, px3, py3, pz3);
+        const float hw = xform_row(Pm, 3, px3, py3, pz3);
+        const float pw = __frcp_rn(fadd(hw, 0.0000001f));
+        const float projx = fmul(hx, pw), projy = fmul(hy, pw);
+        float c3[6], c3l[6];
+        if (a.cov3D_precomp) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) c3[k] = a.cov3D_precomp[(size_t)6 * i + k];
+        } else {
+            const float4 q = reinterpret_cast<const float4*>(a.rotations)[i];
+            cov3d_from_scale_rot(a.scales[3 * (size_t)i], a.scales[3 * (size_t)i + 1], a.scales[3 * (size_t)i + 2],
+                                 a.scale_modifier, q, c3);
+#pragma unroll
+            for (int k = 0; k < 6; k++) a.cov3D[(size_t)6 * i + k] = c3[k];
+        }
+        if (a.cov3D_precomp_lang) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) c3l[k] = a.cov3D_precomp_lang[(size_t)6 * i + k];
+        } else {
+            const float4 q = reinterpret_cast<const float4*>(a.rotations_lang)[i];
+            cov3d_from_scale_rot(a.scales_lang[3 * (size_t)i], a.scales_lang[3 * (size_t)i + 1],
+                                 a.scales_lang[3 * (size_t)i + 2], a.scale_modifier, q, c3l);
+#pragma unroll
+            for (int k = 0; k < 6; k++) a.cov3D_lang[(size_t)6 * i + k] = c3l[k];
+        }
+        float ca, cb, cc, la, lb, lc;
+        cov2d_from_cov3d(V, px3, py3, pz3, vz, a.tanfovx, a.tanfovy, a.focal_x, a.focal_y, c3, ca, cb, cc);
+        cov2d_from_cov3d(V, px3, py3, pz3, vz, a.tanfovx, a.tanfovy, a.focal_x, a.focal_y, c3l, la, lb, lc);
+        const float det = ffma(ca, cc, -fmul(cb, cb));
+        const float det_l = ffma(la, lc, -fmul(lb, lb));
+        if (det == 0.0f && det_l == 0.0f) continue;  // D/forward.cu:357-366: only when BOTH are singular
+        const float det_inv = __frcp_rn(det), det_inv_l = __frcp_rn(det_l);
+        const float pix_x = ndc2pix(projx, a.W), pix_y = ndc2pix(projy, a.H);
+        const int ri = __float2int_rz(splat_radius(ca, cc, det));
+        const int ril = __float2int_rz(splat_radius(la, lc, det_l));
+        int mn[2], mx[2], mnl[2], mxl[2];
+        get_rect(pix_x, pix_y, ri, a.tile, a.gx, a.gy, mn, mx);
+        get_rect(pix_x, pix_y, ril, a.tile, a.gx, a.gy, mnl, mxl);
+        const uint32_t tiles = (uint32_t)(mx[0] - mn[0]) * (uint32_t)(mx[1] - mn[1]);
+        const uint32_t tiles_l = (uint32_t)(mxl[0] - mnl[0]) * (uint32_t)(mxl[1] - mnl[1]);
+        if (tiles == 0 && tiles_l == 0) continue;  // D/forward.cu:391-394
+        float rgb[3] = {0.0f, 0.0f, 0.0f};
+        if (a.colors_precomp) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) rgb[c] = a.colors_precomp[(size_t)3 * i + c];
+        } else if (tiles != 0) {  // D/forward.cu:398-411: zero colour (and no clamp flags) when the colour rect is empty
+            a.clamped[i] = rgb_from_sh(a.sh_degree, a.M, a.shs + (size_t)i * a.M * 3, px3 - a.campos[0],
+                                       py3 - a.campos[1], pz3 - a.campos[2], rgb);
+        }
+        rc[REC_CH] = rgb[0];
+        rc[REC_CH + 1] = rgb[1];
+        rc[REC_CH + 2] = rgb[2];
+        for (int c = REC_CH + 3; c < a.rec_c - 2; c++) rc[c] = 0.0f;
+        write_record_frame(rc, a.rec_c, pix_x, pix_y, fmul(cc, det_inv), fmul(cb, -det_inv), fmul(ca, det_inv),
+                           a.opacities[i], vz);
+        write_record_frame(rl, a.rec_l, pix_x, pix_y, fmul(lc, det_inv_l), fmul(lb, -det_inv_l), fmul(la, det_inv_l),
+                           a.opacities_lang[i], vz);
+        a.depths[i] = vz;
+        a.radii[i] = ri;            // both radii are stored even when one rect is empty (D/forward.cu:416-428)
+        a.radii_lang[i] = ril;
+        a.rect_c[i] = make_uint2((uint32_t)mn[0] | ((uint32_t)mn[1] << 16), (uint32_t)mx[0] | ((uint32_t)mx[1] << 16));
+        a.rect_l[i] = make_uint2((uint32_t)mnl[0] | ((uint32_t)mnl[1] << 16), (uint32_t)mxl[0] | ((uint32_t)mxl[1] << 16));
+        a.tiles_touched_c[i] = tiles;
+        a.tiles_touched_l[i] = tiles_l;
+        vis_c += ri > 0;
+        vis_l += ril > 0;
+        for (int y = mn[1]; y < mx[1]; y++)
+            for (int x = mn[0]; x < mx[0]; x++) atomicAdd(&hist_c[y * a.gx + x], 1u);
+        for (int y = mnl[1]; y < mxl[1]; y++)
+            for (int x = mnl[0]; x < mxl[0]; x++) atomicAdd(&hist_l[y * a.gx + x], 1u);
+    }
+    __syncthreads();
+    uint32_t* out_c = a.cta_hist_c + (size_t)blockIdx.x * n_tiles;
+    uint32_t* out_l = a.cta_hist_l + (size_t)blockIdx.x * n_tiles;
+    for (int t = tid; t < n_tiles; t += PRE_THREADS) { out_c[t] = hist_c[t]; out_l[t] = hist_l[t]; }
+    for (int o = 16; o > 0; o >>= 1) {
+        vis_c += __shfl_xor_sync(0xffffffffu, vis_c, o);
+        vis_l += __shfl_xor_sync(0xffffffffu, vis_l, o);
+    }
+    if ((tid & 31) == 0) {
+        if (vis_c) atomicAdd(&a.info_c->n_visible, vis_c);
+        if (vis_l) atomicAdd(&a.info_l->n_visible, vis_l);
+    }
 }
 
 // Column scan of cta_hist: afterwards cta_hist[c][t] = instances of tile t emitted by CTAs < c, and
@@ -747,14 +907,18 @@ __device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {  // per-component mul
     return r;
 }
 
-template <int TILE, int F, bool BITEXACT>
+// NCOL = 3: the pass blends rgb (+ background) and depth; NCOL = 0: language channels only (second pass of D/).
+template <int TILE, int NCOL, int F, bool BITEXACT>
 __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const BlendArgs a) {
-    static_assert(TILE <= 16 && (3 + F) % 2 == 0, "8 warps of 8x4 pixels cover at most 16x16; channel pairs");
-    constexpr int REC = rec_floats(F);
+    static_assert(TILE <= 16, "8 warps of 8x4 pixels cover at most 16x16");
+    static_assert(NCOL == 0 || NCOL == 3, "colour channels");
+    constexpr int NCH = NCOL + F;               // channels stored from REC_CH on (an odd count is zero-padded)
+    constexpr int REC = rec_floats_nch(NCH);
     constexpr int R4 = REC / 4;                 // float4 chunks per record
     constexpr int CHUNKS = BLEND_BATCH * R4;    // 16-byte chunks per batch
-    constexpr int NPAIR = (3 + F) / 2;          // (r,g) (b,L0) (L1,L2) ... as stored from REC_RGB on
-    constexpr int EXT = rec_ext(F);
+    constexpr int NPAIR = (NCH + 1) / 2;        // (r,g) (b,L0) (L1,L2) ... as stored
+    constexpr int EXT = REC - 2;
+    static_assert(REC_CH + 2 * NPAIR <= EXT, "channel pairs must not run into the extents");
     __shared__ __align__(16) float s_rec[2][BLEND_BATCH * REC];
     __shared__ uint32_t s_id[2][BLEND_BATCH];
 
@@ -839,23 +1003,23 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const BlendArgs a) {
                                 f32x2 v[NPAIR];
 #pragma unroll
                                 for (int p = 0; p + 1 < NPAIR; p += 2) {
-                                    const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(rj + REC_RGB + 2 * p);
+                                    const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(rj + REC_CH + 2 * p);
                                     v[p] = t.x;
                                     v[p + 1] = t.y;
                                 }
                                 if (NPAIR & 1)
-                                    v[NPAIR - 1] = *reinterpret_cast<const f32x2*>(rj + REC_RGB + 2 * (NPAIR - 1));
+                                    v[NPAIR - 1] = *reinterpret_cast<const f32x2*>(rj + REC_CH + 2 * (NPAIR - 1));
                                 if (BITEXACT) {  // acc = fma(T, alpha * c, acc) like the compiled reference
                                     const f32x2 a2 = pack2(alpha, alpha), T2 = pack2(T, T);
 #pragma unroll
                                     for (int p = 0; p < NPAIR; p++) acc2[p] = ffma2(T2, fmul2(a2, v[p]), acc2[p]);
-                                    acc_d = ffma(T, fmul(alpha, g1.w), acc_d);
+                                    if (NCOL) acc_d = ffma(T, fmul(alpha, g1.w), acc_d);
                                 } else {
                                     const float w = fmul(alpha, T);
                                     const f32x2 w2 = pack2(w, w);
 #pragma unroll
                                     for (int p = 0; p < NPAIR; p++) acc2[p] = ffma2(w2, v[p], acc2[p]);
-                                    acc_d = ffma(w, g1.w, acc_d);
+                                    if (NCOL) acc_d = ffma(w, g1.w, acc_d);
                                 }
                                 touch = test_T > 0.5f;
                                 T = test_T;
@@ -878,21 +1042,23 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const BlendArgs a) {
         for (int p = 0; p < NPAIR; p++) unpack2(acc2[p], acc[2 * p], acc[2 * p + 1]);
         a.final_T[pix] = T;
         a.n_contrib[pix] = last_contributor;
+        if (NCOL) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) a.out_color[c * HW + pix] = ffma(a.bg[c], T, acc[c]);
+            for (int c = 0; c < NCOL; c++) a.out_color[c * HW + pix] = ffma(a.bg[c], T, acc[c]);
+            a.out_depth[pix] = acc_d;
+        }
 #pragma unroll
-        for (int c = 0; c < F; c++) a.out_language[c * HW + pix] = acc[3 + c];
-        a.out_depth[pix] = acc_d;
+        for (int c = 0; c < F; c++) a.out_language[c * HW + pix] = acc[NCOL + c];
         a.out_opacity[pix] = fsub(1.0f, T);
     }
 }
 
-template <int TILE, int F>
+template <int TILE, int NCOL, int F>
 static int launch_blend(const BlendArgs& ba, int n_tiles, bool bitexact, cudaStream_t st) {
     if (bitexact)
-        k_blend<TILE, F, true><<<n_tiles, BLEND_THREADS, 0, st>>>(ba);
+        k_blend<TILE, NCOL, F, true><<<n_tiles, BLEND_THREADS, 0, st>>>(ba);
     else
-        k_blend<TILE, F, false><<<n_tiles, BLEND_THREADS, 0, st>>>(ba);
+        k_blend<TILE, NCOL, F, false><<<n_tiles, BLEND_THREADS, 0, st>>>(ba);
     return 0;
 }
 
@@ -900,10 +1066,6 @@ static int launch_blend(const BlendArgs& ba, int n_tiles, bool bitexact, cudaStr
 
 using namespace ols;
 
-int ols_launch_forward(const ols_raster_args* a, const ols_fwd_out* o, const WsLayout& L, cudaStream_t st) {
-    char* ws = (char*)a->d_workspace;
-    DeviceInfo* info = (DeviceInfo*)(ws + L.info);
-    const bool debug = (a->flags & OLS_FLAG_DEBUG) != 0;
 #define OLS_DEBUG_SYNC(name)                                                              \
     do {                                                                                  \
         OLS_CUDA_TRY(cudaGetLastError());                                                 \
@@ -916,6 +1078,88 @@ int ols_launch_forward(const ols_raster_args* a, const ols_fwd_out* o, const WsL
         }                                                                                 \
     } while (0)
 
+static int set_hist_smem(size_t hist_smem, int n_tiles) {
+    if (hist_smem > 40 * 1024) {
+        if (hist_smem > 200 * 1024) {
+            ols_set_error("image too large: %d tiles exceed the shared-memory tile histogram", n_tiles);
+            return OLS_ERR_UNSUPPORTED;
+        }
+        OLS_CUDA_TRY(cudaFuncSetAttribute(k_preprocess, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
+        OLS_CUDA_TRY(cudaFuncSetAttribute(k_preprocess_dis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
+        OLS_CUDA_TRY(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
+    }
+    return OLS_OK;
+}
+
+// One footprint's binning + per-tile sort + blend (everything after preprocess).  `ws` / `L` locate the
+// pass' own arrays; `depths` may live in another pass' workspace (D/ shares them between its two lists).
+struct PassOut {
+    float *color, *language, *depth, *opacity;
+    int32_t* n_touched;
+};
+static int run_pass(int P, int W, int H, int tile, int ncol, int F, unsigned flags, int64_t R_cap, char* ws, const WsLayout& L,
+                    const float* depths, const float* d_bg, const PassOut& o, cudaStream_t st) {
+    const bool debug = (flags & OLS_FLAG_DEBUG) != 0;
+    DeviceInfo* info = (DeviceInfo*)(ws + L.info);
+    uint32_t* cta_hist = (uint32_t*)(ws + L.cta_hist);
+    const size_t hist_smem = sizeof(uint32_t) * (size_t)L.n_tiles;
+    k_tile_offsets<<<(L.n_tiles + 31) / 32, 32 * TO_WARPS, 0, st>>>(cta_hist, (uint32_t*)(ws + L.tile_count), L.n_tiles, L.n_ctas);
+    OLS_DEBUG_SYNC("tile_offsets");
+    k_tile_scan<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)(ws + L.tile_count), (uint32_t*)(ws + L.tile_cursor),
+                                           (uint2*)(ws + L.ranges), L.n_tiles, (unsigned long long)R_cap, info);
+    OLS_DEBUG_SYNC("tile_scan");
+    k_scatter<<<L.n_ctas, PRE_THREADS, hist_smem, st>>>(P, L.gx, L.n_tiles, L.chunk, (const uint32_t*)(ws + L.tiles_touched),
+                                                        (const uint2*)(ws + L.rect), depths, cta_hist,
+                                                        (const uint32_t*)(ws + L.tile_cursor),
+                                                        (unsigned long long*)(ws + L.keys), info);
+    OLS_DEBUG_SYNC("scatter");
+    ols_timing_mark(OLS_T_BINNING, st);
+    k_sort_tiles_radix<<<L.n_tiles, RS_THREADS, 0, st>>>((unsigned long long*)(ws + L.keys),
+                                                         (uint32_t*)(ws + L.point_list), (const uint2*)(ws + L.ranges), info);
+    OLS_DEBUG_SYNC("sort_tiles_radix");
+    // buckets longer than the radix kernel's shared-memory capacity (rare): bitonic fallback
+    k_sort_tiles<<<L.n_tiles, SORT_THREADS, 0, st>>>((unsigned long long*)(ws + L.keys), (uint32_t*)(ws + L.point_list),
+                                                     (const uint2*)(ws + L.ranges), info, RS_CAP);
+    OLS_DEBUG_SYNC("sort_tiles");
+    ols_timing_mark(OLS_T_SORT, st);
+
+    BlendArgs ba;
+    ba.W = W; ba.H = H; ba.gx = L.gx;
+    ba.ranges = (const uint2*)(ws + L.ranges); ba.point_list = (const uint32_t*)(ws + L.point_list);
+    ba.records = (const float*)(ws + L.records); ba.bg = d_bg; ba.info = info;
+    ba.final_T = (float*)(ws + L.final_T); ba.n_contrib = (uint32_t*)(ws + L.n_contrib);
+    ba.out_color = o.color; ba.out_language = o.language; ba.out_depth = o.depth;
+    ba.out_opacity = o.opacity; ba.n_touched = o.n_touched;
+    const bool bitexact = (flags & OLS_FLAG_BITEXACT_BLEND) != 0;
+    const int key = tile * 10000 + ncol * 100 + F;
+    switch (key) {
+        case 150315: launch_blend<15, 3, 15>(ba, L.n_tiles, bitexact, st); break;
+        case 160315: launch_blend<16, 3, 15>(ba, L.n_tiles, bitexact, st); break;
+        case 150303: launch_blend<15, 3, 3>(ba, L.n_tiles, bitexact, st); break;
+        case 160303: launch_blend<16, 3, 3>(ba, L.n_tiles, bitexact, st); break;
+        case 150300: launch_blend<15, 3, 0>(ba, L.n_tiles, bitexact, st); break;   // D/ colour pass
+        case 160300: launch_blend<16, 3, 0>(ba, L.n_tiles, bitexact, st); break;
+        case 150003: launch_blend<15, 0, 3>(ba, L.n_tiles, bitexact, st); break;   // D/ language pass
+        case 160003: launch_blend<16, 0, 3>(ba, L.n_tiles, bitexact, st); break;
+        case 150015: launch_blend<15, 0, 15>(ba, L.n_tiles, bitexact, st); break;
+        case 160015: launch_blend<16, 0, 15>(ba, L.n_tiles, bitexact, st); break;
+        default:
+            ols_set_error("unsupported (tile=%d, F=%d): compiled variants are tile in {15,16} x F in {3,15}", tile, F);
+            return OLS_ERR_UNSUPPORTED;
+    }
+    OLS_DEBUG_SYNC("blend");
+    ols_timing_mark(OLS_T_BLEND_FWD, st);
+    return OLS_OK;
+}
+
+int ols_launch_forward(const ols_raster_args* a, const ols_fwd_out* o, const WsLayout& L, cudaStream_t st) {
+    char* ws = (char*)a->d_workspace;
+    DeviceInfo* info = (DeviceInfo*)(ws + L.info);
+    const bool debug = (a->flags & OLS_FLAG_DEBUG) != 0;
+    if (a->F != 3 && a->F != 15) {
+        ols_set_error("unsupported (tile=%d, F=%d): compiled variants are tile in {15,16} x F in {3,15}", a->tile, a->F);
+        return OLS_ERR_UNSUPPORTED;
+    }
     OLS_CUDA_TRY(cudaMemsetAsync(ws + L.info, 0, 256, st));
     OLS_CUDA_TRY(cudaMemsetAsync(o->d_n_touched, 0, sizeof(int32_t) * (size_t)a->P, st));
 
@@ -935,54 +1179,64 @@ int ols_launch_forward(const ols_raster_args* a, const ols_fwd_out* o, const WsL
     p.rect = (uint2*)(ws + L.rect); p.cta_hist = (uint32_t*)(ws + L.cta_hist); p.chunk = L.chunk; p.radii = o->d_radii;
     p.info = info;
     const size_t hist_smem = sizeof(uint32_t) * (size_t)L.n_tiles;
-    if (hist_smem > 40 * 1024) {
-        if (hist_smem > 200 * 1024) {
-            ols_set_error("image too large: %d tiles exceed the shared-memory tile histogram", L.n_tiles);
-            return OLS_ERR_UNSUPPORTED;
-        }
-        OLS_CUDA_TRY(cudaFuncSetAttribute(k_preprocess, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
-        OLS_CUDA_TRY(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
-    }
+    int rc = set_hist_smem(hist_smem, L.n_tiles);
+    if (rc != OLS_OK) return rc;
     ols_timing_mark(-1, st);
     k_preprocess<<<L.n_ctas, PRE_THREADS, hist_smem, st>>>(p);
     OLS_DEBUG_SYNC("preprocess");
     ols_timing_mark(OLS_T_PREPROCESS, st);
-    k_tile_offsets<<<(L.n_tiles + 31) / 32, 32 * TO_WARPS, 0, st>>>(p.cta_hist, (uint32_t*)(ws + L.tile_count), L.n_tiles, L.n_ctas);
-    OLS_DEBUG_SYNC("tile_offsets");
-    k_tile_scan<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)(ws + L.tile_count), (uint32_t*)(ws + L.tile_cursor),
-                                           (uint2*)(ws + L.ranges), L.n_tiles, (unsigned long long)a->R_cap, info);
-    OLS_DEBUG_SYNC("tile_scan");
-    k_scatter<<<L.n_ctas, PRE_THREADS, hist_smem, st>>>(a->P, L.gx, L.n_tiles, L.chunk, p.tiles_touched, p.rect, p.depths,
-                                                        p.cta_hist, (const uint32_t*)(ws + L.tile_cursor),
-                                                        (unsigned long long*)(ws + L.keys), info);
-    OLS_DEBUG_SYNC("scatter");
-    ols_timing_mark(OLS_T_BINNING, st);
-    k_sort_tiles_radix<<<L.n_tiles, RS_THREADS, 0, st>>>((unsigned long long*)(ws + L.keys),
-                                                         (uint32_t*)(ws + L.point_list), (const uint2*)(ws + L.ranges), info);
-    OLS_DEBUG_SYNC("sort_tiles_radix");
-    // buckets longer than the radix kernel's shared-memory capacity (rare): bitonic fallback
-    k_sort_tiles<<<L.n_tiles, SORT_THREADS, 0, st>>>((unsigned long long*)(ws + L.keys), (uint32_t*)(ws + L.point_list),
-                                                     (const uint2*)(ws + L.ranges), info, RS_CAP);
-    OLS_DEBUG_SYNC("sort_tiles");
-    ols_timing_mark(OLS_T_SORT, st);
+    PassOut po{o->d_color, o->d_language, o->d_depth, o->d_opacity, o->d_n_touched};
+    return run_pass(a->P, a->W, a->H, a->tile, 3, a->F, a->flags, a->R_cap, ws, L, p.depths, a->d_bg, po, st);
+}
 
-    BlendArgs ba;
-    ba.W = a->W; ba.H = a->H; ba.gx = L.gx;
-    ba.ranges = (const uint2*)(ws + L.ranges); ba.point_list = (const uint32_t*)(ws + L.point_list);
-    ba.records = (const float*)(ws + L.records); ba.bg = a->d_bg; ba.info = info;
-    ba.final_T = (float*)(ws + L.final_T); ba.n_contrib = (uint32_t*)(ws + L.n_contrib);
-    ba.out_color = o->d_color; ba.out_language = o->d_language; ba.out_depth = o->d_depth;
-    ba.out_opacity = o->d_opacity; ba.n_touched = o->d_n_touched;
-    const bool bitexact = (a->flags & OLS_FLAG_BITEXACT_BLEND) != 0;
-    if (a->tile == 15 && a->F == 15) launch_blend<15, 15>(ba, L.n_tiles, bitexact, st);
-    else if (a->tile == 16 && a->F == 15) launch_blend<16, 15>(ba, L.n_tiles, bitexact, st);
-    else if (a->tile == 15 && a->F == 3) launch_blend<15, 3>(ba, L.n_tiles, bitexact, st);
-    else if (a->tile == 16 && a->F == 3) launch_blend<16, 3>(ba, L.n_tiles, bitexact, st);
-    else {
+// Disentangled forward (D/rasterizer_impl.cu:364-620): one preprocess, then the colour footprint's and
+// the language footprint's binning / sort / blend.  Lc / Ll are the two workspace layouts, Ll placed
+// right after Lc in the same buffer.
+int ols_launch_forward_dis(const ols_dis_args* d, const ols_dis_fwd_out* o, const WsLayout& Lc, const WsLayout& Ll,
+                           size_t lang_base, cudaStream_t st) {
+    const ols_raster_args* a = &d->base;
+    char* wc = (char*)a->d_workspace;
+    char* wl = wc + lang_base;
+    const bool debug = (a->flags & OLS_FLAG_DEBUG) != 0;
+    if (a->F != 3 && a->F != 15) {
         ols_set_error("unsupported (tile=%d, F=%d): compiled variants are tile in {15,16} x F in {3,15}", a->tile, a->F);
         return OLS_ERR_UNSUPPORTED;
     }
-    OLS_DEBUG_SYNC("blend");
-    ols_timing_mark(OLS_T_BLEND_FWD, st);
-    return OLS_OK;
+    OLS_CUDA_TRY(cudaMemsetAsync(wc + Lc.info, 0, 256, st));
+    OLS_CUDA_TRY(cudaMemsetAsync(wl + Ll.info, 0, 256, st));
+    OLS_CUDA_TRY(cudaMemsetAsync(o->d_n_touched, 0, sizeof(int32_t) * (size_t)a->P, st));
+    OLS_CUDA_TRY(cudaMemsetAsync(o->d_n_touched_lang, 0, sizeof(int32_t) * (size_t)a->P, st));
+    PreDisArgs p;
+    p.P = a->P; p.F = a->F; p.sh_degree = a->sh_degree; p.M = a->M; p.W = a->W; p.H = a->H; p.tile = a->tile;
+    p.gx = Lc.gx; p.gy = Lc.gy; p.rec_c = Lc.rec; p.rec_l = Ll.rec; p.chunk = Lc.chunk; p.flags = a->flags;
+    p.tanfovx = a->tanfovx; p.tanfovy = a->tanfovy;
+    p.focal_y = a->H / (2.0f * a->tanfovy);
+    p.focal_x = a->W / (2.0f * a->tanfovx);
+    p.scale_modifier = a->scale_modifier;
+    p.means3D = a->d_means3D; p.shs = a->d_shs; p.colors_precomp = a->d_colors_precomp; p.language = a->d_language;
+    p.opacities = a->d_opacities; p.scales = a->d_scales; p.rotations = a->d_rotations; p.cov3D_precomp = a->d_cov3D_precomp;
+    p.opacities_lang = d->d_opacities_lang; p.scales_lang = d->d_scales_lang; p.rotations_lang = d->d_rotations_lang;
+    p.cov3D_precomp_lang = d->d_cov3D_precomp_lang;
+    p.viewmatrix = a->d_viewmatrix; p.projmatrix = a->d_projmatrix; p.campos = a->d_campos;
+    p.records_c = (float*)(wc + Lc.records); p.records_l = (float*)(wl + Ll.records);
+    p.depths = (float*)(wc + Lc.depths); p.cov3D = (float*)(wc + Lc.cov3D); p.cov3D_lang = (float*)(wl + Ll.cov3D);
+    p.clamped = (uint32_t*)(wc + Lc.clamped);
+    p.tiles_touched_c = (uint32_t*)(wc + Lc.tiles_touched); p.tiles_touched_l = (uint32_t*)(wl + Ll.tiles_touched);
+    p.cta_hist_c = (uint32_t*)(wc + Lc.cta_hist); p.cta_hist_l = (uint32_t*)(wl + Ll.cta_hist);
+    p.rect_c = (uint2*)(wc + Lc.rect); p.rect_l = (uint2*)(wl + Ll.rect);
+    p.radii = o->d_radii; p.radii_lang = o->d_radii_lang;
+    p.info_c = (DeviceInfo*)(wc + Lc.info); p.info_l = (DeviceInfo*)(wl + Ll.info);
+    const size_t hist_smem = sizeof(uint32_t) * (size_t)Lc.n_tiles;
+    int rc = set_hist_smem(2 * hist_smem, Lc.n_tiles);
+    if (rc != OLS_OK) return rc;
+    ols_timing_mark(-1, st);
+    k_preprocess_dis<<<Lc.n_ctas, PRE_THREADS, 2 * hist_smem, st>>>(p);
+    OLS_DEBUG_SYNC("preprocess_dis");
+    ols_timing_mark(OLS_T_PREPROCESS, st);
+    PassOut pc{o->d_color, nullptr, o->d_depth, o->d_opacity, o->d_n_touched};
+    rc = run_pass(a->P, a->W, a->H, a->tile, 3, 0, a->flags, a->R_cap, wc, Lc, p.depths, a->d_bg, pc, st);
+    if (rc != OLS_OK) return rc;
+    ols_timing_mark(-1, st);
+    PassOut pl{nullptr, o->d_language, nullptr, o->d_opacity_lang, o->d_n_touched_lang};
+    return run_pass(a->P, a->W, a->H, a->tile, 0, a->F, a->flags, d->R_cap_lang, wl, Ll, p.depths, a->d_bg, pl, st);
 }

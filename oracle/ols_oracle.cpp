@@ -106,6 +106,47 @@ struct OracleGrads {
     float* dL_dtau;       // [P,6]
 };
 
+// ---- disentangled variant (D/ = submodules/diff-gaussian-rasterization-disentangle-optim) ----
+struct OracleDisExtra {   // the language footprint (D/rasterize_points.h:51-80)
+    const float* opacities_lang;      // [P]
+    const float* scales_lang;         // [P,3] or null
+    const float* rotations_lang;      // [P,4] or null
+    const float* cov3D_precomp_lang;  // [P,6] or null
+};
+
+struct OracleDisGeom {    // the *_lang members of D/'s LanguageGeometryState (D/rasterizer_impl.cu:173-200)
+    int32_t* radii_lang;           // [P]
+    float* cov3D_lang;             // [P,6]
+    float* conic_opacity_lang;     // [P,4]
+    uint32_t* tiles_touched_lang;  // [P]
+    uint32_t* point_offsets_lang;  // [P]
+};
+
+struct OracleDisGrads {
+    const float* dL_dcolor;    // [3,H,W]
+    const float* dL_dlanguage; // [F,H,W]
+    const float* dL_ddepth;    // [H,W]
+    int32_t compat;            // 1: reference behaviour incl. Q1/Q2 and the joint-visibility early return; 0: exact
+    int32_t _pad;
+    float* dL_dmeans2D;      // [P,3]
+    float* dL_dconic;        // [P,4]
+    float* dL_dconic_lang;   // [P,4]
+    float* dL_dopacity;      // [P]
+    float* dL_dopacity_lang; // [P]
+    float* dL_dcolors;       // [P,3]
+    float* dL_dlang;         // [P,F]
+    float* dL_ddepths;       // [P]
+    float* dL_dmeans3D;      // [P,3]
+    float* dL_dcov3D;        // [P,6]
+    float* dL_dcov3D_lang;   // [P,6]
+    float* dL_dsh;           // [P,M,3]
+    float* dL_dscales;       // [P,3]
+    float* dL_dscales_lang;  // [P,3]
+    float* dL_drots;         // [P,4]
+    float* dL_drots_lang;    // [P,4]
+    float* dL_dtau;          // [P,6]
+};
+
 }  // extern "C"
 
 namespace {
@@ -357,24 +398,28 @@ int64_t ols_oracle_preprocess(const OracleScene* s, OracleGeom* g) {
     return (int64_t)acc;
 }
 
-// Phase 2: duplicateWithKeys + stable sort + identifyTileRanges + forward blend.
-int ols_oracle_render(const OracleScene* s, const OracleGeom* g, OracleBin* b, OracleImage* o) {
-    const int P = s->P, W = s->W, H = s->H, tile = s->tile, F = s->F;
+// Phase 2 of one blending pass: duplicateWithKeys + stable sort + identifyTileRanges + forward blend.
+// The joint pass of P/ blends rgb + depth + F language channels over one list; D/ runs it twice
+// (colour + depth with F = 0, then language only with has_color = false; D/forward.cu:437-655).
+static int render_pass(const OracleScene* s, int F, bool has_color, const int32_t* radii, const float* conic_opacity,
+                       const uint32_t* point_offsets, const float* means2D, const float* depths, const float* feat,
+                       OracleBin* b, OracleImage* o) {
+    const int P = s->P, W = s->W, H = s->H, tile = s->tile;
     const int gx = (W + tile - 1) / tile, gy = (H + tile - 1) / tile;
     const int64_t R = b->R;
     std::vector<uint64_t> keys((size_t)R);
     std::vector<uint32_t> vals((size_t)R);
 #pragma omp parallel for schedule(dynamic, 1024)
     for (int i = 0; i < P; i++) {  // rasterizer_impl.cu:70-111
-        if (g->radii[i] > 0) {
-            uint32_t off = (i == 0) ? 0 : g->point_offsets[i - 1];
+        if (radii[i] > 0) {
+            uint32_t off = (i == 0) ? 0 : point_offsets[i - 1];
             int mn[2], mx[2];
-            get_rect(g->means2D[2 * (size_t)i], g->means2D[2 * (size_t)i + 1], g->radii[i], tile, gx, gy, mn, mx);
+            get_rect(means2D[2 * (size_t)i], means2D[2 * (size_t)i + 1], radii[i], tile, gx, gy, mn, mx);
             for (int y = mn[1]; y < mx[1]; y++)
                 for (int x = mn[0]; x < mx[0]; x++) {
                     uint64_t key = (uint64_t)(uint32_t)(y * gx + x);
                     key <<= 32;
-                    key |= f2u(g->depths[i]);
+                    key |= f2u(depths[i]);
                     keys[off] = key;
                     vals[off] = (uint32_t)i;
                     off++;
@@ -402,7 +447,6 @@ int ols_oracle_render(const OracleScene* s, const OracleGeom* g, OracleBin* b, O
         }
         if (i == R - 1) b->ranges[2 * cur + 1] = (uint32_t)R;
     }
-    const float* feat = s->colors_precomp ? s->colors_precomp : g->rgb;
     const size_t HW = (size_t)H * W;
     std::memset(o->n_touched, 0, sizeof(int32_t) * (size_t)P);
     // forward.cu:377-513, one tile at a time; pixels within a tile are independent
@@ -410,7 +454,7 @@ int ols_oracle_render(const OracleScene* s, const OracleGeom* g, OracleBin* b, O
     for (int ty = 0; ty < gy; ty++)
         for (int tx = 0; tx < gx; tx++) {
             const uint32_t r0 = b->ranges[2 * (ty * gx + tx)], r1 = b->ranges[2 * (ty * gx + tx) + 1];
-            std::vector<float> L((size_t)F);
+            std::vector<float> L((size_t)std::max(F, 1));
             for (int ly = 0; ly < tile; ly++)
                 for (int lx = 0; lx < tile; lx++) {
                     const int pxi = tx * tile + lx, pyi = ty * tile + ly;
@@ -422,8 +466,8 @@ int ols_oracle_render(const OracleScene* s, const OracleGeom* g, OracleBin* b, O
                     for (uint32_t k = r0; k < r1; k++) {
                         contributor++;
                         const uint32_t id = b->point_list[k];
-                        const float* co = g->conic_opacity + 4 * (size_t)id;
-                        const float dx = g->means2D[2 * (size_t)id] - pfx, dy = g->means2D[2 * (size_t)id + 1] - pfy;
+                        const float* co = conic_opacity + 4 * (size_t)id;
+                        const float dx = means2D[2 * (size_t)id] - pfx, dy = means2D[2 * (size_t)id + 1] - pfy;
                         const float q = fmaf(dx, dx * co[0], dy * (dy * co[2]));
                         const float power = fmaf(q, -0.5f, -(dy * (dx * co[1])));
                         if (power > 0.0f) continue;
@@ -431,10 +475,11 @@ int ols_oracle_render(const OracleScene* s, const OracleGeom* g, OracleBin* b, O
                         if (alpha < 1.0f / 255.0f) continue;
                         const float test_T = T * (1.0f - alpha);
                         if (test_T < 0.0001f) break;  // done: entry not blended
-                        for (int ch = 0; ch < 3; ch++) C[ch] = fmaf(T, alpha * feat[3 * (size_t)id + ch], C[ch]);
+                        if (has_color)
+                            for (int ch = 0; ch < 3; ch++) C[ch] = fmaf(T, alpha * feat[3 * (size_t)id + ch], C[ch]);
                         const float* lf = s->language + (size_t)F * id;
                         for (int ch = 0; ch < F; ch++) L[ch] = fmaf(T, alpha * lf[ch], L[ch]);
-                        D = fmaf(T, alpha * g->depths[id], D);
+                        if (has_color) D = fmaf(T, alpha * depths[id], D);
                         if (test_T > 0.5f) {
 #pragma omp atomic
                             o->n_touched[id] += 1;
@@ -445,26 +490,245 @@ int ols_oracle_render(const OracleScene* s, const OracleGeom* g, OracleBin* b, O
                     const size_t pix = (size_t)pyi * W + pxi;
                     b->final_T[pix] = T;
                     b->n_contrib[pix] = last;
-                    for (int ch = 0; ch < 3; ch++) o->color[ch * HW + pix] = fmaf(s->bg[ch], T, C[ch]);
+                    if (has_color) {
+                        for (int ch = 0; ch < 3; ch++) o->color[ch * HW + pix] = fmaf(s->bg[ch], T, C[ch]);
+                        o->depth[pix] = D;
+                    }
                     for (int ch = 0; ch < F; ch++) o->language[ch * HW + pix] = L[ch];
-                    o->depth[pix] = D;
                     o->opacity[pix] = 1.0f - T;
                 }
         }
     return 0;
 }
 
-// Backward: blend (backward.cu:932-1201) then per-Gaussian (backward.cu:150-346, 541-682).
-// Per-pixel arithmetic in fp32 as the reference; per-Gaussian sums in fp64 (order independent referee).
-int ols_oracle_backward(const OracleScene* s, const OracleGeom* g, const OracleBin* b, OracleGrads* gr) {
-    const int P = s->P, W = s->W, H = s->H, tile = s->tile, F = s->F, M = s->M;
+int ols_oracle_render(const OracleScene* s, const OracleGeom* g, OracleBin* b, OracleImage* o) {
+    const float* feat = s->colors_precomp ? s->colors_precomp : g->rgb;
+    return render_pass(s, s->F, true, g->radii, g->conic_opacity, g->point_offsets, g->means2D, g->depths, feat, b, o);
+}
+
+// ---- per-Gaussian backward pieces (shared by the P/ and D/ entry points) ---------------------------------
+// computeCov2DCUDA (backward.cu:150-346).  D/'s computeCov2DCUDA_no_tau (D/backward.cu:354-446) is the same
+// arithmetic keeping only dL/dcov3D; callers pass scratch for dmean / dtau in that case.
+static void cov2d_bwd_cpu(const OracleScene* s, float fx, float fy, const float* V, const float* mp, const float* c3,
+                          float dcx, float dcy, float dcz, float* dcov, float* dmean, float* dtau) {
+    // ---- computeCov2DCUDA (backward.cu:150-346)
+    float t[3] = {V[0] * mp[0] + V[4] * mp[1] + V[8] * mp[2] + V[12], V[1] * mp[0] + V[5] * mp[1] + V[9] * mp[2] + V[13],
+                  V[2] * mp[0] + V[6] * mp[1] + V[10] * mp[2] + V[14]};
+    const float limx = 1.3f * s->tanfovx, limy = 1.3f * s->tanfovy;
+    const float txtz = t[0] / t[2], tytz = t[1] / t[2];
+    t[0] = fminf_(limx, fmaxf_(-limx, txtz)) * t[2];
+    t[1] = fminf_(limy, fmaxf_(-limy, tytz)) * t[2];
+    const float xgm = (txtz < -limx || txtz > limx) ? 0.0f : 1.0f;
+    const float ygm = (tytz < -limy || tytz > limy) ? 0.0f : 1.0f;
+    // GLM column-major: J[c][r]
+    float J[3][3] = {{fx / t[2], 0, -(fx * t[0]) / (t[2] * t[2])}, {0, fy / t[2], -(fy * t[1]) / (t[2] * t[2])}, {0, 0, 0}};
+    float Wm[3][3] = {{V[0], V[4], V[8]}, {V[1], V[5], V[9]}, {V[2], V[6], V[10]}};
+    float Vrk[3][3] = {{c3[0], c3[1], c3[2]}, {c3[1], c3[3], c3[4]}, {c3[2], c3[4], c3[5]}};
+    float Tm[3][3];  // T = W * J : T[c][r] = sum_k W[k][r] * J[c][k]
+    for (int c = 0; c < 3; c++)
+        for (int r = 0; r < 3; r++) Tm[c][r] = Wm[0][r] * J[c][0] + Wm[1][r] * J[c][1] + Wm[2][r] * J[c][2];
+    // cov2D = T^T * Vrk^T * T ; only [0][0],[0][1],[1][1] needed
+    auto quad = [&](int i0, int i1) {
+        float r = 0;
+        for (int p_ = 0; p_ < 3; p_++)
+            for (int q_ = 0; q_ < 3; q_++) r += Tm[i0][p_] * Vrk[p_][q_] * Tm[i1][q_];
+        return r;
+    };
+    const float a = quad(0, 0) + 0.3f, bb = quad(0, 1), c = quad(1, 1) + 0.3f;
+    const float denom = a * c - bb * bb;
+    float dL_da = 0, dL_db = 0, dL_dc = 0;
+    const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+    if (denom2inv != 0) {
+        dL_da = denom2inv * (-c * c * dcx + 2 * bb * c * dcy + (denom - a * c) * dcz);
+        dL_dc = denom2inv * (-a * a * dcz + 2 * a * bb * dcy + (denom - a * c) * dcx);
+        dL_db = denom2inv * 2 * (bb * c * dcx - (denom + 2 * bb * bb) * dcy + a * bb * dcz);
+        dcov[0] = (Tm[0][0] * Tm[0][0] * dL_da + Tm[0][0] * Tm[1][0] * dL_db + Tm[1][0] * Tm[1][0] * dL_dc);
+        dcov[3] = (Tm[0][1] * Tm[0][1] * dL_da + Tm[0][1] * Tm[1][1] * dL_db + Tm[1][1] * Tm[1][1] * dL_dc);
+        dcov[5] = (Tm[0][2] * Tm[0][2] * dL_da + Tm[0][2] * Tm[1][2] * dL_db + Tm[1][2] * Tm[1][2] * dL_dc);
+        dcov[1] = 2 * Tm[0][0] * Tm[0][1] * dL_da + (Tm[0][0] * Tm[1][1] + Tm[0][1] * Tm[1][0]) * dL_db + 2 * Tm[1][0] * Tm[1][1] * dL_dc;
+        dcov[2] = 2 * Tm[0][0] * Tm[0][2] * dL_da + (Tm[0][0] * Tm[1][2] + Tm[0][2] * Tm[1][0]) * dL_db + 2 * Tm[1][0] * Tm[1][2] * dL_dc;
+        dcov[4] = 2 * Tm[0][2] * Tm[0][1] * dL_da + (Tm[0][1] * Tm[1][2] + Tm[0][2] * Tm[1][1]) * dL_db + 2 * Tm[1][1] * Tm[1][2] * dL_dc;
+    }
+    auto tv = [&](int r_, int k) { return Tm[r_][0] * Vrk[k][0] + Tm[r_][1] * Vrk[k][1] + Tm[r_][2] * Vrk[k][2]; };
+    const float dT00 = 2 * tv(0, 0) * dL_da + tv(1, 0) * dL_db, dT01 = 2 * tv(0, 1) * dL_da + tv(1, 1) * dL_db,
+                dT02 = 2 * tv(0, 2) * dL_da + tv(1, 2) * dL_db;
+    const float dT10 = 2 * tv(1, 0) * dL_dc + tv(0, 0) * dL_db, dT11 = 2 * tv(1, 1) * dL_dc + tv(0, 1) * dL_db,
+                dT12 = 2 * tv(1, 2) * dL_dc + tv(0, 2) * dL_db;
+    const float dJ00 = Wm[0][0] * dT00 + Wm[0][1] * dT01 + Wm[0][2] * dT02;
+    const float dJ02 = Wm[2][0] * dT00 + Wm[2][1] * dT01 + Wm[2][2] * dT02;
+    const float dJ11 = Wm[1][0] * dT10 + Wm[1][1] * dT11 + Wm[1][2] * dT12;
+    const float dJ12 = Wm[2][0] * dT10 + Wm[2][1] * dT11 + Wm[2][2] * dT12;
+    const float tz = 1.f / t[2], tz2 = tz * tz, tz3 = tz2 * tz;
+    const float dtx = xgm * -fx * tz2 * dJ02;
+    const float dty = ygm * -fy * tz2 * dJ12;
+    const float dtz = -fx * tz2 * dJ00 - fy * tz2 * dJ11 + (2 * fx * t[0]) * tz3 * dJ02 + (2 * fy * t[1]) * tz3 * dJ12;
+    // pose part: dpC_drho = I ; dpC_dtheta = -skew(t) with columns (0,-tz,ty),(tz,0,-tx),(-ty,tx,0)
+    {
+        const float th[3][3] = {{0, -t[2], t[1]}, {t[2], 0, -t[0]}, {-t[1], t[0], 0}};
+        const float d3[3] = {dtx, dty, dtz};
+        for (int k = 0; k < 3; k++) {
+            dtau[k] += d3[k];
+            dtau[k + 3] += dtx * th[k][0] + dty * th[k][1] + dtz * th[k][2];
+        }
+    }
+    dmean[0] = V[0] * dtx + V[1] * dty + V[2] * dtz;
+    dmean[1] = V[4] * dtx + V[5] * dty + V[6] * dtz;
+    dmean[2] = V[8] * dtx + V[9] * dty + V[10] * dtz;
+    {
+        const float dW00 = J[0][0] * dT00, dW01 = J[0][0] * dT01, dW02 = J[0][0] * dT02;
+        const float dW10 = J[1][1] * dT10, dW11 = J[1][1] * dT11, dW12 = J[1][1] * dT12;
+        const float dW20 = J[0][2] * dT00 + J[1][2] * dT10, dW21 = J[0][2] * dT01 + J[1][2] * dT11,
+                    dW22 = J[0][2] * dT02 + J[1][2] * dT12;
+        // R columns (W2C rotation): c_k = (V[4k], V[4k+1], V[4k+2]); dL_dW columns likewise
+        const float c1[3] = {V[0], V[1], V[2]}, c2[3] = {V[4], V[5], V[6]}, c3_[3] = {V[8], V[9], V[10]};
+        const float w1[3] = {dW00, dW10, dW20}, w2[3] = {dW01, dW11, dW21}, w3[3] = {dW02, dW12, dW22};
+        auto nskew_col = [](const float* v, int k, float* o3) {  // column k of -skew(v)
+            const float S[3][3] = {{0, -v[2], v[1]}, {v[2], 0, -v[0]}, {-v[1], v[0], 0}};
+            o3[0] = S[k][0]; o3[1] = S[k][1]; o3[2] = S[k][2];
+        };
+        for (int k = 0; k < 3; k++) {
+            float n1[3], n2[3], n3[3];
+            nskew_col(c1, k, n1); nskew_col(c2, k, n2); nskew_col(c3_, k, n3);
+            dtau[3 + k] += (w1[0] * n1[0] + w1[1] * n1[1] + w1[2] * n1[2]) + (w2[0] * n2[0] + w2[1] * n2[1] + w2[2] * n2[2]) +
+                           (w3[0] * n3[0] + w3[1] * n3[1] + w3[2] * n3[2]);
+        }
+    }
+}
+
+// language_preprocessCUDA (backward.cu:541-682): projection + depth paths
+static void proj_bwd_cpu(const float* V, const float* Pm, const float* Praw, const float* mp, float g2x, float g2y, float dzv,
+                         float* dmean, float* dtau) {
+    // ---- language_preprocessCUDA (backward.cu:541-682)
+    const float hxw = Pm[0] * mp[0] + Pm[4] * mp[1] + Pm[8] * mp[2] + Pm[12];
+    const float hyw = Pm[1] * mp[0] + Pm[5] * mp[1] + Pm[9] * mp[2] + Pm[13];
+    const float hww = Pm[3] * mp[0] + Pm[7] * mp[1] + Pm[11] * mp[2] + Pm[15];
+    const float m_w = 1.0f / (hww + 0.0000001f);
+    const float mul1 = hxw * m_w * m_w, mul2 = hyw * m_w * m_w;
+    dmean[0] += (Pm[0] * m_w - Pm[3] * mul1) * g2x + (Pm[1] * m_w - Pm[3] * mul2) * g2y;
+    dmean[1] += (Pm[4] * m_w - Pm[7] * mul1) * g2x + (Pm[5] * m_w - Pm[7] * mul2) * g2y;
+    dmean[2] += (Pm[8] * m_w - Pm[11] * mul1) * g2x + (Pm[9] * m_w - Pm[11] * mul2) * g2y;
+    {
+        const float alpha = 1.0f * m_w, beta = -hxw * m_w * m_w, gamma = -hyw * m_w * m_w;
+        const float pa = Praw[0], pb = Praw[5], pe = Praw[11];
+        const float pC[3] = {V[0] * mp[0] + V[4] * mp[1] + V[8] * mp[2] + V[12], V[1] * mp[0] + V[5] * mp[1] + V[9] * mp[2] + V[13],
+                             V[2] * mp[0] + V[6] * mp[1] + V[10] * mp[2] + V[14]};
+        const float d1[3] = {alpha * pa, 0.f, beta * pe}, d2[3] = {0.f, alpha * pb, gamma * pe};
+        // dp_C_d_theta = -skew(p_C); (A^T x)_k = dot(column k of A, x)
+        const float th[3][3] = {{0, -pC[2], pC[1]}, {pC[2], 0, -pC[0]}, {-pC[1], pC[0], 0}};
+        for (int k = 0; k < 3; k++) {
+            dtau[k] += g2x * d1[k] + g2y * d2[k];
+            const float t1 = th[k][0] * d1[0] + th[k][1] * d1[1] + th[k][2] * d1[2];
+            const float t2 = th[k][0] * d2[0] + th[k][1] * d2[1] + th[k][2] * d2[2];
+            dtau[3 + k] += g2x * t1 + g2y * t2;
+        }
+        const float dz = dzv;
+        dmean[0] += dz * V[2]; dmean[1] += dz * V[6]; dmean[2] += dz * V[10];
+        for (int k = 0; k < 3; k++) {
+            dtau[k] += dz * (k == 2 ? 1.0f : 0.0f);
+            dtau[3 + k] += dz * th[k][2];
+        }
+    }
+}
+
+static void sh_bwd_cpu(const OracleScene* s, int i, const float* mp, const uint8_t* clamped, const float* dL_dcolors,
+                       float* dL_dsh, float* dmean, float* dtau) {
+    const int M = s->M;
+    if (s->shs) {  // backward.cu:21-145
+        const float* sh = s->shs + (size_t)i * M * 3;
+        float* dsh = dL_dsh + (size_t)i * M * 3;
+        const int deg = s->sh_degree;
+        float dir0[3] = {mp[0] - s->campos[0], mp[1] - s->campos[1], mp[2] - s->campos[2]};
+        const float len = std::sqrt(dir0[0] * dir0[0] + dir0[1] * dir0[1] + dir0[2] * dir0[2]);
+        const float x = dir0[0] / len, y = dir0[1] / len, z = dir0[2] / len;
+        float dRGB[3];
+        for (int c_ = 0; c_ < 3; c_++) dRGB[c_] = dL_dcolors[3 * (size_t)i + c_] * (clamped[3 * (size_t)i + c_] ? 0.f : 1.f);
+        float dx_[3] = {0, 0, 0}, dy_[3] = {0, 0, 0}, dz_[3] = {0, 0, 0};
+        for (int c_ = 0; c_ < 3; c_++) dsh[c_] = SH_C0 * dRGB[c_];
+        if (deg > 0) {
+            for (int c_ = 0; c_ < 3; c_++) {
+                dsh[3 + c_] = -SH_C1 * y * dRGB[c_]; dsh[6 + c_] = SH_C1 * z * dRGB[c_]; dsh[9 + c_] = -SH_C1 * x * dRGB[c_];
+                dx_[c_] = -SH_C1 * sh[9 + c_]; dy_[c_] = -SH_C1 * sh[3 + c_]; dz_[c_] = SH_C1 * sh[6 + c_];
+            }
+            if (deg > 1) {
+                const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                for (int c_ = 0; c_ < 3; c_++) {
+                    dsh[12 + c_] = SH_C2[0] * xy * dRGB[c_]; dsh[15 + c_] = SH_C2[1] * yz * dRGB[c_];
+                    dsh[18 + c_] = SH_C2[2] * (2.f * zz - xx - yy) * dRGB[c_]; dsh[21 + c_] = SH_C2[3] * xz * dRGB[c_];
+                    dsh[24 + c_] = SH_C2[4] * (xx - yy) * dRGB[c_];
+                    dx_[c_] += SH_C2[0] * y * sh[12 + c_] + SH_C2[2] * 2.f * -x * sh[18 + c_] + SH_C2[3] * z * sh[21 + c_] + SH_C2[4] * 2.f * x * sh[24 + c_];
+                    dy_[c_] += SH_C2[0] * x * sh[12 + c_] + SH_C2[1] * z * sh[15 + c_] + SH_C2[2] * 2.f * -y * sh[18 + c_] + SH_C2[4] * 2.f * -y * sh[24 + c_];
+                    dz_[c_] += SH_C2[1] * y * sh[15 + c_] + SH_C2[2] * 2.f * 2.f * z * sh[18 + c_] + SH_C2[3] * x * sh[21 + c_];
+                }
+                if (deg > 2) {
+                    for (int c_ = 0; c_ < 3; c_++) {
+                        dsh[27 + c_] = SH_C3[0] * y * (3.f * xx - yy) * dRGB[c_]; dsh[30 + c_] = SH_C3[1] * xy * z * dRGB[c_];
+                        dsh[33 + c_] = SH_C3[2] * y * (4.f * zz - xx - yy) * dRGB[c_];
+                        dsh[36 + c_] = SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy) * dRGB[c_];
+                        dsh[39 + c_] = SH_C3[4] * x * (4.f * zz - xx - yy) * dRGB[c_]; dsh[42 + c_] = SH_C3[5] * z * (xx - yy) * dRGB[c_];
+                        dsh[45 + c_] = SH_C3[6] * x * (xx - 3.f * yy) * dRGB[c_];
+                        dx_[c_] += (SH_C3[0] * sh[27 + c_] * 3.f * 2.f * xy + SH_C3[1] * sh[30 + c_] * yz + SH_C3[2] * sh[33 + c_] * -2.f * xy +
+                                    SH_C3[3] * sh[36 + c_] * -3.f * 2.f * xz + SH_C3[4] * sh[39 + c_] * (-3.f * xx + 4.f * zz - yy) +
+                                    SH_C3[5] * sh[42 + c_] * 2.f * xz + SH_C3[6] * sh[45 + c_] * 3.f * (xx - yy));
+                        dy_[c_] += (SH_C3[0] * sh[27 + c_] * 3.f * (xx - yy) + SH_C3[1] * sh[30 + c_] * xz + SH_C3[2] * sh[33 + c_] * (-3.f * yy + 4.f * zz - xx) +
+                                    SH_C3[3] * sh[36 + c_] * -3.f * 2.f * yz + SH_C3[4] * sh[39 + c_] * -2.f * xy + SH_C3[5] * sh[42 + c_] * -2.f * yz +
+                                    SH_C3[6] * sh[45 + c_] * -3.f * 2.f * xy);
+                        dz_[c_] += (SH_C3[1] * sh[30 + c_] * xy + SH_C3[2] * sh[33 + c_] * 4.f * 2.f * yz + SH_C3[3] * sh[36 + c_] * 3.f * (2.f * zz - xx - yy) +
+                                    SH_C3[4] * sh[39 + c_] * 4.f * 2.f * xz + SH_C3[5] * sh[42 + c_] * (xx - yy));
+                    }
+                }
+            }
+        }
+        const float ddir[3] = {dx_[0] * dRGB[0] + dx_[1] * dRGB[1] + dx_[2] * dRGB[2], dy_[0] * dRGB[0] + dy_[1] * dRGB[1] + dy_[2] * dRGB[2],
+                               dz_[0] * dRGB[0] + dz_[1] * dRGB[1] + dz_[2] * dRGB[2]};
+        const float sum2 = dir0[0] * dir0[0] + dir0[1] * dir0[1] + dir0[2] * dir0[2];
+        const float inv32 = 1.0f / std::sqrt(sum2 * sum2 * sum2);
+        const float dm[3] = {((+sum2 - dir0[0] * dir0[0]) * ddir[0] - dir0[1] * dir0[0] * ddir[1] - dir0[2] * dir0[0] * ddir[2]) * inv32,
+                             (-dir0[0] * dir0[1] * ddir[0] + (sum2 - dir0[1] * dir0[1]) * ddir[1] - dir0[2] * dir0[1] * ddir[2]) * inv32,
+                             (-dir0[0] * dir0[2] * ddir[0] - dir0[1] * dir0[2] * ddir[1] + (sum2 - dir0[2] * dir0[2]) * ddir[2]) * inv32};
+        for (int k = 0; k < 3; k++) { dmean[k] += dm[k]; dtau[k] += -dm[k]; }
+    }
+}
+
+static void cov3d_bwd_cpu(const OracleScene* s, const float* scales, const float* rotations, int i, const float* dcov,
+                          float* dL_dscales, float* dL_drots) {
+    if (scales) {  // backward.cu:350-413
+        const float* q = rotations + 4 * (size_t)i; const float* sc = scales + 3 * (size_t)i;
+        const float r = q[0], x = q[1], y = q[2], z = q[3];
+        // GLM column-major R[c][r] built from the 9 literals (columns)
+        const float Rm[3][3] = {{1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
+                                {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
+                                {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};
+        const float sv[3] = {s->scale_modifier * sc[0], s->scale_modifier * sc[1], s->scale_modifier * sc[2]};
+        float Mm[3][3];  // M = S * R : M[c][r] = s_r * R[c][r]
+        for (int c_ = 0; c_ < 3; c_++) for (int r_ = 0; r_ < 3; r_++) Mm[c_][r_] = sv[r_] * Rm[c_][r_];
+        const float dS[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]}, {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]}, {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
+        float dM[3][3];  // dL_dM = 2 * M * dL_dSigma : [c][r] = 2 * sum_k M[k][r] * dS[c][k]
+        for (int c_ = 0; c_ < 3; c_++) for (int r_ = 0; r_ < 3; r_++) dM[c_][r_] = 2.0f * (Mm[0][r_] * dS[c_][0] + Mm[1][r_] * dS[c_][1] + Mm[2][r_] * dS[c_][2]);
+        float Rt[3][3], dMt[3][3];
+        for (int c_ = 0; c_ < 3; c_++) for (int r_ = 0; r_ < 3; r_++) { Rt[c_][r_] = Rm[r_][c_]; dMt[c_][r_] = dM[r_][c_]; }
+        float* dsc = dL_dscales + 3 * (size_t)i;
+        for (int k = 0; k < 3; k++) dsc[k] = Rt[k][0] * dMt[k][0] + Rt[k][1] * dMt[k][1] + Rt[k][2] * dMt[k][2];
+        for (int k = 0; k < 3; k++) for (int r_ = 0; r_ < 3; r_++) dMt[k][r_] *= sv[k];
+        float* dq = dL_drots + 4 * (size_t)i;
+        dq[0] = 2 * z * (dMt[0][1] - dMt[1][0]) + 2 * y * (dMt[2][0] - dMt[0][2]) + 2 * x * (dMt[1][2] - dMt[2][1]);
+        dq[1] = 2 * y * (dMt[1][0] + dMt[0][1]) + 2 * z * (dMt[2][0] + dMt[0][2]) + 2 * r * (dMt[1][2] - dMt[2][1]) - 4 * x * (dMt[2][2] + dMt[1][1]);
+        dq[2] = 2 * x * (dMt[1][0] + dMt[0][1]) + 2 * r * (dMt[2][0] - dMt[0][2]) + 2 * z * (dMt[1][2] + dMt[2][1]) - 4 * y * (dMt[2][2] + dMt[0][0]);
+        dq[3] = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) - 4 * z * (dMt[1][1] + dMt[0][0]);
+    }
+}
+
+// Backward blend of one pass (backward.cu:932-1201; D/backward.cu:1052-1427 runs it once per footprint:
+// colour + depth with F = 0, then language only with has_color = false, where the mean2D gradient and the
+// background term do not exist).  Per-pixel arithmetic in fp32 as the reference; per-Gaussian sums in fp64
+// (order independent referee).  acc is [P, 10 + F]: mean2D.xy, conic.xyw, opacity, color.xyz, depth, lang[F].
+static void blend_bwd_pass(const OracleScene* s, int F, bool has_color, const float* conic_opacity, const float* means2D,
+                           const float* depths, const float* feat, const OracleBin* b, const float* dL_dcolor,
+                           const float* dL_dlanguage, const float* dL_ddepth, bool compat, std::vector<double>& acc) {
+    const int W = s->W, H = s->H, tile = s->tile;
     const int gx = (W + tile - 1) / tile, gy = (H + tile - 1) / tile;
     const int BS = tile * tile;
     const size_t HW = (size_t)H * W;
-    const bool compat = gr->compat != 0;
-    const float* feat = s->colors_precomp ? s->colors_precomp : g->rgb;
-    const int NV = 10 + F;  // mean2D.xy, conic.xyw, opacity, color.xyz, depth, lang[F]
-    std::vector<double> acc((size_t)P * NV, 0.0);
+    const int NV = 10 + F;
     std::vector<uint8_t> lane_ok = compat ? reduce_lane_mask(BS) : std::vector<uint8_t>(BS, 1);
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
 
@@ -478,7 +742,7 @@ int ols_oracle_backward(const OracleScene* s, const OracleGeom* g, const OracleB
                 float acc[3], lastc[3], gc[3];
             };
             std::vector<Px> px(BS);
-            std::vector<float> accF((size_t)BS * F, 0.0f), lastF((size_t)BS * F, 0.0f), gF((size_t)BS * F, 0.0f);
+            std::vector<float> accF((size_t)BS * F + 1, 0.0f), lastF((size_t)BS * F + 1, 0.0f), gF((size_t)BS * F + 1, 0.0f);
             for (int t = 0; t < BS; t++) {
                 Px& q = px[t];
                 const int pxi = tx * tile + t % tile, pyi = ty * tile + t / tile;
@@ -489,16 +753,16 @@ int ols_oracle_backward(const OracleScene* s, const OracleGeom* g, const OracleB
                 q.contributor = r1 - r0;
                 q.last_contributor = q.inside ? b->n_contrib[pix] : 0;
                 q.last_alpha = 0; q.accd = 0; q.lastd = 0;
-                q.gd = q.inside ? gr->dL_ddepth[pix] : 0.0f;
-                for (int c = 0; c < 3; c++) { q.acc[c] = 0; q.lastc[c] = 0; q.gc[c] = q.inside ? gr->dL_dcolor[c * HW + pix] : 0.0f; }
-                for (int c = 0; c < F; c++) gF[(size_t)t * F + c] = q.inside ? gr->dL_dlanguage[c * HW + pix] : 0.0f;
+                q.gd = (q.inside && has_color) ? dL_ddepth[pix] : 0.0f;
+                for (int c = 0; c < 3; c++) { q.acc[c] = 0; q.lastc[c] = 0; q.gc[c] = (q.inside && has_color) ? dL_dcolor[c * HW + pix] : 0.0f; }
+                for (int c = 0; c < F; c++) gF[(size_t)t * F + c] = q.inside ? dL_dlanguage[c * HW + pix] : 0.0f;
             }
             std::vector<uint8_t> skipv(BS);
             std::vector<float> alphav(BS), Gv(BS), dxv(BS), dyv(BS);
             std::vector<double> sum(NV);
             for (uint32_t k = r1; k-- > r0;) {
                 const uint32_t id = b->point_list[k];
-                const float* co = g->conic_opacity + 4 * (size_t)id;
+                const float* co = conic_opacity + 4 * (size_t)id;
                 int nskip = 0;
                 for (int t = 0; t < BS; t++) {
                     Px& q = px[t];
@@ -507,7 +771,7 @@ int ols_oracle_backward(const OracleScene* s, const OracleGeom* g, const OracleB
                     q.contributor = done ? q.contributor : q.contributor - 1;
                     skip |= q.contributor >= q.last_contributor;
                     const float pfx = (float)(tx * tile + t % tile), pfy = (float)(ty * tile + t / tile);
-                    const float dx = g->means2D[2 * (size_t)id] - pfx, dy = g->means2D[2 * (size_t)id + 1] - pfy;
+                    const float dx = means2D[2 * (size_t)id] - pfx, dy = means2D[2 * (size_t)id + 1] - pfy;
                     const float qd = fmaf(dx, dx * co[0], dy * (dy * co[2]));
                     const float power = fmaf(qd, -0.5f, -(dy * (dx * co[1])));
                     skip |= power > 0.0f;
@@ -520,7 +784,7 @@ int ols_oracle_backward(const OracleScene* s, const OracleGeom* g, const OracleB
                 if (nskip == BS) continue;  // backward.cu:1091-1093 (whole block skips)
                 std::fill(sum.begin(), sum.end(), 0.0);
                 const float* lf = s->language + (size_t)F * id;
-                const float depth = g->depths[id];
+                const float depth = depths[id];
                 for (int t = 0; t < BS; t++) {
                     Px& q = px[t];
                     const bool skip = skipv[t];
@@ -530,17 +794,22 @@ int ols_oracle_backward(const OracleScene* s, const OracleGeom* g, const OracleB
                     const float dch = alpha * q.T;
                     float dL_dalpha = 0.0f;
                     float lc[3];
-                    for (int c = 0; c < 3; c++) {
+                    for (int c = 0; c < (has_color ? 3 : 0); c++) {
                         const float col = feat[3 * (size_t)id + c];
                         q.acc[c] = skip ? q.acc[c] : q.last_alpha * q.lastc[c] + (1.0f - q.last_alpha) * q.acc[c];
                         q.lastc[c] = skip ? q.lastc[c] : col;
                         dL_dalpha += (col - q.acc[c]) * q.gc[c];
                         lc[c] = skip ? 0.0f : dch * q.gc[c];
                     }
-                    q.accd = skip ? q.accd : q.last_alpha * q.lastd + (1.0f - q.last_alpha) * q.accd;
-                    q.lastd = skip ? q.lastd : depth;
-                    dL_dalpha += (depth - q.accd) * q.gd;
-                    const float ld = skip ? 0.0f : dch * q.gd;
+                    float ld = 0.0f;
+                    if (has_color) {
+                        q.accd = skip ? q.accd : q.last_alpha * q.lastd + (1.0f - q.last_alpha) * q.accd;
+                        q.lastd = skip ? q.lastd : depth;
+                        dL_dalpha += (depth - q.accd) * q.gd;
+                        ld = skip ? 0.0f : dch * q.gd;
+                    } else {
+                        lc[0] = lc[1] = lc[2] = 0.0f;
+                    }
                     float* aF = &accF[(size_t)t * F]; float* lF = &lastF[(size_t)t * F]; const float* gFp = &gF[(size_t)t * F];
                     const bool lang_lane = compat ? (t == 0) : true;  // Q1
                     for (int c = 0; c < F; c++) {
@@ -553,16 +822,20 @@ int ols_oracle_backward(const OracleScene* s, const OracleGeom* g, const OracleB
                     }
                     dL_dalpha *= q.T;
                     q.last_alpha = skip ? q.last_alpha : alpha;
-                    float bgdot = 0.0f;
-                    for (int c = 0; c < 3; c++) bgdot += s->bg[c] * q.gc[c];
-                    dL_dalpha += (-q.T_final / (1.0f - alpha)) * bgdot;
+                    if (has_color) {
+                        float bgdot = 0.0f;
+                        for (int c = 0; c < 3; c++) bgdot += s->bg[c] * q.gc[c];
+                        dL_dalpha += (-q.T_final / (1.0f - alpha)) * bgdot;
+                    }
                     const float dL_dG = co[3] * dL_dalpha;
                     const float gdx = G * dx, gdy = G * dy;
                     const float dG_ddelx = -gdx * co[0] - gdy * co[1];
                     const float dG_ddely = -gdy * co[2] - gdx * co[1];
                     if (skip || !lane_ok[t]) continue;  // Q3 lane mask (all ones unless compat && 225 threads)
-                    sum[0] += dL_dG * dG_ddelx * ddelx_dx;
-                    sum[1] += dL_dG * dG_ddely * ddely_dy;
+                    if (has_color) {  // D/ drops dL_dmean2D of the language footprint (D/backward.cu:1074,1117)
+                        sum[0] += dL_dG * dG_ddelx * ddelx_dx;
+                        sum[1] += dL_dG * dG_ddely * ddely_dy;
+                    }
                     sum[2] += -0.5f * gdx * dx * dL_dG;
                     sum[3] += -0.5f * gdx * dy * dL_dG;
                     sum[4] += -0.5f * gdy * dy * dL_dG;
@@ -579,6 +852,17 @@ int ols_oracle_backward(const OracleScene* s, const OracleGeom* g, const OracleB
                 }
             }
         }
+}
+
+// Backward: blend then per-Gaussian (backward.cu:150-346, 541-682).
+int ols_oracle_backward(const OracleScene* s, const OracleGeom* g, const OracleBin* b, OracleGrads* gr) {
+    const int P = s->P, W = s->W, H = s->H, F = s->F, M = s->M;
+    const bool compat = gr->compat != 0;
+    const float* feat = s->colors_precomp ? s->colors_precomp : g->rgb;
+    const int NV = 10 + F;
+    std::vector<double> acc((size_t)P * NV, 0.0);
+    blend_bwd_pass(s, F, true, g->conic_opacity, g->means2D, g->depths, feat, b, gr->dL_dcolor, gr->dL_dlanguage,
+                   gr->dL_ddepth, compat, acc);
     // scatter to the reference's gradient tensors
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < P; i++) {
@@ -611,198 +895,162 @@ int ols_oracle_backward(const OracleScene* s, const OracleGeom* g, const OracleB
         if (!(g->radii[i] > 0)) continue;
         const float* c3 = s->cov3D_precomp ? s->cov3D_precomp + 6 * (size_t)i : g->cov3D + 6 * (size_t)i;
         const float* mp = s->means3D + 3 * (size_t)i;
-        // ---- computeCov2DCUDA (backward.cu:150-346)
-        const float dcx = gr->dL_dconic[4 * (size_t)i], dcy = gr->dL_dconic[4 * (size_t)i + 1], dcz = gr->dL_dconic[4 * (size_t)i + 3];
-        float t[3] = {V[0] * mp[0] + V[4] * mp[1] + V[8] * mp[2] + V[12], V[1] * mp[0] + V[5] * mp[1] + V[9] * mp[2] + V[13],
-                      V[2] * mp[0] + V[6] * mp[1] + V[10] * mp[2] + V[14]};
-        const float limx = 1.3f * s->tanfovx, limy = 1.3f * s->tanfovy;
-        const float txtz = t[0] / t[2], tytz = t[1] / t[2];
-        t[0] = fminf_(limx, fmaxf_(-limx, txtz)) * t[2];
-        t[1] = fminf_(limy, fmaxf_(-limy, tytz)) * t[2];
-        const float xgm = (txtz < -limx || txtz > limx) ? 0.0f : 1.0f;
-        const float ygm = (tytz < -limy || tytz > limy) ? 0.0f : 1.0f;
-        // GLM column-major: J[c][r]
-        float J[3][3] = {{fx / t[2], 0, -(fx * t[0]) / (t[2] * t[2])}, {0, fy / t[2], -(fy * t[1]) / (t[2] * t[2])}, {0, 0, 0}};
-        float Wm[3][3] = {{V[0], V[4], V[8]}, {V[1], V[5], V[9]}, {V[2], V[6], V[10]}};
-        float Vrk[3][3] = {{c3[0], c3[1], c3[2]}, {c3[1], c3[3], c3[4]}, {c3[2], c3[4], c3[5]}};
-        float Tm[3][3];  // T = W * J : T[c][r] = sum_k W[k][r] * J[c][k]
-        for (int c = 0; c < 3; c++)
-            for (int r = 0; r < 3; r++) Tm[c][r] = Wm[0][r] * J[c][0] + Wm[1][r] * J[c][1] + Wm[2][r] * J[c][2];
-        // cov2D = T^T * Vrk^T * T ; only [0][0],[0][1],[1][1] needed
-        auto quad = [&](int i0, int i1) {
-            float r = 0;
-            for (int p_ = 0; p_ < 3; p_++)
-                for (int q_ = 0; q_ < 3; q_++) r += Tm[i0][p_] * Vrk[p_][q_] * Tm[i1][q_];
-            return r;
+        cov2d_bwd_cpu(s, fx, fy, V, mp, c3, gr->dL_dconic[4 * (size_t)i], gr->dL_dconic[4 * (size_t)i + 1],
+                      gr->dL_dconic[4 * (size_t)i + 3], dcov, dmean, dtau);
+        proj_bwd_cpu(V, Pm, Praw, mp, gr->dL_dmeans2D[3 * (size_t)i], gr->dL_dmeans2D[3 * (size_t)i + 1], gr->dL_ddepths[i],
+                     dmean, dtau);
+        sh_bwd_cpu(s, i, mp, g->clamped, gr->dL_dcolors, gr->dL_dsh, dmean, dtau);
+        cov3d_bwd_cpu(s, s->scales, s->rotations, i, dcov, gr->dL_dscales, gr->dL_drots);
+    }
+    return 0;
+}
+
+// =====================================================================================================
+// Disentangled variant.  Restates D/cuda_rasterizer/forward.cu:262-430 (preprocess), :437-655 (two-pass
+// render), D/cuda_rasterizer/rasterizer_impl.cu:494-567 (doubled scan / duplicate / sort / ranges),
+// D/cuda_rasterizer/backward.cu:1052-1427 (two-loop backward render), :354-446 (no_tau), :641-803 and
+// :1504-1618 (per-Gaussian backward and its launch order).
+// =====================================================================================================
+int64_t ols_oracle_dis_preprocess(const OracleScene* s, const OracleDisExtra* x, OracleGeom* g, OracleDisGeom* gl,
+                                  int64_t* R_lang) {
+    const int P = s->P, W = s->W, H = s->H, tile = s->tile;
+    const int gx = (W + tile - 1) / tile, gy = (H + tile - 1) / tile;
+    const float fy = H / (2.0f * s->tanfovy), fx = W / (2.0f * s->tanfovx);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < P; i++) {
+        g->radii[i] = 0; gl->radii_lang[i] = 0;
+        g->tiles_touched[i] = 0; gl->tiles_touched_lang[i] = 0;
+        const float* p = s->means3D + 3 * (size_t)i;
+        const float* V = s->viewmatrix;
+        const float* Pm = s->projmatrix;
+        const float vz = xform_row(V, 2, p[0], p[1], p[2]);
+        if (!(vz > 0.2f)) continue;
+        const float hx = xform_row(Pm, 0, p[0], p[1], p[2]);
+        const float hy = xform_row(Pm, 1, p[0], p[1], p[2]);
+        const float hw = xform_row(Pm, 3, p[0], p[1], p[2]);
+        const float pw = 1.0f / (hw + 0.0000001f);
+        const float projx = hx * pw, projy = hy * pw;
+        const float *c3, *c3l;
+        if (s->cov3D_precomp) c3 = s->cov3D_precomp + 6 * (size_t)i;
+        else {
+            cov3d_from_scale_rot(s->scales + 3 * (size_t)i, s->scale_modifier, s->rotations + 4 * (size_t)i, g->cov3D + 6 * (size_t)i);
+            c3 = g->cov3D + 6 * (size_t)i;
+        }
+        if (x->cov3D_precomp_lang) c3l = x->cov3D_precomp_lang + 6 * (size_t)i;
+        else {
+            cov3d_from_scale_rot(x->scales_lang + 3 * (size_t)i, s->scale_modifier, x->rotations_lang + 4 * (size_t)i,
+                                 gl->cov3D_lang + 6 * (size_t)i);
+            c3l = gl->cov3D_lang + 6 * (size_t)i;
+        }
+        const Cov2D cv = cov2d(p, fx, fy, s->tanfovx, s->tanfovy, c3, V);
+        const Cov2D cl = cov2d(p, fx, fy, s->tanfovx, s->tanfovy, c3l, V);
+        const float det = fmaf(cv.a, cv.c, -(cv.b * cv.b));
+        const float det_l = fmaf(cl.a, cl.c, -(cl.b * cl.b));
+        if (det == 0.0f && det_l == 0.0f) continue;  // D/forward.cu:357-366
+        const float det_inv = 1.0f / det, det_inv_l = 1.0f / det_l;
+        auto radius_of = [](const Cov2D& c, float d) {
+            const float mid = (c.a + c.c) * 0.5f;
+            const float sq = std::sqrt(fmaxf_(fmaf(mid, mid, -d), 0.1f));
+            return std::ceil(std::sqrt(fmaxf_(mid + sq, mid - sq)) * 3.0f);
         };
-        const float a = quad(0, 0) + 0.3f, bb = quad(0, 1), c = quad(1, 1) + 0.3f;
-        const float denom = a * c - bb * bb;
-        float dL_da = 0, dL_db = 0, dL_dc = 0;
-        const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
-        if (denom2inv != 0) {
-            dL_da = denom2inv * (-c * c * dcx + 2 * bb * c * dcy + (denom - a * c) * dcz);
-            dL_dc = denom2inv * (-a * a * dcz + 2 * a * bb * dcy + (denom - a * c) * dcx);
-            dL_db = denom2inv * 2 * (bb * c * dcx - (denom + 2 * bb * bb) * dcy + a * bb * dcz);
-            dcov[0] = (Tm[0][0] * Tm[0][0] * dL_da + Tm[0][0] * Tm[1][0] * dL_db + Tm[1][0] * Tm[1][0] * dL_dc);
-            dcov[3] = (Tm[0][1] * Tm[0][1] * dL_da + Tm[0][1] * Tm[1][1] * dL_db + Tm[1][1] * Tm[1][1] * dL_dc);
-            dcov[5] = (Tm[0][2] * Tm[0][2] * dL_da + Tm[0][2] * Tm[1][2] * dL_db + Tm[1][2] * Tm[1][2] * dL_dc);
-            dcov[1] = 2 * Tm[0][0] * Tm[0][1] * dL_da + (Tm[0][0] * Tm[1][1] + Tm[0][1] * Tm[1][0]) * dL_db + 2 * Tm[1][0] * Tm[1][1] * dL_dc;
-            dcov[2] = 2 * Tm[0][0] * Tm[0][2] * dL_da + (Tm[0][0] * Tm[1][2] + Tm[0][2] * Tm[1][0]) * dL_db + 2 * Tm[1][0] * Tm[1][2] * dL_dc;
-            dcov[4] = 2 * Tm[0][2] * Tm[0][1] * dL_da + (Tm[0][1] * Tm[1][2] + Tm[0][2] * Tm[1][1]) * dL_db + 2 * Tm[1][1] * Tm[1][2] * dL_dc;
+        const int ri = f2i_rz(radius_of(cv, det)), ril = f2i_rz(radius_of(cl, det_l));
+        const float px = ndc2pix(projx, W), py = ndc2pix(projy, H);
+        int mn[2], mx[2], mnl[2], mxl[2];
+        get_rect(px, py, ri, tile, gx, gy, mn, mx);
+        get_rect(px, py, ril, tile, gx, gy, mnl, mxl);
+        const uint32_t tiles = (uint32_t)(mx[0] - mn[0]) * (uint32_t)(mx[1] - mn[1]);
+        const uint32_t tiles_l = (uint32_t)(mxl[0] - mnl[0]) * (uint32_t)(mxl[1] - mnl[1]);
+        if (tiles == 0 && tiles_l == 0) continue;  // D/forward.cu:391-394
+        if (!s->colors_precomp) {
+            if (tiles == 0) { g->rgb[3 * (size_t)i] = 0; g->rgb[3 * (size_t)i + 1] = 0; g->rgb[3 * (size_t)i + 2] = 0; }
+            else sh_to_rgb(i, s->sh_degree, s->M, s->means3D, s->campos, s->shs, g->clamped, g->rgb);
         }
-        auto tv = [&](int r_, int k) { return Tm[r_][0] * Vrk[k][0] + Tm[r_][1] * Vrk[k][1] + Tm[r_][2] * Vrk[k][2]; };
-        const float dT00 = 2 * tv(0, 0) * dL_da + tv(1, 0) * dL_db, dT01 = 2 * tv(0, 1) * dL_da + tv(1, 1) * dL_db,
-                    dT02 = 2 * tv(0, 2) * dL_da + tv(1, 2) * dL_db;
-        const float dT10 = 2 * tv(1, 0) * dL_dc + tv(0, 0) * dL_db, dT11 = 2 * tv(1, 1) * dL_dc + tv(0, 1) * dL_db,
-                    dT12 = 2 * tv(1, 2) * dL_dc + tv(0, 2) * dL_db;
-        const float dJ00 = Wm[0][0] * dT00 + Wm[0][1] * dT01 + Wm[0][2] * dT02;
-        const float dJ02 = Wm[2][0] * dT00 + Wm[2][1] * dT01 + Wm[2][2] * dT02;
-        const float dJ11 = Wm[1][0] * dT10 + Wm[1][1] * dT11 + Wm[1][2] * dT12;
-        const float dJ12 = Wm[2][0] * dT10 + Wm[2][1] * dT11 + Wm[2][2] * dT12;
-        const float tz = 1.f / t[2], tz2 = tz * tz, tz3 = tz2 * tz;
-        const float dtx = xgm * -fx * tz2 * dJ02;
-        const float dty = ygm * -fy * tz2 * dJ12;
-        const float dtz = -fx * tz2 * dJ00 - fy * tz2 * dJ11 + (2 * fx * t[0]) * tz3 * dJ02 + (2 * fy * t[1]) * tz3 * dJ12;
-        // pose part: dpC_drho = I ; dpC_dtheta = -skew(t) with columns (0,-tz,ty),(tz,0,-tx),(-ty,tx,0)
-        {
-            const float th[3][3] = {{0, -t[2], t[1]}, {t[2], 0, -t[0]}, {-t[1], t[0], 0}};
-            const float d3[3] = {dtx, dty, dtz};
-            for (int k = 0; k < 3; k++) {
-                dtau[k] += d3[k];
-                dtau[k + 3] += dtx * th[k][0] + dty * th[k][1] + dtz * th[k][2];
-            }
+        g->depths[i] = vz;
+        g->radii[i] = ri;
+        g->means2D[2 * (size_t)i] = px;
+        g->means2D[2 * (size_t)i + 1] = py;
+        float* co = g->conic_opacity + 4 * (size_t)i;
+        co[0] = cv.c * det_inv; co[1] = cv.b * -det_inv; co[2] = cv.a * det_inv; co[3] = s->opacities[i];
+        g->tiles_touched[i] = tiles;
+        gl->radii_lang[i] = ril;
+        float* col = gl->conic_opacity_lang + 4 * (size_t)i;
+        col[0] = cl.c * det_inv_l; col[1] = cl.b * -det_inv_l; col[2] = cl.a * det_inv_l; col[3] = x->opacities_lang[i];
+        gl->tiles_touched_lang[i] = tiles_l;
+    }
+    uint64_t acc = 0, accl = 0;
+    for (int i = 0; i < P; i++) {
+        acc += g->tiles_touched[i]; g->point_offsets[i] = (uint32_t)acc;
+        accl += gl->tiles_touched_lang[i]; gl->point_offsets_lang[i] = (uint32_t)accl;
+    }
+    *R_lang = (int64_t)accl;
+    return (int64_t)acc;
+}
+
+// oc: color / depth / opacity / n_touched of the colour pass; ol: language / opacity (= opacity_lang) / n_touched (= n_touched_lang)
+int ols_oracle_dis_render(const OracleScene* s, const OracleGeom* g, const OracleDisGeom* gl, OracleBin* bc, OracleBin* bl,
+                          OracleImage* oc, OracleImage* ol) {
+    const float* feat = s->colors_precomp ? s->colors_precomp : g->rgb;
+    render_pass(s, 0, true, g->radii, g->conic_opacity, g->point_offsets, g->means2D, g->depths, feat, bc, oc);
+    render_pass(s, s->F, false, gl->radii_lang, gl->conic_opacity_lang, gl->point_offsets_lang, g->means2D, g->depths, nullptr,
+                bl, ol);
+    return 0;
+}
+
+int ols_oracle_dis_backward(const OracleScene* s, const OracleDisExtra* x, const OracleGeom* g, const OracleDisGeom* gl,
+                            const OracleBin* bc, const OracleBin* bl, OracleDisGrads* gr) {
+    const int P = s->P, W = s->W, H = s->H, F = s->F, M = s->M;
+    const bool compat = gr->compat != 0;
+    const float* feat = s->colors_precomp ? s->colors_precomp : g->rgb;
+    std::vector<double> accc((size_t)P * 10, 0.0), accl((size_t)P * (10 + F), 0.0);
+    blend_bwd_pass(s, 0, true, g->conic_opacity, g->means2D, g->depths, feat, bc, gr->dL_dcolor, nullptr, gr->dL_ddepth,
+                   compat, accc);
+    blend_bwd_pass(s, F, false, gl->conic_opacity_lang, g->means2D, g->depths, nullptr, bl, nullptr, gr->dL_dlanguage, nullptr,
+                   compat, accl);
+    const float fy = H / (2.0f * s->tanfovy), fx = W / (2.0f * s->tanfovx);
+    const float* V = s->viewmatrix; const float* Pm = s->projmatrix; const float* Praw = s->projmatrix_raw;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < P; i++) {
+        const double* a = &accc[(size_t)i * 10];
+        const double* al = &accl[(size_t)i * (10 + F)];
+        gr->dL_dmeans2D[3 * (size_t)i] = (float)a[0];
+        gr->dL_dmeans2D[3 * (size_t)i + 1] = (float)a[1];
+        gr->dL_dmeans2D[3 * (size_t)i + 2] = 0.0f;
+        float* dc = gr->dL_dconic + 4 * (size_t)i; float* dcl = gr->dL_dconic_lang + 4 * (size_t)i;
+        dc[0] = (float)a[2]; dc[1] = (float)a[3]; dc[2] = 0.0f; dc[3] = (float)a[4];
+        dcl[0] = (float)al[2]; dcl[1] = (float)al[3]; dcl[2] = 0.0f; dcl[3] = (float)al[4];
+        gr->dL_dopacity[i] = (float)a[5];
+        gr->dL_dopacity_lang[i] = (float)al[5];
+        for (int c = 0; c < 3; c++) gr->dL_dcolors[3 * (size_t)i + c] = (float)a[6 + c];
+        gr->dL_ddepths[i] = (float)a[9];
+        for (int c = 0; c < F; c++) gr->dL_dlang[(size_t)F * i + c] = (float)al[10 + c];
+
+        float* dmean = gr->dL_dmeans3D + 3 * (size_t)i;
+        float* dcov = gr->dL_dcov3D + 6 * (size_t)i;
+        float* dcovl = gr->dL_dcov3D_lang + 6 * (size_t)i;
+        float* dtau = gr->dL_dtau + 6 * (size_t)i;
+        for (int k = 0; k < 3; k++) dmean[k] = 0;
+        for (int k = 0; k < 6; k++) { dcov[k] = 0; dcovl[k] = 0; dtau[k] = 0; }
+        for (int k = 0; k < 3; k++) { gr->dL_dscales[3 * (size_t)i + k] = 0; gr->dL_dscales_lang[3 * (size_t)i + k] = 0; }
+        for (int k = 0; k < 4; k++) { gr->dL_drots[4 * (size_t)i + k] = 0; gr->dL_drots_lang[4 * (size_t)i + k] = 0; }
+        if (gr->dL_dsh) for (int k = 0; k < 3 * M; k++) gr->dL_dsh[(size_t)3 * M * i + k] = 0;
+        const bool vis_c = g->radii[i] > 0, vis_l = gl->radii_lang[i] > 0;
+        const float* mp = s->means3D + 3 * (size_t)i;
+        const float* c3 = s->cov3D_precomp ? s->cov3D_precomp + 6 * (size_t)i : g->cov3D + 6 * (size_t)i;
+        const float* c3l = x->cov3D_precomp_lang ? x->cov3D_precomp_lang + 6 * (size_t)i : gl->cov3D_lang + 6 * (size_t)i;
+        if (vis_c) cov2d_bwd_cpu(s, fx, fy, V, mp, c3, dc[0], dc[1], dc[3], dcov, dmean, dtau);  // D/backward.cu:1552
+        if (vis_l) {                                                                               // D/backward.cu:1566 (no_tau)
+            float dm_unused[3] = {0, 0, 0}, dt_unused[6] = {0, 0, 0, 0, 0, 0};
+            cov2d_bwd_cpu(s, fx, fy, V, mp, c3l, dcl[0], dcl[1], dcl[3], dcovl, dm_unused, dt_unused);
         }
-        dmean[0] = V[0] * dtx + V[1] * dty + V[2] * dtz;
-        dmean[1] = V[4] * dtx + V[5] * dty + V[6] * dtz;
-        dmean[2] = V[8] * dtx + V[9] * dty + V[10] * dtz;
-        {
-            const float dW00 = J[0][0] * dT00, dW01 = J[0][0] * dT01, dW02 = J[0][0] * dT02;
-            const float dW10 = J[1][1] * dT10, dW11 = J[1][1] * dT11, dW12 = J[1][1] * dT12;
-            const float dW20 = J[0][2] * dT00 + J[1][2] * dT10, dW21 = J[0][2] * dT01 + J[1][2] * dT11,
-                        dW22 = J[0][2] * dT02 + J[1][2] * dT12;
-            // R columns (W2C rotation): c_k = (V[4k], V[4k+1], V[4k+2]); dL_dW columns likewise
-            const float c1[3] = {V[0], V[1], V[2]}, c2[3] = {V[4], V[5], V[6]}, c3_[3] = {V[8], V[9], V[10]};
-            const float w1[3] = {dW00, dW10, dW20}, w2[3] = {dW01, dW11, dW21}, w3[3] = {dW02, dW12, dW22};
-            auto nskew_col = [](const float* v, int k, float* o3) {  // column k of -skew(v)
-                const float S[3][3] = {{0, -v[2], v[1]}, {v[2], 0, -v[0]}, {-v[1], v[0], 0}};
-                o3[0] = S[k][0]; o3[1] = S[k][1]; o3[2] = S[k][2];
-            };
-            for (int k = 0; k < 3; k++) {
-                float n1[3], n2[3], n3[3];
-                nskew_col(c1, k, n1); nskew_col(c2, k, n2); nskew_col(c3_, k, n3);
-                dtau[3 + k] += (w1[0] * n1[0] + w1[1] * n1[1] + w1[2] * n1[2]) + (w2[0] * n2[0] + w2[1] * n2[1] + w2[2] * n2[2]) +
-                               (w3[0] * n3[0] + w3[1] * n3[1] + w3[2] * n3[2]);
-            }
+        // D/backward.cu:676-677: language_preprocessCUDA returns unless BOTH radii are positive
+        const bool both = vis_c && vis_l;
+        if (compat ? both : vis_c) {
+            proj_bwd_cpu(V, Pm, Praw, mp, gr->dL_dmeans2D[3 * (size_t)i], gr->dL_dmeans2D[3 * (size_t)i + 1], gr->dL_ddepths[i],
+                         dmean, dtau);
+            sh_bwd_cpu(s, i, mp, g->clamped, gr->dL_dcolors, gr->dL_dsh, dmean, dtau);
+            cov3d_bwd_cpu(s, s->scales, s->rotations, i, dcov, gr->dL_dscales, gr->dL_drots);
         }
-        // ---- language_preprocessCUDA (backward.cu:541-682)
-        const float hxw = Pm[0] * mp[0] + Pm[4] * mp[1] + Pm[8] * mp[2] + Pm[12];
-        const float hyw = Pm[1] * mp[0] + Pm[5] * mp[1] + Pm[9] * mp[2] + Pm[13];
-        const float hww = Pm[3] * mp[0] + Pm[7] * mp[1] + Pm[11] * mp[2] + Pm[15];
-        const float m_w = 1.0f / (hww + 0.0000001f);
-        const float g2x = gr->dL_dmeans2D[3 * (size_t)i], g2y = gr->dL_dmeans2D[3 * (size_t)i + 1];
-        const float mul1 = hxw * m_w * m_w, mul2 = hyw * m_w * m_w;
-        dmean[0] += (Pm[0] * m_w - Pm[3] * mul1) * g2x + (Pm[1] * m_w - Pm[3] * mul2) * g2y;
-        dmean[1] += (Pm[4] * m_w - Pm[7] * mul1) * g2x + (Pm[5] * m_w - Pm[7] * mul2) * g2y;
-        dmean[2] += (Pm[8] * m_w - Pm[11] * mul1) * g2x + (Pm[9] * m_w - Pm[11] * mul2) * g2y;
-        {
-            const float alpha = 1.0f * m_w, beta = -hxw * m_w * m_w, gamma = -hyw * m_w * m_w;
-            const float pa = Praw[0], pb = Praw[5], pe = Praw[11];
-            const float pC[3] = {V[0] * mp[0] + V[4] * mp[1] + V[8] * mp[2] + V[12], V[1] * mp[0] + V[5] * mp[1] + V[9] * mp[2] + V[13],
-                                 V[2] * mp[0] + V[6] * mp[1] + V[10] * mp[2] + V[14]};
-            const float d1[3] = {alpha * pa, 0.f, beta * pe}, d2[3] = {0.f, alpha * pb, gamma * pe};
-            // dp_C_d_theta = -skew(p_C); (A^T x)_k = dot(column k of A, x)
-            const float th[3][3] = {{0, -pC[2], pC[1]}, {pC[2], 0, -pC[0]}, {-pC[1], pC[0], 0}};
-            for (int k = 0; k < 3; k++) {
-                dtau[k] += g2x * d1[k] + g2y * d2[k];
-                const float t1 = th[k][0] * d1[0] + th[k][1] * d1[1] + th[k][2] * d1[2];
-                const float t2 = th[k][0] * d2[0] + th[k][1] * d2[1] + th[k][2] * d2[2];
-                dtau[3 + k] += g2x * t1 + g2y * t2;
-            }
-            const float dz = gr->dL_ddepths[i];
-            dmean[0] += dz * V[2]; dmean[1] += dz * V[6]; dmean[2] += dz * V[10];
-            for (int k = 0; k < 3; k++) {
-                dtau[k] += dz * (k == 2 ? 1.0f : 0.0f);
-                dtau[3 + k] += dz * th[k][2];
-            }
-        }
-        if (s->shs) {  // backward.cu:21-145
-            const float* sh = s->shs + (size_t)i * M * 3;
-            float* dsh = gr->dL_dsh + (size_t)i * M * 3;
-            const int deg = s->sh_degree;
-            float dir0[3] = {mp[0] - s->campos[0], mp[1] - s->campos[1], mp[2] - s->campos[2]};
-            const float len = std::sqrt(dir0[0] * dir0[0] + dir0[1] * dir0[1] + dir0[2] * dir0[2]);
-            const float x = dir0[0] / len, y = dir0[1] / len, z = dir0[2] / len;
-            float dRGB[3];
-            for (int c_ = 0; c_ < 3; c_++) dRGB[c_] = gr->dL_dcolors[3 * (size_t)i + c_] * (g->clamped[3 * (size_t)i + c_] ? 0.f : 1.f);
-            float dx_[3] = {0, 0, 0}, dy_[3] = {0, 0, 0}, dz_[3] = {0, 0, 0};
-            for (int c_ = 0; c_ < 3; c_++) dsh[c_] = SH_C0 * dRGB[c_];
-            if (deg > 0) {
-                for (int c_ = 0; c_ < 3; c_++) {
-                    dsh[3 + c_] = -SH_C1 * y * dRGB[c_]; dsh[6 + c_] = SH_C1 * z * dRGB[c_]; dsh[9 + c_] = -SH_C1 * x * dRGB[c_];
-                    dx_[c_] = -SH_C1 * sh[9 + c_]; dy_[c_] = -SH_C1 * sh[3 + c_]; dz_[c_] = SH_C1 * sh[6 + c_];
-                }
-                if (deg > 1) {
-                    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-                    for (int c_ = 0; c_ < 3; c_++) {
-                        dsh[12 + c_] = SH_C2[0] * xy * dRGB[c_]; dsh[15 + c_] = SH_C2[1] * yz * dRGB[c_];
-                        dsh[18 + c_] = SH_C2[2] * (2.f * zz - xx - yy) * dRGB[c_]; dsh[21 + c_] = SH_C2[3] * xz * dRGB[c_];
-                        dsh[24 + c_] = SH_C2[4] * (xx - yy) * dRGB[c_];
-                        dx_[c_] += SH_C2[0] * y * sh[12 + c_] + SH_C2[2] * 2.f * -x * sh[18 + c_] + SH_C2[3] * z * sh[21 + c_] + SH_C2[4] * 2.f * x * sh[24 + c_];
-                        dy_[c_] += SH_C2[0] * x * sh[12 + c_] + SH_C2[1] * z * sh[15 + c_] + SH_C2[2] * 2.f * -y * sh[18 + c_] + SH_C2[4] * 2.f * -y * sh[24 + c_];
-                        dz_[c_] += SH_C2[1] * y * sh[15 + c_] + SH_C2[2] * 2.f * 2.f * z * sh[18 + c_] + SH_C2[3] * x * sh[21 + c_];
-                    }
-                    if (deg > 2) {
-                        for (int c_ = 0; c_ < 3; c_++) {
-                            dsh[27 + c_] = SH_C3[0] * y * (3.f * xx - yy) * dRGB[c_]; dsh[30 + c_] = SH_C3[1] * xy * z * dRGB[c_];
-                            dsh[33 + c_] = SH_C3[2] * y * (4.f * zz - xx - yy) * dRGB[c_];
-                            dsh[36 + c_] = SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy) * dRGB[c_];
-                            dsh[39 + c_] = SH_C3[4] * x * (4.f * zz - xx - yy) * dRGB[c_]; dsh[42 + c_] = SH_C3[5] * z * (xx - yy) * dRGB[c_];
-                            dsh[45 + c_] = SH_C3[6] * x * (xx - 3.f * yy) * dRGB[c_];
-                            dx_[c_] += (SH_C3[0] * sh[27 + c_] * 3.f * 2.f * xy + SH_C3[1] * sh[30 + c_] * yz + SH_C3[2] * sh[33 + c_] * -2.f * xy +
-                                        SH_C3[3] * sh[36 + c_] * -3.f * 2.f * xz + SH_C3[4] * sh[39 + c_] * (-3.f * xx + 4.f * zz - yy) +
-                                        SH_C3[5] * sh[42 + c_] * 2.f * xz + SH_C3[6] * sh[45 + c_] * 3.f * (xx - yy));
-                            dy_[c_] += (SH_C3[0] * sh[27 + c_] * 3.f * (xx - yy) + SH_C3[1] * sh[30 + c_] * xz + SH_C3[2] * sh[33 + c_] * (-3.f * yy + 4.f * zz - xx) +
-                                        SH_C3[3] * sh[36 + c_] * -3.f * 2.f * yz + SH_C3[4] * sh[39 + c_] * -2.f * xy + SH_C3[5] * sh[42 + c_] * -2.f * yz +
-                                        SH_C3[6] * sh[45 + c_] * -3.f * 2.f * xy);
-                            dz_[c_] += (SH_C3[1] * sh[30 + c_] * xy + SH_C3[2] * sh[33 + c_] * 4.f * 2.f * yz + SH_C3[3] * sh[36 + c_] * 3.f * (2.f * zz - xx - yy) +
-                                        SH_C3[4] * sh[39 + c_] * 4.f * 2.f * xz + SH_C3[5] * sh[42 + c_] * (xx - yy));
-                        }
-                    }
-                }
-            }
-            const float ddir[3] = {dx_[0] * dRGB[0] + dx_[1] * dRGB[1] + dx_[2] * dRGB[2], dy_[0] * dRGB[0] + dy_[1] * dRGB[1] + dy_[2] * dRGB[2],
-                                   dz_[0] * dRGB[0] + dz_[1] * dRGB[1] + dz_[2] * dRGB[2]};
-            const float sum2 = dir0[0] * dir0[0] + dir0[1] * dir0[1] + dir0[2] * dir0[2];
-            const float inv32 = 1.0f / std::sqrt(sum2 * sum2 * sum2);
-            const float dm[3] = {((+sum2 - dir0[0] * dir0[0]) * ddir[0] - dir0[1] * dir0[0] * ddir[1] - dir0[2] * dir0[0] * ddir[2]) * inv32,
-                                 (-dir0[0] * dir0[1] * ddir[0] + (sum2 - dir0[1] * dir0[1]) * ddir[1] - dir0[2] * dir0[1] * ddir[2]) * inv32,
-                                 (-dir0[0] * dir0[2] * ddir[0] - dir0[1] * dir0[2] * ddir[1] + (sum2 - dir0[2] * dir0[2]) * ddir[2]) * inv32};
-            for (int k = 0; k < 3; k++) { dmean[k] += dm[k]; dtau[k] += -dm[k]; }
-        }
-        if (s->scales) {  // backward.cu:350-413
-            const float* q = s->rotations + 4 * (size_t)i; const float* sc = s->scales + 3 * (size_t)i;
-            const float r = q[0], x = q[1], y = q[2], z = q[3];
-            // GLM column-major R[c][r] built from the 9 literals (columns)
-            const float Rm[3][3] = {{1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
-                                    {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
-                                    {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};
-            const float sv[3] = {s->scale_modifier * sc[0], s->scale_modifier * sc[1], s->scale_modifier * sc[2]};
-            float Mm[3][3];  // M = S * R : M[c][r] = s_r * R[c][r]
-            for (int c_ = 0; c_ < 3; c_++) for (int r_ = 0; r_ < 3; r_++) Mm[c_][r_] = sv[r_] * Rm[c_][r_];
-            const float dS[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]}, {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]}, {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
-            float dM[3][3];  // dL_dM = 2 * M * dL_dSigma : [c][r] = 2 * sum_k M[k][r] * dS[c][k]
-            for (int c_ = 0; c_ < 3; c_++) for (int r_ = 0; r_ < 3; r_++) dM[c_][r_] = 2.0f * (Mm[0][r_] * dS[c_][0] + Mm[1][r_] * dS[c_][1] + Mm[2][r_] * dS[c_][2]);
-            float Rt[3][3], dMt[3][3];
-            for (int c_ = 0; c_ < 3; c_++) for (int r_ = 0; r_ < 3; r_++) { Rt[c_][r_] = Rm[r_][c_]; dMt[c_][r_] = dM[r_][c_]; }
-            float* dsc = gr->dL_dscales + 3 * (size_t)i;
-            for (int k = 0; k < 3; k++) dsc[k] = Rt[k][0] * dMt[k][0] + Rt[k][1] * dMt[k][1] + Rt[k][2] * dMt[k][2];
-            for (int k = 0; k < 3; k++) for (int r_ = 0; r_ < 3; r_++) dMt[k][r_] *= sv[k];
-            float* dq = gr->dL_drots + 4 * (size_t)i;
-            dq[0] = 2 * z * (dMt[0][1] - dMt[1][0]) + 2 * y * (dMt[2][0] - dMt[0][2]) + 2 * x * (dMt[1][2] - dMt[2][1]);
-            dq[1] = 2 * y * (dMt[1][0] + dMt[0][1]) + 2 * z * (dMt[2][0] + dMt[0][2]) + 2 * r * (dMt[1][2] - dMt[2][1]) - 4 * x * (dMt[2][2] + dMt[1][1]);
-            dq[2] = 2 * x * (dMt[1][0] + dMt[0][1]) + 2 * r * (dMt[2][0] - dMt[0][2]) + 2 * z * (dMt[1][2] + dMt[2][1]) - 4 * y * (dMt[2][2] + dMt[0][0]);
-            dq[3] = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) - 4 * z * (dMt[1][1] + dMt[0][0]);
-        }
+        if (compat ? both : vis_l) cov3d_bwd_cpu(s, x->scales_lang, x->rotations_lang, i, dcovl, gr->dL_dscales_lang, gr->dL_drots_lang);
     }
     return 0;
 }

@@ -43,48 +43,90 @@ struct BwdBlendArgs {
     const float* dL_dcolor;
     const float* dL_dlanguage;
     const float* dL_ddepth;
+    const uint8_t* warp_hits;  // [R] from the forward: which pixel blocks of the tile blended each list entry
     float* gacc;             // [P, grad_floats(F)] zero-initialised
     uint32_t lane_ok[8];     // Q3 lane mask (compat); all ones otherwise
 };
 
-// Sum NV per-lane values over the 32 lanes of a warp; afterwards v[0] of lane L holds the total of
-// value index (L * NV / 32).  NV/2 + NV/4 + ... shuffles instead of 5 * NV.
-template <int NV>
-__device__ __forceinline__ void warp_multi_reduce(float (&v)[NV], int lane) {
-    static_assert(NV == 32 || NV == 16, "NV must be 16 or 32");
-    int off = 16;
+typedef unsigned long long f32x2;  // two floats in one 64-bit register pair
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float hsum2(f32x2 v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo + hi;
+}
+
+// Sum N per-lane values over the 32 lanes of a warp with N/2 + N/4 + ... shuffles instead of 5 * N: at the
+// level that exchanges lane bit OFF, the lanes with the bit clear keep the lower half of the values and the
+// others the upper half (an odd middle value is kept by both).  Afterwards v[0] of lane L holds the total
+// of value multi_reduce_owner<N>(L) (or a duplicate when that returns -1).
+template <int N, int OFF>
+__device__ __forceinline__ void multi_reduce_level(float* v, int lane) {
+    constexpr int H = (N + 1) / 2;
+    if (N > 1) {
+        const bool hi = (lane & OFF) != 0;
 #pragma unroll
-    for (int n = NV / 2; n >= 1; n >>= 1) {
-        const bool hi = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < n; i++) {
-            const float send = hi ? v[i] : v[i + n];
-            const float keep = hi ? v[i + n] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        for (int i = 0; i < N / 2; i++) {
+            const float send = hi ? v[i] : v[i + H];
+            const float keep = hi ? v[i + H] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
         }
-        off >>= 1;
+        if (N & 1) v[H - 1] += __shfl_xor_sync(0xffffffffu, v[H - 1], OFF);
+    } else {
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], OFF);
     }
-    if (NV == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    if constexpr (OFF > 1) multi_reduce_level<H, OFF / 2>(v, lane);
+}
+template <int N>
+__device__ __forceinline__ void warp_multi_reduce(float* v, int lane) {
+    static_assert(N >= 1 && N <= 32, "one value per lane at the end");
+    multi_reduce_level<N, 16>(v, lane);
+}
+template <int N>
+__device__ __forceinline__ int multi_reduce_owner(int lane) {
+    int ns[6];
+    ns[0] = N;
+#pragma unroll
+    for (int k = 0; k < 5; k++) ns[k + 1] = (ns[k] + 1) / 2;
+    int s = 0;
+    bool owner = true;
+#pragma unroll
+    for (int k = 4; k >= 0; k--) {
+        const int n = ns[k], h = (n + 1) / 2;
+        const bool b = (lane & (16 >> k)) != 0;
+        if (n == 1) owner = owner && !b;
+        else if (s < n / 2) s += b ? h : 0;
+        else owner = owner && !b;  // the odd middle value lives in both halves
+    }
+    return owner ? s : -1;
 }
 
 // NCOL = 3: colour + depth channels take part (joint pass of P/, colour pass of D/); NCOL = 0: the
 // language-only pass of D/ (no mean2D gradient, no background term: D/backward.cu:1318-1427).
-// Thread -> pixel mapping: warp w owns the 8x4 pixel block ((w & 1) * 8, (w >> 1) * 4) of the tile, as in
-// the forward; a Gaussian whose conservative extents miss the block is never evaluated by that warp.
+// Thread -> pixel mapping as in the forward: warp w owns the 8x4 pixel block ((w & 1) * 8, (w >> 1) * 4).
+// The forward left one byte per list entry saying which pixel blocks blended it (warp_hits); an entry is
+// "visited" by the reference's block-wide loop iff that byte is non-zero (a pixel blends an entry in the
+// forward exactly when the backward's skip tests pass for it), so no separate scan of the list is needed.
 template <int TILE, int NCOL, int F, bool COMPAT>
-__global__ void __launch_bounds__(BWD_THREADS) k_blend_bwd(const BwdBlendArgs a) {
+__global__ void __launch_bounds__(BWD_THREADS, 4) k_blend_bwd(const BwdBlendArgs a) {
     static_assert(TILE <= 16 && BWD_BATCH == 32, "8 warps of 8x4 pixels; one ballot per batch");
+    static_assert(NCOL == 0 || NCOL == 3, "colour channels");
     constexpr int NCH = NCOL + F;
     constexpr int REC = rec_floats_nch(NCH);
     constexpr int R4 = REC / 4;
-    constexpr int EXT = REC - 2;
     constexpr int GR = grad_floats(F);
-    constexpr int NQ = (NCH + 3) / 4;  // float4 chunks holding the channels
+    constexpr int NPAIR = (NCH + 1) / 2;          // channel pairs as stored from REC_CH on
+    constexpr int LP0 = (NCOL + 1) / 2;           // first pair made of language channels only
+    constexpr int NGEO = NCOL ? 10 : 4;           // reduced values before the language block
+    constexpr int NV = COMPAT ? NGEO : NGEO + F;  // values reduced per (warp, Gaussian)
     __shared__ __align__(16) float s_rec[BWD_BATCH * REC];
     __shared__ uint32_t s_id[BWD_BATCH];
     __shared__ float s_acc[BWD_BATCH * GR];
     __shared__ uint32_t s_maxc;
-    __shared__ uint32_t s_mask;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int tile_x = blockIdx.x % a.gx, tile_y = blockIdx.x / a.gx;
@@ -95,15 +137,12 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_bwd(const BwdBlendArgs a)
     const float pfx = (float)pxi, pfy = (float)pyi;
     const size_t HW = (size_t)a.W * a.H;
     const size_t pix = inside ? (size_t)pyi * a.W + pxi : 0;
-    const float fx0 = (float)(tile_x * TILE + bx0), fy0 = (float)(tile_y * TILE + by0);
-    const float fx1 = (float)min(min(tile_x * TILE + bx0 + 7, tile_x * TILE + TILE - 1), a.W - 1);
-    const float fy1 = (float)min(min(tile_y * TILE + by0 + 3, tile_y * TILE + TILE - 1), a.H - 1);
 
     uint2 rg = a.ranges[blockIdx.x];
     if (a.info->overflow) rg = make_uint2(0u, 0u);
     const uint32_t last_contributor = inside ? a.n_contrib[pix] : 0u;
     const uint32_t warp_maxc = __reduce_max_sync(0xffffffffu, last_contributor);
-    if (tid == 0) { s_maxc = 0; s_mask = 0; }
+    if (tid == 0) s_maxc = 0;
     for (int e = tid; e < BWD_BATCH * GR; e += BWD_THREADS) s_acc[e] = 0.0f;
     __syncthreads();
     if (lane == 0 && warp_maxc) atomicMax(&s_maxc, warp_maxc);
@@ -114,10 +153,10 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_bwd(const BwdBlendArgs a)
 
     const float T_final = inside ? a.final_T[pix] : 0.0f;
     float T = T_final;
-    float g[NCH > 0 ? NCH : 1];
+    float g[NCH > 0 ? NCH + 1 : 1];  // dL/dpixel per channel (+1: the zero partner of an odd last channel)
     float gd = 0.0f;
 #pragma unroll
-    for (int c = 0; c < NCH; c++) g[c] = 0.0f;
+    for (int c = 0; c < NCH + 1; c++) g[c] = 0.0f;
     if (inside) {
 #pragma unroll
         for (int c = 0; c < NCOL; c++) g[c] = a.dL_dcolor[c * HW + pix];
@@ -125,16 +164,38 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_bwd(const BwdBlendArgs a)
         for (int c = 0; c < F; c++) g[NCOL + c] = a.dL_dlanguage[c * HW + pix];
         if (NCOL) gd = a.dL_ddepth[pix];
     }
+    f32x2 g2[NPAIR > LP0 ? NPAIR - LP0 : 1];  // language-only pairs of g, packed for FFMA2
+#pragma unroll
+    for (int p = LP0; p < NPAIR; p++) asm("mov.b64 %0, {%1, %2};" : "=l"(g2[p - LP0]) : "f"(g[2 * p]), "f"(g[2 * p + 1]));
     float bg_dot = 0.0f;
     if (NCOL) bg_dot = a.bg[0] * g[0] + a.bg[1] * g[1] + a.bg[2] * g[2];
     const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
     // Q3: the lane mask is indexed by the reference's thread rank ly * TILE + lx
     const int ref_rank = ly * TILE + lx;
     const bool lane_ok = COMPAT ? (inside && ((a.lane_ok[(ref_rank >> 5) & 7] >> (ref_rank & 31)) & 1u) != 0) : true;
+    const int own = multi_reduce_owner<NV>(lane);
+    const int own_dst = own < 0 ? -1 : (NCOL ? own : (own < NGEO ? GR_CX + own : GR_LANG + (own - NGEO)));
 
     float last_alpha = 0.0f;
     float A_c = 0.0f, Dl_c = 0.0f;  // rgb + depth part of sum_ch accum_rec*g and of last_color*g
     float A_f = 0.0f, Dl_f = 0.0f;  // language part (separate because of Q2 in compat mode)
+    // Q2 bookkeeping (compat): until a pixel of this warp has blended anything, last_alpha is 0 for all of
+    // its lanes and the unguarded recurrence only replaces Dl_f, so only the latest visited entry matters.
+    bool fresh = true;
+
+    // language part of sum_ch c_ch * dL/dpix_ch for the record at rj
+    auto lang_dot = [&](const float* rj) -> float {
+        float d = 0.0f;
+        if (F > 0) {
+            if (NCOL & 1) d = rj[REC_CH + NCOL] * g[NCOL];  // the language channel sharing a pair with blue
+            f32x2 acc = 0ull;
+#pragma unroll
+            for (int p = LP0; p < NPAIR; p++)
+                acc = ffma2(*reinterpret_cast<const f32x2*>(rj + REC_CH + 2 * p), g2[p - LP0], acc);
+            d += hsum2(acc);
+        }
+        return d;
+    };
 
     const int n_batches = (total + BWD_BATCH - 1) / BWD_BATCH;
     for (int b = n_batches - 1; b >= 0; b--) {
@@ -149,89 +210,62 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_bwd(const BwdBlendArgs a)
                 cp_async16(&s_rec[gi * REC + q * 4], a.records + (size_t)id * REC + q * 4);
             }
         }
-        if (COMPAT && tid == 0) s_mask = 0;
         cp_async_commit();
+        const uint32_t hit = lane < cnt ? (uint32_t)a.warp_hits[rg.x + base + lane] : 0u;
+        const uint32_t mine = __ballot_sync(0xffffffffu, (hit >> wid) & 1u);  // entries a pixel of this warp blended
+        uint32_t visit = COMPAT ? __ballot_sync(0xffffffffu, hit != 0u) : mine;
         cp_async_wait<0>();
         __syncthreads();
-        const float4* r4 = reinterpret_cast<const float4*>(s_rec);
-
-        // entries this warp's pixel block can reach at all (one entry per lane), then, per pixel, which of
-        // those it contributes to (same decisions as the forward)
-        unsigned cand;
-        {
-            bool hit = false;
-            if (lane < cnt && (uint32_t)(base + lane) < warp_maxc) {
-                const float2 c = *reinterpret_cast<const float2*>(s_rec + lane * REC + REC_X);
-                const float2 h = *reinterpret_cast<const float2*>(s_rec + lane * REC + EXT);
-                hit = (c.x + h.x >= fx0) && (c.x - h.x <= fx1) && (c.y + h.y >= fy0) && (c.y - h.y <= fy1);
-            }
-            cand = __ballot_sync(0xffffffffu, hit);
-        }
-        uint32_t mymask = 0;
-        for (unsigned m = cand; m; m &= m - 1) {
-            const int j = __ffs(m) - 1;
-            if (inside && (uint32_t)(base + j) < last_contributor) {
-                const float4 g0 = r4[j * R4 + 0];
-                const float4 g1 = r4[j * R4 + 1];
-                const float dx = fsub(g0.x, pfx), dy = fsub(g0.y, pfy);
-                const float power =
-                    ffma(ffma(dx, fmul(dx, g0.z), fmul(dy, fmul(dy, g1.x))), -0.5f, -fmul(dy, fmul(dx, g0.w)));
-                if (!(power > 0.0f) && !(power < g1.z)) {
-                    const float alpha = fminf(0.99f, fmul(g1.y, expf(power)));
-                    if (!(alpha < 1.0f / 255.0f)) mymask |= 1u << j;
-                }
-            }
-        }
-        uint32_t visit;  // Gaussians somebody in the block (compat) / warp (exact) contributes to
-        if (COMPAT) {
-            const uint32_t wm = __reduce_or_sync(0xffffffffu, mymask);
-            if (lane == 0 && wm) atomicOr(&s_mask, wm);
-            __syncthreads();
-            visit = s_mask;
-        } else {
-            visit = __reduce_or_sync(0xffffffffu, mymask);
-        }
+        int pend = -1;  // compat: visited entry whose Dl_f update is still owed (warp still fresh)
 
         while (visit) {
             const int j = 31 - __clz(visit);  // back to front
             visit &= ~(1u << j);
-            const bool contrib = (mymask >> j) & 1u;
-            const float4 g0 = r4[j * R4 + 0];  // x y A B
-            const float4 g1 = r4[j * R4 + 1];  // C op pth depth
-            constexpr int NV = COMPAT ? 16 : 32;
+            const float* rj = s_rec + j * REC;
+            const bool warp_blends = (mine >> j) & 1u;
+            if (!warp_blends) {  // compat only: another pixel block of the tile blends this entry
+                if (F > 0) {
+                    if (fresh) { pend = j; continue; }
+                    if (inside) {  // Q2: the language recurrence advances for every pixel of a visited Gaussian
+                        A_f = last_alpha * Dl_f + (1.0f - last_alpha) * A_f;
+                        Dl_f = lang_dot(rj);
+                    }
+                }
+                continue;
+            }
+            if (COMPAT && F > 0) {
+                if (pend >= 0) { Dl_f = lang_dot(s_rec + pend * REC); pend = -1; }
+                fresh = false;
+            }
+            const float4 g0 = *reinterpret_cast<const float4*>(rj);      // x y A B
+            const float4 g1 = *reinterpret_cast<const float4*>(rj + 4);  // C op pth depth
+            const float dx = fsub(g0.x, pfx), dy = fsub(g0.y, pfy);
+            const float power = ffma(ffma(dx, fmul(dx, g0.z), fmul(dy, fmul(dy, g1.x))), -0.5f, -fmul(dy, fmul(dx, g0.w)));
+            float G = 0.0f, alpha = 0.0f;
+            bool contrib = false;
+            if (inside && (uint32_t)(base + j) < last_contributor && !(power > 0.0f) && !(power < g1.z)) {
+                G = expf(power);
+                alpha = fminf(0.99f, fmul(g1.y, G));
+                contrib = !(alpha < 1.0f / 255.0f);
+            }
             float v[NV];
 #pragma unroll
             for (int i = 0; i < NV; i++) v[i] = 0.0f;
-            float D_f = 0.0f, D_c = 0.0f;
+            float D_f = 0.0f;
             if (inside && ((COMPAT && F > 0) || contrib)) {
-                // D = sum_ch c_ch * dL/dpix_ch over rgb (+ depth) / language
-#pragma unroll
-                for (int q = 0; q < NQ; q++) {
-                    const float4 c = r4[j * R4 + 2 + q];
-                    const float cv[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const int k = 4 * q + e;
-                        if (k < NCOL) D_c = fmaf(cv[e], g[k], D_c);
-                        else if (k < NCH) D_f = fmaf(cv[e], g[k], D_f);
-                    }
-                }
-                if (NCOL) D_c = fmaf(g1.w, gd, D_c);
-                if (COMPAT && F > 0) {  // Q2: recurrence advances for every pixel of a visited Gaussian
+                D_f = lang_dot(rj);
+                if (COMPAT && F > 0) {
                     A_f = last_alpha * Dl_f + (1.0f - last_alpha) * A_f;
                     Dl_f = D_f;
                 }
             }
             float w = 0.0f;
             if (contrib) {
-                const float dx = fsub(g0.x, pfx), dy = fsub(g0.y, pfy);
-                const float power =
-                    ffma(ffma(dx, fmul(dx, g0.z), fmul(dy, fmul(dy, g1.x))), -0.5f, -fmul(dy, fmul(dx, g0.w)));
-                const float G = expf(power);
-                const float alpha = fminf(0.99f, fmul(g1.y, G));
                 T = T / (1.0f - alpha);
                 w = alpha * T;
+                float D_c = 0.0f;
                 if (NCOL) {
+                    D_c = rj[REC_CH] * g[0] + rj[REC_CH + 1] * g[1] + rj[REC_CH + 2] * g[2] + g1.w * gd;
                     A_c = last_alpha * Dl_c + (1.0f - last_alpha) * A_c;
                     Dl_c = D_c;
                 }
@@ -245,6 +279,7 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_bwd(const BwdBlendArgs a)
                 const float dL_dG = g1.y * dL_dalpha;
                 const float gdx = G * dx, gdy = G * dy;
                 if (lane_ok) {
+                    constexpr int C0 = NCOL ? GR_CX : 0;  // position of conic.x in v[]
                     if (NCOL) {  // D/ drops the mean gradient of the language footprint (D/backward.cu:1074,1117)
                         const float dG_ddelx = -gdx * g0.z - gdy * g0.w;
                         const float dG_ddely = -gdy * g1.x - gdx * g0.w;
@@ -255,34 +290,27 @@ __global__ void __launch_bounds__(BWD_THREADS) k_blend_bwd(const BwdBlendArgs a)
                         v[GR_RGB + 1] = w * g[1];
                         v[GR_RGB + 2] = w * g[2];
                     }
-                    v[GR_CX] = -0.5f * gdx * dx * dL_dG;
-                    v[GR_CY] = -0.5f * gdx * dy * dL_dG;
-                    v[GR_CW] = -0.5f * gdy * dy * dL_dG;
-                    v[GR_OP] = G * dL_dalpha;
+                    v[C0 + 0] = -0.5f * gdx * dx * dL_dG;
+                    v[C0 + 1] = -0.5f * gdx * dy * dL_dG;
+                    v[C0 + 2] = -0.5f * gdy * dy * dL_dG;
+                    v[C0 + 3] = G * dL_dalpha;
                     if (!COMPAT) {
 #pragma unroll
-                        for (int c = 0; c < F; c++) v[GR_LANG + c] = w * g[NCOL + c];
+                        for (int c = 0; c < F; c++) v[NGEO + c] = w * g[NCOL + c];
                     }
                 }
             }
-            if (COMPAT) {
-                // Q1: only the tile's first thread contributes its own pixel's language gradient
-                if (F > 0 && tid == 0 && contrib) {
+            // Q1 (compat): only the tile's first thread contributes its own pixel's language gradient
+            if (COMPAT && F > 0 && tid == 0 && contrib) {
 #pragma unroll
-                    for (int c = 0; c < F; c++) s_acc[j * GR + GR_LANG + c] += w * g[NCOL + c];
-                }
-                if (__any_sync(0xffffffffu, contrib && lane_ok)) {
-                    warp_multi_reduce<NV>(v, lane);
-                    const int vi = lane >> 1;
-                    if ((lane & 1) == 0 && vi < 10 && v[0] != 0.0f) atomicAdd(&s_acc[j * GR + vi], v[0]);
-                }
-            } else {
-                if (__any_sync(0xffffffffu, contrib)) {
-                    warp_multi_reduce<NV>(v, lane);
-                    if (lane < 10 + F && v[0] != 0.0f) atomicAdd(&s_acc[j * GR + lane], v[0]);
-                }
+                for (int c = 0; c < F; c++) s_acc[j * GR + GR_LANG + c] += w * g[NCOL + c];
+            }
+            if (__any_sync(0xffffffffu, contrib && lane_ok)) {
+                warp_multi_reduce<NV>(v, lane);
+                if (own_dst >= 0 && v[0] != 0.0f) atomicAdd(&s_acc[j * GR + own_dst], v[0]);
             }
         }
+        if (COMPAT && F > 0 && pend >= 0) Dl_f = lang_dot(s_rec + pend * REC);
         __syncthreads();
         // flush the batch: one global atomic per (Gaussian, value) that received something
         for (int e = tid; e < cnt * GR; e += BWD_THREADS) {
@@ -775,6 +803,7 @@ static int run_blend_bwd(int W, int H, int tile, int ncol, int F, unsigned flags
     ba.final_T = (const float*)(ws + L.final_T); ba.n_contrib = (const uint32_t*)(ws + L.n_contrib);
     ba.dL_dcolor = dL_dcolor; ba.dL_dlanguage = dL_dlanguage; ba.dL_ddepth = dL_ddepth;
     ba.gacc = gacc;
+    ba.warp_hits = (const uint8_t*)(ws + L.warp_hits);
     reduce_lane_mask(tile * tile, exact, ba.lane_ok);
     const int key = tile * 10000 + ncol * 100 + F;
     switch (key) {

@@ -885,6 +885,7 @@ struct BlendArgs {
     float* out_depth;
     float* out_opacity;
     int32_t* n_touched;
+    uint8_t* warp_hits;  // [R] per list entry: which of the tile's 8 pixel blocks blended it (read by the backward)
 };
 
 typedef unsigned long long f32x2;  // two floats in one 64-bit register pair (lo = first)
@@ -909,7 +910,7 @@ __device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {  // per-component mul
 
 // NCOL = 3: the pass blends rgb (+ background) and depth; NCOL = 0: language channels only (second pass of D/).
 template <int TILE, int NCOL, int F, bool BITEXACT>
-__global__ void __launch_bounds__(BLEND_THREADS) k_blend(const BlendArgs a) {
+__global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend(const BlendArgs a) {
     static_assert(TILE <= 16, "8 warps of 8x4 pixels cover at most 16x16");
     static_assert(NCOL == 0 || NCOL == 3, "colour channels");
     constexpr int NCH = NCOL + F;               // channels stored from REC_CH on (an odd count is zero-padded)
@@ -921,6 +922,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const BlendArgs a) {
     static_assert(REC_CH + 2 * NPAIR <= EXT, "channel pairs must not run into the extents");
     __shared__ __align__(16) float s_rec[2][BLEND_BATCH * REC];
     __shared__ uint32_t s_id[2][BLEND_BATCH];
+    __shared__ uint32_t s_hit[2][BLEND_THREADS / 32][BLEND_BATCH / 32];  // per warp: bit j = the warp blended entry j of the batch
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int tile_x = blockIdx.x % a.gx, tile_y = blockIdx.x / a.gx;
@@ -929,6 +931,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const BlendArgs a) {
     const int pxi = tile_x * TILE + lx, pyi = tile_y * TILE + ly;
     const bool inside = lx < TILE && ly < TILE && pxi < a.W && pyi < a.H;
     const float pfx = (float)pxi, pfy = (float)pyi;
+    if (tid < 2 * (BLEND_THREADS / 32) * (BLEND_BATCH / 32)) (&s_hit[0][0][0])[tid] = 0u;
     // this warp's pixel rectangle, clipped to the tile and the image
     const float fx0 = (float)(tile_x * TILE + bx0), fy0 = (float)(tile_y * TILE + by0);
     const float fx1 = (float)min(min(tile_x * TILE + bx0 + 7, tile_x * TILE + TILE - 1), a.W - 1);
@@ -939,6 +942,15 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const BlendArgs a) {
     const int total = (int)(rg.y - rg.x);
     const int n_batches = (total + BLEND_BATCH - 1) / BLEND_BATCH;
 
+    auto flush_hits = [&](int b) {  // batch b is complete: its hit bytes go to global memory, the buffer is cleared
+        if (tid < BLEND_BATCH) {  // thread t gathers the byte of entry t from the 8 per-warp masks
+            uint32_t byte = 0;
+#pragma unroll
+            for (int w = 0; w < BLEND_THREADS / 32; w++) byte |= ((s_hit[b & 1][w][tid >> 5] >> (tid & 31)) & 1u) << w;
+            const int e = b * BLEND_BATCH + tid;
+            if (e < total) a.warp_hits[rg.x + e] = (uint8_t)byte;
+        }
+    };
     auto issue = [&](int b) {  // cp.async the records of batch b into buffer b&1
         const int cnt = min(BLEND_BATCH, total - b * BLEND_BATCH);
         const int buf = b & 1;
@@ -962,10 +974,12 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const BlendArgs a) {
     bool done = !inside;
 
     if (n_batches > 0) issue(0);
-    for (int b = 0; b < n_batches; b++) {
+    int b = 0;
+    for (; b < n_batches; b++) {
         cp_async_wait<0>();
         // all threads done -> stop (forward.cu:425-427); also publishes batch b and frees buffer (b+1)&1
         if (__syncthreads_count(done) == BLEND_THREADS) break;
+        if (b > 0) flush_hits(b - 1);
         if (b + 1 < n_batches) issue(b + 1);
         const int cnt = min(BLEND_BATCH, total - b * BLEND_BATCH);
         const float* rec = s_rec[b & 1];
@@ -973,7 +987,8 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const BlendArgs a) {
         const uint32_t cbase = (uint32_t)b * BLEND_BATCH;
 #pragma unroll 1
         for (int half = 0; half < BLEND_BATCH / 32; half++) {
-            if (__all_sync(0xffffffffu, done)) break;
+            uint32_t hitmask = 0;  // warp-uniform: entries of this half some lane blended
+            if (__all_sync(0xffffffffu, done)) { if (lane == 0) s_hit[b & 1][wid][half] = 0u; continue; }
             const int e = half * 32 + lane;
             bool hit = false;
             if (e < cnt) {
@@ -983,10 +998,11 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const BlendArgs a) {
             }
             unsigned m = __ballot_sync(0xffffffffu, hit);
             while (m) {
-                const int j = half * 32 + __ffs(m) - 1;
+                const int jl = __ffs(m) - 1;
+                const int j = half * 32 + jl;
                 m &= m - 1;
                 const float* rj = rec + j * REC;
-                bool touch = false;
+                bool touch = false, blended = false;
                 if (!done) {
                     const float4 g0 = *reinterpret_cast<const float4*>(rj);      // x y A B
                     const float4 g1 = *reinterpret_cast<const float4*>(rj + 4);  // C op pth depth
@@ -1022,18 +1038,27 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const BlendArgs a) {
                                     if (NCOL) acc_d = ffma(w, g1.w, acc_d);
                                 }
                                 touch = test_T > 0.5f;
+                                blended = true;
                                 T = test_T;
                                 last_contributor = cbase + (uint32_t)j + 1u;
                             }
                         }
                     }
                 }
-                const unsigned tm = __ballot_sync(0xffffffffu, touch);
-                if (tm != 0u && lane == 0) atomicAdd(&a.n_touched[ids[j]], __popc(tm));
+                if (__any_sync(0xffffffffu, blended)) {
+                    hitmask |= 1u << jl;
+                    const unsigned tm = __ballot_sync(0xffffffffu, touch);
+                    if (tm != 0u && lane == 0) atomicAdd(&a.n_touched[ids[j]], __popc(tm));
+                }
             }
+            if (lane == 0) s_hit[b & 1][wid][half] = hitmask;
         }
     }
     cp_async_wait<0>();
+    if (b > 0) {  // the last batch that was worked on (a `break` leaves before flushing it)
+        __syncthreads();
+        flush_hits(b - 1);
+    }
     if (inside) {
         const size_t HW = (size_t)a.W * a.H;
         const size_t pix = (size_t)pyi * a.W + pxi;
@@ -1130,6 +1155,7 @@ static int run_pass(int P, int W, int H, int tile, int ncol, int F, unsigned fla
     ba.final_T = (float*)(ws + L.final_T); ba.n_contrib = (uint32_t*)(ws + L.n_contrib);
     ba.out_color = o.color; ba.out_language = o.language; ba.out_depth = o.depth;
     ba.out_opacity = o.opacity; ba.n_touched = o.n_touched;
+    ba.warp_hits = (uint8_t*)(ws + L.warp_hits);
     const bool bitexact = (flags & OLS_FLAG_BITEXACT_BLEND) != 0;
     const int key = tile * 10000 + ncol * 100 + F;
     switch (key) {

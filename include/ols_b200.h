@@ -246,6 +246,35 @@ int ols_dis_backward(const ols_dis_args* args, const ols_dis_bwd_args* grads, vo
 /* workspace views of the two lists (tests / debugging) */
 int ols_dis_workspace_view(const ols_dis_args* args, ols_ws_view* view_color, ols_ws_view* view_lang);
 
+/* ---------------------------------------------------------------------------------------------
+ * Mapping loss on the rasterizer's outputs (the caller either side of render() in the mapping loop):
+ *   get_loss_mapping / get_loss_mapping_rgbd  (utils/slam_utils.py:121-165)  +
+ *   F.interpolate(gt_lang_feat, bilinear, align_corners=False) + l1_loss      (utils/slam_backend.py:576-592)
+ *   loss = alpha * mean|(exp(a) image + b - gt) m_rgb| + (1 - alpha) * mean|(depth - gt_depth) m_d|
+ *          + lambda_lang * mean|language - upsample(gt_lang)|
+ * The low-resolution language target stays on the device; no 15 x H x W copy per iteration.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ols_loss_args {
+    int32_t W, H;              /* rendered size                                                        */
+    int32_t F;                 /* language channels, 0 = no language term                              */
+    int32_t lang_w, lang_h;    /* size of the low-resolution language target (192 x 192 in the reference) */
+    float alpha;               /* config["Training"]["alpha"], default 0.95                            */
+    float rgb_boundary_threshold;
+    float exposure_a, exposure_b;  /* viewpoint.exposure_a / _b; pass 0, 0 for initialization=True      */
+    float lambda_lang;         /* self.lamda_lang                                                      */
+    const float* d_image;      /* [3,H,W] render()["render"]                                           */
+    const float* d_depth;      /* [1,H,W] render()["depth"]                                            */
+    const float* d_language;   /* [F,H,W] render()["language"] or NULL                                 */
+    const float* d_gt_image;   /* [3,H,W] viewpoint.original_image                                     */
+    const float* d_gt_depth;   /* [1,H,W] viewpoint.depth                                              */
+    const float* d_gt_lang;    /* [F,lang_h,lang_w] viewpoint.gt_lang_feat or NULL                     */
+} ols_loss_args;
+/* d_out6 = [l1_rgb, l1_depth, l1_lang, dloss/dexposure_a, dloss/dexposure_b, loss]; d_scratch8: 8 floats */
+int ols_mapping_loss_forward(const ols_loss_args* args, float* d_out6, float* d_scratch8, void* stream);
+/* gradients w.r.t. the three rendered tensors, scaled by the device scalar *d_upstream (dL/dloss) */
+int ols_mapping_loss_backward(const ols_loss_args* args, const float* d_upstream, float* d_dL_dimage, float* d_dL_ddepth,
+                              float* d_dL_dlanguage, void* stream);
+
 /* Per-kernel device timing (CUDA events recorded between the kernels of every call while enabled).
  * ols_timing_begin() allocates `max_marks` events and enables recording on the calling thread;
  * ols_timing_end() synchronises, sums the elapsed milliseconds per tag, reports how many intervals

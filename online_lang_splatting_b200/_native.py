@@ -28,6 +28,7 @@ EXPORTED_SYMBOLS = (
     "ols_abi_version", "ols_last_error", "ols_cuda_available", "ols_lang_workspace_size", "ols_lang_forward",
     "ols_lang_read_info", "ols_lang_backward", "ols_mark_visible", "ols_lang_workspace_view",
     "ols_lang_forward_host", "ols_timing_begin", "ols_timing_end", "ols_ae_plan_create", "ols_ae_plan_destroy", "ols_ae_forward",
+    "ols_mapping_loss_forward", "ols_mapping_loss_backward",
     "ols_dis_workspace_size", "ols_dis_forward", "ols_dis_read_info", "ols_dis_backward", "ols_dis_workspace_view",
 )
 
@@ -76,6 +77,13 @@ class DisBwdArgs(C.Structure):
                                           "d_dL_dopacity", "d_dL_dopacity_lang", "d_dL_dmeans3D", "d_dL_dcov3D",
                                           "d_dL_dcov3D_lang", "d_dL_dsh", "d_dL_dscales", "d_dL_dscales_lang",
                                           "d_dL_drotations", "d_dL_drotations_lang", "d_dL_dtau")]
+
+
+class LossArgs(C.Structure):
+    _fields_ = [("W", C.c_int32), ("H", C.c_int32), ("F", C.c_int32), ("lang_w", C.c_int32), ("lang_h", C.c_int32),
+                ("alpha", C.c_float), ("rgb_boundary_threshold", C.c_float), ("exposure_a", C.c_float),
+                ("exposure_b", C.c_float), ("lambda_lang", C.c_float)] + \
+               [(n, C.c_void_p) for n in ("d_image", "d_depth", "d_language", "d_gt_image", "d_gt_depth", "d_gt_lang")]
 
 
 class WsView(C.Structure):
@@ -129,6 +137,8 @@ def lib() -> C.CDLL:
     L.ols_dis_read_info.argtypes = [C.POINTER(DisArgs), C.POINTER(FwdInfo), C.POINTER(FwdInfo), C.c_void_p]
     L.ols_dis_backward.argtypes = [C.POINTER(DisArgs), C.POINTER(DisBwdArgs), C.c_void_p]
     L.ols_dis_workspace_view.argtypes = [C.POINTER(DisArgs), C.POINTER(WsView), C.POINTER(WsView)]
+    L.ols_mapping_loss_forward.argtypes = [C.POINTER(LossArgs), C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ols_mapping_loss_backward.argtypes = [C.POINTER(LossArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.ols_timing_begin.argtypes = [C.c_int32]
     L.ols_timing_end.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int32)]
     L.ols_ae_plan_create.argtypes = [C.POINTER(AEChain), C.POINTER(C.c_void_p), C.c_void_p]

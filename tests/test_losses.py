@@ -1,0 +1,57 @@
+"""Fused mapping loss (SURVEY 8f N2+N3) against the plain-torch restatement of the reference's lines
+(utils/slam_utils.py:121-165, utils/slam_backend.py:576-592).  fp32, tolerance 1e-5 relative on the loss and
+2e-6 absolute on the per-pixel gradients (they are +-w/numel; a sign can only differ where |diff| ~ 1e-7)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(H, W, F, lh, lw, seed, exposure):
+    from online_lang_splatting_b200 import losses as LS
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    r = lambda *s: torch.rand(*s, generator=g)
+    image, depth = r(3, H, W).to(dev).requires_grad_(True), (r(1, H, W) * 5).to(dev).requires_grad_(True)
+    gt_image = r(3, H, W)
+    gt_image[:, : H // 4] *= 0.001            # pixels below the rgb boundary threshold
+    gt_depth = r(1, H, W) * 5
+    gt_depth[:, :, : W // 5] = 0.0            # invalid depth
+    gt_image, gt_depth = gt_image.to(dev), gt_depth.to(dev)
+    lang = (torch.randn(F, H, W, generator=g) * 0.3).to(dev).requires_grad_(True) if F else None
+    gt_lang = (torch.randn(F, lh, lw, generator=g) * 0.3).to(dev) if F else None
+    ea = torch.tensor(0.07, device=dev, requires_grad=True) if exposure else None
+    eb = torch.tensor(-0.02, device=dev, requires_grad=True) if exposure else None
+    kw = dict(alpha=0.9, rgb_boundary_threshold=0.01, lambda_lang=0.7)
+    ref = LS.reference_mapping_loss(image, depth, gt_image, gt_depth, lang, gt_lang, exposure_a=ea, exposure_b=eb, **kw)
+    leaves = [t for t in (image, depth, lang, ea, eb) if t is not None]
+    g_ref = torch.autograd.grad(ref * 1.7, leaves)
+    ours = LS.mapping_loss(image, depth, gt_image, gt_depth, lang, gt_lang, exposure_a=ea, exposure_b=eb, **kw)
+    g_ours = torch.autograd.grad(ours * 1.7, leaves)
+    assert abs(ours.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    for a, b in zip(g_ours, g_ref):
+        if a.dim() == 0:
+            assert abs(a.item() - b.item()) <= 1e-4 * max(abs(b.item()), 1e-6)
+        else:
+            bad = (a - b).abs() > 2e-6 * b.abs().max().clamp_min(1e-12) + 1e-12
+            assert bad.float().mean().item() < 1e-4
+
+
+def test_mapping_loss_headline_shape():
+    _case(540, 960, 15, 192, 192, seed=0, exposure=True)
+
+
+def test_mapping_loss_ragged_and_upsample_edges():
+    _case(75, 121, 3, 17, 23, seed=1, exposure=False)     # odd sizes, non-integer scale
+    _case(64, 64, 15, 192, 192, seed=2, exposure=True)    # down-sampling direction of the same formula
+
+
+def test_mapping_loss_without_language_term():
+    _case(48, 80, 0, 0, 0, seed=3, exposure=True)
+
+
+def test_mapping_loss_needs_cuda_tensors():
+    from online_lang_splatting_b200 import losses as LS
+    with pytest.raises(RuntimeError):
+        LS.mapping_loss(torch.zeros(3, 4, 4), torch.zeros(1, 4, 4), torch.zeros(3, 4, 4), torch.zeros(1, 4, 4))

@@ -10,9 +10,9 @@ P = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 modes = sys.argv[3].split(",") if len(sys.argv) > 3 else ["compat", "exact"]
 dev = torch.device("cuda:0")
-sc = U.make_scene(P=P, F=15, W=960, H=540, seed=0, scale=0.01)
+sc = U.make_scene(P=P, F=15, W=960, H=540, seed=0, scale=0.01, view=int(os.environ.get("OLS_VIEW", "0")))
 grads = [g.to(dev) for g in U.loss_weights(15, 960, 540, seed=1)]
-for tile in (15, 16):
+for tile in ((15,) if os.environ.get("OLS_TILE15") else (15, 16)):
     for mode in modes:
         rs = U.settings(sc, dev, tile=tile, bitexact=False, backward_mode=mode)._replace(debug=False)
         d = lambda k: sc[k].to(dev)

@@ -613,17 +613,162 @@ __global__ void __launch_bounds__(PRE_THREADS) k_scatter(int P, int gx, int n_ti
     for (int t = tid; t < n_tiles; t += PRE_THREADS) s_cur[t] = tile_start[t] + mine[t];
     __syncthreads();
     const int chunk_begin = min(P, (int)blockIdx.x * chunk), chunk_end = min(P, chunk_begin + chunk);
-    for (int i = chunk_begin + tid; i < chunk_end; i += PRE_THREADS) {
-        if (tiles_touched[i] == 0) continue;
-        const uint2 r = rect[i];
-        const int x0 = r.x & 0xffff, y0 = r.x >> 16, x1 = r.y & 0xffff, y1 = r.y >> 16;
-        const unsigned long long key = ((unsigned long long)__float_as_uint(depths[i]) << 32) | (unsigned)i;
-        for (int y = y0; y < y1; y++)
-            for (int x = x0; x < x1; x++) {
-                const uint32_t slot = atomicAdd(&s_cur[y * gx + x], 1u);
-                keys[slot] = key;
+    const int lane = tid & 31;
+    // A warp takes 32 Gaussians at a time and spreads their (Gaussian, tile) instances evenly over its lanes:
+    // lane L emits instances L, L + 32, ... of the warp's flattened list, so a Gaussian covering many tiles does
+    // not serialise one thread, and 32 independent slot requests are in flight per step.
+    for (int i0 = chunk_begin + (tid & ~31); i0 < chunk_end; i0 += PRE_THREADS) {
+        const int i = i0 + lane;
+        uint32_t cnt = 0;
+        uint2 r = make_uint2(0u, 0u);
+        unsigned long long key = 0ull;
+        if (i < chunk_end) {
+            cnt = tiles_touched[i];
+            if (cnt) {
+                r = rect[i];
+                key = ((unsigned long long)__float_as_uint(depths[i]) << 32) | (unsigned)i;
             }
+        }
+        uint32_t incl = cnt;  // inclusive prefix over the lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        for (uint32_t k = lane; k < ((total + 31u) & ~31u); k += 32) {
+            // owner = first lane whose inclusive prefix exceeds k (binary search over the lanes)
+            int owner = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const uint32_t v = __shfl_sync(0xffffffffu, incl, owner + step - 1);
+                if (v <= k) owner += step;
+            }
+            owner = min(owner, 31);
+            const uint32_t o_incl = __shfl_sync(0xffffffffu, incl, owner);
+            const uint32_t o_cnt = __shfl_sync(0xffffffffu, cnt, owner);
+            const uint32_t rx = __shfl_sync(0xffffffffu, r.x, owner), ry = __shfl_sync(0xffffffffu, r.y, owner);
+            const unsigned long long okey = __shfl_sync(0xffffffffu, key, owner);
+            if (k < total) {
+                const uint32_t local = k - (o_incl - o_cnt);
+                const int x0 = rx & 0xffff, y0 = rx >> 16, x1 = ry & 0xffff;
+                const int w = x1 - x0;
+                const int yy = y0 + (int)(local / (uint32_t)w), xx = x0 + (int)(local % (uint32_t)w);
+                const uint32_t slot = atomicAdd(&s_cur[yy * gx + xx], 1u);
+                keys[slot] = okey;
+            }
+        }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Per-tile sort, fast path: one distribution pass + exact ranking inside tiny buckets.
+// The depths of a tile's bucket are spread over [dmin, dmax]; a key goes to bucket
+// floor((depth - dmin) * NB / (dmax - dmin)), which is monotone in the depth bits (positive floats), so the
+// buckets are already in final order and only the few keys sharing a bucket have to be ordered -- by
+// counting, for each key, the keys of its bucket that compare lower on the full 64-bit (depth, id) key.
+// The result is the same permutation the reference's stable 44-bit radix sort produces.  Tiles whose depth
+// distribution is too clumped for this (a bucket with more than BS_LIMIT keys) or that hold non-finite depths
+// are left to the radix kernel below; tile_count[tile] = BS_DONE marks the tiles finished here.
+// ---------------------------------------------------------------------------------------------------
+constexpr int BS_THREADS = 256;
+constexpr int BS_CAP = 4096;                     // keys per tile handled in shared memory
+constexpr int BS_ITEMS = BS_CAP / BS_THREADS;
+constexpr int BS_NB = 2048;                      // buckets
+constexpr int BS_LIMIT = 48;                     // largest bucket this path accepts
+constexpr uint32_t BS_DONE = 0xffffffffu;
+
+__global__ void __launch_bounds__(BS_THREADS) k_sort_tiles_bucket(unsigned long long* __restrict__ keys,
+                                                                 uint32_t* __restrict__ point_list,
+                                                                 const uint2* __restrict__ ranges,
+                                                                 uint32_t* __restrict__ tile_count,
+                                                                 const DeviceInfo* __restrict__ info) {
+    __shared__ unsigned long long s_key[BS_CAP];  // 32 KB
+    __shared__ uint32_t s_cnt[BS_NB];             // 8 KB: counts -> exclusive starts -> ends
+    __shared__ uint32_t s_warp[BS_THREADS / 32];
+    __shared__ float s_lohi[2];
+    if (info->overflow) return;
+    const uint2 rg = ranges[blockIdx.x];
+    const int n = (int)(rg.y - rg.x);
+    if (n <= 0 || n > BS_CAP) return;
+    unsigned long long* g = keys + rg.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    unsigned long long k[BS_ITEMS];
+    float lo = CUDART_INF_F, hi = 0.0f;  // depths are non-negative here, so 0 is the identity of max
+    bool finite = true;
+#pragma unroll
+    for (int r = 0; r < BS_ITEMS; r++) {
+        const int idx = r * BS_THREADS + tid;
+        if (idx < n) {
+            k[r] = g[idx];
+            const float d = __uint_as_float((uint32_t)(k[r] >> 32));
+            finite = finite && (d >= 0.0f) && (d < CUDART_INF_F);
+            lo = fminf(lo, d);
+            hi = fmaxf(hi, d);
+        }
+    }
+    for (int e = tid; e < BS_NB; e += BS_THREADS) s_cnt[e] = 0;
+    if (tid == 0) { s_lohi[0] = CUDART_INF_F; s_lohi[1] = 0.0f; }
+    // a tile this path cannot take (non-finite / negative depths) is declined by every thread together
+    if (__syncthreads_or(!finite)) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) {  // non-negative floats order like their bit patterns
+        atomicMin(reinterpret_cast<unsigned*>(&s_lohi[0]), __float_as_uint(lo));
+        atomicMax(reinterpret_cast<unsigned*>(&s_lohi[1]), __float_as_uint(hi));
+    }
+    __syncthreads();
+    const float dmin = s_lohi[0], dmax = s_lohi[1];
+    const float inv = dmax > dmin ? (float)BS_NB / (dmax - dmin) : 0.0f;
+    auto bucket_of = [&](unsigned long long key) -> int {
+        const float d = __uint_as_float((uint32_t)(key >> 32));
+        return min(BS_NB - 1, __float2int_rz(fmul(fsub(d, dmin), inv)));
+    };
+#pragma unroll
+    for (int r = 0; r < BS_ITEMS; r++)
+        if (r * BS_THREADS + tid < n) atomicAdd(&s_cnt[bucket_of(k[r])], 1u);
+    __syncthreads();
+    // exclusive scan of the counters (thread t owns BS_NB / BS_THREADS consecutive ones) + largest bucket
+    constexpr int PER = BS_NB / BS_THREADS;
+    uint32_t c[PER], sum = 0, big = 0;
+#pragma unroll
+    for (int q = 0; q < PER; q++) { c[q] = s_cnt[tid * PER + q]; sum += c[q]; big = max(big, c[q]); }
+    if (__syncthreads_or(big > (uint32_t)BS_LIMIT)) return;  // clumped depths: the radix kernel sorts this tile
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    uint32_t base = incl - sum;
+    for (int w = 0; w < wid; w++) base += s_warp[w];
+#pragma unroll
+    for (int q = 0; q < PER; q++) { s_cnt[tid * PER + q] = base; base += c[q]; }
+    __syncthreads();
+    // distribute: afterwards s_cnt[b] is the END of bucket b (its start is the end of bucket b - 1)
+#pragma unroll
+    for (int r = 0; r < BS_ITEMS; r++)
+        if (r * BS_THREADS + tid < n) s_key[atomicAdd(&s_cnt[bucket_of(k[r])], 1u)] = k[r];
+    __syncthreads();
+    // exact position inside the bucket = number of its keys that compare lower; write out in final order
+#pragma unroll
+    for (int r = 0; r < BS_ITEMS; r++) {
+        if (r * BS_THREADS + tid < n) {
+            const int b = bucket_of(k[r]);
+            const uint32_t s0 = b ? s_cnt[b - 1] : 0u, s1 = s_cnt[b];
+            uint32_t pos = s0;
+            for (uint32_t q = s0; q < s1; q++) pos += s_key[q] < k[r] ? 1u : 0u;
+            g[pos] = k[r];
+            point_list[rg.x + pos] = (uint32_t)k[r];
+        }
+    }
+    if (tid == 0) tile_count[blockIdx.x] = BS_DONE;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -641,11 +786,13 @@ constexpr int RS_ITEMS = RS_CAP / RS_THREADS;  // 16 keys per thread at most
 __global__ void __launch_bounds__(RS_THREADS) k_sort_tiles_radix(unsigned long long* __restrict__ keys,
                                                                 uint32_t* __restrict__ point_list,
                                                                 const uint2* __restrict__ ranges,
+                                                                const uint32_t* __restrict__ tile_count,
                                                                 const DeviceInfo* __restrict__ info) {
     __shared__ unsigned long long s_key[RS_CAP];       // 32 KB
     __shared__ uint32_t s_cnt[RS_WARPS][256];          // 8 KB  per-warp digit counters / bases
     __shared__ uint32_t s_scan[RS_WARPS];
     if (info->overflow) return;
+    if (tile_count[blockIdx.x] == BS_DONE) return;  // sorted by the bucket kernel
     const uint2 rg = ranges[blockIdx.x];
     const int n = (int)(rg.y - rg.x);
     if (n <= 0 || n > RS_CAP) return;
@@ -1139,8 +1286,11 @@ static int run_pass(int P, int W, int H, int tile, int ncol, int F, unsigned fla
                                                         (unsigned long long*)(ws + L.keys), info);
     OLS_DEBUG_SYNC("scatter");
     ols_timing_mark(OLS_T_BINNING, st);
-    k_sort_tiles_radix<<<L.n_tiles, RS_THREADS, 0, st>>>((unsigned long long*)(ws + L.keys),
-                                                         (uint32_t*)(ws + L.point_list), (const uint2*)(ws + L.ranges), info);
+    k_sort_tiles_bucket<<<L.n_tiles, BS_THREADS, 0, st>>>((unsigned long long*)(ws + L.keys), (uint32_t*)(ws + L.point_list),
+                                                          (const uint2*)(ws + L.ranges), (uint32_t*)(ws + L.tile_count), info);
+    OLS_DEBUG_SYNC("sort_tiles_bucket");
+    k_sort_tiles_radix<<<L.n_tiles, RS_THREADS, 0, st>>>((unsigned long long*)(ws + L.keys), (uint32_t*)(ws + L.point_list),
+                                                         (const uint2*)(ws + L.ranges), (const uint32_t*)(ws + L.tile_count), info);
     OLS_DEBUG_SYNC("sort_tiles_radix");
     // buckets longer than the radix kernel's shared-memory capacity (rare): bitonic fallback
     k_sort_tiles<<<L.n_tiles, SORT_THREADS, 0, st>>>((unsigned long long*)(ws + L.keys), (uint32_t*)(ws + L.point_list),

@@ -70,6 +70,23 @@ def test_long_tiles_use_hybrid_sort(cuda):
     assert np.array_equal(ours["ws"]["point_list"].astype(np.uint32), ora["point_list"])
 
 
+def test_sort_paths_equal_depths_and_clumps(cuda):
+    """Collisions in the sort key: many Gaussians at exactly the same depth (ties are ordered by Gaussian id,
+    like the reference's stable radix sort) and a clumped depth distribution that overflows the bucket path."""
+    sc = U.make_scene(P=4000, F=3, W=60, H=45, seed=4, scale=0.6)
+    z = sc["means3D"][:, 2].clone()
+    sc["means3D"][:1500, 2] = 2.0                 # 1500 exact ties
+    sc["means3D"][1500:3000, 2] = 3.0 + 1e-6 * torch.arange(1500)   # one tight clump (neighbouring float values)
+    sc["means3D"][3000:, 2] = z[3000:].clamp_min(0.5)
+    ours = U.run_ours(sc, cuda, tile=15)
+    ora = U.run_oracle(sc, tile=15)
+    assert ours["R"] == ora["R"] > 20000
+    assert np.array_equal(ours["ws"]["point_list"].astype(np.uint32), ora["point_list"])
+    assert np.array_equal(U.keys_from_ours(ours["ws"], 4), ora["keys_sorted"])
+    assert np.array_equal(ours["ws"]["n_contrib"].astype(np.uint32), ora["n_contrib"]) or \
+        (ours["ws"]["n_contrib"].astype(np.uint32) != ora["n_contrib"]).mean() < 2e-3
+
+
 def test_edge_cases(cuda):
     # all Gaussians behind the camera: empty lists, background only
     sc = U.make_scene(P=64, F=15, W=40, H=30, seed=1, bg=(0.3, 0.6, 0.9))

@@ -268,12 +268,15 @@ typedef struct ols_loss_args {
     const float* d_gt_image;   /* [3,H,W] viewpoint.original_image                                     */
     const float* d_gt_depth;   /* [1,H,W] viewpoint.depth                                              */
     const float* d_gt_lang;    /* [F,lang_h,lang_w] viewpoint.gt_lang_feat or NULL                     */
+    /* tracking form, get_loss_tracking_rgbd (utils/slam_utils.py:96-118); both NULL for the mapping form */
+    const float* d_opacity;    /* [1,H,W] render()["opacity"]: weights the colour residual, gates depth at > 0.95 */
+    const float* d_grad_mask;  /* [1,H,W] viewpoint.grad_mask (0/1 floats) or NULL                     */
 } ols_loss_args;
 /* d_out6 = [l1_rgb, l1_depth, l1_lang, dloss/dexposure_a, dloss/dexposure_b, loss]; d_scratch8: 8 floats */
 int ols_mapping_loss_forward(const ols_loss_args* args, float* d_out6, float* d_scratch8, void* stream);
 /* gradients w.r.t. the three rendered tensors, scaled by the device scalar *d_upstream (dL/dloss) */
 int ols_mapping_loss_backward(const ols_loss_args* args, const float* d_upstream, float* d_dL_dimage, float* d_dL_ddepth,
-                              float* d_dL_dlanguage, void* stream);
+                              float* d_dL_dlanguage, float* d_dL_dopacity /* tracking form only, may be NULL */, void* stream);
 
 /* Per-kernel device timing (CUDA events recorded between the kernels of every call while enabled).
  * ols_timing_begin() allocates `max_marks` events and enables recording on the calling thread;

@@ -83,7 +83,8 @@ class LossArgs(C.Structure):
     _fields_ = [("W", C.c_int32), ("H", C.c_int32), ("F", C.c_int32), ("lang_w", C.c_int32), ("lang_h", C.c_int32),
                 ("alpha", C.c_float), ("rgb_boundary_threshold", C.c_float), ("exposure_a", C.c_float),
                 ("exposure_b", C.c_float), ("lambda_lang", C.c_float)] + \
-               [(n, C.c_void_p) for n in ("d_image", "d_depth", "d_language", "d_gt_image", "d_gt_depth", "d_gt_lang")]
+               [(n, C.c_void_p) for n in ("d_image", "d_depth", "d_language", "d_gt_image", "d_gt_depth", "d_gt_lang",
+                                          "d_opacity", "d_grad_mask")]
 
 
 class WsView(C.Structure):
@@ -138,7 +139,8 @@ def lib() -> C.CDLL:
     L.ols_dis_backward.argtypes = [C.POINTER(DisArgs), C.POINTER(DisBwdArgs), C.c_void_p]
     L.ols_dis_workspace_view.argtypes = [C.POINTER(DisArgs), C.POINTER(WsView), C.POINTER(WsView)]
     L.ols_mapping_loss_forward.argtypes = [C.POINTER(LossArgs), C.c_void_p, C.c_void_p, C.c_void_p]
-    L.ols_mapping_loss_backward.argtypes = [C.POINTER(LossArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ols_mapping_loss_backward.argtypes = [C.POINTER(LossArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p]
     L.ols_timing_begin.argtypes = [C.c_int32]
     L.ols_timing_end.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int32)]
     L.ols_ae_plan_create.argtypes = [C.POINTER(AEChain), C.POINTER(C.c_void_p), C.c_void_p]

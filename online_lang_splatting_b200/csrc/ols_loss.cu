@@ -21,6 +21,8 @@ struct LossArgs {
     float alpha, thr, ea, eb, lambda_lang;  // ea = exp(exposure_a)
     float sx, sy;                           // lw / W, lh / H as PyTorch computes them (float division)
     const float *image, *depth, *language, *gt_image, *gt_depth, *gt_lang;
+    const float *opacity, *grad_mask;       // tracking form only (get_loss_tracking_rgbd), else NULL
+    float* dopacity;                        // optional dL/dopacity of the tracking form
     const float* upstream;                  // device scalar dL/dloss (backward)
     float *dimage, *ddepth, *dlanguage;
     float* sums;                            // [8]: |rgb|, |depth|, |lang|, d/d exposure_a, d/d exposure_b
@@ -51,17 +53,23 @@ __global__ void __launch_bounds__(LOSS_THREADS) k_mapping_loss(const LossArgs a)
         const int y = (int)(pix / a.W), x = (int)(pix - (size_t)y * a.W);
         // colour: | (ea * image + eb) * m - gt * m |
         const float g0 = a.gt_image[pix], g1 = a.gt_image[HW + pix], g2 = a.gt_image[2 * HW + pix];
-        const float m = (g0 + g1 + g2) > a.thr ? 1.0f : 0.0f;
+        float m = (g0 + g1 + g2) > a.thr ? 1.0f : 0.0f;
+        // tracking form (utils/slam_utils.py:96-118): the colour mask also carries viewpoint.grad_mask, every colour
+        // residual is weighted by the rendered opacity, and depth only counts where opacity > 0.95
+        const float op = a.opacity ? a.opacity[pix] : 1.0f;
+        if (a.grad_mask) m *= a.grad_mask[pix];
         const float gts[3] = {g0, g1, g2};
+        float abs_sum = 0.0f;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             const float im = a.image[c * HW + pix];
             const float diff = (a.ea * im + a.eb) * m - gts[c] * m;
+            abs_sum += fabsf(diff);
             if (BACKWARD) {
-                a.dimage[c * HW + pix] = up * w_rgb * sgn(diff) * m * a.ea;
+                a.dimage[c * HW + pix] = up * w_rgb * op * sgn(diff) * m * a.ea;
             } else {
-                s_rgb += fabsf(diff);
-                const float sg = sgn(diff) * m;
+                s_rgb += op * fabsf(diff);
+                const float sg = op * sgn(diff) * m;
                 s_ea += sg * a.ea * im;  // d|diff| / d exposure_a
                 s_eb += sg;              // d|diff| / d exposure_b
             }
@@ -69,7 +77,9 @@ __global__ void __launch_bounds__(LOSS_THREADS) k_mapping_loss(const LossArgs a)
         // depth
         {
             const float gd = a.gt_depth[pix];
-            const float md = gd > 0.01f ? 1.0f : 0.0f;
+            float md = gd > 0.01f ? 1.0f : 0.0f;
+            if (a.opacity && !(op > 0.95f)) md = 0.0f;
+            if (BACKWARD && a.dopacity) a.dopacity[pix] = up * w_rgb * abs_sum;
             const float diff = a.depth[pix] * md - gd * md;
             if (BACKWARD) a.ddepth[pix] = up * w_d * sgn(diff) * md;
             else s_d += fabsf(diff);
@@ -142,6 +152,7 @@ static int fill(const ols_loss_args* p, LossArgs* a) {
     a->sy = p->F > 0 ? (float)p->lang_h / (float)p->H : 0.0f;
     a->image = p->d_image; a->depth = p->d_depth; a->language = p->d_language;
     a->gt_image = p->d_gt_image; a->gt_depth = p->d_gt_depth; a->gt_lang = p->d_gt_lang;
+    a->opacity = p->d_opacity; a->grad_mask = p->d_grad_mask; a->dopacity = nullptr;
     a->upstream = nullptr; a->dimage = nullptr; a->ddepth = nullptr; a->dlanguage = nullptr; a->sums = nullptr;
     return OLS_OK;
 }
@@ -168,7 +179,7 @@ int ols_mapping_loss_forward(const ols_loss_args* p, float* d_out6, float* d_scr
 }
 
 int ols_mapping_loss_backward(const ols_loss_args* p, const float* d_upstream, float* d_dL_dimage, float* d_dL_ddepth,
-                              float* d_dL_dlanguage, void* stream) {
+                              float* d_dL_dlanguage, float* d_dL_dopacity, void* stream) {
     LossArgs a;
     int rc = fill(p, &a);
     if (rc != OLS_OK) return rc;
@@ -177,6 +188,7 @@ int ols_mapping_loss_backward(const ols_loss_args* p, const float* d_upstream, f
         return OLS_ERR_INVALID;
     }
     a.upstream = d_upstream; a.dimage = d_dL_dimage; a.ddepth = d_dL_ddepth; a.dlanguage = d_dL_dlanguage;
+    a.dopacity = p->d_opacity ? d_dL_dopacity : nullptr;
     k_mapping_loss<true><<<loss_grid(p->W, p->H), LOSS_THREADS, 0, (cudaStream_t)stream>>>(a);
     OLS_CUDA_TRY(cudaGetLastError());
     return OLS_OK;

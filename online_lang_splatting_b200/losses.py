@@ -23,7 +23,7 @@ from . import _native as N
 class _MappingLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image, depth, language, gt_image, gt_depth, gt_lang, exposure_a, exposure_b, alpha, threshold,
-                lambda_lang):
+                lambda_lang, opacity=None, grad_mask=None):
         N.require_cuda()
         if not image.is_cuda:
             raise RuntimeError("mapping_loss needs CUDA tensors: there is no CPU path")
@@ -34,6 +34,8 @@ class _MappingLoss(torch.autograd.Function):
         has_lang = language is not None and gt_lang is not None
         lang_ = f32(language) if has_lang else None
         gt_lang_ = f32(gt_lang) if has_lang else None
+        opacity_ = f32(opacity) if opacity is not None else None
+        grad_mask_ = f32(grad_mask) if grad_mask is not None else None
         F = int(lang_.shape[0]) if has_lang else 0
         ea = float(exposure_a) if exposure_a is not None else 0.0
         eb = float(exposure_b) if exposure_b is not None else 0.0
@@ -42,13 +44,13 @@ class _MappingLoss(torch.autograd.Function):
                           rgb_boundary_threshold=float(threshold), exposure_a=ea, exposure_b=eb,
                           lambda_lang=float(lambda_lang), d_image=image_.data_ptr(), d_depth=depth_.data_ptr(),
                           d_language=N.ptr(lang_), d_gt_image=gt_image_.data_ptr(), d_gt_depth=gt_depth_.data_ptr(),
-                          d_gt_lang=N.ptr(gt_lang_))
+                          d_gt_lang=N.ptr(gt_lang_), d_opacity=N.ptr(opacity_), d_grad_mask=N.ptr(grad_mask_))
         out = torch.empty(14, dtype=torch.float32, device=dev)  # [0:6] results, [6:14] reduction scratch
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             N.check(N.lib().ols_mapping_loss_forward(C.byref(args), out.data_ptr(), out[6:].data_ptr(), stream))
         ctx.args = args
-        ctx.keep = (image_, depth_, lang_, gt_image_, gt_depth_, gt_lang_)
+        ctx.keep = (image_, depth_, lang_, gt_image_, gt_depth_, gt_lang_, opacity_, grad_mask_)
         ctx.terms = out
         ctx.exposure_tensors = (torch.is_tensor(exposure_a) and exposure_a.requires_grad,
                                 torch.is_tensor(exposure_b) and exposure_b.requires_grad)
@@ -56,18 +58,19 @@ class _MappingLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_loss):
-        image_, depth_, lang_, *_ = ctx.keep
+        image_, depth_, lang_, _, _, _, opacity_, _ = ctx.keep
         dev = image_.device
         up = grad_loss.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
         d_image, d_depth = torch.empty_like(image_), torch.empty_like(depth_)
         d_lang = torch.empty_like(lang_) if lang_ is not None else None
+        d_op = torch.empty_like(opacity_) if opacity_ is not None else None
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             N.check(N.lib().ols_mapping_loss_backward(C.byref(ctx.args), up.data_ptr(), d_image.data_ptr(),
-                                                      d_depth.data_ptr(), N.ptr(d_lang), stream))
+                                                      d_depth.data_ptr(), N.ptr(d_lang), N.ptr(d_op), stream))
         ga = ctx.terms[3] * up[0] if ctx.exposure_tensors[0] else None
         gb = ctx.terms[4] * up[0] if ctx.exposure_tensors[1] else None
-        return d_image, d_depth, d_lang, None, None, None, ga, gb, None, None, None
+        return d_image, d_depth, d_lang, None, None, None, ga, gb, None, None, None, d_op, None
 
 
 def mapping_loss(image: torch.Tensor, depth: torch.Tensor, gt_image: torch.Tensor, gt_depth: torch.Tensor,
@@ -82,6 +85,30 @@ def mapping_loss(image: torch.Tensor, depth: torch.Tensor, gt_image: torch.Tenso
     """
     return _MappingLoss.apply(image, depth, language, gt_image, gt_depth, gt_lang_feat, exposure_a, exposure_b, alpha,
                               rgb_boundary_threshold, lambda_lang)
+
+
+def tracking_loss(image: torch.Tensor, depth: torch.Tensor, opacity: torch.Tensor, gt_image: torch.Tensor,
+                  gt_depth: torch.Tensor, grad_mask: Optional[torch.Tensor] = None, *, alpha: float = 0.95,
+                  rgb_boundary_threshold: float = 0.01, exposure_a=None, exposure_b=None) -> torch.Tensor:
+    """``get_loss_tracking`` / ``get_loss_tracking_rgbd`` (utils/slam_utils.py:91-118): the colour residual is weighted
+    by the rendered opacity and masked by ``viewpoint.grad_mask``; depth counts where ``opacity > 0.95``.  The gradient
+    w.r.t. ``opacity`` is produced, but -- as in the reference -- the rasterizer does not propagate it further."""
+    return _MappingLoss.apply(image, depth, None, gt_image, gt_depth, None, exposure_a, exposure_b, alpha,
+                              rgb_boundary_threshold, 0.0, opacity, grad_mask)
+
+
+def reference_tracking_loss(image, depth, opacity, gt_image, gt_depth, grad_mask=None, *, alpha=0.95,
+                            rgb_boundary_threshold=0.01, exposure_a=None, exposure_b=None):
+    """Plain-torch restatement of utils/slam_utils.py:91-118 (test reference)."""
+    if exposure_a is not None:
+        image = torch.exp(torch.as_tensor(exposure_a, device=image.device)) * image + torch.as_tensor(exposure_b, device=image.device)
+    rgb_pixel_mask = (gt_image.sum(dim=0) > rgb_boundary_threshold).view(*depth.shape)
+    if grad_mask is not None:
+        rgb_pixel_mask = rgb_pixel_mask * grad_mask
+    l1 = opacity * torch.abs(image * rgb_pixel_mask - gt_image * rgb_pixel_mask)
+    depth_mask = (gt_depth > 0.01).view(*depth.shape) * (opacity > 0.95).view(*depth.shape)
+    l1_depth = torch.abs(depth * depth_mask - gt_depth * depth_mask)
+    return alpha * l1.mean() + (1 - alpha) * l1_depth.mean()
 
 
 def reference_mapping_loss(image, depth, gt_image, gt_depth, language=None, gt_lang_feat=None, *, alpha=0.95,

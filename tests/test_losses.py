@@ -55,3 +55,29 @@ def test_mapping_loss_needs_cuda_tensors():
     from online_lang_splatting_b200 import losses as LS
     with pytest.raises(RuntimeError):
         LS.mapping_loss(torch.zeros(3, 4, 4), torch.zeros(1, 4, 4), torch.zeros(3, 4, 4), torch.zeros(1, 4, 4))
+
+
+def test_tracking_loss_matches_reference_lines():
+    from online_lang_splatting_b200 import losses as LS
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    H, W = 120, 161
+    image = torch.rand(3, H, W, generator=g).to(dev).requires_grad_(True)
+    depth = (torch.rand(1, H, W, generator=g) * 5).to(dev).requires_grad_(True)
+    opacity = torch.rand(1, H, W, generator=g).pow(0.1).to(dev).requires_grad_(True)   # mostly > 0.95, some below
+    gt_image, gt_depth = torch.rand(3, H, W, generator=g).to(dev), (torch.rand(1, H, W, generator=g) * 5).to(dev)
+    gt_depth[:, :10] = 0
+    grad_mask = (torch.rand(1, H, W, generator=g) > 0.4).float().to(dev)
+    ea = torch.tensor(-0.05, device=dev, requires_grad=True)
+    eb = torch.tensor(0.03, device=dev, requires_grad=True)
+    kw = dict(alpha=0.9, rgb_boundary_threshold=0.01, exposure_a=ea, exposure_b=eb)
+    ref = LS.reference_tracking_loss(image, depth, opacity, gt_image, gt_depth, grad_mask, **kw)
+    g_ref = torch.autograd.grad(ref, [image, depth, opacity, ea, eb])
+    ours = LS.tracking_loss(image, depth, opacity, gt_image, gt_depth, grad_mask, **kw)
+    g_ours = torch.autograd.grad(ours, [image, depth, opacity, ea, eb])
+    assert abs(ours.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    for a, b in zip(g_ours, g_ref):
+        if a.dim() == 0:
+            assert abs(a.item() - b.item()) <= 1e-4 * max(abs(b.item()), 1e-6)
+        else:
+            assert (a - b).abs().max().item() <= 1e-5 * b.abs().max().item() + 1e-12

@@ -1,0 +1,29 @@
+"""Small end-to-end pass for compute-sanitizer (memcheck / racecheck): joint + disentangled rasterizer forward and
+backward in both gradient modes, the fused mapping loss and the autoencoder."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+import _util as U
+dev = torch.device("cuda:0")
+for tile, F in ((15, 15), (16, 3)):
+    sc = U.make_scene(P=1500, F=F, W=100, H=70, seed=2, scale=0.1, bg=(0.1, 0.2, 0.3))
+    grads = U.loss_weights(F, 100, 70, seed=1)
+    for mode in ("compat", "exact"):
+        o = U.run_ours(sc, dev, tile=tile, grads=grads, backward_mode=mode, bitexact=(mode == "exact"))
+    scd = U.add_lang_footprint(sc, seed=3)
+    for mode in ("compat", "exact"):
+        o = U.run_ours_dis(scd, dev, tile=tile, grads=grads, backward_mode=mode)
+from online_lang_splatting_b200 import losses as LS, autoencoder as AE
+img = torch.rand(3, 70, 100, device=dev, requires_grad=True); dep = torch.rand(1, 70, 100, device=dev, requires_grad=True)
+lang = torch.randn(15, 70, 100, device=dev, requires_grad=True)
+l = LS.mapping_loss(img, dep, torch.rand(3, 70, 100, device=dev), torch.rand(1, 70, 100, device=dev), lang,
+                    torch.randn(15, 19, 23, device=dev), exposure_a=0.1, exposure_b=0.0)
+l.backward()
+torch.manual_seed(0)
+ae = AE.AutoencoderMLP([384, 192, 96, 48, 24, 15], [24, 48, 96, 192, 384, 384, 768]).eval().to(dev)
+x = torch.randn(300, 768, device=dev)
+with torch.no_grad():
+    y = ae.decode(ae.encode(x))
+torch.cuda.synchronize()
+print("sanitize pass done", float(l), tuple(y.shape))

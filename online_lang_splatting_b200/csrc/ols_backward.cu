@@ -595,10 +595,24 @@ __global__ void __launch_bounds__(256) k_geometry_bwd(const GeomBwdArgs a) {
     }
     float dmean[3] = {0, 0, 0}, dcov[6] = {0, 0, 0, 0, 0, 0}, dtau[6] = {0, 0, 0, 0, 0, 0};
     float dsc[3] = {0, 0, 0}, dq[4] = {0, 0, 0, 0};
-    const bool vis = a.radii[i] > 0;
+    // Most Gaussians of a view receive no gradient at all (they lie behind the saturation depth of every pixel
+    // they cover).  Everything below is linear in the record, so a zero record yields exactly zero gradients:
+    // nothing has to be recomputed for it, and when accumulating nothing has to be read or rewritten either.
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < GRF; k++) any = any || (gr[k] != 0.0f);
+    const bool acc = a.accumulate;
+    if (acc && !any) {
+        a.dL_dmeans2D[3 * (size_t)i] = 0.0f;
+        a.dL_dmeans2D[3 * (size_t)i + 1] = 0.0f;
+        a.dL_dmeans2D[3 * (size_t)i + 2] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 6; k++) a.dL_dtau[6 * (size_t)i + k] = 0.0f;  // per-view outputs are always written
+        return;
+    }
+    const bool vis = any && a.radii[i] > 0;
     // unpack what the blend pass accumulated (zero for invisible Gaussians); all stores happen at the end
     const float g2x = gr[GR_MX], g2y = gr[GR_MY];
-    const bool acc = a.accumulate;
     float dcol[3] = {gr[GR_RGB], gr[GR_RGB + 1], gr[GR_RGB + 2]};
     float dsh0[3] = {0, 0, 0};
     if (a.dL_dsh && !acc && M > 1)

@@ -36,6 +36,7 @@ struct BwdBlendArgs {
     const uint2* ranges;
     const uint32_t* point_list;
     const float* records;
+    const float* language;   // [P,F] caller's language rows (joint pass), else unused
     const float* bg;
     const DeviceInfo* info;
     const float* final_T;
@@ -117,7 +118,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 4) k_blend_bwd(const BwdBlendArgs
     static_assert(NCOL == 0 || NCOL == 3, "colour channels");
     constexpr int NCH = NCOL + F;
     constexpr int REC = rec_floats_nch(NCH);
-    constexpr int R4 = REC / 4;
+    using Stage = RecordStage<NCOL, F>;
+    constexpr int OPS = Stage::OPS;
     constexpr int GR = grad_floats(F);
     constexpr int NPAIR = (NCH + 1) / 2;          // channel pairs as stored from REC_CH on
     constexpr int LP0 = (NCOL + 1) / 2;           // first pair made of language channels only
@@ -202,12 +204,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 4) k_blend_bwd(const BwdBlendArgs
         const int base = b * BWD_BATCH;
         const int cnt = min(BWD_BATCH, total - base);
         __syncthreads();  // previous batch fully consumed / flushed
-        for (int c = tid; c < BWD_BATCH * R4; c += BWD_THREADS) {
-            const int gi = c / R4, q = c - gi * R4;
+        {   // BWD_THREADS / BWD_BATCH threads share one record: one list lookup each, pieces dealt round-robin
+            constexpr int TPE = BWD_THREADS / BWD_BATCH;
+            const int gi = tid / TPE;
             if (gi < cnt) {
                 const uint32_t id = a.point_list[rg.x + base + gi];
-                if (q == 0) s_id[gi] = id;
-                cp_async16(&s_rec[gi * REC + q * 4], a.records + (size_t)id * REC + q * 4);
+                if ((tid % TPE) == 0) s_id[gi] = id;
+#pragma unroll
+                for (int q = tid % TPE; q < OPS; q += TPE) Stage::copy(&s_rec[gi * REC], a.records, a.language, id, q);
             }
         }
         cp_async_commit();
@@ -807,13 +811,13 @@ static void reduce_lane_mask(int n, bool exact, uint32_t* mask8) {
 
 // backward blend of one pass (its own sorted list, records, final_T, n_contrib and gradient scratch)
 static int run_blend_bwd(int W, int H, int tile, int ncol, int F, unsigned flags, char* ws, const WsLayout& L, const float* d_bg,
-                         const float* dL_dcolor, const float* dL_dlanguage, const float* dL_ddepth, cudaStream_t st) {
+                         const float* language, const float* dL_dcolor, const float* dL_dlanguage, const float* dL_ddepth, cudaStream_t st) {
     const bool exact = (flags & OLS_FLAG_BWD_EXACT) != 0;
     float* gacc = (float*)(ws + L.gacc);
     BwdBlendArgs ba;
     ba.W = W; ba.H = H; ba.gx = L.gx;
     ba.ranges = (const uint2*)(ws + L.ranges); ba.point_list = (const uint32_t*)(ws + L.point_list);
-    ba.records = (const float*)(ws + L.records); ba.bg = d_bg; ba.info = (const DeviceInfo*)(ws + L.info);
+    ba.records = (const float*)(ws + L.records); ba.language = language; ba.bg = d_bg; ba.info = (const DeviceInfo*)(ws + L.info);
     ba.final_T = (const float*)(ws + L.final_T); ba.n_contrib = (const uint32_t*)(ws + L.n_contrib);
     ba.dL_dcolor = dL_dcolor; ba.dL_dlanguage = dL_dlanguage; ba.dL_ddepth = dL_ddepth;
     ba.gacc = gacc;
@@ -859,7 +863,7 @@ int ols_launch_backward(const ols_raster_args* a, const ols_bwd_args* g, const W
     const bool debug = (a->flags & OLS_FLAG_DEBUG) != 0;
     OLS_CUDA_TRY(cudaMemsetAsync(ws + L.gacc, 0, ols_bwd_scratch_bytes(a->P, a->F), st));
     ols_timing_mark(-1, st);
-    int rc = run_blend_bwd(a->W, a->H, a->tile, 3, a->F, a->flags, ws, L, a->d_bg, g->d_dL_dout_color, g->d_dL_dout_language,
+    int rc = run_blend_bwd(a->W, a->H, a->tile, 3, a->F, a->flags, ws, L, a->d_bg, a->d_language, g->d_dL_dout_color, g->d_dL_dout_language,
                            g->d_dL_dout_depth, st);
     if (rc != OLS_OK) return rc;
     ols_timing_mark(OLS_T_BLEND_BWD, st);
@@ -891,9 +895,9 @@ int ols_launch_backward_dis(const ols_dis_args* d, const ols_dis_bwd_args* g, co
     OLS_CUDA_TRY(cudaMemsetAsync(wc + Lc.gacc, 0, ols_bwd_scratch_bytes(a->P, 0), st));
     OLS_CUDA_TRY(cudaMemsetAsync(wl + Ll.gacc, 0, ols_bwd_scratch_bytes(a->P, a->F), st));
     ols_timing_mark(-1, st);
-    int rc = run_blend_bwd(a->W, a->H, a->tile, 3, 0, a->flags, wc, Lc, a->d_bg, g->d_dL_dout_color, nullptr, g->d_dL_dout_depth, st);
+    int rc = run_blend_bwd(a->W, a->H, a->tile, 3, 0, a->flags, wc, Lc, a->d_bg, nullptr, g->d_dL_dout_color, nullptr, g->d_dL_dout_depth, st);
     if (rc != OLS_OK) return rc;
-    rc = run_blend_bwd(a->W, a->H, a->tile, 0, a->F, a->flags, wl, Ll, a->d_bg, nullptr, g->d_dL_dout_language, nullptr, st);
+    rc = run_blend_bwd(a->W, a->H, a->tile, 0, a->F, a->flags, wl, Ll, a->d_bg, nullptr, nullptr, g->d_dL_dout_language, nullptr, st);
     if (rc != OLS_OK) return rc;
     ols_timing_mark(OLS_T_BLEND_BWD, st);
     GeomDisArgs ga;

@@ -20,7 +20,11 @@ namespace ols {
 constexpr int REC_X = 0, REC_Y = 1, REC_A = 2, REC_B = 3, REC_C = 4, REC_OP = 5, REC_PTH = 6, REC_DEPTH = 7,
               REC_CH = 8;
 __host__ __device__ constexpr int rec_floats_nch(int nch) { return ((10 + nch) + 3) / 4 * 4; }
-__host__ __device__ constexpr int rec_floats(int F) { return rec_floats_nch(3 + F); }  // joint pass
+__host__ __device__ constexpr int rec_floats(int F) { return rec_floats_nch(3 + F); }  // joint pass, as staged in shared memory
+// In global memory the joint pass keeps only the 16-float colour record (x .. depth | r g b 0 | 0 0 ex ey); the
+// language channels are staged from the caller's language[P,F] rows when a tile's batch is fetched, so the
+// preprocess neither reads nor copies them (only the few entries a tile really traverses are ever fetched).
+__host__ __device__ constexpr int rec_floats_global(int ncol, int F) { return (ncol && F) ? rec_floats_nch(ncol) : rec_floats_nch(ncol + F); }
 
 struct WsLayout {
     size_t info, tile_count, tile_cursor, ranges, cta_hist, records, depths, cov3D, clamped, tiles_touched, rect, final_T,
@@ -38,7 +42,7 @@ inline __host__ WsLayout ws_layout(int P, int F, int W, int H, int tile, int64_t
     L.gx = (W + tile - 1) / tile;
     L.gy = (H + tile - 1) / tile;
     L.n_tiles = L.gx * L.gy;
-    L.rec = rec_floats_nch(ncol + F);
+    L.rec = rec_floats_global(ncol, F);
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
     const size_t Pz = (size_t)(P > 0 ? P : 1), HW = (size_t)W * H, Rz = (size_t)(R_cap > 0 ? R_cap : 1);
@@ -90,6 +94,43 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
+}
+
+// Stages piece `op` of one Gaussian's blend record into shared memory (layout: x..depth | channels | pad | ex ey).
+// Without external language the record is copied as REC/4 16-byte chunks; with it, the 16-float colour record is
+// split (header 2 x 16 B, r g 8 B, b 4 B, extents 8 B) and the F language floats come from language[id*F..].
+template <int NCOL, int F>
+struct RecordStage {
+    static constexpr bool EXT_LANG = NCOL > 0 && F > 0;
+    static constexpr int REC_S = rec_floats_nch(NCOL + F);      // shared-memory record
+    static constexpr int REC_G = rec_floats_global(NCOL, F);    // global-memory record
+    static constexpr int OPS = EXT_LANG ? 5 + F : REC_S / 4;
+    static_assert(!EXT_LANG || REC_CH + NCOL + F == REC_S - 2, "joint layout: language ends where the extents start");
+    __device__ static __forceinline__ void copy(float* s, const float* __restrict__ records,
+                                                const float* __restrict__ language, uint32_t id, int op) {
+        const float* g = records + (size_t)id * REC_G;
+        if (!EXT_LANG) {
+            cp_async16(s + 4 * op, g + 4 * op);
+        } else if (op < 2) {
+            cp_async16(s + 4 * op, g + 4 * op);
+        } else if (op == 2) {
+            cp_async8(s + REC_CH, g + REC_CH);
+        } else if (op == 3) {
+            cp_async4(s + REC_CH + 2, g + REC_CH + 2);
+        } else if (op == 4) {
+            cp_async8(s + REC_S - 2, g + REC_G - 2);
+        } else {
+            cp_async4(s + REC_CH + NCOL + (op - 5), language + (size_t)id * F + (op - 5));
+        }
+    }
+};
 
 }  // namespace ols
 

@@ -168,28 +168,6 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreArgs a) {
             s_mean[e] = a.means3D[(size_t)base * 3 + e];
             if (a.scales) s_scale[e] = a.scales[(size_t)base * 3 + e];
         }
-        {   // language rows -> records: coalesced reads issued as one batch (up to 16 per thread), then the stores
-            const int F = a.F, rec = a.rec;
-            const float* __restrict__ src = a.language + (size_t)base * F;
-            float* __restrict__ dst = a.records + (size_t)base * rec;
-            const int n_el = nloc * F;
-            for (int e0 = 0; e0 < n_el; e0 += 16 * PRE_THREADS) {
-                float tmp[16];
-#pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    const int e = e0 + k * PRE_THREADS + tid;
-                    tmp[k] = e < n_el ? __ldg(src + e) : 0.0f;
-                }
-#pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    const int e = e0 + k * PRE_THREADS + tid;
-                    if (e < n_el) {
-                        const int g = e / F, c = e - g * F;
-                        dst[(size_t)g * rec + REC_CH + 3 + c] = tmp[k];
-                    }
-                }
-            }
-        }
         __syncthreads();
         if (tid < nloc) preprocess_one(a, base + tid, tid, s_mean, s_scale, s_V, s_Pm, s_hist, visible);
     }
@@ -338,7 +316,7 @@ __device__ void preprocess_one(const PreArgs& a, int i, int tid, const float* s_
     rf[REC_CH] = rgb[0];
     rf[REC_CH + 1] = rgb[1];
     rf[REC_CH + 2] = rgb[2];
-    for (int c = REC_CH + 3 + a.F; c < a.rec - 2; c++) rf[c] = 0.0f;
+    for (int c = REC_CH + 3; c < a.rec - 2; c++) rf[c] = 0.0f;  // the language channels are not part of the global record
     write_record_frame(rf, a.rec, pix_x, pix_y, fmul(cc, det_inv), fmul(cb, -det_inv), fmul(ca, det_inv), a.opacities[i], vz);
     a.depths[i] = vz;
     a.radii[i] = ri;
@@ -1023,6 +1001,7 @@ struct BlendArgs {
     const uint2* ranges;
     const uint32_t* point_list;
     const float* records;
+    const float* language;  // [P,F] caller's language rows (joint pass), else unused
     const float* bg;
     const DeviceInfo* info;
     float* final_T;
@@ -1062,8 +1041,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend(const BlendArgs a) {
     static_assert(NCOL == 0 || NCOL == 3, "colour channels");
     constexpr int NCH = NCOL + F;               // channels stored from REC_CH on (an odd count is zero-padded)
     constexpr int REC = rec_floats_nch(NCH);
-    constexpr int R4 = REC / 4;                 // float4 chunks per record
-    constexpr int CHUNKS = BLEND_BATCH * R4;    // 16-byte chunks per batch
+    using Stage = RecordStage<NCOL, F>;
+    constexpr int OPS = Stage::OPS;             // cp.async pieces per record
     constexpr int NPAIR = (NCH + 1) / 2;        // (r,g) (b,L0) (L1,L2) ... as stored
     constexpr int EXT = REC - 2;
     static_assert(REC_CH + 2 * NPAIR <= EXT, "channel pairs must not run into the extents");
@@ -1101,13 +1080,14 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend(const BlendArgs a) {
     auto issue = [&](int b) {  // cp.async the records of batch b into buffer b&1
         const int cnt = min(BLEND_BATCH, total - b * BLEND_BATCH);
         const int buf = b & 1;
-        for (int c = tid; c < CHUNKS; c += BLEND_THREADS) {
-            const int g = c / R4, q = c - g * R4;
-            if (g < cnt) {
-                const uint32_t id = a.point_list[rg.x + b * BLEND_BATCH + g];
-                if (q == 0) s_id[buf][g] = id;
-                cp_async16(&s_rec[buf][g * REC + q * 4], a.records + (size_t)id * REC + q * 4);
-            }
+        // BLEND_THREADS / BLEND_BATCH threads share one record: one list lookup each, pieces dealt round-robin
+        constexpr int TPE = BLEND_THREADS / BLEND_BATCH;
+        const int g = tid / TPE;
+        if (g < cnt) {
+            const uint32_t id = a.point_list[rg.x + b * BLEND_BATCH + g];
+            if ((tid % TPE) == 0) s_id[buf][g] = id;
+#pragma unroll
+            for (int q = tid % TPE; q < OPS; q += TPE) Stage::copy(&s_rec[buf][g * REC], a.records, a.language, id, q);
         }
         cp_async_commit();
     };
@@ -1270,7 +1250,7 @@ struct PassOut {
     int32_t* n_touched;
 };
 static int run_pass(int P, int W, int H, int tile, int ncol, int F, unsigned flags, int64_t R_cap, char* ws, const WsLayout& L,
-                    const float* depths, const float* d_bg, const PassOut& o, cudaStream_t st) {
+                    const float* depths, const float* language, const float* d_bg, const PassOut& o, cudaStream_t st) {
     const bool debug = (flags & OLS_FLAG_DEBUG) != 0;
     DeviceInfo* info = (DeviceInfo*)(ws + L.info);
     uint32_t* cta_hist = (uint32_t*)(ws + L.cta_hist);
@@ -1301,7 +1281,7 @@ static int run_pass(int P, int W, int H, int tile, int ncol, int F, unsigned fla
     BlendArgs ba;
     ba.W = W; ba.H = H; ba.gx = L.gx;
     ba.ranges = (const uint2*)(ws + L.ranges); ba.point_list = (const uint32_t*)(ws + L.point_list);
-    ba.records = (const float*)(ws + L.records); ba.bg = d_bg; ba.info = info;
+    ba.records = (const float*)(ws + L.records); ba.language = language; ba.bg = d_bg; ba.info = info;
     ba.final_T = (float*)(ws + L.final_T); ba.n_contrib = (uint32_t*)(ws + L.n_contrib);
     ba.out_color = o.color; ba.out_language = o.language; ba.out_depth = o.depth;
     ba.out_opacity = o.opacity; ba.n_touched = o.n_touched;
@@ -1362,7 +1342,7 @@ int ols_launch_forward(const ols_raster_args* a, const ols_fwd_out* o, const WsL
     OLS_DEBUG_SYNC("preprocess");
     ols_timing_mark(OLS_T_PREPROCESS, st);
     PassOut po{o->d_color, o->d_language, o->d_depth, o->d_opacity, o->d_n_touched};
-    return run_pass(a->P, a->W, a->H, a->tile, 3, a->F, a->flags, a->R_cap, ws, L, p.depths, a->d_bg, po, st);
+    return run_pass(a->P, a->W, a->H, a->tile, 3, a->F, a->flags, a->R_cap, ws, L, p.depths, a->d_language, a->d_bg, po, st);
 }
 
 // Disentangled forward (D/rasterizer_impl.cu:364-620): one preprocess, then the colour footprint's and
@@ -1410,9 +1390,9 @@ int ols_launch_forward_dis(const ols_dis_args* d, const ols_dis_fwd_out* o, cons
     OLS_DEBUG_SYNC("preprocess_dis");
     ols_timing_mark(OLS_T_PREPROCESS, st);
     PassOut pc{o->d_color, nullptr, o->d_depth, o->d_opacity, o->d_n_touched};
-    rc = run_pass(a->P, a->W, a->H, a->tile, 3, 0, a->flags, a->R_cap, wc, Lc, p.depths, a->d_bg, pc, st);
+    rc = run_pass(a->P, a->W, a->H, a->tile, 3, 0, a->flags, a->R_cap, wc, Lc, p.depths, nullptr, a->d_bg, pc, st);
     if (rc != OLS_OK) return rc;
     ols_timing_mark(-1, st);
     PassOut pl{nullptr, o->d_language, nullptr, o->d_opacity_lang, o->d_n_touched_lang};
-    return run_pass(a->P, a->W, a->H, a->tile, 0, a->F, a->flags, d->R_cap_lang, wl, Ll, p.depths, a->d_bg, pl, st);
+    return run_pass(a->P, a->W, a->H, a->tile, 0, a->F, a->flags, d->R_cap_lang, wl, Ll, p.depths, nullptr, a->d_bg, pl, st);
 }

@@ -1114,7 +1114,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend(const BlendArgs a) {
         const uint32_t cbase = (uint32_t)b * BLEND_BATCH;
 #pragma unroll 1
         for (int half = 0; half < BLEND_BATCH / 32; half++) {
-            uint32_t hitmask = 0;  // warp-uniform: entries of this half some lane blended
+            uint32_t myhits = 0, mytouch = 0;  // per lane: entries of this half this pixel blended / "touched" (T' > 0.5)
             if (__all_sync(0xffffffffu, done)) { if (lane == 0) s_hit[b & 1][wid][half] = 0u; continue; }
             const int e = half * 32 + lane;
             bool hit = false;
@@ -1129,7 +1129,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend(const BlendArgs a) {
                 const int j = half * 32 + jl;
                 m &= m - 1;
                 const float* rj = rec + j * REC;
-                bool touch = false, blended = false;
+                const uint32_t jbit = 1u << jl;
                 if (!done) {
                     const float4 g0 = *reinterpret_cast<const float4*>(rj);      // x y A B
                     const float4 g1 = *reinterpret_cast<const float4*>(rj + 4);  // C op pth depth
@@ -1164,21 +1164,23 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend(const BlendArgs a) {
                                     for (int p = 0; p < NPAIR; p++) acc2[p] = ffma2(w2, v[p], acc2[p]);
                                     if (NCOL) acc_d = ffma(w, g1.w, acc_d);
                                 }
-                                touch = test_T > 0.5f;
-                                blended = true;
+                                myhits |= jbit;
+                                if (test_T > 0.5f) mytouch |= jbit;
                                 T = test_T;
                                 last_contributor = cbase + (uint32_t)j + 1u;
                             }
                         }
                     }
                 }
-                if (__any_sync(0xffffffffu, blended)) {
-                    hitmask |= 1u << jl;
-                    const unsigned tm = __ballot_sync(0xffffffffu, touch);
-                    if (tm != 0u && lane == 0) atomicAdd(&a.n_touched[ids[j]], __popc(tm));
-                }
             }
+            // once per 32 entries: which entries did the warp blend (for the backward), and the n_touched counts
+            const uint32_t hitmask = __reduce_or_sync(0xffffffffu, myhits);
             if (lane == 0) s_hit[b & 1][wid][half] = hitmask;
+            for (uint32_t tmask = __reduce_or_sync(0xffffffffu, mytouch); tmask; tmask &= tmask - 1) {
+                const int jl = __ffs(tmask) - 1;
+                const unsigned tm = __ballot_sync(0xffffffffu, (mytouch >> jl) & 1u);
+                if (lane == 0) atomicAdd(&a.n_touched[ids[half * 32 + jl]], __popc(tm));
+            }
         }
     }
     cp_async_wait<0>();

@@ -265,7 +265,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 4) k_blend_bwd(const BwdBlendArgs
             }
             float w = 0.0f;
             if (contrib) {
-                T = T / (1.0f - alpha);
+                // 1 - alpha >= 0.01: the approximate reciprocal (2 ulp) is far inside the gradient tolerance and
+                // is shared by the transmittance update and the background term
+                const float inv_1ma = __fdividef(1.0f, 1.0f - alpha);
+                T = T * inv_1ma;
                 w = alpha * T;
                 float D_c = 0.0f;
                 if (NCOL) {
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 4) k_blend_bwd(const BwdBlendArgs
                 }
                 float dL_dalpha = ((D_c - A_c) + (D_f - A_f)) * T;
                 last_alpha = alpha;
-                if (NCOL) dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot;
+                if (NCOL) dL_dalpha += (-T_final * inv_1ma) * bg_dot;
                 const float dL_dG = g1.y * dL_dalpha;
                 const float gdx = G * dx, gdy = G * dy;
                 if (lane_ok) {

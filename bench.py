@@ -202,7 +202,7 @@ def workload_config(args):
             "gaussians": args.gaussians, "feature_dim": 15, "width": args.width, "height": args.height,
             "keyframes_per_gpu": args.keyframes, "tile": args.tile, "backward_mode": args.backward_mode,
             "autoencoder": "768-384-192-96-48-24-15 (1-stage, BN folded)", "parallelism": f"frames x{args.gpus}",
-            "l2_policy": "per-step inputs (8 CLIP maps = 906 MB + 112 MB records) exceed the 126 MB L2"}
+            "l2_policy": "per-step inputs (8 CLIP maps = 906 MB, 56 MB of Gaussian parameters + 64 MB records per view) exceed the 126 MB L2"}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -526,7 +526,8 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
             "roofline": roofline, "kernels": per_kernel, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": args.steps * KF * 10, "clocks": clocks,
+            "gpu_launches": args.steps * KF * 11,  # per keyframe: AE, preprocess, tile offsets, tile scan, scatter, 3 sort kernels, blend, blend backward, geometry backward
+            "clocks": clocks,
             "launch_mode": {"value": "cuda_graph_replay" if graph is not None else "eager", "ms_per_step_eager": ms_eager / args.steps,
                             "note": "per-kernel times and the roofline come from a second, eagerly launched region of the same "
                                     "K steps with CUDA events recorded between the kernels"}}

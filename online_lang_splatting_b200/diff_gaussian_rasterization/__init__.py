@@ -95,9 +95,13 @@ def _forward_native(means3D, sh, colors_precomp, language_precomp, opacities, sc
     P = means3D.shape[0]
     H, W = int(rs.image_height), int(rs.image_width)
     tile = int(getattr(rs, "tile_size", 15))
-    if language_precomp is None or language_precomp.numel() == 0:
+    if language_precomp is None or language_precomp.dim() != 2 or (P > 0 and language_precomp.numel() == 0):
         raise RuntimeError("language_precomp is required by the language rasterizer")
     F = int(language_precomp.shape[1])
+    if P == 0:  # nothing to rasterize (render() returns None before getting here, reference :76,:210)
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
+        e = torch.empty((0,), dtype=torch.int32, device=dev)
+        return 0, z(3, H, W), z(F, H, W), e, z(1, H, W), z(1, H, W), e.clone(), None
     keep = {
         "means3D": _f32c(means3D), "language": _f32c(language_precomp), "opacities": _f32c(opacities),
         "bg": _f32c(rs.bg).to(dev), "viewmatrix": _f32c(rs.viewmatrix).to(dev),
@@ -118,9 +122,6 @@ def _forward_native(means3D, sh, colors_precomp, language_precomp, opacities, sc
     opacity = torch.empty((1, H, W), dtype=torch.float32, device=dev)
     radii = torch.empty((P,), dtype=torch.int32, device=dev)
     n_touched = torch.empty((P,), dtype=torch.int32, device=dev)
-    if P == 0:
-        return 0, color.zero_(), language.zero_(), radii, depth.zero_(), opacity.zero_(), n_touched, None
-
     lib = N.lib()
     key = (dev.index, P, W, H, tile)
     stream = torch.cuda.current_stream(dev).cuda_stream

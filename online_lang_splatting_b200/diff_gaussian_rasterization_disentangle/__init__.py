@@ -64,9 +64,13 @@ def _forward_native(means3D, sh, colors_precomp, language_precomp, opacities, op
     P = means3D.shape[0]
     H, W = int(rs.image_height), int(rs.image_width)
     tile = int(getattr(rs, "tile_size", 16))
-    if language_precomp is None or language_precomp.numel() == 0:
+    if language_precomp is None or language_precomp.dim() != 2 or (P > 0 and language_precomp.numel() == 0):
         raise RuntimeError("language_precomp is required by the language rasterizer")
     F = int(language_precomp.shape[1])
+    if P == 0:  # nothing to rasterize
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
+        e = lambda: torch.empty((0,), dtype=torch.int32, device=dev)
+        return 0, 0, z(3, H, W), z(F, H, W), e(), e(), z(1, H, W), z(1, H, W), z(1, H, W), e(), e(), None
     keep = {
         "means3D": _f32c(means3D), "language": _f32c(language_precomp), "opacities": _f32c(opacities),
         "opacities_lang": _f32c(opacities_lang),
@@ -87,11 +91,6 @@ def _forward_native(means3D, sh, colors_precomp, language_precomp, opacities, op
     color, language = torch.empty((3, H, W), **f32), torch.empty((F, H, W), **f32)
     depth, opacity, opacity_lang = (torch.empty((1, H, W), **f32) for _ in range(3))
     radii, radii_lang, n_touched, n_touched_lang = (torch.empty((P,), **i32) for _ in range(4))
-    if P == 0:
-        for t in (color, language, depth, opacity, opacity_lang):
-            t.zero_()
-        return 0, 0, color, language, radii, radii_lang, depth, opacity, opacity_lang, n_touched, n_touched_lang, None
-
     lib = N.lib()
     key = (dev.index, P, W, H, tile)
     stream = torch.cuda.current_stream(dev).cuda_stream

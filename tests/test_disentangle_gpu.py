@@ -129,3 +129,36 @@ def test_dis_argument_validation():
         rast(means3D=d("means3D"), means2D=None, opacities=d("opacities"), opacities_lang=d("opacities_lang"),
              language_precomp=d("language"), scales=d("scales"), rotations=d("rotations"), scales_lang=d("scales_lang"),
              rotations_lang=d("rotations_lang"))
+
+
+def test_dis_edge_cases():
+    """empty lists (everything behind the camera), a footprint that is invisible in one list only, single Gaussian"""
+    from online_lang_splatting_b200 import diff_gaussian_rasterization_disentangle as dd
+    sc = U.add_lang_footprint(U.make_scene(P=64, F=3, W=48, H=32, seed=1, bg=(0.3, 0.6, 0.9)))
+    sc["means3D"][:, 2] = -1.0
+    o = U.run_ours_dis(sc, _dev())
+    assert o["R"] == 0 and o["R_lang"] == 0 and (o["radii"] == 0).all() and (o["radii_lang"] == 0).all()
+    assert np.allclose(o["color"][0], 0.3) and (o["language"] == 0).all() and (o["opacity_lang"] == 0).all()
+    # language footprints shrunk to nothing but the 0.3 px dilation: still listed; colour footprints huge
+    sc = U.add_lang_footprint(U.make_scene(P=500, F=3, W=64, H=48, seed=2, scale=0.1), seed=1)
+    sc["scales_lang"] = sc["scales_lang"] * 1e-4
+    grads = U.loss_weights(3, 64, 48, seed=1)
+    o = U.run_ours_dis(sc, _dev(), grads=grads, backward_mode="compat")
+    r = U.run_oracle_dis(sc, grads=grads, compat=True)
+    assert (o["R"], o["R_lang"]) == (r["R"], r["R_lang"]) and o["R_lang"] < o["R"]
+    assert np.array_equal(o["radii_lang"], r["radii_lang"])
+    assert np.array_equal(o["ws_lang"]["point_list"].astype(np.uint32), r["point_list_lang"])
+    assert _l2rel(o["grads"]["opacities_lang"].reshape(-1), r["grads"]["dL_dopacity_lang"].reshape(-1)) < 2e-3
+    # one Gaussian
+    sc = U.add_lang_footprint(U.make_scene(P=1, F=3, W=40, H=30, seed=1, scale=0.2))
+    sc["means3D"][0] = torch.tensor([0.0, 0.0, 2.0])
+    o, r = U.run_ours_dis(sc, _dev()), U.run_oracle_dis(sc)
+    assert o["R"] == r["R"] > 0 and U.rel_err(o["language"], r["language"]) < 1e-5
+    # P == 0 returns zero images like the joint module
+    e = torch.zeros(0, 3, device=_dev())
+    rs = U.settings_dis(sc, _dev())
+    out = dd._forward_native(e, torch.zeros(0, 1, 3, device=_dev()), torch.Tensor([]), torch.zeros(0, 3, device=_dev()),
+                             torch.zeros(0, 1, device=_dev()), torch.zeros(0, 1, device=_dev()), e, e,
+                             torch.zeros(0, 4, device=_dev()), torch.zeros(0, 4, device=_dev()), torch.Tensor([]),
+                             torch.Tensor([]), rs)
+    assert out[0] == 0 and out[2].abs().sum().item() == 0

@@ -47,6 +47,8 @@ typedef enum ols_status {
 #define OLS_FLAG_BITEXACT_BLEND  (1u << 2)  /* accumulate c*alpha*T in the reference's operation order      */
 #define OLS_FLAG_BWD_EXACT       (1u << 3)  /* backward: mathematically exact gradients instead of the
                                                reference's Q1-Q3 behaviour          */
+#define OLS_FLAG_BWD_NO_PACK     (1u << 5)  /* compat backward: keep one thread per pixel even where the reference's
+                                               lossy reduction drops the pixel (debugging / A-B comparison)  */
 #define OLS_FLAG_BWD_ACCUMULATE  (1u << 4)  /* backward: add into dL_dmeans3D/sh/opacity/scales/rotations/
                                                language/cov3D instead of overwriting (sums the views of a
                                                mapping iteration, utils/slam_backend.py:510-670)            */

@@ -47,6 +47,7 @@ struct BwdBlendArgs {
     const uint8_t* warp_hits;  // [R] from the forward: which pixel blocks of the tile blended each list entry
     float* gacc;             // [P, grad_floats(F)] zero-initialised
     uint32_t lane_ok[8];     // Q3 lane mask (compat); all ones otherwise
+    uint8_t packed_rank[128];  // packed compat variant: reference thread rank handled by thread t (255 = none)
 };
 
 typedef unsigned long long f32x2;  // two floats in one 64-bit register pair
@@ -112,9 +113,16 @@ __device__ __forceinline__ int multi_reduce_owner(int lane) {
 // The forward left one byte per list entry saying which pixel blocks blended it (warp_hits); an entry is
 // "visited" by the reference's block-wide loop iff that byte is non-zero (a pixel blends an entry in the
 // forward exactly when the backward's skip tests pass for it), so no separate scan of the list is needed.
-template <int TILE, int NCOL, int F, bool COMPAT>
-__global__ void __launch_bounds__(BWD_THREADS, 4) k_blend_bwd(const BwdBlendArgs a) {
+// PACKED (compat, 15x15 tiles): the reference's lossy block reduction (Q3) lets only 128 of the 225 pixels of a
+// tile reach any reduced gradient, and nothing else a dropped pixel computes is ever used.  The packed variant
+// therefore runs 128 threads per tile, one per surviving pixel (in reference rank order), instead of carrying 97
+// dead lanes through every step.  Its warps are 15-pixel-wide strips, so the forward's per-8x4-block hit bits do
+// not apply; a warp decides by a vote after evaluating an entry.
+template <int TILE, int NCOL, int F, bool COMPAT, bool PACKED>
+__global__ void __launch_bounds__(PACKED ? 128 : BWD_THREADS, PACKED ? 8 : 4) k_blend_bwd(const BwdBlendArgs a) {
     static_assert(TILE <= 16 && BWD_BATCH == 32, "8 warps of 8x4 pixels; one ballot per batch");
+    static_assert(!PACKED || COMPAT, "packing follows the compat lane mask");
+    constexpr int NT = PACKED ? 128 : BWD_THREADS;
     static_assert(NCOL == 0 || NCOL == 3, "colour channels");
     constexpr int NCH = NCOL + F;
     constexpr int REC = rec_floats_nch(NCH);
@@ -132,8 +140,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 4) k_blend_bwd(const BwdBlendArgs
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int tile_x = blockIdx.x % a.gx, tile_y = blockIdx.x / a.gx;
-    const int bx0 = (wid & 1) * 8, by0 = (wid >> 1) * 4;
-    const int lx = bx0 + (lane & 7), ly = by0 + (lane >> 3);
+    int lx, ly;
+    if (PACKED) {
+        const int rank = a.packed_rank[tid];
+        lx = rank == 255 ? TILE : rank % TILE;
+        ly = rank == 255 ? TILE : rank / TILE;
+    } else {
+        lx = (wid & 1) * 8 + (lane & 7);
+        ly = (wid >> 1) * 4 + (lane >> 3);
+    }
     const int pxi = tile_x * TILE + lx, pyi = tile_y * TILE + ly;
     const bool inside = lx < TILE && ly < TILE && pxi < a.W && pyi < a.H;
     const float pfx = (float)pxi, pfy = (float)pyi;
@@ -142,10 +157,20 @@ __global__ void __launch_bounds__(BWD_THREADS, 4) k_blend_bwd(const BwdBlendArgs
 
     uint2 rg = a.ranges[blockIdx.x];
     if (a.info->overflow) rg = make_uint2(0u, 0u);
-    const uint32_t last_contributor = inside ? a.n_contrib[pix] : 0u;
-    const uint32_t warp_maxc = __reduce_max_sync(0xffffffffu, last_contributor);
+    // the list is walked as far as ANY pixel of the tile got (also the pixels the packed variant does not carry:
+    // the reference's block visits those entries and advances the language recurrence of every pixel, Q2)
+    uint32_t last_contributor = inside ? a.n_contrib[pix] : 0u;
+    uint32_t warp_maxc = __reduce_max_sync(0xffffffffu, last_contributor);
+    if (PACKED) {
+        uint32_t other = 0;
+        for (int r = tid; r < TILE * TILE; r += NT) {
+            const int ox = tile_x * TILE + r % TILE, oy = tile_y * TILE + r / TILE;
+            if (ox < a.W && oy < a.H) other = max(other, a.n_contrib[(size_t)oy * a.W + ox]);
+        }
+        warp_maxc = max(warp_maxc, __reduce_max_sync(0xffffffffu, other));
+    }
     if (tid == 0) s_maxc = 0;
-    for (int e = tid; e < BWD_BATCH * GR; e += BWD_THREADS) s_acc[e] = 0.0f;
+    for (int e = tid; e < BWD_BATCH * GR; e += NT) s_acc[e] = 0.0f;
     __syncthreads();
     if (lane == 0 && warp_maxc) atomicMax(&s_maxc, warp_maxc);
     __syncthreads();
@@ -174,7 +199,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 4) k_blend_bwd(const BwdBlendArgs
     const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
     // Q3: the lane mask is indexed by the reference's thread rank ly * TILE + lx
     const int ref_rank = ly * TILE + lx;
-    const bool lane_ok = COMPAT ? (inside && ((a.lane_ok[(ref_rank >> 5) & 7] >> (ref_rank & 31)) & 1u) != 0) : true;
+    const bool lane_ok = PACKED ? inside : (COMPAT ? (inside && ((a.lane_ok[(ref_rank >> 5) & 7] >> (ref_rank & 31)) & 1u) != 0) : true);
     const int own = multi_reduce_owner<NV>(lane);
     const int own_dst = own < 0 ? -1 : (NCOL ? own : (own < NGEO ? GR_CX + own : GR_LANG + (own - NGEO)));
 
@@ -205,7 +230,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 4) k_blend_bwd(const BwdBlendArgs
         const int cnt = min(BWD_BATCH, total - base);
         __syncthreads();  // previous batch fully consumed / flushed
         {   // BWD_THREADS / BWD_BATCH threads share one record: one list lookup each, pieces dealt round-robin
-            constexpr int TPE = BWD_THREADS / BWD_BATCH;
+            constexpr int TPE = NT / BWD_BATCH;
             const int gi = tid / TPE;
             if (gi < cnt) {
                 const uint32_t id = a.point_list[rg.x + base + gi];
@@ -216,7 +241,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 4) k_blend_bwd(const BwdBlendArgs
         }
         cp_async_commit();
         const uint32_t hit = lane < cnt ? (uint32_t)a.warp_hits[rg.x + base + lane] : 0u;
-        const uint32_t mine = __ballot_sync(0xffffffffu, (hit >> wid) & 1u);  // entries a pixel of this warp blended
+        // entries a pixel of this warp blended (packed variant: not known in advance, decided by a vote below)
+        const uint32_t mine = PACKED ? 0xffffffffu : __ballot_sync(0xffffffffu, (hit >> wid) & 1u);
         uint32_t visit = COMPAT ? __ballot_sync(0xffffffffu, hit != 0u) : mine;
         cp_async_wait<0>();
         __syncthreads();
@@ -226,7 +252,28 @@ __global__ void __launch_bounds__(BWD_THREADS, 4) k_blend_bwd(const BwdBlendArgs
             const int j = 31 - __clz(visit);  // back to front
             visit &= ~(1u << j);
             const float* rj = s_rec + j * REC;
-            const bool warp_blends = (mine >> j) & 1u;
+            float4 g0, g1;
+            float dx = 0.0f, dy = 0.0f, G = 0.0f, alpha = 0.0f;
+            bool contrib = false;
+            auto evaluate = [&]() {
+                g0 = *reinterpret_cast<const float4*>(rj);      // x y A B
+                g1 = *reinterpret_cast<const float4*>(rj + 4);  // C op pth depth
+                dx = fsub(g0.x, pfx);
+                dy = fsub(g0.y, pfy);
+                const float power = ffma(ffma(dx, fmul(dx, g0.z), fmul(dy, fmul(dy, g1.x))), -0.5f, -fmul(dy, fmul(dx, g0.w)));
+                if (inside && (uint32_t)(base + j) < last_contributor && !(power > 0.0f) && !(power < g1.z)) {
+                    G = expf(power);
+                    alpha = fminf(0.99f, fmul(g1.y, G));
+                    contrib = !(alpha < 1.0f / 255.0f);
+                }
+            };
+            bool warp_blends;
+            if (PACKED) {
+                evaluate();
+                warp_blends = __any_sync(0xffffffffu, contrib);
+            } else {
+                warp_blends = (mine >> j) & 1u;
+            }
             if (!warp_blends) {  // compat only: another pixel block of the tile blends this entry
                 if (F > 0) {
                     if (fresh) { pend = j; continue; }
@@ -241,17 +288,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 4) k_blend_bwd(const BwdBlendArgs
                 if (pend >= 0) { Dl_f = lang_dot(s_rec + pend * REC); pend = -1; }
                 fresh = false;
             }
-            const float4 g0 = *reinterpret_cast<const float4*>(rj);      // x y A B
-            const float4 g1 = *reinterpret_cast<const float4*>(rj + 4);  // C op pth depth
-            const float dx = fsub(g0.x, pfx), dy = fsub(g0.y, pfy);
-            const float power = ffma(ffma(dx, fmul(dx, g0.z), fmul(dy, fmul(dy, g1.x))), -0.5f, -fmul(dy, fmul(dx, g0.w)));
-            float G = 0.0f, alpha = 0.0f;
-            bool contrib = false;
-            if (inside && (uint32_t)(base + j) < last_contributor && !(power > 0.0f) && !(power < g1.z)) {
-                G = expf(power);
-                alpha = fminf(0.99f, fmul(g1.y, G));
-                contrib = !(alpha < 1.0f / 255.0f);
-            }
+            if (!PACKED) evaluate();
             float v[NV];
 #pragma unroll
             for (int i = 0; i < NV; i++) v[i] = 0.0f;
@@ -320,7 +357,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 4) k_blend_bwd(const BwdBlendArgs
         if (COMPAT && F > 0 && pend >= 0) Dl_f = lang_dot(s_rec + pend * REC);
         __syncthreads();
         // flush the batch: one global atomic per (Gaussian, value) that received something
-        for (int e = tid; e < cnt * GR; e += BWD_THREADS) {
+        for (int e = tid; e < cnt * GR; e += NT) {
             const float val = s_acc[e];
             if (val != 0.0f) {
                 const int gi = e / GR, vi = e - gi * GR;
@@ -774,11 +811,13 @@ __global__ void __launch_bounds__(256) k_geometry_bwd_dis(const GeomDisArgs a) {
 }
 
 template <int TILE, int NCOL, int F>
-static void launch_blend_bwd(const BwdBlendArgs& ba, int n_tiles, bool exact, cudaStream_t st) {
+static void launch_blend_bwd(const BwdBlendArgs& ba, int n_tiles, bool exact, bool packed, cudaStream_t st) {
     if (exact)
-        k_blend_bwd<TILE, NCOL, F, false><<<n_tiles, BWD_THREADS, 0, st>>>(ba);
+        k_blend_bwd<TILE, NCOL, F, false, false><<<n_tiles, BWD_THREADS, 0, st>>>(ba);
+    else if (packed)
+        k_blend_bwd<TILE, NCOL, F, true, true><<<n_tiles, 128, 0, st>>>(ba);
     else
-        k_blend_bwd<TILE, NCOL, F, true><<<n_tiles, BWD_THREADS, 0, st>>>(ba);
+        k_blend_bwd<TILE, NCOL, F, true, false><<<n_tiles, BWD_THREADS, 0, st>>>(ba);
 }
 
 }  // namespace ols
@@ -826,18 +865,31 @@ static int run_blend_bwd(int W, int H, int tile, int ncol, int F, unsigned flags
     ba.gacc = gacc;
     ba.warp_hits = (const uint8_t*)(ws + L.warp_hits);
     reduce_lane_mask(tile * tile, exact, ba.lane_ok);
+    // packed compat variant: possible when at most 128 pixels of a tile survive the reference's reduction (15x15: 128)
+    bool packed = false;
+    if (!exact && !(flags & OLS_FLAG_BWD_NO_PACK)) {
+        int n_ok = 0;
+        for (int r = 0; r < tile * tile; r++) {
+            if ((ba.lane_ok[r >> 5] >> (r & 31)) & 1u) {
+                if (n_ok < 128) ba.packed_rank[n_ok] = (uint8_t)r;
+                n_ok++;
+            }
+        }
+        packed = n_ok <= 128;
+        for (int t = n_ok; t < 128; t++) ba.packed_rank[t] = 255;
+    }
     const int key = tile * 10000 + ncol * 100 + F;
     switch (key) {
-        case 150315: launch_blend_bwd<15, 3, 15>(ba, L.n_tiles, exact, st); break;
-        case 160315: launch_blend_bwd<16, 3, 15>(ba, L.n_tiles, exact, st); break;
-        case 150303: launch_blend_bwd<15, 3, 3>(ba, L.n_tiles, exact, st); break;
-        case 160303: launch_blend_bwd<16, 3, 3>(ba, L.n_tiles, exact, st); break;
-        case 150300: launch_blend_bwd<15, 3, 0>(ba, L.n_tiles, exact, st); break;
-        case 160300: launch_blend_bwd<16, 3, 0>(ba, L.n_tiles, exact, st); break;
-        case 150003: launch_blend_bwd<15, 0, 3>(ba, L.n_tiles, exact, st); break;
-        case 160003: launch_blend_bwd<16, 0, 3>(ba, L.n_tiles, exact, st); break;
-        case 150015: launch_blend_bwd<15, 0, 15>(ba, L.n_tiles, exact, st); break;
-        case 160015: launch_blend_bwd<16, 0, 15>(ba, L.n_tiles, exact, st); break;
+        case 150315: launch_blend_bwd<15, 3, 15>(ba, L.n_tiles, exact, packed, st); break;
+        case 160315: launch_blend_bwd<16, 3, 15>(ba, L.n_tiles, exact, packed, st); break;
+        case 150303: launch_blend_bwd<15, 3, 3>(ba, L.n_tiles, exact, packed, st); break;
+        case 160303: launch_blend_bwd<16, 3, 3>(ba, L.n_tiles, exact, packed, st); break;
+        case 150300: launch_blend_bwd<15, 3, 0>(ba, L.n_tiles, exact, packed, st); break;
+        case 160300: launch_blend_bwd<16, 3, 0>(ba, L.n_tiles, exact, packed, st); break;
+        case 150003: launch_blend_bwd<15, 0, 3>(ba, L.n_tiles, exact, packed, st); break;
+        case 160003: launch_blend_bwd<16, 0, 3>(ba, L.n_tiles, exact, packed, st); break;
+        case 150015: launch_blend_bwd<15, 0, 15>(ba, L.n_tiles, exact, packed, st); break;
+        case 160015: launch_blend_bwd<16, 0, 15>(ba, L.n_tiles, exact, packed, st); break;
         default: ols_set_error("unsupported (tile=%d, F=%d)", tile, F); return OLS_ERR_UNSUPPORTED;
     }
     OLS_CUDA_TRY(cudaGetLastError());

@@ -509,7 +509,10 @@ int ols_ae_plan_create(const ols_ae_chain* chain, ols_ae_plan** out_plan, void* 
     if (n_stages < 2) { ols_set_error("layer chain does not fit shared memory (stage %d B, act %d B)", stage_bytes, act_bytes); return fail(OLS_ERR_UNSUPPORTED); }
     p.n_stages = n_stages; p.stage_bytes = stage_bytes; p.act_bytes = act_bytes;
     plan->smem_bytes = (size_t)n_stages * stage_bytes + act_bytes + 256 + 1024;
-    if (cudaFuncSetAttribute(k_ae_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes) != cudaSuccess) {
+    // the attribute belongs to the kernel, not to the plan: always reserve the opt-in maximum so that plans with
+    // different shared-memory needs (encoder / decoder) can be launched in any order
+    if (plan->smem_bytes > 227 * 1024 ||
+        cudaFuncSetAttribute(k_ae_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
         ols_set_error("cannot reserve %zu bytes of shared memory", plan->smem_bytes); return fail(OLS_ERR_CUDA);
     }
     *out_plan = plan;

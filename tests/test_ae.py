@@ -147,3 +147,30 @@ def test_online_autoencoder_train_step_uses_autograd(cuda):
     assert (after - before).abs().max() > 0
     cos, rel = _metrics(after.cpu(), ref_after.cpu())
     assert cos > 0.9995 and rel < 3e-2
+
+
+@pytest.mark.gpu
+def test_config4_batch32_full_size(cuda):
+    """BASELINE config 4: batch 32 of 192x192x768 maps (1,179,648 rows) through encode -> decode.  The kernel is
+    row-independent, so parity at full size is a random subset of rows against torch fp32 plus size-independent
+    properties: unit norm of every code / reconstruction row, finite values, and equality with a separate run on
+    the subset alone (the result of a row does not depend on which tile it lands in)."""
+    model, din = build("ae_1stage")
+    model = model.to(cuda)
+    M = 32 * 192 * 192
+    g = torch.Generator(device=cuda).manual_seed(0)
+    x = torch.randn(M, din, device=cuda, generator=g)
+    x /= x.norm(dim=-1, keepdim=True)
+    with torch.no_grad():
+        code = model.encode(x)
+        rec = model.decode(code)
+        idx = torch.randint(0, M, (4096,), device=cuda, generator=g)
+        ref_code = AE.reference_chain(list(model.encoder), x[idx])
+        sub_code = model.encode(x[idx].contiguous())
+    assert code.shape == (M, 15) and rec.shape == (M, din)
+    assert torch.isfinite(code).all() and torch.isfinite(rec).all()
+    assert torch.allclose(code.norm(dim=-1), torch.ones(M, device=cuda), atol=1e-4)
+    assert torch.allclose(rec.norm(dim=-1), torch.ones(M, device=cuda), atol=1e-4)
+    cos = torch.nn.functional.cosine_similarity(code[idx], ref_code, dim=-1)
+    assert cos.min().item() > 0.9995
+    assert torch.equal(code[idx], sub_code)

@@ -71,11 +71,12 @@ def test_backward_compat_vs_golden_reference(cuda, path):
 
 
 def test_backward_compat_vs_compiled_reference_full_size(cuda):
-    """BASELINE config 2 shape (960x540, F=15) at a size the box handles in seconds."""
+    """BASELINE config 2 exactly: 500k Gaussians, 15-dim features, 960x540, forward + backward, against the compiled
+    reference CUDA submodule run side by side."""
     mod = U.ref_module("ref_P_C")
     if mod is None:
         pytest.skip("oracle/_ref/ref_P_C.so not present")
-    sc = U.make_scene(P=100000, F=15, W=960, H=540, seed=0, scale=0.01)
+    sc = U.make_scene(P=500000, F=15, W=960, H=540, seed=0, scale=0.01)
     grads = U.loss_weights(15, 960, 540, seed=1)
     ours = U.run_ours(sc, cuda, tile=15, grads=grads, backward_mode="compat")["grads"]
     ref = U.run_ref(mod, sc, cuda, grads=grads)["grads"]
@@ -107,3 +108,16 @@ def test_render_backward_through_public_api(cuda):
     assert vg is not None and float(vg[:, 2].abs().max()) == 0.0 and float(vg[:, :2].abs().sum()) > 0
     assert cam.cam_rot_delta.grad is not None and cam.cam_trans_delta.grad is not None
     assert cam.cam_rot_delta.grad.abs().sum() > 0
+
+
+def test_replica_shape_1200x680(cuda):
+    """BASELINE config 5 image shape (Replica room0: 1200x680, fx = fy = 600): forward + both backward modes vs the oracle."""
+    sc = U.make_scene(P=20000, F=15, W=1200, H=680, seed=6, scale=0.03)
+    grads = U.loss_weights(15, 1200, 680, seed=2)
+    for mode in ("compat", "exact"):
+        ours = U.run_ours(sc, cuda, tile=15, grads=grads, backward_mode=mode, bitexact=True)
+        ora = U.run_oracle(sc, tile=15, grads=grads, compat=(mode == "compat"))
+        assert ours["R"] == ora["R"] and np.array_equal(ours["ws"]["point_list"].astype(np.uint32), ora["point_list"])
+        assert U.rel_err(ours["language"], ora["language"]) < 1e-4
+        for k, rk in (("means3D", "dL_dmeans3D"), ("language", "dL_dlang"), ("opacities", "dL_dopacity"), ("scales", "dL_dscales")):
+            assert _l2rel(ours["grads"][k].reshape(ora["grads"][rk].shape), ora["grads"][rk]) < 2e-3, (mode, k)

@@ -280,6 +280,24 @@ int ols_mapping_loss_forward(const ols_loss_args* args, float* d_out6, float* d_
 int ols_mapping_loss_backward(const ols_loss_args* args, const float* d_upstream, float* d_dL_dimage, float* d_dL_ddepth,
                               float* d_dL_dlanguage, float* d_dL_dopacity /* tracking form only, may be NULL */, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Adam step over the flat parameter / gradient buffers (the step right after backward + all-reduce).
+ * Reference: torch.optim.Adam(param_groups, lr=0.0, eps=1e-15) of GaussianModel.training_setup
+ * (gaussian_splatting/scene/gaussian_model.py:393-437), one group per parameter tensor.  Groups are
+ * consecutive segments of the flat buffer (sharding.FlatGradBuffer layout), each with its own lr.
+ * ------------------------------------------------------------------------------------------- */
+#define OLS_ADAM_MAX_GROUPS 8
+typedef struct ols_adam_group {
+    int64_t offset;   /* first element of the group in the flat buffers */
+    int64_t count;    /* elements                                        */
+    float lr;
+    float _pad;
+} ols_adam_group;
+/* `step` is the 1-based step count after this update (torch's state["step"]). */
+int ols_adam_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n,
+                  const ols_adam_group* groups, int32_t n_groups, double beta1, double beta2, double eps, int64_t step,
+                  void* stream);
+
 /* Per-kernel device timing (CUDA events recorded between the kernels of every call while enabled).
  * ols_timing_begin() allocates `max_marks` events and enables recording on the calling thread;
  * ols_timing_end() synchronises, sums the elapsed milliseconds per tag, reports how many intervals

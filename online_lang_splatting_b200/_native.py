@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = (
     "ols_abi_version", "ols_last_error", "ols_cuda_available", "ols_lang_workspace_size", "ols_lang_forward",
     "ols_lang_read_info", "ols_lang_backward", "ols_mark_visible", "ols_lang_workspace_view",
     "ols_lang_forward_host", "ols_timing_begin", "ols_timing_end", "ols_ae_plan_create", "ols_ae_plan_destroy", "ols_ae_forward",
-    "ols_mapping_loss_forward", "ols_mapping_loss_backward",
+    "ols_mapping_loss_forward", "ols_mapping_loss_backward", "ols_adam_step",
     "ols_dis_workspace_size", "ols_dis_forward", "ols_dis_read_info", "ols_dis_backward", "ols_dis_workspace_view",
 )
 
@@ -87,6 +87,10 @@ class LossArgs(C.Structure):
                                           "d_opacity", "d_grad_mask")]
 
 
+class AdamGroup(C.Structure):
+    _fields_ = [("offset", C.c_int64), ("count", C.c_int64), ("lr", C.c_float), ("_pad", C.c_float)]
+
+
 class WsView(C.Structure):
     _fields_ = [("d_records", C.c_void_p), ("rec_floats", C.c_int32), ("n_tiles", C.c_int32)] + \
                [(n, C.c_void_p) for n in ("d_cov3D", "d_clamped", "d_tiles_touched", "d_ranges", "d_point_list",
@@ -141,6 +145,8 @@ def lib() -> C.CDLL:
     L.ols_mapping_loss_forward.argtypes = [C.POINTER(LossArgs), C.c_void_p, C.c_void_p, C.c_void_p]
     L.ols_mapping_loss_backward.argtypes = [C.POINTER(LossArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p]
+    L.ols_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(AdamGroup), C.c_int32,
+                                C.c_double, C.c_double, C.c_double, C.c_int64, C.c_void_p]
     L.ols_timing_begin.argtypes = [C.c_int32]
     L.ols_timing_end.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int32)]
     L.ols_ae_plan_create.argtypes = [C.POINTER(AEChain), C.POINTER(C.c_void_p), C.c_void_p]

@@ -48,6 +48,7 @@ struct BwdBlendArgs {
     float* gacc;             // [P, grad_floats(F)] zero-initialised
     uint32_t lane_ok[8];     // Q3 lane mask (compat); all ones otherwise
     uint8_t packed_rank[128];  // packed compat variant: reference thread rank handled by thread t (255 = none)
+    uint8_t packed_fmask[4];   // packed variant: forward 8x4 pixel blocks (bit w) that contain a pixel of packed warp k
 };
 
 typedef unsigned long long f32x2;  // two floats in one 64-bit register pair
@@ -242,7 +243,9 @@ __global__ void __launch_bounds__(PACKED ? 128 : BWD_THREADS, PACKED ? 8 : 4) k_
         cp_async_commit();
         const uint32_t hit = lane < cnt ? (uint32_t)a.warp_hits[rg.x + base + lane] : 0u;
         // entries a pixel of this warp blended (packed variant: not known in advance, decided by a vote below)
-        const uint32_t mine = PACKED ? 0xffffffffu : __ballot_sync(0xffffffffu, (hit >> wid) & 1u);
+        // (packed: entries some forward block overlapping this warp's pixels blended -- a superset, the vote decides)
+        const uint32_t mine = PACKED ? __ballot_sync(0xffffffffu, (hit & a.packed_fmask[wid & 3]) != 0u)
+                                     : __ballot_sync(0xffffffffu, (hit >> wid) & 1u);
         uint32_t visit = COMPAT ? __ballot_sync(0xffffffffu, hit != 0u) : mine;
         cp_async_wait<0>();
         __syncthreads();
@@ -267,12 +270,10 @@ __global__ void __launch_bounds__(PACKED ? 128 : BWD_THREADS, PACKED ? 8 : 4) k_
                     contrib = !(alpha < 1.0f / 255.0f);
                 }
             };
-            bool warp_blends;
-            if (PACKED) {
+            bool warp_blends = (mine >> j) & 1u;
+            if (PACKED && warp_blends) {
                 evaluate();
                 warp_blends = __any_sync(0xffffffffu, contrib);
-            } else {
-                warp_blends = (mine >> j) & 1u;
             }
             if (!warp_blends) {  // compat only: another pixel block of the tile blends this entry
                 if (F > 0) {
@@ -877,6 +878,14 @@ static int run_blend_bwd(int W, int H, int tile, int ncol, int F, unsigned flags
         }
         packed = n_ok <= 128;
         for (int t = n_ok; t < 128; t++) ba.packed_rank[t] = 255;
+        for (int k = 0; k < 4; k++) {
+            ba.packed_fmask[k] = 0;
+            for (int t = 32 * k; t < 32 * k + 32 && packed; t++) {
+                if (ba.packed_rank[t] == 255) continue;
+                const int lx = ba.packed_rank[t] % tile, ly = ba.packed_rank[t] / tile;
+                ba.packed_fmask[k] |= (uint8_t)(1u << ((ly / 4) * 2 + lx / 8));  // forward: warp = (y / 4) * 2 + x / 8
+            }
+        }
     }
     const int key = tile * 10000 + ncol * 100 + F;
     switch (key) {

@@ -21,6 +21,8 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -60,6 +62,7 @@ struct AeParams {
     float* y;
     long long M;
     int n_tiles;
+    unsigned long long* trace;  // development aid (OLS_AE_TRACE=1): globaltimer stamps of CTA 0's epilogue thread
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
@@ -149,6 +152,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 // byte offset of 16-byte chunk j of row r inside a [rows x 128 B] SWIZZLE_128B slab
 __device__ __forceinline__ uint32_t sw128(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
@@ -272,6 +280,9 @@ __global__ void __launch_bounds__(AE_THREADS, 1) k_ae_chain(const __grid_constan
         const int row = quad * 32 + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
         uint32_t done_phase = 0;
+        const bool tracer = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64;
+        int tr_n = 1;
+        if (tracer) p.trace[tr_n++] = gtimer();
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             const long long grow = (long long)tile * AE_M + row;
             if (p.manual_x) {
@@ -301,23 +312,32 @@ __global__ void __launch_bounds__(AE_THREADS, 1) k_ae_chain(const __grid_constan
                     mbar_wait(mma_done, done_phase);
                     done_phase ^= 1;
                     tcgen05_fence_after();
-                    for (int c = 0; c < w; c += 32) {
-                        uint32_t r[32];
-                        const int nc = min(32, w - c);
-                        if (nc == 32) tmem_ld32(t_lane + (uint32_t)c, r);
+                    if (tracer && tr_n < 250) p.trace[tr_n++] = gtimer();  // accumulator of (layer l, pass) ready
+                    // TMEM -> registers is double buffered: the load of chunk c + 1 is in flight while chunk c gets its
+                    // bias / ReLU / bf16 packing (tcgen05.wait::ld waits for every outstanding load of the thread)
+                    auto issue_ld = [&](int c, uint32_t (&r)[32]) {
+                        if (w - c >= 32) tmem_ld32(t_lane + (uint32_t)c, r);
                         else {
                             tmem_ld16(t_lane + (uint32_t)c, r);
 #pragma unroll
                             for (int i = 16; i < 32; i++) r[i] = 0u;
                         }
-                        tmem_ld_wait();
+                    };
+                    auto process = [&](int c, uint32_t (&r)[32]) {
+                        const int nc = min(32, w - c);
                         float v[32];
+                        const float4* b4 = reinterpret_cast<const float4*>(L.bias + n0 + c);  // N is a multiple of 16
 #pragma unroll
-                        for (int i = 0; i < 32; i++) {
-                            const int col = n0 + c + i;
-                            float f = __uint_as_float(r[i]) + (i < nc ? __ldg(L.bias + col) : 0.0f);
-                            if (L.relu) f = fmaxf(f, 0.0f);
-                            v[i] = f;
+                        for (int q = 0; q < 8; q++) {
+                            const float4 bq = (q * 4 < nc) ? __ldg(b4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + bq.x;
+                            v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bq.y;
+                            v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bq.z;
+                            v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bq.w;
+                        }
+                        if (L.relu) {
+#pragma unroll
+                            for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.0f);
                         }
                         if (!last) {
                             // next layer's A operand: bf16, K-major, 128-byte swizzle; column col -> slab col/64
@@ -344,6 +364,20 @@ __global__ void __launch_bounds__(AE_THREADS, 1) k_ae_chain(const __grid_constan
                                 }
                             }
                         }
+                    };
+                    {
+                        uint32_t ra[32], rb[32];
+                        issue_ld(0, ra);
+                        for (int c = 0; c < w; c += 64) {
+                            tmem_ld_wait();
+                            if (c + 32 < w) issue_ld(c + 32, rb);
+                            process(c, ra);
+                            if (c + 32 < w) {
+                                tmem_ld_wait();
+                                if (c + 64 < w) issue_ld(c + 64, ra);
+                                process(c + 32, rb);
+                            }
+                        }
                     }
                     if (!last) {
                         // zero the K padding of the next layer's A operand (its K may exceed this layer's N)
@@ -355,6 +389,7 @@ __global__ void __launch_bounds__(AE_THREADS, 1) k_ae_chain(const __grid_constan
                     tcgen05_fence_before();
                     if (!last) fence_proxy_async_smem();
                     mbar_arrive(epi_done);
+                    if (tracer && tr_n < 250) p.trace[tr_n++] = gtimer();  // epilogue of (layer l, pass) done
                 }
                 if (last && p.normalize && grow < p.M) {
                     // x / ||x||_2 (model.py:55,61) -- the un-normalised row was just written by this thread
@@ -365,6 +400,7 @@ __global__ void __launch_bounds__(AE_THREADS, 1) k_ae_chain(const __grid_constan
             }
         }
     }
+    if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64) p.trace[0] = 0xffffffffull;  // marks a finished trace
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -537,10 +573,26 @@ int ols_ae_forward(const ols_ae_plan* plan, const float* d_x, float* d_y, int64_
         if (rc != OLS_OK) return rc;
     }
     const int grid = p.n_tiles < plan->sm_count ? p.n_tiles : plan->sm_count;
+    static const bool trace_on = getenv("OLS_AE_TRACE") != nullptr;  // development aid: phase timeline of CTA 0 on stderr
+    p.trace = nullptr;
+    if (trace_on) {
+        static unsigned long long* d_trace = nullptr;
+        if (!d_trace) cudaMalloc(&d_trace, 256 * sizeof(unsigned long long));
+        cudaMemsetAsync(d_trace, 0, 256 * sizeof(unsigned long long), (cudaStream_t)stream);
+        p.trace = d_trace;
+    }
     ols_timing_mark(-1, (cudaStream_t)stream);
     k_ae_chain<<<grid, AE_THREADS, plan->smem_bytes, (cudaStream_t)stream>>>(p);
     OLS_CUDA_TRY(cudaGetLastError());
     ols_timing_mark(OLS_T_AE, (cudaStream_t)stream);
+    if (trace_on) {
+        unsigned long long h[256];
+        cudaStreamSynchronize((cudaStream_t)stream);
+        cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[ae trace] M=%lld tiles=%d grid=%d stages=%d:", (long long)M, p.n_tiles, grid, p.n_stages);
+        for (int i = 2; i < 256 && h[i]; i++) fprintf(stderr, " %.2f", (double)(h[i] - h[1]) * 1e-3);
+        fprintf(stderr, " us\n");
+    }
     return OLS_OK;
 }
 

@@ -734,17 +734,27 @@ __global__ void __launch_bounds__(BS_THREADS) k_sort_tiles_bucket(unsigned long 
     for (int r = 0; r < BS_ITEMS; r++)
         if (r * BS_THREADS + tid < n) s_key[atomicAdd(&s_cnt[bucket_of(k[r])], 1u)] = k[r];
     __syncthreads();
-    // exact position inside the bucket = number of its keys that compare lower; write out in final order
+    // exact position inside the bucket = number of its keys that compare lower
+    uint32_t pos[BS_ITEMS];
 #pragma unroll
     for (int r = 0; r < BS_ITEMS; r++) {
         if (r * BS_THREADS + tid < n) {
             const int b = bucket_of(k[r]);
             const uint32_t s0 = b ? s_cnt[b - 1] : 0u, s1 = s_cnt[b];
-            uint32_t pos = s0;
-            for (uint32_t q = s0; q < s1; q++) pos += s_key[q] < k[r] ? 1u : 0u;
-            g[pos] = k[r];
-            point_list[rg.x + pos] = (uint32_t)k[r];
+            uint32_t p = s0;
+            for (uint32_t q = s0; q < s1; q++) p += s_key[q] < k[r] ? 1u : 0u;
+            pos[r] = p;
         }
+    }
+    __syncthreads();  // every thread has finished reading the bucketed array: overwrite it in final order
+#pragma unroll
+    for (int r = 0; r < BS_ITEMS; r++)
+        if (r * BS_THREADS + tid < n) s_key[pos[r]] = k[r];
+    __syncthreads();
+    for (int i = tid; i < n; i += BS_THREADS) {  // coalesced write-out
+        const unsigned long long v = s_key[i];
+        g[i] = v;
+        point_list[rg.x + i] = (uint32_t)v;
     }
     if (tid == 0) tile_count[blockIdx.x] = BS_DONE;
 }

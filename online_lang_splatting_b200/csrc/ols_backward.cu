@@ -623,7 +623,7 @@ __device__ __forceinline__ void geom_cov3d_bwd(const float* scales, const float*
 }
 
 template <int F>
-__global__ void __launch_bounds__(256) k_geometry_bwd(const GeomBwdArgs a) {
+__global__ void __launch_bounds__(256, 4) k_geometry_bwd(const GeomBwdArgs a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.P) return;
     const int M = a.M;

@@ -595,18 +595,19 @@ __global__ void __launch_bounds__(PRE_THREADS) k_scatter(int P, int gx, int n_ti
     // A warp takes 32 Gaussians at a time and spreads their (Gaussian, tile) instances evenly over its lanes:
     // lane L emits instances L, L + 32, ... of the warp's flattened list, so a Gaussian covering many tiles does
     // not serialise one thread, and 32 independent slot requests are in flight per step.
+    // the three per-Gaussian loads of the next round are issued before the current round is emitted
+    auto fetch = [&](int i, uint32_t& cnt, uint2& r, float& d) {
+        cnt = 0; r = make_uint2(0u, 0u); d = 0.0f;
+        if (i < chunk_end) { cnt = tiles_touched[i]; r = rect[i]; d = depths[i]; }
+    };
+    uint32_t n_cnt; uint2 n_r; float n_d;
+    fetch(chunk_begin + (tid & ~31) + lane, n_cnt, n_r, n_d);
     for (int i0 = chunk_begin + (tid & ~31); i0 < chunk_end; i0 += PRE_THREADS) {
         const int i = i0 + lane;
-        uint32_t cnt = 0;
-        uint2 r = make_uint2(0u, 0u);
-        unsigned long long key = 0ull;
-        if (i < chunk_end) {
-            cnt = tiles_touched[i];
-            if (cnt) {
-                r = rect[i];
-                key = ((unsigned long long)__float_as_uint(depths[i]) << 32) | (unsigned)i;
-            }
-        }
+        const uint32_t cnt = n_cnt;
+        const uint2 r = n_r;
+        const unsigned long long key = ((unsigned long long)__float_as_uint(n_d) << 32) | (unsigned)i;
+        fetch(i + PRE_THREADS, n_cnt, n_r, n_d);
         uint32_t incl = cnt;  // inclusive prefix over the lanes
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {

@@ -298,11 +298,18 @@ def main():
     empty = torch.Tensor([])
     Rs = []
 
-    def step_resident(reduce=True):
+    def phase_encode():
+        """the step's autoencoder work: independent of the Gaussians (and therefore of the gradient all-reduce)"""
+        with torch.no_grad():
+            for k in range(KF):
+                ae.encode(clip_dev[k])
+
+    def step_resident(reduce=True, encode=True):
         flat.zero_()
         for k in range(KF):
-            with torch.no_grad():
-                ae.encode(clip_dev[k])
+            if encode:
+                with torch.no_grad():
+                    ae.encode(clip_dev[k])
             R, color, language, radii, depth, opacity, n_touched, st = dgr._forward_native(
                 act["means3D"], act["shs"], empty, act["language"], act["opacities"], act["scales"], act["rotations"],
                 empty, rs_list[k])
@@ -434,31 +441,71 @@ def main():
     dgr.CHECK_OVERFLOW = False  # capacity is established by the warm-up; the timed region is fully asynchronous
     # The step has no host synchronisation and fixed launch geometry, so its ~100 launches are captured once
     # into a CUDA graph and replayed (the all-reduce stays outside the graph).
-    graph = None
+    # With N > 1 the step is two graphs: the keyframes' AE encodes (independent of the Gaussians) and the render
+    # forward + backward.  The all-reduce of step i runs on a communication stream while the encodes of step
+    # i + 1 replay; the render graph of step i + 1 (which zeroes the gradient buffer) waits for it.
+    graph = graph_enc = None
+    split = world > 1
     if not args.no_graph:
         try:
+            if split:
+                graph_enc = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph_enc):
+                    phase_encode()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                step_resident(reduce=False)
+                step_resident(reduce=False, encode=not split)
             graph.replay()
             torch.cuda.synchronize()
         except Exception as ex:  # pragma: no cover -- fall back to eager launches, say so in the JSON line
             sys.stderr.write(f"CUDA graph capture failed ({ex}); timing eager launches\n")
-            graph = None
+            graph = graph_enc = None
+    comm_stream = torch.cuda.Stream(device=dev) if split else None
+    comm_done = [None]
 
     def step_value():
         if graph is None:
             step_resident()
-        else:
+            return
+        main = torch.cuda.current_stream(dev)
+        if not split:
             graph.replay()
+            return
+        graph_enc.replay()                        # overlaps the previous step's all-reduce
+        if comm_done[0] is not None:
+            main.wait_event(comm_done[0])         # gradients of the previous step are reduced (the optimiser step goes here)
+        graph.replay()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(comm_stream):
+            comm_stream.wait_event(ready)
             fbuf.all_reduce()
+            ev = torch.cuda.Event()
+            ev.record(comm_stream)
+        comm_done[0] = ev
+
+    def drain():
+        if comm_done[0] is not None:
+            torch.cuda.current_stream(dev).wait_event(comm_done[0])
 
     for _ in range(2):
         step_value()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms, _ = timed(step_value, args.steps)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_value()
+    drain()                                       # the last step's all-reduce is inside the timed region
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t_ = torch.tensor([ms], device=dev)
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        ms = float(t_.item())
     # second region, same K steps launched eagerly: CUDA events between the kernels give the per-kernel times
     Rs.clear()
     ms_eager, marks = timed(step_resident, args.steps, with_marks=True)
@@ -529,6 +576,9 @@ def main():
             "gpu_launches": args.steps * KF * 11,  # per keyframe: AE, preprocess, tile offsets, tile scan, scatter, 3 sort kernels, blend, blend backward, geometry backward
             "clocks": clocks,
             "launch_mode": {"value": "cuda_graph_replay" if graph is not None else "eager", "ms_per_step_eager": ms_eager / args.steps,
+                            "collective": ("all-reduce of step i on a communication stream, overlapped with the AE encodes of step i+1; "
+                                           "the render graph of step i+1 waits for it") if (split and graph is not None) else
+                                          ("all-reduce after the step" if world > 1 else "none (N=1)"),
                             "note": "per-kernel times and the roofline come from a second, eagerly launched region of the same "
                                     "K steps with CUDA events recorded between the kernels"}}
     emit(line)

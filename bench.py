@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--backward-mode", default="compat", choices=["compat", "exact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-balance", action="store_true", help="N>1: keep contiguous blocks of views per rank (no cost balancing)")
     ap.add_argument("--no-graph", action="store_true", help="launch the resident step eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -200,7 +201,7 @@ def workload_config(args):
                         f"{args.keyframes} keyframes per GPU per step: AE encode of a 192x192x768 CLIP map + render "
                         f"forward + backward per keyframe, NCCL all-reduce of the flat gradient buffer per step (N>1)",
             "gaussians": args.gaussians, "feature_dim": 15, "width": args.width, "height": args.height,
-            "keyframes_per_gpu": args.keyframes, "tile": args.tile, "backward_mode": args.backward_mode,
+            "keyframes_per_gpu": args.keyframes, "view_assignment": "cost-balanced over ranks (sharding.balanced_views)" if (args.gpus > 1 and not args.no_balance) else "views rank*K .. rank*K+K-1", "tile": args.tile, "backward_mode": args.backward_mode,
             "autoencoder": "768-384-192-96-48-24-15 (1-stage, BN folded)", "parallelism": f"frames x{args.gpus}",
             "l2_policy": "per-step inputs (8 CLIP maps = 906 MB, 56 MB of Gaussian parameters + 64 MB records per view) exceed the 126 MB L2"}
 
@@ -289,14 +290,17 @@ def main():
         act = {"means3D": pc.get_xyz.detach(), "shs": pc.get_features.detach().contiguous(),
                "language": pc.get_language_features.detach(), "opacities": pc.get_opacity.detach(),
                "scales": pc.get_scaling.detach(), "rotations": pc.get_rotation.detach()}
-    for cam in cams:
-        rs_list.append(dgr.GaussianRasterizationSettings(
+    def settings_of(cam):
+        return dgr.GaussianRasterizationSettings(
             image_height=H, image_width=W, tanfovx=math.tan(cam.FoVx * 0.5), tanfovy=math.tan(cam.FoVy * 0.5), bg=bg,
             scale_modifier=1.0, viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform,
             projmatrix_raw=cam.projection_matrix, sh_degree=0, campos=cam.camera_center, prefiltered=False, debug=False,
-            tile_size=args.tile, backward_mode=args.backward_mode))
+            tile_size=args.tile, backward_mode=args.backward_mode)
+
+    rs_list.extend(settings_of(cam) for cam in cams)
     empty = torch.Tensor([])
     Rs = []
+    view_ids = [rank * KF + k for k in range(KF)]
 
     def phase_encode():
         """the step's autoencoder work: independent of the Gaussians (and therefore of the gradient all-reduce)"""
@@ -438,6 +442,32 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step_resident()
     torch.cuda.synchronize()
+    if world > 1 and not args.no_balance:
+        # Keyframes differ in cost (how far a tile's list is traversed), and a step ends when the slowest rank does:
+        # every rank times its own views once, the costs are gathered, and the world's views are re-dealt so that
+        # the per-rank sums are even (sharding.balanced_views).  Each rank still renders KF distinct keyframes.
+        from online_lang_splatting_b200.sharding import balanced_views
+        cost = torch.zeros(KF, device=dev)
+        for k in range(KF):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(2):
+                R, color, language, radii, depth, opacity, n_touched, st = dgr._forward_native(
+                    act["means3D"], act["shs"], empty, act["language"], act["opacities"], act["scales"], act["rotations"],
+                    empty, rs_list[k])
+                dgr._backward_native(st, radii, wc, wl, wd, out=out_bufs, accumulate=True)
+            a1.record()
+            torch.cuda.synchronize()
+            cost[k] = a0.elapsed_time(a1)
+        all_cost = [torch.zeros(KF, device=dev) for _ in range(world)]
+        dist.all_gather(all_cost, cost)
+        flat_cost = torch.cat(all_cost).tolist()          # index = global view id (rank-major blocks)
+        view_ids = balanced_views(flat_cost, world)[rank]
+        cams[:] = [S.make_camera(W, H, view=v, seed=0, device=str(dev)) for v in view_ids]
+        rs_list[:] = [settings_of(cam) for cam in cams]
+        for _ in range(2):
+            step_resident()
+        torch.cuda.synchronize()
     dgr.CHECK_OVERFLOW = False  # capacity is established by the warm-up; the timed region is fully asynchronous
     # The step has no host synchronisation and fixed launch geometry, so its ~100 launches are captured once
     # into a CUDA graph and replayed (the all-reduce stays outside the graph).
@@ -460,7 +490,7 @@ def main():
         except Exception as ex:  # pragma: no cover -- fall back to eager launches, say so in the JSON line
             sys.stderr.write(f"CUDA graph capture failed ({ex}); timing eager launches\n")
             graph = graph_enc = None
-    comm_stream = torch.cuda.Stream(device=dev) if split else None
+    comm_stream = torch.cuda.Stream(device=dev, priority=-1) if split else None  # high priority: its CTAs are placed first
     comm_done = [None]
 
     def step_value():

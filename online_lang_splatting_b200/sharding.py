@@ -24,6 +24,25 @@ def shard_views(n_views: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_views, world))
 
 
+def balanced_views(costs: Sequence[float], world: int) -> List[List[int]]:
+    """Assign views to ranks so that the per-rank sums of ``costs`` are as even as possible, every rank getting the
+    same number of views (``len(costs)`` must be a multiple of ``world``).  Greedy longest-processing-time-first:
+    views in order of decreasing cost, each to the least loaded rank that still has room.  Views differ in cost by
+    up to ~1.7x (how much of a tile's list is traversed before the pixels saturate), and a step ends when the
+    slowest rank does, so contiguous or round-robin blocks leave the other GPUs waiting."""
+    n = len(costs)
+    if world <= 0 or n % world != 0:
+        raise ValueError(f"{n} views cannot be split evenly over {world} ranks")
+    per = n // world
+    load = [0.0] * world
+    out: List[List[int]] = [[] for _ in range(world)]
+    for v in sorted(range(n), key=lambda i: (-float(costs[i]), i)):
+        r = min((r for r in range(world) if len(out[r]) < per), key=lambda r: (load[r], r))
+        out[r].append(v)
+        load[r] += float(costs[v])
+    return [sorted(x) for x in out]
+
+
 class FlatGradBuffer:
     """One contiguous fp32 buffer holding every per-Gaussian parameter gradient of the rasterizer."""
 

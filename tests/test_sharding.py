@@ -74,3 +74,18 @@ def test_allreduce_equals_single_process_sum():
     for r in range(world):
         assert torch.allclose(got[r], ref.flat, atol=1e-5)
     assert torch.equal(got[0], got[1])  # identical reduced gradients on every rank -> identical optimiser steps
+
+
+def test_balanced_views_evens_out_rank_loads():
+    from online_lang_splatting_b200.sharding import balanced_views
+    import random
+    rnd = random.Random(0)
+    costs = [1.0 + 0.7 * rnd.random() ** 3 for _ in range(64)]   # a few expensive views, like the synthetic keyframes
+    blocks = [list(range(r * 8, r * 8 + 8)) for r in range(8)]
+    a = balanced_views(costs, 8)
+    assert sorted(v for x in a for v in x) == list(range(64)) and all(len(x) == 8 for x in a)
+    load = lambda parts: [sum(costs[v] for v in x) for x in parts]
+    assert max(load(a)) <= max(load(blocks)) and max(load(a)) - min(load(a)) < 0.05 * max(load(a))
+    assert balanced_views([3.0, 1.0], 1) == [[0, 1]]
+    with pytest.raises(ValueError):
+        balanced_views([1.0] * 7, 2)

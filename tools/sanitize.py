@@ -25,5 +25,16 @@ ae = AE.AutoencoderMLP([384, 192, 96, 48, 24, 15], [24, 48, 96, 192, 384, 384, 7
 x = torch.randn(300, 768, device=dev)
 with torch.no_grad():
     y = ae.decode(ae.encode(x))
+from online_lang_splatting_b200.optim import FlatAdam
+fp, fg = torch.randn(1003, device=dev), torch.randn(1003, device=dev)
+opt = FlatAdam(fp, fg, [("a", 500, 1e-3), ("b", 503, 1e-2)])
+opt.step(); opt.step()
+t = LS.tracking_loss(img, dep, torch.rand(1, 70, 100, device=dev, requires_grad=True), torch.rand(3, 70, 100, device=dev),
+                     torch.rand(1, 70, 100, device=dev), (torch.rand(1, 70, 100, device=dev) > 0.5).float())
+t.backward()
+# sort paths: exact depth ties + a clump (radix kernel) next to spread depths (bucket kernel)
+sc = U.make_scene(P=3000, F=3, W=60, H=45, seed=4, scale=0.6)
+sc["means3D"][:1200, 2] = 2.0
+o = U.run_ours(sc, dev, tile=15)
 torch.cuda.synchronize()
 print("sanitize pass done", float(l), tuple(y.shape))

@@ -1,16 +1,22 @@
 // ols_forward.cu -- forward pass of the language-feature Gaussian rasterizer for sm_100a.
 //
-// Pipeline (all on the caller's stream, no host synchronisation):
-//   k_preprocess   one thread per Gaussian: cull / project / covariance / conic / radius / tile rect,
-//                  packs the blend record, counts instances per tile            (reference: forward.cu:262-371)
-//   k_tile_scan    one CTA: exclusive scan of per-tile counts -> ranges, R        (replaces the InclusiveSum over
-//                  Gaussians + D2H read of rasterizer_impl.cu:451-455)
-//   k_scatter      one thread per Gaussian: writes (depth_bits<<32 | id) into its tiles' buckets
-//                                                                               (reference: duplicateWithKeys :70-111)
-//   k_sort_tiles   one CTA per tile: bitonic sort of the bucket in shared memory  (replaces the global 44-bit
-//                  cub::DeviceRadixSort of :478-483; result order is identical: (tile, depth bits, id) ascending)
-//   k_blend        one CTA per tile: front-to-back alpha blend of RGB + depth + F language channels
-//                                                                               (reference: forward.cu:377-513)
+// Pipeline (all on the caller's stream, no host synchronisation, fixed launch geometry -> graph capturable):
+//   k_preprocess        one thread per Gaussian: cull / project / covariance / conic / radius / tile rect, packs the
+//                       16-float colour record, counts instances per tile in per-CTA shared-memory histograms
+//                                                                               (reference: forward.cu:262-371)
+//   k_preprocess_dis    the same for the two footprints of the disentangled variant   (D/forward.cu:262-430)
+//   k_tile_offsets      column scan of the per-CTA histograms -> per-CTA write cursors and per-tile counts
+//   k_tile_scan         one CTA: exclusive scan of per-tile counts -> ranges, R        (replaces the InclusiveSum over
+//                       Gaussians + D2H read of rasterizer_impl.cu:451-455 and identifyTileRanges :116-138)
+//   k_scatter           writes (depth_bits << 32 | id) into the tiles' buckets; a warp spreads its Gaussians'
+//                       (Gaussian, tile) instances evenly over its lanes           (reference: duplicateWithKeys :70-111)
+//   k_sort_tiles_bucket one CTA per tile: distribution into depth buckets + exact in-bucket ranking in shared memory
+//   k_sort_tiles_radix  tiles the bucket path declines (clumped / tied depths): LSD radix sort in shared memory
+//   k_sort_tiles        tiles longer than 4096 entries: bitonic sort, wide strides in global memory
+//                       (together they replace the global 44-bit cub::DeviceRadixSort of :478-483; the result order
+//                       is identical: (tile, depth bits, id) ascending)
+//   k_blend             one CTA per tile, one warp per 8x4 pixel block: front-to-back alpha blend of RGB + depth + F
+//                       language channels with per-warp culling                     (reference: forward.cu:377-513)
 //
 // Bit-exactness: the per-Gaussian arithmetic mirrors the compiled reference operation by operation
 // (oracle/REF_ARITHMETIC.md), written with explicit-rounding intrinsics so that radii, tile rects,
@@ -34,7 +40,7 @@ struct PreArgs {
     int P, F, sh_degree, M, W, H, tile, gx, gy, rec;
     unsigned flags;
     float tanfovx, tanfovy, focal_x, focal_y, scale_modifier;
-    const float *means3D, *shs, *colors_precomp, *language, *opacities, *scales, *rotations, *cov3D_precomp;
+    const float *means3D, *shs, *colors_precomp, *opacities, *scales, *rotations, *cov3D_precomp;
     const float *viewmatrix, *projmatrix, *campos;
     float* records;
     float* depths;
@@ -1339,7 +1345,7 @@ int ols_launch_forward(const ols_raster_args* a, const ols_fwd_out* o, const WsL
     p.focal_y = a->H / (2.0f * a->tanfovy);  // rasterizer_impl.cu:394-395
     p.focal_x = a->W / (2.0f * a->tanfovx);
     p.scale_modifier = a->scale_modifier;
-    p.means3D = a->d_means3D; p.shs = a->d_shs; p.colors_precomp = a->d_colors_precomp; p.language = a->d_language;
+    p.means3D = a->d_means3D; p.shs = a->d_shs; p.colors_precomp = a->d_colors_precomp;
     p.opacities = a->d_opacities; p.scales = a->d_scales; p.rotations = a->d_rotations;
     p.cov3D_precomp = a->d_cov3D_precomp; p.viewmatrix = a->d_viewmatrix; p.projmatrix = a->d_projmatrix;
     p.campos = a->d_campos;

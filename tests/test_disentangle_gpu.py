@@ -162,3 +162,18 @@ def test_dis_edge_cases():
                              torch.zeros(0, 4, device=_dev()), torch.zeros(0, 4, device=_dev()), torch.Tensor([]),
                              torch.Tensor([]), rs)
     assert out[0] == 0 and out[2].abs().sum().item() == 0
+
+
+def test_dis_reduces_to_joint_at_full_size():
+    """BASELINE config 2 size (500k Gaussians, 15-dim, 960x540) through a size-independent property: with coinciding
+    footprints the disentangled rasterizer's two lists are the joint rasterizer's list, and every image is bit-identical."""
+    sc = U.make_scene(P=500000, F=15, W=960, H=540, seed=0, scale=0.01)
+    sd = dict(sc, opacities_lang=sc["opacities"].clone(), scales_lang=sc["scales"].clone(), rotations_lang=sc["rotations"].clone())
+    d = U.run_ours_dis(sd, _dev(), tile=15, bitexact=True)
+    j = U.run_ours(sc, _dev(), tile=15, bitexact=True)
+    assert d["R"] == d["R_lang"] == j["R"] > 2_000_000
+    assert np.array_equal(d["ws"]["point_list"], j["ws"]["point_list"]) and np.array_equal(d["ws_lang"]["point_list"], j["ws"]["point_list"])
+    for k in ("color", "depth", "language", "opacity"):
+        assert np.array_equal(d[k].view(np.uint32), j[k].view(np.uint32)), k
+    assert np.array_equal(d["opacity_lang"].view(np.uint32), j["opacity"].view(np.uint32))
+    assert np.array_equal(d["n_touched_lang"], j["n_touched"]) and np.array_equal(d["radii_lang"], j["radii"])

@@ -179,3 +179,16 @@ def test_oracle_dis_exact_language_gradient_matches_finite_differences():
     good = sum(abs(fd - an) <= 5e-2 * max(abs(fd), abs(an)) + 2e-3 for _, fd, an in checks)
     # the alpha >= 1/255 and radius thresholds make the forward piecewise smooth: a few probes straddle a jump
     assert good >= 0.75 * len(checks), checks
+
+
+def test_oracle_dis_reduces_to_joint_when_footprints_coincide():
+    """Size-independent property: with opacities_lang = opacities, scales_lang = scales, rotations_lang = rotations the
+    two lists of D/ are the same list, so its colour / depth / language images equal the joint (P/) rasterizer's."""
+    sc = U.make_scene(P=3000, F=3, W=112, H=80, seed=12, scale=0.06, bg=(0.3, 0.2, 0.1))
+    sd = dict(sc, opacities_lang=sc["opacities"].clone(), scales_lang=sc["scales"].clone(), rotations_lang=sc["rotations"].clone())
+    d, j = U.run_oracle_dis(sd, tile=16), U.run_oracle(sc, tile=16)
+    assert d["R"] == d["R_lang"] == j["R"]
+    assert np.array_equal(d["point_list"], j["point_list"]) and np.array_equal(d["point_list_lang"], j["point_list"])
+    for k in ("color", "depth", "language", "opacity"):
+        assert np.array_equal(d[k], j[k]), k
+    assert np.array_equal(d["opacity_lang"], j["opacity"]) and np.array_equal(d["n_touched_lang"], j["n_touched"])

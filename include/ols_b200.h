@@ -298,6 +298,15 @@ int ols_adam_step(float* d_param, const float* d_grad, float* d_exp_avg, float* 
                   const ols_adam_group* groups, int32_t n_groups, double beta1, double beta2, double eps, int64_t step,
                   void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * distCUDA2 (submodules/simple-knn/spatial.cu + simple_knn.cu:120-220): mean squared distance of every
+ * point to its 3 nearest neighbours; GaussianModel uses it to size new Gaussians
+ * (gaussian_splatting/scene/gaussian_model.py:256-262).  Asynchronous, no host round trips.
+ * ------------------------------------------------------------------------------------------- */
+size_t ols_knn_workspace_size(int32_t P);
+int ols_knn_mean_dist2(int32_t P, const float* d_points /* [P,3] */, float* d_mean_dist2 /* [P] */, void* d_workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* Per-kernel device timing (CUDA events recorded between the kernels of every call while enabled).
  * ols_timing_begin() allocates `max_marks` events and enables recording on the calling thread;
  * ols_timing_end() synchronises, sums the elapsed milliseconds per tag, reports how many intervals

@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = (
     "ols_abi_version", "ols_last_error", "ols_cuda_available", "ols_lang_workspace_size", "ols_lang_forward",
     "ols_lang_read_info", "ols_lang_backward", "ols_mark_visible", "ols_lang_workspace_view",
     "ols_lang_forward_host", "ols_timing_begin", "ols_timing_end", "ols_ae_plan_create", "ols_ae_plan_destroy", "ols_ae_forward",
-    "ols_mapping_loss_forward", "ols_mapping_loss_backward", "ols_adam_step",
+    "ols_mapping_loss_forward", "ols_mapping_loss_backward", "ols_adam_step", "ols_knn_workspace_size", "ols_knn_mean_dist2",
     "ols_dis_workspace_size", "ols_dis_forward", "ols_dis_read_info", "ols_dis_backward", "ols_dis_workspace_view",
 )
 
@@ -147,6 +147,9 @@ def lib() -> C.CDLL:
                                             C.c_void_p]
     L.ols_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(AdamGroup), C.c_int32,
                                 C.c_double, C.c_double, C.c_double, C.c_int64, C.c_void_p]
+    L.ols_knn_workspace_size.restype = C.c_size_t
+    L.ols_knn_workspace_size.argtypes = [C.c_int32]
+    L.ols_knn_mean_dist2.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.ols_timing_begin.argtypes = [C.c_int32]
     L.ols_timing_end.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int32)]
     L.ols_ae_plan_create.argtypes = [C.POINTER(AEChain), C.POINTER(C.c_void_p), C.c_void_p]

@@ -8,6 +8,7 @@ objects
 
     oracle/_ref/ref_P_C.so   <- submodules/diff-gaussian-rasterization            (F=15, 15x15 tiles)
     oracle/_ref/ref_D_C.so   <- submodules/diff-gaussian-rasterization-disentangle-optim (F=3, 16x16)
+    oracle/_ref/ref_knn_C.so <- submodules/simple-knn (distCUDA2)
 
 Both are pybind11/torch extension modules exporting the five functions of the
 reference's ext.cpp (rasterize_language_gaussians, ..._backward, ...).  They
@@ -33,7 +34,9 @@ REF = os.environ.get("OLS_REFERENCE_ROOT", "/root/reference")
 VARIANTS = {
     "ref_P_C": "submodules/diff-gaussian-rasterization",
     "ref_D_C": "submodules/diff-gaussian-rasterization-disentangle-optim",
+    "ref_knn_C": "submodules/simple-knn",        # distCUDA2 (mean squared distance to the 3 nearest neighbours)
 }
+VARIANT_SOURCES = {"ref_knn_C": ["simple_knn.cu", "spatial.cu", "ext.cpp"]}
 SOURCES = [
     "cuda_rasterizer/rasterizer_impl.cu",
     "cuda_rasterizer/forward.cu",
@@ -59,7 +62,7 @@ def build_variant(name, rel, arch="100"):
     os.makedirs(obj_dir, exist_ok=True)
     target = os.path.join(OUT, name + ".so")
     incs = ce.include_paths(device_type="cuda") + [sysconfig.get_paths()["include"],
-                                                    os.path.join(src_root, "third_party/glm")]
+                                                    os.path.join(src_root, "third_party/glm"), src_root]
     inc_flags = [f"-I{p}" for p in incs]
     cxx11 = int(torch._C._GLIBCXX_USE_CXX11_ABI)
     common = [f"-DTORCH_EXTENSION_NAME={name}", "-DTORCH_API_INCLUDE_EXTENSION_H",
@@ -68,9 +71,9 @@ def build_variant(name, rel, arch="100"):
                   "-D__CUDA_NO_BFLOAT16_CONVERSIONS__", "-D__CUDA_NO_HALF2_OPERATORS__",
                   "--expt-relaxed-constexpr", "--compiler-options", "-fPIC",
                   "-gencode", f"arch=compute_{arch},code=sm_{arch}",
-                  "--pre-include", "cstdint", "-w"]
+                  "--pre-include", "cstdint", "--pre-include", "cfloat", "-w"]
     objs, jobs = [], []
-    for s in SOURCES:
+    for s in VARIANT_SOURCES.get(name, SOURCES):
         o = os.path.join(obj_dir, os.path.basename(s) + ".o")
         objs.append(o)
         src = os.path.join(src_root, s)

@@ -57,6 +57,17 @@ def parse():
     return ap.parse_args()
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -148,7 +159,8 @@ def reference_arm(args):
             "steps": len(sec), "warmup": 1 if args.warmup else 0, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args),
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
+                             "cpu_model": cpu_model()},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     gpu_ref = compiled_reference_ms(args)
     if gpu_ref is not None:
@@ -596,7 +608,7 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         dt, cores = cpu_frame_seconds(args)
-        cpu = {"value": 1.0 / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+        cpu = {"value": 1.0 / dt, "unit": "frames/s", "cores": cores, "kind": "port", "cpu_model": cpu_model(),
                "sample": "1 keyframe of the same workload: oracle forward+backward (OpenMP, all cores) + reference AE "
                          "encode on torch-CPU"}
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,

@@ -340,6 +340,38 @@ void ols_ae_plan_destroy(ols_ae_plan* plan);
 /* y[M, dims[n]] = chain(x[M, dims[0]]); replaces AutoencoderMLP.encode / .decode. */
 int ols_ae_forward(const ols_ae_plan* plan, const float* d_x, float* d_y, int64_t M, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * HR module (language/supervisedNet.py:45-109 HighResLanguageFeatureNet, called with torch.no_grad() in eval
+ * mode at utils/slam_backend.py:381-386,547-552): fv [768,S,S] + res3 [384,h3,w3] + res2 [192,h2,w2] ->
+ * [768,8S,8S] dense CLIP map, the autoencoder's input.  13 convolutions in the order
+ *   0 initial_conv.0        Conv2d 768->512 3x3        7 attention_fusion2.low_res_align  Conv2d 192->256 1x1
+ *   1 upsample1.0           ConvT  512->512 4/2/1      8 attention_fusion2.fusion.0       Conv2d 512->256 3x3
+ *   2 af1.low_res_align     Conv2d 384->512 1x1        9 attention_fusion2.attention.0    Conv2d 256->256 3x3
+ *   3 af1.fusion.0          Conv2d 1024->512 3x3      10 attention_fusion2.attention.3    Conv2d 256->256 1x1
+ *   4 af1.attention.0       Conv2d 512->512 3x3       11 upsample3.0                      ConvT  256->128 4/2/1
+ *   5 af1.attention.3       Conv2d 512->512 1x1       12 final_conv                       Conv2d 128->768 1x1
+ *   6 upsample2.0           ConvT  512->256 4/2/1
+ * Weights are float32 in torch layout (Conv2d [Cout,Cin,kh,kw], ConvTranspose2d [Cin,Cout,4,4]) with the
+ * eval-mode BatchNorm that follows a convolution already folded in by the caller (as for the autoencoder).
+ * The plan owns bf16 re-laid-out weights and the bf16 NHWC activations between the layers.
+ * ------------------------------------------------------------------------------------------- */
+#define OLS_HR_N_CONV 13
+typedef struct ols_hr_weights {
+    const float* d_weight[OLS_HR_N_CONV];
+    const float* d_bias[OLS_HR_N_CONV];
+} ols_hr_weights;
+typedef struct ols_hr_plan ols_hr_plan;
+/* S_h x S_w = spatial size of fv (24 x 24 in the reference) */
+int ols_hr_plan_create(const ols_hr_weights* w, int32_t S_h, int32_t S_w, ols_hr_plan** plan, void* stream);
+void ols_hr_plan_destroy(ols_hr_plan* plan);
+/* d_out: float32 [8*S_h, 8*S_w, 768] (channels last: the layout `permute(0,2,3,1).view(-1,768)` at
+ * slam_backend.py:392-394 produces, i.e. the autoencoder's [M,768] input).  f3 / f2 are resized to 2S / 4S with
+ * bilinear interpolation, align_corners = False (supervisedNet.py:88,97). */
+int ols_hr_forward(const ols_hr_plan* plan, const float* d_fv, const float* d_f3, int32_t h3, int32_t w3,
+                   const float* d_f2, int32_t h2, int32_t w2, float* d_out, void* stream);
+/* development aid: copy of an intermediate activation (bf16 NHWC) as float32; which = conv index 0..11 */
+int ols_hr_read_activation(const ols_hr_plan* plan, int32_t which, float* d_out, int64_t capacity_floats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

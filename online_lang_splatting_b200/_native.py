@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = (
     "ols_lang_forward_host", "ols_timing_begin", "ols_timing_end", "ols_ae_plan_create", "ols_ae_plan_destroy", "ols_ae_forward",
     "ols_mapping_loss_forward", "ols_mapping_loss_backward", "ols_adam_step", "ols_knn_workspace_size", "ols_knn_mean_dist2",
     "ols_dis_workspace_size", "ols_dis_forward", "ols_dis_read_info", "ols_dis_backward", "ols_dis_workspace_view",
+    "ols_hr_plan_create", "ols_hr_plan_destroy", "ols_hr_forward", "ols_hr_read_activation",
 )
 
 
@@ -106,6 +107,13 @@ class AEChain(C.Structure):
                 ("_pad", C.c_int32), ("d_weight", C.c_void_p * AE_MAX_LAYERS), ("d_bias", C.c_void_p * AE_MAX_LAYERS)]
 
 
+HR_N_CONV = 13
+
+
+class HRWeights(C.Structure):
+    _fields_ = [("d_weight", C.c_void_p * HR_N_CONV), ("d_bias", C.c_void_p * HR_N_CONV)]
+
+
 _LIB: Optional[C.CDLL] = None
 
 
@@ -156,6 +164,12 @@ def lib() -> C.CDLL:
     L.ols_ae_plan_destroy.argtypes = [C.c_void_p]
     L.ols_ae_plan_destroy.restype = None
     L.ols_ae_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    L.ols_hr_plan_create.argtypes = [C.POINTER(HRWeights), C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_void_p]
+    L.ols_hr_plan_destroy.argtypes = [C.c_void_p]
+    L.ols_hr_plan_destroy.restype = None
+    L.ols_hr_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                 C.c_void_p, C.c_void_p]
+    L.ols_hr_read_activation.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
     _LIB = L
     return L
 

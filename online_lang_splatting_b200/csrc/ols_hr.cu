@@ -14,8 +14,12 @@
 //   * ConvTranspose2d(4, 2, 1) = four 2x2 convolutions, one per output parity class (blockIdx.z), each writing a
 //     strided quarter of the output;
 //   * BatchNorm is folded into the weights, bias + ReLU / the sigmoid gate `fused * att + fused` / the fp32 store of
-//     the last layer run in the epilogue straight out of TMEM;
-//   * warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue; mbarrier ring of 4-8 stages.
+//     the last layer run in the epilogue straight out of TMEM; the finished tile is staged in the (now idle) ring in
+//     the swizzled layout and leaves by TMA store, which also clips partial tiles and scatters the parity classes of a
+//     transposed convolution through a strided tensor map; the gate's `fused` tile arrives by TMA during the main loop;
+//   * warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue; mbarrier ring of 4-8 stages;
+//   * the 13 launches are chained with programmatic dependent launch: a layer's prologue (barrier init, TMEM
+//     allocation, descriptor prefetch) overlaps the tail of the previous layer (griddepcontrol).
 #include "ols_common.cuh"
 #include "ols_tc.cuh"
 
@@ -45,9 +49,10 @@ struct HrConv {
     int out_w, out_h, scale;      // output pixel = grid pixel * scale + class offset
     int mode, relu;
     const float* bias;
-    const __nv_bfloat16* gate;    // HR_MODE_GATE: the fused feature the attention map multiplies
-    void* out;
-    int n_stages, stage_bytes;
+    CUtensorMap tmap_gate;        // HR_MODE_GATE: the fused feature the attention map multiplies (same layout as the output)
+    CUtensorMap tmap_out[4];      // output tile store, one per parity class
+    int n_stages, stage_bytes, gate_bytes;
+    unsigned long long* trace;    // development aid (OLS_HR_TRACE): globaltimer stamps of CTA (0,0,0)
 };
 
 __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
@@ -57,30 +62,46 @@ __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, 
         : "memory");
 }
 
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+                 "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+// programmatic dependent launch: wait for the producer grid's memory / allow the consumer grid to start its prologue
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __global__ void __launch_bounds__(HR_THREADS, 1) k_hr_conv(const __grid_constant__ HrConv p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* ring = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = (uint64_t*)(ring + (size_t)p.n_stages * p.stage_bytes);
+    uint8_t* gate_smem = ring + (size_t)p.n_stages * p.stage_bytes;  // [bn/64][128 px][128 B], swizzled
+    uint64_t* bars = (uint64_t*)(gate_smem + p.gate_bytes);
     uint64_t* full = bars;
     uint64_t* empty = bars + 8;
     uint64_t* mma_done = bars + 16;
-    uint32_t* tmem_slot = (uint32_t*)(bars + 17);
+    uint64_t* gate_full = bars + 17;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 18);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool tracer = p.trace != nullptr && threadIdx.x == 64 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0;
+    if (tracer) p.trace[0] = gtimer();
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.n_stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(mma_done, 1);
+        mbar_init(gate_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
+        // bn (64 / 128 / 256) accumulator columns: several CTAs of a narrow layer can share one SM's TMEM
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "n"(HR_TMEM_COLS));
+                     "r"((uint32_t)p.bn));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();  // the next layer may start its prologue; it blocks in pdl_wait() until this grid is done
 
     const int tile = blockIdx.x;
     const int x0 = (tile % p.tiles_x) * HR_BOX_W, y0 = (tile / p.tiles_x) * HR_BOX_H;
@@ -92,6 +113,12 @@ __global__ void __launch_bounds__(HR_THREADS, 1) k_hr_conv(const __grid_constant
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_a[0]) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_b) : "memory");
+            pdl_wait();  // everything below reads what the previous layers wrote
+            if (p.mode == HR_MODE_GATE) {
+                mbar_expect_tx(gate_full, (uint32_t)p.gate_bytes);
+                for (int j = 0; j < p.bn / 64; j++)
+                    tma_load_3d(gate_smem + (size_t)j * HR_A_BYTES, &p.tmap_gate, gate_full, n0 + j * 64, x0, y0);
+            }
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t bytes = (uint32_t)(HR_A_BYTES + p.bn * 128);
@@ -135,18 +162,16 @@ __global__ void __launch_bounds__(HR_THREADS, 1) k_hr_conv(const __grid_constant
         // epilogue: thread = one pixel of the patch = one TMEM lane
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
-        const int gx = x0 + (row & (HR_BOX_W - 1)), gy = y0 + (row >> 3);
-        const bool valid = gx < p.grid_w && gy < p.grid_h;
-        const int ox = gx * p.scale + (cls & 1), oy = gy * p.scale + (cls >> 1);
-        const size_t opix = (size_t)oy * p.out_w + ox;
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
-        mbar_wait(mma_done, 0);
+        if (tracer) p.trace[1] = gtimer();
+        mbar_wait(mma_done, 0);  // all MMAs retired: the accumulator is complete and the ring is idle
         tcgen05_fence_after();
+        if (p.mode == HR_MODE_GATE) mbar_wait(gate_full, 0);
+        if (tracer) p.trace[2] = gtimer();
         for (int c = 0; c < p.bn; c += 32) {
             uint32_t r[32];
             tmem_ld32(t_lane + (uint32_t)c, r);
             tmem_ld_wait();
-            if (!valid) continue;
             float v[32];
             const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c);
 #pragma unroll
@@ -161,29 +186,32 @@ __global__ void __launch_bounds__(HR_THREADS, 1) k_hr_conv(const __grid_constant
 #pragma unroll
                 for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.0f);
             }
-            const size_t o = opix * p.cout + n0 + c;
             if (p.mode == HR_MODE_F32) {
-                float4* dst = reinterpret_cast<float4*>((float*)p.out + o);
+                // staging slab = 32 fp32 channels x 128 pixels
+                uint8_t* slab = ring + (size_t)(c >> 5) * HR_A_BYTES;
 #pragma unroll
-                for (int q = 0; q < 8; q++) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                for (int q = 0; q < 8; q++)
+                    *reinterpret_cast<float4*>(slab + sw128(row, q)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             } else {
+                // staging slab = 64 bf16 channels x 128 pixels; this pass fills 16-byte chunks j0 .. j0+3 of the row
+                const int j0 = (c & 63) >> 3;
                 if (p.mode == HR_MODE_GATE) {
                     // out = fused * sigmoid(att) + fused  (supervisedNet.py:40-41)
-                    const uint4* g4 = reinterpret_cast<const uint4*>(p.gate + o);
+                    const uint8_t* gslab = gate_smem + (size_t)(c >> 6) * HR_A_BYTES;
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        const uint4 g = __ldg(g4 + q);
+                        const uint4 g = *reinterpret_cast<const uint4*>(gslab + sw128(row, j0 + q));
                         const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
                         for (int h = 0; h < 4; h++) {
                             const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[h]));
                             const int i = q * 8 + h * 2;
-                            v[i] = f.x * (1.0f / (1.0f + __expf(-v[i]))) + f.x;
-                            v[i + 1] = f.y * (1.0f / (1.0f + __expf(-v[i + 1]))) + f.y;
+                            v[i] = fmaf(f.x, __fdividef(1.0f, 1.0f + __expf(-v[i])), f.x);
+                            v[i + 1] = fmaf(f.y, __fdividef(1.0f, 1.0f + __expf(-v[i + 1])), f.y);
                         }
                     }
                 }
-                uint4* dst = reinterpret_cast<uint4*>((__nv_bfloat16*)p.out + o);
+                uint8_t* slab = ring + (size_t)(c >> 6) * HR_A_BYTES;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     uint4 pk;
@@ -192,16 +220,28 @@ __global__ void __launch_bounds__(HR_THREADS, 1) k_hr_conv(const __grid_constant
                     __nv_bfloat162 h2 = __floats2bfloat162_rn(v[q * 8 + 4], v[q * 8 + 5]);
                     __nv_bfloat162 h3 = __floats2bfloat162_rn(v[q * 8 + 6], v[q * 8 + 7]);
                     pk.x = *(uint32_t*)&h0; pk.y = *(uint32_t*)&h1; pk.z = *(uint32_t*)&h2; pk.w = *(uint32_t*)&h3;
-                    dst[q] = pk;
+                    *reinterpret_cast<uint4*>(slab + sw128(row, j0 + q)) = pk;
                 }
             }
         }
+        // the tile leaves by TMA store (clips partial tiles; strided map for the parity classes of a transposed conv)
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 2 && lane == 0) {
+            const int per = p.mode == HR_MODE_F32 ? 32 : 64;
+            for (int j = 0; j < p.bn / per; j++)
+                tma_store_3d(&p.tmap_out[cls], ring + (size_t)j * HR_A_BYTES, n0 + j * per, x0, y0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
     }
+    if (tracer) p.trace[3] = gtimer();
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(HR_TMEM_COLS));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.bn));
     }
+    if (tracer) p.trace[4] = gtimer();
 }
 
 // ---- weight re-layout --------------------------------------------------------------------------------------------
@@ -304,19 +344,31 @@ static PFN_encodeTiledHr hr_encode() {
     return fn;
 }
 
-// NHWC bf16 activation [H, W, C]: box {64 channels, 8, 16}
-static int hr_map_act(CUtensorMap* map, const void* base, int H, int W, int C) {
+// pixel-major tensor [H, W, C] seen through arbitrary pixel strides: box {128 bytes of channels, 8, 16}
+static int hr_map_px(CUtensorMap* map, const void* base, bool f32, int H, int W, int C, size_t stride_w_bytes,
+                     size_t stride_h_bytes) {
     PFN_encodeTiledHr enc = hr_encode();
     if (!enc) { ols_set_error("cuTensorMapEncodeTiled not available"); return OLS_ERR_CUDA; }
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H};
-    cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2};
-    cuuint32_t box[3] = {64, HR_BOX_W, HR_BOX_H};
+    cuuint64_t strides[2] = {(cuuint64_t)stride_w_bytes, (cuuint64_t)stride_h_bytes};
+    cuuint32_t box[3] = {f32 ? 32u : 64u, HR_BOX_W, HR_BOX_H};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { ols_set_error("cuTensorMapEncodeTiled (activation) failed (%d)", (int)r); return OLS_ERR_CUDA; }
     return OLS_OK;
+}
+// NHWC bf16 activation [H, W, C]
+static int hr_map_act(CUtensorMap* map, const void* base, int H, int W, int C) {
+    return hr_map_px(map, base, false, H, W, C, (size_t)C * 2, (size_t)W * C * 2);
+}
+// output of a layer: class (py, px) of a scale-2 layer owns the pixels (2y + py, 2x + px)
+static int hr_map_out(CUtensorMap* map, void* base, bool f32, const ols::HrConv& c, int cls) {
+    const size_t esz = f32 ? 4 : 2;
+    const size_t px = (size_t)c.cout * esz;
+    uint8_t* b = (uint8_t*)base + ((size_t)(cls >> 1) * c.out_w + (cls & 1)) * px;
+    return hr_map_px(map, b, f32, c.grid_h, c.grid_w, c.cout, px * c.scale, px * c.out_w * c.scale);
 }
 // packed weights [rows, K] bf16: box {64, bn}
 static int hr_map_w(CUtensorMap* map, const void* base, int rows, int K, int bn) {
@@ -341,23 +393,24 @@ struct Spec {
     int level;     // pixel grid of the GEMM = S << level
     int src0, src1;  // activation ids: >= 0 conv output, -1 fv, -2 f3 resized, -3 f2 resized; src1 = -100: none
     int mode, relu, gate;
-    int bn;        // output channels per CTA
+    int bn;        // output channels per CTA (64, 128 or 256 = TMEM columns)
+    int max_stages;  // ring depth cap (a short K loop needs no deep ring: several CTAs then fit one SM)
 };
 // supervisedNet.py:83-109, one row per convolution
 const Spec SPECS[OLS_HR_N_CONV] = {
-    {K_CONV3, 768, 0, 512, 0, -1, -100, HR_MODE_BF16, 1, -1, 64},     // initial_conv (+BN+ReLU)
-    {K_CONVT, 512, 0, 512, 0, 0, -100, HR_MODE_BF16, 1, -1, 128},     // upsample1 (+BN+ReLU) -> 2S
-    {K_CONV1, 384, 0, 512, 1, -2, -100, HR_MODE_BF16, 0, -1, 128},    // af1.low_res_align
-    {K_CONV3, 512, 512, 512, 1, 1, 2, HR_MODE_BF16, 1, -1, 64},       // af1.fusion (+BN+ReLU) on cat[x, low]
-    {K_CONV3, 512, 0, 512, 1, 3, -100, HR_MODE_BF16, 1, -1, 64},      // af1.attention.0 (+BN+ReLU)
-    {K_CONV1, 512, 0, 512, 1, 4, -100, HR_MODE_GATE, 0, 3, 128},      // af1.attention.3 + sigmoid, gate on fused
-    {K_CONVT, 512, 0, 256, 1, 5, -100, HR_MODE_BF16, 1, -1, 128},     // upsample2 -> 4S
-    {K_CONV1, 192, 0, 256, 2, -3, -100, HR_MODE_BF16, 0, -1, 128},    // af2.low_res_align
-    {K_CONV3, 256, 256, 256, 2, 6, 7, HR_MODE_BF16, 1, -1, 128},      // af2.fusion
-    {K_CONV3, 256, 0, 256, 2, 8, -100, HR_MODE_BF16, 1, -1, 128},     // af2.attention.0
-    {K_CONV1, 256, 0, 256, 2, 9, -100, HR_MODE_GATE, 0, 8, 128},      // af2.attention.3 + gate
-    {K_CONVT, 256, 0, 128, 2, 10, -100, HR_MODE_BF16, 1, -1, 128},    // upsample3 -> 8S
-    {K_CONV1, 128, 0, 768, 3, 11, -100, HR_MODE_F32, 0, -1, 256},     // final_conv -> fp32
+    {K_CONV3, 768, 0, 512, 0, -1, -100, HR_MODE_BF16, 1, -1, 64, 8},     // initial_conv (+BN+ReLU)
+    {K_CONVT, 512, 0, 512, 0, 0, -100, HR_MODE_BF16, 1, -1, 128, 8},     // upsample1 (+BN+ReLU) -> 2S
+    {K_CONV1, 384, 0, 512, 1, -2, -100, HR_MODE_BF16, 0, -1, 128, 8},    // af1.low_res_align
+    {K_CONV3, 512, 512, 512, 1, 1, 2, HR_MODE_BF16, 1, -1, 64, 8},       // af1.fusion (+BN+ReLU) on cat[x, low]
+    {K_CONV3, 512, 0, 512, 1, 3, -100, HR_MODE_BF16, 1, -1, 64, 8},      // af1.attention.0 (+BN+ReLU)
+    {K_CONV1, 512, 0, 512, 1, 4, -100, HR_MODE_GATE, 0, 3, 128, 8},      // af1.attention.3 + sigmoid, gate on fused
+    {K_CONVT, 512, 0, 256, 1, 5, -100, HR_MODE_BF16, 1, -1, 128, 8},     // upsample2 -> 4S
+    {K_CONV1, 192, 0, 256, 2, -3, -100, HR_MODE_BF16, 0, -1, 128, 8},    // af2.low_res_align
+    {K_CONV3, 256, 256, 256, 2, 6, 7, HR_MODE_BF16, 1, -1, 128, 8},      // af2.fusion
+    {K_CONV3, 256, 0, 256, 2, 8, -100, HR_MODE_BF16, 1, -1, 128, 8},     // af2.attention.0
+    {K_CONV1, 256, 0, 256, 2, 9, -100, HR_MODE_GATE, 0, 8, 128, 8},      // af2.attention.3 + gate
+    {K_CONVT, 256, 0, 128, 2, 10, -100, HR_MODE_BF16, 1, -1, 128, 8},    // upsample3 -> 8S
+    {K_CONV1, 128, 0, 768, 3, 11, -100, HR_MODE_F32, 0, -1, 128, 2},     // final_conv -> fp32
 };
 }  // namespace
 
@@ -422,7 +475,7 @@ int ols_hr_plan_create(const ols_hr_weights* w, int32_t S_h, int32_t S_w, ols_hr
         }
         pk.n_taps = c.n_taps; pk.n_classes = c.n_classes;
         c.out_w = gw * c.scale; c.out_h = gh * c.scale;
-        if (s.cout % c.bn != 0 || c.bn % 32 != 0 || c.bn > HR_TMEM_COLS) { ols_set_error("HR conv %d: bad channel block", i); return fail(OLS_ERR_INVALID); }
+        if (s.cout % c.bn != 0 || (c.bn != 64 && c.bn != 128 && c.bn != 256)) { ols_set_error("HR conv %d: bad channel block", i); return fail(OLS_ERR_INVALID); }
         // packed weights + bias copy
         const int K = c.n_taps * pk.cin, rows = c.n_classes * s.cout;
         __nv_bfloat16* wbuf = (__nv_bfloat16*)alloc((size_t)rows * K * 2);
@@ -440,7 +493,10 @@ int ols_hr_plan_create(const ols_hr_weights* w, int32_t S_h, int32_t S_w, ols_hr
         if (s.mode != HR_MODE_F32) {
             plan->act[i] = (__nv_bfloat16*)alloc(plan->act_elems[i] * 2);
             if (!plan->act[i]) { ols_set_error("out of device memory"); return fail(OLS_ERR_CUDA); }
-            c.out = plan->act[i];
+            for (int cls = 0; cls < c.n_classes; cls++) {
+                rc = hr_map_out(&c.tmap_out[cls], plan->act[i], false, c, cls);
+                if (rc != OLS_OK) return fail(rc);
+            }
         }
         // sources
         const int srcs[2] = {s.src0, s.src1};
@@ -450,11 +506,21 @@ int ols_hr_plan_create(const ols_hr_weights* w, int32_t S_h, int32_t S_w, ols_hr
             rc = hr_map_act(&c.tmap_a[k], base, gh, gw, cins[k]);
             if (rc != OLS_OK) return fail(rc);
         }
-        c.gate = s.gate >= 0 ? plan->act[s.gate] : nullptr;
+        c.gate_bytes = 0;
+        if (s.gate >= 0) {
+            rc = hr_map_act(&c.tmap_gate, plan->act[s.gate], gh, gw, s.cout);
+            if (rc != OLS_OK) return fail(rc);
+            c.gate_bytes = c.bn / 64 * HR_A_BYTES;
+        }
         c.stage_bytes = HR_A_BYTES + c.bn * 128;
-        int ns = (227 * 1024 - 1024 - 256) / c.stage_bytes;
-        c.n_stages = ns > 8 ? 8 : ns;
-        plan->smem[i] = (size_t)c.n_stages * c.stage_bytes + 256 + 1024;
+        int ns = (227 * 1024 - 1024 - 256 - c.gate_bytes) / c.stage_bytes;
+        c.n_stages = ns > s.max_stages ? s.max_stages : ns;
+        // the finished tile is staged in the ring: 128 px x bn channels (bf16, or fp32 for the last layer)
+        const int staging = c.bn * 128 * (s.mode == HR_MODE_F32 ? 4 : 2);
+        if (c.n_stages < 2 || staging > c.n_stages * c.stage_bytes || c.bn % 64 != 0) {
+            ols_set_error("HR conv %d: tile does not fit shared memory", i); return fail(OLS_ERR_UNSUPPORTED);
+        }
+        plan->smem[i] = (size_t)c.n_stages * c.stage_bytes + c.gate_bytes + 256 + 1024;
         plan->grid[i] = dim3((unsigned)(c.tiles_x * tiles_y), (unsigned)(s.cout / c.bn), (unsigned)c.n_classes);
     }
     if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { ols_set_error("HR weight packing failed"); return fail(OLS_ERR_CUDA); }
@@ -479,13 +545,61 @@ int ols_hr_forward(const ols_hr_plan* plan, const float* d_fv, const float* d_f3
         const int ho = plan->S_h << i, wo = plan->S_w << i;
         k_hr_resize<<<dim3((wo + 31) / 32, ho, C[i] / 64), 256, 0, st>>>(src[i], C[i], hin[i], win[i], plan->act_in[i], ho, wo);
     }
+    static const bool trace_on = getenv("OLS_HR_TRACE") != nullptr;  // development aid: per-layer times on stderr
+    cudaEvent_t ev[OLS_HR_N_CONV + 1];
+    static unsigned long long* d_trace = nullptr;
+    if (trace_on && !d_trace) cudaMalloc(&d_trace, OLS_HR_N_CONV * 8 * sizeof(unsigned long long));
+    if (trace_on) {
+        for (auto& e : ev) cudaEventCreate(&e);
+        cudaEventRecord(ev[0], st);
+    }
+    static const bool no_pdl = getenv("OLS_HR_NO_PDL") != nullptr;
     for (int i = 0; i < OLS_HR_N_CONV; i++) {
         HrConv c = plan->conv[i];
-        if (c.mode == HR_MODE_F32) c.out = d_out;
-        k_hr_conv<<<plan->grid[i], HR_THREADS, plan->smem[i], st>>>(c);
+        if (c.mode == HR_MODE_F32) {
+            int rc = hr_map_out(&c.tmap_out[0], d_out, true, c, 0);
+            if (rc != OLS_OK) return rc;
+        }
+        c.trace = trace_on ? d_trace + i * 8 : nullptr;
+        // programmatic dependent launch: layer i+1 may begin its prologue while layer i drains
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = plan->grid[i];
+        cfg.blockDim = dim3(HR_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = plan->smem[i];
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = (no_pdl || trace_on) ? 0 : 1;
+        OLS_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_hr_conv, c));
+        if (trace_on) cudaEventRecord(ev[i + 1], st);
     }
     OLS_CUDA_TRY(cudaGetLastError());
     ols_timing_mark(OLS_T_OTHER, st);
+    if (trace_on) {
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "[hr trace]");
+        for (int i = 0; i < OLS_HR_N_CONV; i++) {
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            const HrConv& c = plan->conv[i];
+            const double flop = 2.0 * c.grid_w * c.grid_h * c.n_classes * c.cout * 64.0 * c.n_taps *
+                                (c.slabs[0] + (c.n_src > 1 ? c.slabs[1] : 0));
+            fprintf(stderr, " L%d[%ux%ux%u bn%d] %.1fus %.0fTF |", i, plan->grid[i].x, plan->grid[i].y, plan->grid[i].z, c.bn,
+                    ms * 1e3, flop / (ms * 1e-3) * 1e-12);
+        }
+        fprintf(stderr, "\n[hr trace] CTA 0 (setup, main loop, epilogue, exit) us:");
+        unsigned long long h[OLS_HR_N_CONV * 8];
+        cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
+        for (int i = 0; i < OLS_HR_N_CONV; i++) {
+            const unsigned long long* t = h + i * 8;
+            fprintf(stderr, " L%d %.1f %.1f %.1f %.1f (gap to next start %.1f) |", i, (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3,
+                    (t[3] - t[2]) * 1e-3, (t[4] - t[3]) * 1e-3, i + 1 < OLS_HR_N_CONV ? (double)(h[(i + 1) * 8] - t[4]) * 1e-3 : 0.0);
+        }
+        fprintf(stderr, "\n");
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
     return OLS_OK;
 }
 

@@ -30,3 +30,6 @@ with torch.no_grad():
     for _ in range(20): net(fv, f3, f2)
     e1.record(); torch.cuda.synchronize()
 print("HR forward 24x24 -> 192x192x768: %.3f ms" % (e0.elapsed_time(e1) / 20))
+if os.environ.get("OLS_HR_TRACE"):
+    with torch.no_grad():
+        net(fv, f3, f2)

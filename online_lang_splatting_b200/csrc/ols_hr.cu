@@ -52,6 +52,7 @@ struct HrConv {
     CUtensorMap tmap_gate;        // HR_MODE_GATE: the fused feature the attention map multiplies (same layout as the output)
     CUtensorMap tmap_out[4];      // output tile store, one per parity class
     int n_stages, stage_bytes, gate_bytes;
+    int split;                    // split-K: a cluster of `split` CTAs shares one output tile, rank 0 reduces
     unsigned long long* trace;    // development aid (OLS_HR_TRACE): globaltimer stamps of CTA (0,0,0)
 };
 
@@ -67,6 +68,23 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
                  "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+// split-K exchange inside a thread-block cluster: partial accumulators travel through distributed shared memory
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_relacq() {
+    asm volatile("barrier.cluster.arrive.release;\nbarrier.cluster.wait.acquire;" ::: "memory");
+}
 // programmatic dependent launch: wait for the producer grid's memory / allow the consumer grid to start its prologue
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -75,7 +93,8 @@ __global__ void __launch_bounds__(HR_THREADS, 1) k_hr_conv(const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     uint8_t* ring = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* gate_smem = ring + (size_t)p.n_stages * p.stage_bytes;  // [bn/64][128 px][128 B], swizzled
-    uint64_t* bars = (uint64_t*)(gate_smem + p.gate_bytes);
+    uint8_t* part_smem = gate_smem + p.gate_bytes;                   // rank 0: [split-1][bn/32][128 px][128 B] fp32 partials
+    uint64_t* bars = (uint64_t*)(part_smem + (size_t)(p.split - 1) * p.bn * 512);
     uint64_t* full = bars;
     uint64_t* empty = bars + 8;
     uint64_t* mma_done = bars + 16;
@@ -103,18 +122,22 @@ __global__ void __launch_bounds__(HR_THREADS, 1) k_hr_conv(const __grid_constant
     const uint32_t tmem_base = *tmem_slot;
     pdl_launch_dependents();  // the next layer may start its prologue; it blocks in pdl_wait() until this grid is done
 
-    const int tile = blockIdx.x;
+    // split-K: the cluster's CTAs take consecutive ranges of the (tap, source, slab) steps of the same tile
+    const uint32_t rank = p.split > 1 ? cluster_ctarank() : 0u;
+    const int tile = blockIdx.x / p.split;
     const int x0 = (tile % p.tiles_x) * HR_BOX_W, y0 = (tile / p.tiles_x) * HR_BOX_H;
     const int n0 = blockIdx.y * p.bn;
     const int cls = blockIdx.z;
     const int slabs_total = p.slabs[0] + (p.n_src > 1 ? p.slabs[1] : 0);
+    const int ksteps = p.n_taps * slabs_total;
+    const int k_begin = ksteps * (int)rank / p.split, k_end = ksteps * ((int)rank + 1) / p.split;
 
     if (warp == 0) {
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_a[0]) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_b) : "memory");
             pdl_wait();  // everything below reads what the previous layers wrote
-            if (p.mode == HR_MODE_GATE) {
+            if (p.mode == HR_MODE_GATE && rank == 0) {
                 mbar_expect_tx(gate_full, (uint32_t)p.gate_bytes);
                 for (int j = 0; j < p.bn / 64; j++)
                     tma_load_3d(gate_smem + (size_t)j * HR_A_BYTES, &p.tmap_gate, gate_full, n0 + j * 64, x0, y0);
@@ -122,27 +145,23 @@ __global__ void __launch_bounds__(HR_THREADS, 1) k_hr_conv(const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t bytes = (uint32_t)(HR_A_BYTES + p.bn * 128);
-            int kslab = 0;
-            for (int t = 0; t < p.n_taps; t++) {
-                const int ax = x0 + p.dx[cls][t], ay = y0 + p.dy[cls][t];
-                for (int s = 0; s < p.n_src; s++) {
-                    for (int sl = 0; sl < p.slabs[s]; sl++, kslab++) {
-                        mbar_wait(&empty[stage], phase ^ 1);
-                        uint8_t* st = ring + (size_t)stage * p.stage_bytes;
-                        mbar_expect_tx(&full[stage], bytes);
-                        tma_load_3d(st, &p.tmap_a[s], &full[stage], sl * 64, ax, ay);
-                        tma_load_2d(st + HR_A_BYTES, &p.tmap_b, &full[stage], kslab * 64, cls * p.cout + n0);
-                        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
-                    }
-                }
+            for (int ks = k_begin; ks < k_end; ks++) {
+                const int t = ks / slabs_total, rem = ks - t * slabs_total;
+                const int s = rem >= p.slabs[0] ? 1 : 0, sl = rem - (s ? p.slabs[0] : 0);
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* st = ring + (size_t)stage * p.stage_bytes;
+                mbar_expect_tx(&full[stage], bytes);
+                tma_load_3d(st, &p.tmap_a[s], &full[stage], sl * 64, x0 + p.dx[cls][t], y0 + p.dy[cls][t]);
+                tma_load_2d(st + HR_A_BYTES, &p.tmap_b, &full[stage], ks * 64, cls * p.cout + n0);
+                if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
             }
         }
+        if (p.split > 1) cluster_sync_relacq();
     } else if (warp == 1) {
         int stage = 0;
         uint32_t phase = 0;
         const uint32_t idesc = make_idesc(false, p.bn);
-        const int ksteps = p.n_taps * slabs_total;
-        for (int ks = 0; ks < ksteps; ks++) {
+        for (int ks = k_begin; ks < k_end; ks++) {
             mbar_wait(&full[stage], phase);
             tcgen05_fence_after();
             if (lane == 0) {
@@ -150,7 +169,7 @@ __global__ void __launch_bounds__(HR_THREADS, 1) k_hr_conv(const __grid_constant
                 const uint32_t b_addr = a_addr + HR_A_BYTES;
 #pragma unroll
                 for (int k = 0; k < 4; k++)
-                    umma<false>(tmem_base, make_sdesc(a_addr + k * 32), make_sdesc(b_addr + k * 32), idesc, (ks | k) ? 1u : 0u);
+                    umma<false>(tmem_base, make_sdesc(a_addr + k * 32), make_sdesc(b_addr + k * 32), idesc, (ks > k_begin || k) ? 1u : 0u);
                 umma_commit(&empty[stage]);
             }
             __syncwarp();
@@ -158,6 +177,7 @@ __global__ void __launch_bounds__(HR_THREADS, 1) k_hr_conv(const __grid_constant
         }
         if (lane == 0) umma_commit(mma_done);
         __syncwarp();
+        if (p.split > 1) cluster_sync_relacq();
     } else {
         // epilogue: thread = one pixel of the patch = one TMEM lane
         const int quad = warp & 3;
@@ -166,12 +186,39 @@ __global__ void __launch_bounds__(HR_THREADS, 1) k_hr_conv(const __grid_constant
         if (tracer) p.trace[1] = gtimer();
         mbar_wait(mma_done, 0);  // all MMAs retired: the accumulator is complete and the ring is idle
         tcgen05_fence_after();
+        if (rank != 0) {
+            // ship the partial accumulator into rank 0's shared memory, then meet at the cluster barrier
+            const uint32_t remote = map_to_rank(smem_u32(part_smem), 0) + (rank - 1) * (uint32_t)p.bn * 512u;
+            for (int c = 0; c < p.bn; c += 32) {
+                uint32_t r[32];
+                tmem_ld32(t_lane + (uint32_t)c, r);
+                tmem_ld_wait();
+                const uint32_t slab = remote + (uint32_t)(c >> 5) * HR_A_BYTES;
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    st_cluster_f4(slab + sw128(row, q), __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                  __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            }
+            cluster_sync_relacq();
+        } else {
+        if (p.split > 1) cluster_sync_relacq();  // the other ranks' partials have landed in part_smem
         if (p.mode == HR_MODE_GATE) mbar_wait(gate_full, 0);
         if (tracer) p.trace[2] = gtimer();
         for (int c = 0; c < p.bn; c += 32) {
             uint32_t r[32];
             tmem_ld32(t_lane + (uint32_t)c, r);
             tmem_ld_wait();
+            for (int pr = 0; pr < p.split - 1; pr++) {
+                const uint8_t* ps = part_smem + (size_t)pr * p.bn * 512 + (size_t)(c >> 5) * HR_A_BYTES;
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const float4 a = *reinterpret_cast<const float4*>(ps + sw128(row, q));
+                    r[4 * q + 0] = __float_as_uint(__uint_as_float(r[4 * q + 0]) + a.x);
+                    r[4 * q + 1] = __float_as_uint(__uint_as_float(r[4 * q + 1]) + a.y);
+                    r[4 * q + 2] = __float_as_uint(__uint_as_float(r[4 * q + 2]) + a.z);
+                    r[4 * q + 3] = __float_as_uint(__uint_as_float(r[4 * q + 3]) + a.w);
+                }
+            }
             float v[32];
             const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c);
 #pragma unroll
@@ -234,6 +281,7 @@ __global__ void __launch_bounds__(HR_THREADS, 1) k_hr_conv(const __grid_constant
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
+        }  // rank 0
     }
     if (tracer) p.trace[3] = gtimer();
     tcgen05_fence_before();
@@ -327,6 +375,8 @@ struct ols_hr_plan {
     size_t act_elems[OLS_HR_N_CONV];
     std::vector<void*> owned;
     int S_h, S_w;
+    cudaStream_t side;           // the two low_res_align convolutions only depend on the inputs: they run beside layers 0-1
+    cudaEvent_t ev_fork, ev_join;
 };
 
 typedef CUresult (*PFN_encodeTiledHr)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -395,22 +445,23 @@ struct Spec {
     int mode, relu, gate;
     int bn;        // output channels per CTA (64, 128 or 256 = TMEM columns)
     int max_stages;  // ring depth cap (a short K loop needs no deep ring: several CTAs then fit one SM)
+    int split;       // split-K cluster size: the low-resolution layers have too few tiles to fill 148 SMs otherwise
 };
 // supervisedNet.py:83-109, one row per convolution
 const Spec SPECS[OLS_HR_N_CONV] = {
-    {K_CONV3, 768, 0, 512, 0, -1, -100, HR_MODE_BF16, 1, -1, 64, 8},     // initial_conv (+BN+ReLU)
-    {K_CONVT, 512, 0, 512, 0, 0, -100, HR_MODE_BF16, 1, -1, 128, 8},     // upsample1 (+BN+ReLU) -> 2S
-    {K_CONV1, 384, 0, 512, 1, -2, -100, HR_MODE_BF16, 0, -1, 128, 8},    // af1.low_res_align
-    {K_CONV3, 512, 512, 512, 1, 1, 2, HR_MODE_BF16, 1, -1, 64, 8},       // af1.fusion (+BN+ReLU) on cat[x, low]
-    {K_CONV3, 512, 0, 512, 1, 3, -100, HR_MODE_BF16, 1, -1, 64, 8},      // af1.attention.0 (+BN+ReLU)
-    {K_CONV1, 512, 0, 512, 1, 4, -100, HR_MODE_GATE, 0, 3, 128, 8},      // af1.attention.3 + sigmoid, gate on fused
-    {K_CONVT, 512, 0, 256, 1, 5, -100, HR_MODE_BF16, 1, -1, 128, 8},     // upsample2 -> 4S
-    {K_CONV1, 192, 0, 256, 2, -3, -100, HR_MODE_BF16, 0, -1, 128, 8},    // af2.low_res_align
-    {K_CONV3, 256, 256, 256, 2, 6, 7, HR_MODE_BF16, 1, -1, 128, 8},      // af2.fusion
-    {K_CONV3, 256, 0, 256, 2, 8, -100, HR_MODE_BF16, 1, -1, 128, 8},     // af2.attention.0
-    {K_CONV1, 256, 0, 256, 2, 9, -100, HR_MODE_GATE, 0, 8, 128, 8},      // af2.attention.3 + gate
-    {K_CONVT, 256, 0, 128, 2, 10, -100, HR_MODE_BF16, 1, -1, 128, 8},    // upsample3 -> 8S
-    {K_CONV1, 128, 0, 768, 3, 11, -100, HR_MODE_F32, 0, -1, 128, 2},     // final_conv -> fp32
+    {K_CONV3, 768, 0, 512, 0, -1, -100, HR_MODE_BF16, 1, -1, 64, 8, 2},     // initial_conv (+BN+ReLU)
+    {K_CONVT, 512, 0, 512, 0, 0, -100, HR_MODE_BF16, 1, -1, 128, 8, 1},     // upsample1 (+BN+ReLU) -> 2S
+    {K_CONV1, 384, 0, 512, 1, -2, -100, HR_MODE_BF16, 0, -1, 128, 8, 1},    // af1.low_res_align
+    {K_CONV3, 512, 512, 512, 1, 1, 2, HR_MODE_BF16, 1, -1, 128, 8, 2},       // af1.fusion (+BN+ReLU) on cat[x, low]
+    {K_CONV3, 512, 0, 512, 1, 3, -100, HR_MODE_BF16, 1, -1, 128, 8, 2},      // af1.attention.0 (+BN+ReLU)
+    {K_CONV1, 512, 0, 512, 1, 4, -100, HR_MODE_GATE, 0, 3, 128, 8, 1},      // af1.attention.3 + sigmoid, gate on fused
+    {K_CONVT, 512, 0, 256, 1, 5, -100, HR_MODE_BF16, 1, -1, 128, 8, 1},     // upsample2 -> 4S
+    {K_CONV1, 192, 0, 256, 2, -3, -100, HR_MODE_BF16, 0, -1, 128, 8, 1},    // af2.low_res_align
+    {K_CONV3, 256, 256, 256, 2, 6, 7, HR_MODE_BF16, 1, -1, 128, 8, 1},      // af2.fusion
+    {K_CONV3, 256, 0, 256, 2, 8, -100, HR_MODE_BF16, 1, -1, 128, 8, 1},     // af2.attention.0
+    {K_CONV1, 256, 0, 256, 2, 9, -100, HR_MODE_GATE, 0, 8, 128, 8, 1},      // af2.attention.3 + gate
+    {K_CONVT, 256, 0, 128, 2, 10, -100, HR_MODE_BF16, 1, -1, 128, 8, 1},    // upsample3 -> 8S
+    {K_CONV1, 128, 0, 768, 3, 11, -100, HR_MODE_F32, 0, -1, 128, 2, 1},     // final_conv -> fp32
 };
 }  // namespace
 
@@ -419,6 +470,9 @@ extern "C" {
 void ols_hr_plan_destroy(ols_hr_plan* plan) {
     if (!plan) return;
     for (void* q : plan->owned) cudaFree(q);
+    if (plan->side) cudaStreamDestroy(plan->side);
+    if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
+    if (plan->ev_join) cudaEventDestroy(plan->ev_join);
     delete plan;
 }
 
@@ -430,6 +484,12 @@ int ols_hr_plan_create(const ols_hr_weights* w, int32_t S_h, int32_t S_w, ols_hr
     ols_hr_plan* plan = new ols_hr_plan();
     memset(plan->conv, 0, sizeof(plan->conv));
     plan->S_h = S_h; plan->S_w = S_w;
+    plan->side = nullptr; plan->ev_fork = nullptr; plan->ev_join = nullptr;
+    if (cudaStreamCreateWithFlags(&plan->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&plan->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        ols_set_error("cannot create the HR side stream"); ols_hr_plan_destroy(plan); return OLS_ERR_CUDA;
+    }
     auto fail = [&](int rc) { ols_hr_plan_destroy(plan); return rc; };
     auto alloc = [&](size_t bytes) -> void* {
         void* q = nullptr;
@@ -513,15 +573,18 @@ int ols_hr_plan_create(const ols_hr_weights* w, int32_t S_h, int32_t S_w, ols_hr
             c.gate_bytes = c.bn / 64 * HR_A_BYTES;
         }
         c.stage_bytes = HR_A_BYTES + c.bn * 128;
-        int ns = (227 * 1024 - 1024 - 256 - c.gate_bytes) / c.stage_bytes;
+        static const bool no_split = getenv("OLS_HR_NO_SPLIT") != nullptr;
+        c.split = no_split ? 1 : s.split;
+        const int part_bytes = (c.split - 1) * c.bn * 512;
+        int ns = (227 * 1024 - 1024 - 256 - c.gate_bytes - part_bytes) / c.stage_bytes;
         c.n_stages = ns > s.max_stages ? s.max_stages : ns;
         // the finished tile is staged in the ring: 128 px x bn channels (bf16, or fp32 for the last layer)
         const int staging = c.bn * 128 * (s.mode == HR_MODE_F32 ? 4 : 2);
         if (c.n_stages < 2 || staging > c.n_stages * c.stage_bytes || c.bn % 64 != 0) {
             ols_set_error("HR conv %d: tile does not fit shared memory", i); return fail(OLS_ERR_UNSUPPORTED);
         }
-        plan->smem[i] = (size_t)c.n_stages * c.stage_bytes + c.gate_bytes + 256 + 1024;
-        plan->grid[i] = dim3((unsigned)(c.tiles_x * tiles_y), (unsigned)(s.cout / c.bn), (unsigned)c.n_classes);
+        plan->smem[i] = (size_t)c.n_stages * c.stage_bytes + c.gate_bytes + part_bytes + 256 + 1024;
+        plan->grid[i] = dim3((unsigned)(c.tiles_x * tiles_y * c.split), (unsigned)(s.cout / c.bn), (unsigned)c.n_classes);
     }
     if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { ols_set_error("HR weight packing failed"); return fail(OLS_ERR_CUDA); }
     if (cudaFuncSetAttribute(k_hr_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
@@ -554,26 +617,54 @@ int ols_hr_forward(const ols_hr_plan* plan, const float* d_fv, const float* d_f3
         cudaEventRecord(ev[0], st);
     }
     static const bool no_pdl = getenv("OLS_HR_NO_PDL") != nullptr;
-    for (int i = 0; i < OLS_HR_N_CONV; i++) {
+    static const bool no_fork = getenv("OLS_HR_NO_FORK") != nullptr;
+    const bool fork = !no_fork && !trace_on;
+    auto launch = [&](int i, cudaStream_t stream_i, bool pdl) -> int {
         HrConv c = plan->conv[i];
         if (c.mode == HR_MODE_F32) {
             int rc = hr_map_out(&c.tmap_out[0], d_out, true, c, 0);
             if (rc != OLS_OK) return rc;
         }
         c.trace = trace_on ? d_trace + i * 8 : nullptr;
-        // programmatic dependent launch: layer i+1 may begin its prologue while layer i drains
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = plan->grid[i];
         cfg.blockDim = dim3(HR_THREADS, 1, 1);
         cfg.dynamicSmemBytes = plan->smem[i];
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.stream = stream_i;
+        cudaLaunchAttribute attr[2];
+        int na = 0;
+        if (pdl && !no_pdl && !trace_on) {
+            // programmatic dependent launch: this layer may begin its prologue while the previous one drains
+            attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[na].val.programmaticStreamSerializationAllowed = 1;
+            na++;
+        }
+        if (c.split > 1) {
+            attr[na].id = cudaLaunchAttributeClusterDimension;
+            attr[na].val.clusterDim.x = (unsigned)c.split; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+            na++;
+        }
         cfg.attrs = attr;
-        cfg.numAttrs = (no_pdl || trace_on) ? 0 : 1;
+        cfg.numAttrs = na;
         OLS_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_hr_conv, c));
-        if (trace_on) cudaEventRecord(ev[i + 1], st);
+        if (trace_on) cudaEventRecord(ev[i + 1], stream_i);
+        return OLS_OK;
+    };
+    if (fork) {
+        // conv 2 and conv 7 (low_res_align of f3 / f2) beside conv 0 and conv 1; joined before conv 3
+        OLS_CUDA_TRY(cudaEventRecord(plan->ev_fork, st));
+        OLS_CUDA_TRY(cudaStreamWaitEvent(plan->side, plan->ev_fork, 0));
+        int rc = launch(2, plan->side, false);
+        if (rc == OLS_OK) rc = launch(7, plan->side, true);
+        if (rc != OLS_OK) return rc;
+        OLS_CUDA_TRY(cudaEventRecord(plan->ev_join, plan->side));
+    }
+    for (int i = 0; i < OLS_HR_N_CONV; i++) {
+        if (fork && (i == 2 || i == 7)) continue;
+        bool pdl = true;
+        if (fork && i == 3) { OLS_CUDA_TRY(cudaStreamWaitEvent(st, plan->ev_join, 0)); pdl = false; }
+        int rc = launch(i, st, pdl);
+        if (rc != OLS_OK) return rc;
     }
     OLS_CUDA_TRY(cudaGetLastError());
     ols_timing_mark(OLS_T_OTHER, st);

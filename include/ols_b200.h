@@ -372,6 +372,49 @@ int ols_hr_forward(const ols_hr_plan* plan, const float* d_fv, const float* d_f3
 /* development aid: copy of an intermediate activation (bf16 NHWC) as float32; which = conv index 0..11 */
 int ols_hr_read_activation(const ols_hr_plan* plan, int32_t which, float* d_out, int64_t capacity_floats, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * SSIM and the colour-refinement loss (gaussian_splatting/utils/loss_utils.py:41-101 `ssim`, window 11, sigma 1.5,
+ * zero padding, size_average=True; caller utils/slam_backend.py:797-801):
+ *     value = w_l1 * mean|image - gt| + w_ssim * mean(ssim_map(image, gt))
+ * (the caller's loss is  (1 - lambda) * l1 + lambda * (1 - ssim)  =  value + lambda  with w_l1 = 1 - lambda,
+ * w_ssim = -lambda).  Forward stores three per-pixel partial-derivative maps that backward filters once.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ols_ssim_args {
+    int32_t C, H, W;
+    float w_l1, w_ssim;
+    const float* d_image;   /* [C,H,W] render()["render"]        */
+    const float* d_gt;      /* [C,H,W] viewpoint.original_image  */
+} ols_ssim_args;
+/* d_out4 = [l1, ssim, value, 0]; d_partial: [3,C,H,W] floats (may be NULL when no backward follows); d_scratch2: 2 floats */
+int ols_ssim_loss_forward(const ols_ssim_args* args, float* d_out4, float* d_partial, float* d_scratch2, void* stream);
+/* dL/dimage = *d_upstream * d value / d image */
+int ols_ssim_loss_backward(const ols_ssim_args* args, const float* d_partial, const float* d_upstream, float* d_dL_dimage,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Densification bookkeeping over the flat per-Gaussian arrays.
+ * ols_densify_stats: per view, right after backward (utils/slam_backend.py:417-428,719-728 +
+ *   gaussian_model.py:965-969): for radii > 0:  max_radii2D = max(max_radii2D, radii);
+ *   xyz_gradient_accum += |viewspace_grad[:, :2]|;  denom += 1.   d_viewspace_grad may be NULL (colour refinement,
+ *   slam_backend.py:807-812, only updates max_radii2D).  No host synchronisation.
+ * ols_densify_flags: the selection masks of densify_and_prune (gaussian_model.py:948-963, :855-866, :912-921) on the
+ *   current state: bit 0 clone, bit 1 split, bit 2 prune; d_counts3 = how many of each.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ols_densify_params {
+    float max_grad;         /* grad_threshold                                              */
+    float min_opacity;
+    float extent;           /* scene extent                                                */
+    float max_screen_size;  /* <= 0: None (no screen-size / world-size pruning)            */
+    float percent_dense;    /* GaussianModel.percent_dense                                 */
+} ols_densify_params;
+int ols_densify_stats(int32_t P, const int32_t* d_radii, const float* d_viewspace_grad /* [P,3] or NULL */,
+                      float* d_max_radii2D /* [P] */, float* d_xyz_gradient_accum /* [P,1] */, float* d_denom /* [P,1] */,
+                      void* stream);
+int ols_densify_flags(int32_t P, int32_t scale_cols /* 1 or 3 */, const float* d_xyz_gradient_accum, const float* d_denom,
+                      const float* d_scaling_raw /* [P,scale_cols] log-scales */, const float* d_opacity_raw /* [P,1] logits */,
+                      const float* d_max_radii2D, const ols_densify_params* params, uint8_t* d_flags /* [P] */,
+                      int32_t* d_counts3, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = (
     "ols_mapping_loss_forward", "ols_mapping_loss_backward", "ols_adam_step", "ols_knn_workspace_size", "ols_knn_mean_dist2",
     "ols_dis_workspace_size", "ols_dis_forward", "ols_dis_read_info", "ols_dis_backward", "ols_dis_workspace_view",
     "ols_hr_plan_create", "ols_hr_plan_destroy", "ols_hr_forward", "ols_hr_read_activation",
+    "ols_ssim_loss_forward", "ols_ssim_loss_backward", "ols_densify_stats", "ols_densify_flags",
 )
 
 
@@ -107,6 +108,15 @@ class AEChain(C.Structure):
                 ("_pad", C.c_int32), ("d_weight", C.c_void_p * AE_MAX_LAYERS), ("d_bias", C.c_void_p * AE_MAX_LAYERS)]
 
 
+class SsimArgs(C.Structure):
+    _fields_ = [("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("w_l1", C.c_float), ("w_ssim", C.c_float),
+                ("d_image", C.c_void_p), ("d_gt", C.c_void_p)]
+
+
+class DensifyParams(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("max_grad", "min_opacity", "extent", "max_screen_size", "percent_dense")]
+
+
 HR_N_CONV = 13
 
 
@@ -164,6 +174,11 @@ def lib() -> C.CDLL:
     L.ols_ae_plan_destroy.argtypes = [C.c_void_p]
     L.ols_ae_plan_destroy.restype = None
     L.ols_ae_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    L.ols_ssim_loss_forward.argtypes = [C.POINTER(SsimArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ols_ssim_loss_backward.argtypes = [C.POINTER(SsimArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ols_densify_stats.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ols_densify_flags.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.POINTER(DensifyParams), C.c_void_p, C.c_void_p, C.c_void_p]
     L.ols_hr_plan_create.argtypes = [C.POINTER(HRWeights), C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_void_p]
     L.ols_hr_plan_destroy.argtypes = [C.c_void_p]
     L.ols_hr_plan_destroy.restype = None

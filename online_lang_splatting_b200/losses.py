@@ -126,3 +126,79 @@ def reference_mapping_loss(image, depth, gt_image, gt_depth, language=None, gt_l
                                              align_corners=False).squeeze(0)
         loss = loss + lambda_lang * torch.abs(language - up).mean()
     return loss
+
+
+# ---- SSIM and the colour-refinement loss -----------------------------------------------------------
+class _SsimLoss(torch.autograd.Function):
+    """value = w_l1 * mean|image - gt| + w_ssim * ssim(image, gt); gradient w.r.t. image only (gt is data)."""
+
+    @staticmethod
+    def forward(ctx, image, gt, w_l1, w_ssim):
+        N.require_cuda()
+        if not image.is_cuda:
+            raise RuntimeError("ssim needs CUDA tensors: there is no CPU path")
+        dev = image.device
+        x = image.detach().to(device=dev, dtype=torch.float32).contiguous()
+        y = gt.detach().to(device=dev, dtype=torch.float32).contiguous()
+        if x.shape != y.shape or x.dim() < 3:
+            raise RuntimeError("ssim expects two [..., C, H, W] tensors of the same shape")
+        Cc, H, W = int(x.numel() // (x.shape[-1] * x.shape[-2])), int(x.shape[-2]), int(x.shape[-1])
+        args = N.SsimArgs(C=Cc, H=H, W=W, w_l1=float(w_l1), w_ssim=float(w_ssim), d_image=x.data_ptr(), d_gt=y.data_ptr())
+        need_grad = image.requires_grad
+        partial = torch.empty((3,) + tuple(x.shape), dtype=torch.float32, device=dev) if need_grad else None
+        out = torch.empty(4, dtype=torch.float32, device=dev)
+        scratch = torch.empty(2, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            N.check(N.lib().ols_ssim_loss_forward(C.byref(args), out.data_ptr(), N.ptr(partial), scratch.data_ptr(), stream))
+        ctx.args, ctx.keep = args, (x, y, partial)
+        ctx.terms = out
+        return out[2].clone()
+
+    @staticmethod
+    def backward(ctx, grad_value):
+        x, _, partial = ctx.keep
+        if partial is None:
+            return None, None, None, None
+        dev = x.device
+        up = grad_value.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        dx = torch.empty_like(x)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            N.check(N.lib().ols_ssim_loss_backward(C.byref(ctx.args), partial.data_ptr(), up.data_ptr(), dx.data_ptr(), stream))
+        return dx, None, None, None
+
+
+def ssim(img1: torch.Tensor, img2: torch.Tensor, window_size: int = 11, size_average: bool = True) -> torch.Tensor:
+    """Drop-in for ``gaussian_splatting.utils.loss_utils.ssim`` (:61-101) as its two callers use it (window 11,
+    ``size_average=True``; utils/slam_backend.py:801, utils/eval_utils.py:174).  Differentiable w.r.t. ``img1``."""
+    if window_size != 11 or not size_average:
+        raise NotImplementedError("the fused kernel implements the reference's call: window_size=11, size_average=True")
+    return _SsimLoss.apply(img1, img2, 0.0, 1.0)
+
+
+def color_refinement_loss(image: torch.Tensor, gt_image: torch.Tensor, lambda_dssim: float = 0.2) -> torch.Tensor:
+    """``(1 - lambda_dssim) * l1_loss(image, gt) + lambda_dssim * (1 - ssim(image, gt))`` (utils/slam_backend.py:797-801),
+    one forward and one backward kernel."""
+    return _SsimLoss.apply(image, gt_image, 1.0 - lambda_dssim, -lambda_dssim) + lambda_dssim
+
+
+def reference_ssim(img1, img2, window_size=11):
+    """Plain-torch restatement of loss_utils.py:41-101 (test reference)."""
+    import math
+    g = torch.tensor([math.exp(-((x - window_size // 2) ** 2) / float(2 * 1.5 ** 2)) for x in range(window_size)])
+    g = (g / g.sum()).unsqueeze(1)
+    channel = img1.size(-3)
+    window = g.mm(g.t()).float().unsqueeze(0).unsqueeze(0).expand(channel, 1, window_size, window_size).contiguous()
+    window = window.to(img1.device).type_as(img1)
+    conv = lambda t: torch.nn.functional.conv2d(t, window, padding=window_size // 2, groups=channel)
+    mu1, mu2 = conv(img1), conv(img2)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    sigma1_sq, sigma2_sq, sigma12 = conv(img1 * img1) - mu1_sq, conv(img2 * img2) - mu2_sq, conv(img1 * img2) - mu1_mu2
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    ssim_map = ((2 * mu1_mu2 + C1) * (2 * sigma12 + C2)) / ((mu1_sq + mu2_sq + C1) * (sigma1_sq + sigma2_sq + C2))
+    return ssim_map.mean()
+
+
+def reference_color_refinement_loss(image, gt_image, lambda_dssim=0.2):
+    return (1.0 - lambda_dssim) * torch.abs(image - gt_image).mean() + lambda_dssim * (1.0 - reference_ssim(image, gt_image))

@@ -328,7 +328,7 @@ typedef struct ols_ae_chain {
     int32_t n_layers;
     int32_t dims[OLS_AE_MAX_LAYERS + 1];   /* dims[0] = input width, dims[i+1] = output width of layer i */
     int32_t normalize;                     /* 1: y /= ||y||_2 per row after the last layer               */
-    int32_t _pad;
+    int32_t input_bf16;                    /* 1: x is bfloat16 [M, dims[0]] (dims[0] % 64 == 0): ols_ae_forward_bf16      */
     const float* d_weight[OLS_AE_MAX_LAYERS];  /* [dims[i+1], dims[i]]                                  */
     const float* d_bias[OLS_AE_MAX_LAYERS];    /* [dims[i+1]]                                           */
 } ols_ae_chain;
@@ -339,6 +339,9 @@ int ols_ae_plan_create(const ols_ae_chain* chain, ols_ae_plan** plan, void* stre
 void ols_ae_plan_destroy(ols_ae_plan* plan);
 /* y[M, dims[n]] = chain(x[M, dims[0]]); replaces AutoencoderMLP.encode / .decode. */
 int ols_ae_forward(const ols_ae_plan* plan, const float* d_x, float* d_y, int64_t M, void* stream);
+/* the same chain on a bfloat16 input matrix (plan created with input_bf16 = 1): used to run the encoder directly on
+ * the HR module's last 128-channel activation with final_conv folded into the first Linear (ols_hr_forward_features) */
+int ols_ae_forward_bf16(const ols_ae_plan* plan, const void* d_x_bf16, float* d_y, int64_t M, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * HR module (language/supervisedNet.py:45-109 HighResLanguageFeatureNet, called with torch.no_grad() in eval
@@ -369,6 +372,12 @@ void ols_hr_plan_destroy(ols_hr_plan* plan);
  * bilinear interpolation, align_corners = False (supervisedNet.py:88,97). */
 int ols_hr_forward(const ols_hr_plan* plan, const float* d_fv, const float* d_f3, int32_t h3, int32_t w3,
                    const float* d_f2, int32_t h2, int32_t w2, float* d_out, void* stream);
+/* Layers 0..11 only: writes the last hidden activation (upsample3's output, bfloat16 [8*S_h * 8*S_w, 128], pixel-major)
+ * into d_feat_bf16.  final_conv (a 1x1 convolution = a Linear over channels) and the autoencoder's first Linear have
+ * nothing between them (utils/slam_backend.py:392-395), so the caller may fold them (W' = W_ae0 W_final,
+ * b' = W_ae0 b_final + b_ae0) and feed d_feat_bf16 to ols_ae_forward_bf16: the 768-channel fp32 map is never written. */
+int ols_hr_forward_features(const ols_hr_plan* plan, const float* d_fv, const float* d_f3, int32_t h3, int32_t w3,
+                            const float* d_f2, int32_t h2, int32_t w2, void* d_feat_bf16, void* stream);
 /* development aid: copy of an intermediate activation (bf16 NHWC) as float32; which = conv index 0..11 */
 int ols_hr_read_activation(const ols_hr_plan* plan, int32_t which, float* d_out, int64_t capacity_floats, void* stream);
 

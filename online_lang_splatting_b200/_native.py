@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = (
     "ols_dis_workspace_size", "ols_dis_forward", "ols_dis_read_info", "ols_dis_backward", "ols_dis_workspace_view",
     "ols_hr_plan_create", "ols_hr_plan_destroy", "ols_hr_forward", "ols_hr_read_activation",
     "ols_ssim_loss_forward", "ols_ssim_loss_backward", "ols_densify_stats", "ols_densify_flags",
+    "ols_ae_forward_bf16", "ols_hr_forward_features",
 )
 
 
@@ -105,7 +106,7 @@ class HostOut(C.Structure):
 
 class AEChain(C.Structure):
     _fields_ = [("n_layers", C.c_int32), ("dims", C.c_int32 * (AE_MAX_LAYERS + 1)), ("normalize", C.c_int32),
-                ("_pad", C.c_int32), ("d_weight", C.c_void_p * AE_MAX_LAYERS), ("d_bias", C.c_void_p * AE_MAX_LAYERS)]
+                ("input_bf16", C.c_int32), ("d_weight", C.c_void_p * AE_MAX_LAYERS), ("d_bias", C.c_void_p * AE_MAX_LAYERS)]
 
 
 class SsimArgs(C.Structure):
@@ -184,6 +185,9 @@ def lib() -> C.CDLL:
     L.ols_hr_plan_destroy.restype = None
     L.ols_hr_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                  C.c_void_p, C.c_void_p]
+    L.ols_ae_forward_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    L.ols_hr_forward_features.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                          C.c_int32, C.c_void_p, C.c_void_p]
     L.ols_hr_read_activation.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
     _LIB = L
     return L

@@ -43,17 +43,20 @@ class _FusedChain:
             pass
 
     def run(self, layers: Sequence[Tuple[torch.Tensor, Optional[torch.Tensor]]], version_key, normalize: bool,
-            x: torch.Tensor) -> torch.Tensor:
+            x: torch.Tensor, x_bf16: bool = False) -> torch.Tensor:
         N.require_cuda()
         if not x.is_cuda:
             raise RuntimeError("autoencoder input must be a CUDA tensor: the fused kernel has no CPU path")
         lead = x.shape[:-1]
         x2 = x.reshape(-1, x.shape[-1])
-        if x2.dtype != torch.float32:
+        if x_bf16:
+            if x2.dtype != torch.bfloat16:
+                raise RuntimeError("expected a bfloat16 input matrix")
+        elif x2.dtype != torch.float32:
             x2 = x2.float()
         x2 = x2.contiguous()
         dev = x2.device
-        key = (version_key, dev.index, normalize)
+        key = (version_key, dev.index, normalize, x_bf16)
         lib = N.lib()
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
@@ -61,7 +64,7 @@ class _FusedChain:
                 self._destroy()
                 ws = [w.detach().to(dev, torch.float32).contiguous() for w, _ in layers]
                 bs = [None if b is None else b.detach().to(dev, torch.float32).contiguous() for _, b in layers]
-                chain = N.AEChain(n_layers=len(ws), normalize=int(normalize))
+                chain = N.AEChain(n_layers=len(ws), normalize=int(normalize), input_bf16=int(x_bf16))
                 chain.dims[0] = ws[0].shape[1]
                 for i, w in enumerate(ws):
                     chain.dims[i + 1] = w.shape[0]
@@ -73,7 +76,8 @@ class _FusedChain:
             if x2.shape[1] != self._keep[0][0].shape[1]:
                 raise RuntimeError(f"expected input width {self._keep[0][0].shape[1]}, got {x2.shape[1]}")
             y = torch.empty((x2.shape[0], self._keep[0][-1].shape[0]), dtype=torch.float32, device=dev)
-            N.check(lib.ols_ae_forward(self._plan, x2.data_ptr(), y.data_ptr(), x2.shape[0], stream))
+            fwd = lib.ols_ae_forward_bf16 if x_bf16 else lib.ols_ae_forward
+            N.check(fwd(self._plan, x2.data_ptr(), y.data_ptr(), x2.shape[0], stream))
         return y.reshape(*lead, y.shape[-1])
 
 
@@ -116,7 +120,12 @@ class _ChainMixin:
                 x = m(x)
             return x / x.norm(dim=-1, keepdim=True)
         fused = self.__dict__.setdefault("_fused_" + which, _FusedChain())
-        return fused.run(_fold(modules), _version(modules), True, x)
+        # fold BatchNorm only when a parameter or buffer changed (folding launches ~7 small kernels per BatchNorm)
+        key = _version(modules)
+        cache = self.__dict__.get("_folded_" + which)
+        if cache is None or cache[0] != key:
+            cache = self.__dict__["_folded_" + which] = (key, _fold(modules))
+        return fused.run(cache[1], key, True, x)
 
 
 class AutoencoderMLP(nn.Module, _ChainMixin):
@@ -148,6 +157,34 @@ class AutoencoderMLP(nn.Module, _ChainMixin):
 
     def decode(self, x):
         return self._run("dec", list(self.decoder), x)
+
+    def encode_hr(self, hr_model, fv: torch.Tensor, f3: torch.Tensor, f2: torch.Tensor) -> torch.Tensor:
+        """``self.encode(hr_model(fv, f3, f2).permute(0, 2, 3, 1).view(-1, 768))`` (utils/slam_backend.py:381-395) without
+        ever materialising the 768-channel map: the HR module's ``final_conv`` is a per-pixel Linear 128 -> 768 and the
+        encoder starts with a Linear 768 -> h with nothing in between, so the two are folded into one Linear 128 -> h
+        (``W' = W_enc0 W_final``, ``b' = W_enc0 b_final + b_enc0``, done here in float64) and the fused kernel reads the
+        HR module's last bf16 activation directly.  Saves writing and re-reading 113 MB per frame plus 5/6 of the first
+        layer's flops.  Same result up to rounding (``tests/test_hr.py::test_hr_fused_encode``).  Inference only."""
+        net = getattr(hr_model, "model", hr_model)  # LangSupervisedNet or HighResLanguageFeatureNet
+        mods = list(self.encoder)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and any(
+                t.requires_grad for t in (fv, f3, f2)):
+            raise RuntimeError("encode_hr is an inference path (the reference runs it under torch.no_grad())")
+        if any(isinstance(m, nn.BatchNorm1d) and m.training for m in mods):
+            raise RuntimeError("encode_hr needs eval mode (BatchNorm is folded)")
+        feat = net.features(fv, f3, f2)  # [N, M, 128] bf16
+        key = (_version(mods), _version([net.final_conv]))
+        cache = self.__dict__.get("_hr_fold")
+        if cache is None or cache[0] != key:
+            layers = _fold(mods)
+            W0, b0 = layers[0]
+            Wf = net.final_conv.weight.detach().reshape(net.final_conv.out_channels, -1).double()
+            bf = net.final_conv.bias.detach().double()
+            b0d = torch.zeros(W0.shape[0], dtype=torch.float64, device=W0.device) if b0 is None else b0.double()
+            layers[0] = ((W0.double() @ Wf).float(), (W0.double() @ bf + b0d).float())
+            cache = self.__dict__["_hr_fold"] = (key, layers)
+        fused = self.__dict__.setdefault("_fused_enc_hr", _FusedChain())
+        return fused.run(cache[1], key, True, feat.reshape(-1, feat.shape[-1]), x_bf16=True)
 
 
 class EncoderDecoderOnline(nn.Module, _ChainMixin):

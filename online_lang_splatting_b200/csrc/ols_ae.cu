@@ -54,6 +54,7 @@ struct AeParams {
     AeLayer layer[OLS_AE_MAX_LAYERS];
     int n_layers;
     int manual_x;    // 1: layer-0 input is loaded by the epilogue warps (row stride not TMA compatible)
+    int x_bf16;      // 1: the input matrix is bf16 (the HR module's last activation); layer 0 then runs kind::f16
     int K0_real;     // real input width
     int out_real;    // real output width
     int normalize;
@@ -391,13 +392,15 @@ int ols_ae_plan_create(const ols_ae_chain* chain, ols_ae_plan** out_plan, void* 
     p.K0_real = chain->dims[0];
     p.out_real = chain->dims[chain->n_layers];
     p.normalize = chain->normalize;
+    p.x_bf16 = chain->input_bf16 ? 1 : 0;
     p.manual_x = (chain->dims[0] % 32 != 0) ? 1 : 0;  // TMA needs 16-byte row strides; keep whole slabs too
+    if (p.x_bf16 && chain->dims[0] % 64 != 0) { ols_set_error("bf16 input needs a width that is a multiple of 64"); return fail(OLS_ERR_UNSUPPORTED); }
     int stage_bytes = 0, act_cols_bytes = 0;
     for (int l = 0; l < chain->n_layers; l++) {
         const int K = chain->dims[l], N = chain->dims[l + 1];
         if (K <= 0 || N <= 0 || !chain->d_weight[l]) { ols_set_error("bad layer %d", l); return fail(OLS_ERR_INVALID); }
         AeLayer& L = p.layer[l];
-        L.tf32 = l == 0;
+        L.tf32 = (l == 0 && !p.x_bf16) ? 1 : 0;
         const int slab = L.tf32 ? 32 : 64;
         // K of layer l must equal the padded N of layer l-1 (the activation the epilogue wrote)
         L.K = round_up(K, slab);
@@ -465,15 +468,29 @@ void ols_ae_plan_destroy(ols_ae_plan* plan) {
     delete plan;
 }
 
+static int ae_forward(const ols_ae_plan* plan, const void* d_x, float* d_y, int64_t M, void* stream);
+
 int ols_ae_forward(const ols_ae_plan* plan, const float* d_x, float* d_y, int64_t M, void* stream) {
+    if (plan && plan->p.x_bf16) { ols_set_error("this plan takes a bf16 input: call ols_ae_forward_bf16"); return OLS_ERR_INVALID; }
+    return ae_forward(plan, d_x, d_y, M, stream);
+}
+
+int ols_ae_forward_bf16(const ols_ae_plan* plan, const void* d_x_bf16, float* d_y, int64_t M, void* stream) {
+    if (plan && !plan->p.x_bf16) { ols_set_error("this plan takes a float32 input: call ols_ae_forward"); return OLS_ERR_INVALID; }
+    return ae_forward(plan, d_x_bf16, d_y, M, stream);
+}
+
+}  // extern "C"
+
+static int ae_forward(const ols_ae_plan* plan, const void* d_x, float* d_y, int64_t M, void* stream) {
     if (!plan || !d_x || !d_y || M < 0) { ols_set_error("bad arguments"); return OLS_ERR_INVALID; }
     if (M == 0) return OLS_OK;
     AeParams p = plan->p;
-    p.x = d_x; p.y = d_y; p.M = M;
+    p.x = (const float*)d_x; p.y = d_y; p.M = M;
     p.n_tiles = (int)((M + AE_M - 1) / AE_M);
     if (!p.manual_x) {
         if (((uintptr_t)d_x & 15) != 0) { ols_set_error("x must be 16-byte aligned"); return OLS_ERR_INVALID; }
-        int rc = make_map(&p.tmap_x, d_x, false, (uint64_t)M, (uint64_t)p.K0_real, AE_M);
+        int rc = make_map(&p.tmap_x, d_x, p.x_bf16 != 0, (uint64_t)M, (uint64_t)p.K0_real, AE_M);
         if (rc != OLS_OK) return rc;
     }
     const int grid = p.n_tiles < plan->sm_count ? p.n_tiles : plan->sm_count;
@@ -500,4 +517,4 @@ int ols_ae_forward(const ols_ae_plan* plan, const float* d_x, float* d_y, int64_
     return OLS_OK;
 }
 
-}  // extern "C"
+

@@ -594,12 +594,31 @@ int ols_hr_plan_create(const ols_hr_weights* w, int32_t S_h, int32_t S_w, ols_hr
     return OLS_OK;
 }
 
+static int hr_run(const ols_hr_plan* plan, const float* d_fv, const float* d_f3, int32_t h3, int32_t w3, const float* d_f2,
+                  int32_t h2, int32_t w2, float* d_out, void* d_feat, void* stream);
+
 int ols_hr_forward(const ols_hr_plan* plan, const float* d_fv, const float* d_f3, int32_t h3, int32_t w3,
                    const float* d_f2, int32_t h2, int32_t w2, float* d_out, void* stream) {
-    if (!plan || !d_fv || !d_f3 || !d_f2 || !d_out || h3 <= 0 || w3 <= 0 || h2 <= 0 || w2 <= 0) {
+    if (!d_out) { ols_set_error("bad HR forward arguments"); return OLS_ERR_INVALID; }
+    return hr_run(plan, d_fv, d_f3, h3, w3, d_f2, h2, w2, d_out, nullptr, stream);
+}
+
+int ols_hr_forward_features(const ols_hr_plan* plan, const float* d_fv, const float* d_f3, int32_t h3, int32_t w3,
+                            const float* d_f2, int32_t h2, int32_t w2, void* d_feat_bf16, void* stream) {
+    if (!d_feat_bf16) { ols_set_error("bad HR forward arguments"); return OLS_ERR_INVALID; }
+    return hr_run(plan, d_fv, d_f3, h3, w3, d_f2, h2, w2, nullptr, d_feat_bf16, stream);
+}
+
+}  // extern "C"
+
+// d_out != NULL: all 13 convolutions; d_feat != NULL: convolutions 0..11, the last one writing into the caller's buffer
+static int hr_run(const ols_hr_plan* plan, const float* d_fv, const float* d_f3, int32_t h3, int32_t w3, const float* d_f2,
+                  int32_t h2, int32_t w2, float* d_out, void* d_feat, void* stream) {
+    if (!plan || !d_fv || !d_f3 || !d_f2 || h3 <= 0 || w3 <= 0 || h2 <= 0 || w2 <= 0) {
         ols_set_error("bad HR forward arguments"); return OLS_ERR_INVALID;
     }
-    if (((uintptr_t)d_out & 15) != 0) { ols_set_error("HR output must be 16-byte aligned"); return OLS_ERR_INVALID; }
+    if ((((uintptr_t)d_out | (uintptr_t)d_feat) & 15) != 0) { ols_set_error("HR output must be 16-byte aligned"); return OLS_ERR_INVALID; }
+    const int n_conv = d_out ? OLS_HR_N_CONV : OLS_HR_N_CONV - 1;
     cudaStream_t st = (cudaStream_t)stream;
     const float* src[3] = {d_fv, d_f3, d_f2};
     const int hin[3] = {plan->S_h, h3, h2}, win[3] = {plan->S_w, w3, w2}, C[3] = {768, 384, 192};
@@ -624,6 +643,12 @@ int ols_hr_forward(const ols_hr_plan* plan, const float* d_fv, const float* d_f3
         if (c.mode == HR_MODE_F32) {
             int rc = hr_map_out(&c.tmap_out[0], d_out, true, c, 0);
             if (rc != OLS_OK) return rc;
+        }
+        if (d_feat && i == OLS_HR_N_CONV - 2) {
+            for (int cls = 0; cls < c.n_classes; cls++) {
+                int rc = hr_map_out(&c.tmap_out[cls], d_feat, false, c, cls);
+                if (rc != OLS_OK) return rc;
+            }
         }
         c.trace = trace_on ? d_trace + i * 8 : nullptr;
         cudaLaunchConfig_t cfg = {};
@@ -659,7 +684,7 @@ int ols_hr_forward(const ols_hr_plan* plan, const float* d_fv, const float* d_f3
         if (rc != OLS_OK) return rc;
         OLS_CUDA_TRY(cudaEventRecord(plan->ev_join, plan->side));
     }
-    for (int i = 0; i < OLS_HR_N_CONV; i++) {
+    for (int i = 0; i < n_conv; i++) {
         if (fork && (i == 2 || i == 7)) continue;
         bool pdl = true;
         if (fork && i == 3) { OLS_CUDA_TRY(cudaStreamWaitEvent(st, plan->ev_join, 0)); pdl = false; }
@@ -668,7 +693,7 @@ int ols_hr_forward(const ols_hr_plan* plan, const float* d_fv, const float* d_f3
     }
     OLS_CUDA_TRY(cudaGetLastError());
     ols_timing_mark(OLS_T_OTHER, st);
-    if (trace_on) {
+    if (trace_on && d_out) {
         cudaStreamSynchronize(st);
         fprintf(stderr, "[hr trace]");
         for (int i = 0; i < OLS_HR_N_CONV; i++) {
@@ -693,6 +718,8 @@ int ols_hr_forward(const ols_hr_plan* plan, const float* d_fv, const float* d_f3
     }
     return OLS_OK;
 }
+
+extern "C" {
 
 int ols_hr_read_activation(const ols_hr_plan* plan, int32_t which, float* d_out, int64_t capacity_floats, void* stream) {
     if (!plan || which < 0 || which >= OLS_HR_N_CONV - 1 || !d_out) { ols_set_error("bad activation index"); return OLS_ERR_INVALID; }

@@ -165,6 +165,27 @@ class HighResLanguageFeatureNet(nn.Module):
                                            f2[i].data_ptr(), f2.shape[2], f2.shape[3], out[i].data_ptr(), stream))
         return out.permute(0, 3, 1, 2)  # [N,768,8S,8S], channels-last storage
 
+    def features(self, fv: torch.Tensor, f3: torch.Tensor, f2: torch.Tensor) -> torch.Tensor:
+        """Everything up to (not including) ``final_conv``: ``upsample3``'s output as bfloat16 ``[N, 8S*8S, 128]``
+        (pixel-major).  Used by ``AutoencoderMLP.encode_hr``, which folds ``final_conv`` into the encoder."""
+        N.require_cuda()
+        if self.training:
+            raise RuntimeError("HighResLanguageFeatureNet: only the eval-mode inference path exists (call .eval())")
+        if not (fv.is_cuda and f3.is_cuda and f2.is_cuda):
+            raise RuntimeError("HighResLanguageFeatureNet inputs must be CUDA tensors: there is no CPU path")
+        dev = fv.device
+        n, _, S_h, S_w = fv.shape
+        fv, f3, f2 = (t.detach().float().contiguous() for t in (fv, f3, f2))
+        feat = torch.empty((n, 64 * S_h * S_w, 128), dtype=torch.bfloat16, device=dev)
+        lib = N.lib()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            self._ensure_plan(dev, S_h, S_w, stream)
+            for i in range(n):
+                N.check(lib.ols_hr_forward_features(self._plan, fv[i].data_ptr(), f3[i].data_ptr(), f3.shape[2], f3.shape[3],
+                                                    f2[i].data_ptr(), f2.shape[2], f2.shape[3], feat[i].data_ptr(), stream))
+        return feat
+
     def read_activation(self, which: int) -> torch.Tensor:
         """Debug aid: output of convolution ``which`` (0..11) of the last forward as float32 [H,W,C]."""
         if self._plan is None:

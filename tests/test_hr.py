@@ -160,3 +160,33 @@ def test_hr_weight_update_rebuilds_plan():
         net.final_conv.bias.add_(1.0)
         b = net(fv, f3, f2)
     assert torch.allclose(b, a + 1.0, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_hr_fused_encode():
+    """AutoencoderMLP.encode_hr (final_conv folded into the encoder's first Linear, bf16 features fed straight to the
+    autoencoder kernel) against the unfused product path and against the fp32 oracle chain."""
+    from online_lang_splatting_b200 import autoencoder as AE
+    dev = torch.device("cuda:0")
+    sd, net = _build(77, dev)
+    g = torch.Generator().manual_seed(3)
+    fv = torch.randn(1, 768, 24, 24, generator=g)
+    f3 = torch.randn(1, 384, 96, 96, generator=g)
+    f2 = torch.randn(1, 192, 192, 192, generator=g)
+    torch.manual_seed(0)
+    ae = AE.AutoencoderMLP([384, 192, 96, 48, 24, 15], [24, 48, 96, 192, 384, 384, 768]).eval().to(dev)
+    with torch.no_grad():
+        fused = ae.encode_hr(net, fv.to(dev), f3.to(dev), f2.to(dev))
+        unfused = ae.encode(net(fv.to(dev), f3.to(dev), f2.to(dev)).permute(0, 2, 3, 1).view(-1, 768))
+        ref = AE.reference_chain(list(ae.encoder), hr_oracle.hr_forward(sd, fv, f3, f2).to(dev).permute(0, 2, 3, 1).reshape(-1, 768))
+    assert fused.shape == (192 * 192, 15)
+    assert torch.allclose(fused.norm(dim=-1), torch.ones_like(fused[:, 0]), atol=1e-4)
+    cos_u = (fused * unfused).sum(-1)
+    cos_r = (fused * ref).sum(-1)
+    assert cos_u.min().item() > 0.999 and cos_r.min().item() > 0.995, (cos_u.min().item(), cos_r.min().item())
+    # the wrapper class the reference loads from a checkpoint works the same way
+    wrap = SN.LangSupervisedNet()
+    wrap.model = net
+    with torch.no_grad():
+        again = ae.encode_hr(wrap, fv.to(dev), f3.to(dev), f2.to(dev))
+    assert torch.equal(again, fused)

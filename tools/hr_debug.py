@@ -33,3 +33,18 @@ print("HR forward 24x24 -> 192x192x768: %.3f ms" % (e0.elapsed_time(e1) / 20))
 if os.environ.get("OLS_HR_TRACE"):
     with torch.no_grad():
         net(fv, f3, f2)
+# fused HR -> AE encode timing
+from online_lang_splatting_b200 import autoencoder as AE
+torch.manual_seed(0)
+ae = AE.AutoencoderMLP([384, 192, 96, 48, 24, 15], [24, 48, 96, 192, 384, 384, 768]).eval().to(dev)
+def timeit(fn, n=20):
+    with torch.no_grad():
+        for _ in range(3): fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n): fn()
+        e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+print("HR + AE encode, unfused: %.3f ms   fused (final_conv folded into the encoder): %.3f ms" % (
+    timeit(lambda: ae.encode(net(fv, f3, f2).permute(0, 2, 3, 1).view(-1, 768))), timeit(lambda: ae.encode_hr(net, fv, f3, f2))))

@@ -638,6 +638,7 @@ def hr_module_timing(dev, iters=20):
     192x192x768, random weights, timed alone with CUDA events OUTSIDE the benchmark's timed region (the headline
     metric is quoted on random CLIP maps, i.e. without this stage).  Tensor roofline: 104.9 GFLOP per frame against
     the measured dense bf16 peak."""
+    import torch
     from online_lang_splatting_b200 import supervised_net as SN
     torch.manual_seed(11)
     net = SN.HighResLanguageFeatureNet().eval().to(dev)

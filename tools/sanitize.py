@@ -36,5 +36,21 @@ t.backward()
 sc = U.make_scene(P=3000, F=3, W=60, H=45, seed=4, scale=0.6)
 sc["means3D"][:1200, 2] = 2.0
 o = U.run_ours(sc, dev, tile=15)
+# HR up-sampler (TMA loads / stores, clusters with DSMEM split-K, PDL, side stream), fused HR -> AE encode, SSIM, densification
+from online_lang_splatting_b200 import supervised_net as SN, densification as DN
+torch.manual_seed(1)
+hr = SN.HighResLanguageFeatureNet().eval().to(dev)
+fv, f3, f2 = torch.randn(1, 768, 16, 24, device=dev), torch.randn(1, 384, 37, 50, device=dev), torch.randn(1, 192, 70, 111, device=dev)
+with torch.no_grad():
+    hm = hr(fv, f3, f2)
+    code = ae.encode_hr(hr, fv, f3, f2)
+im2 = torch.rand(3, 45, 61, device=dev, requires_grad=True)
+LS.color_refinement_loss(im2, torch.rand(3, 45, 61, device=dev)).backward()
+P = 1237
+radii = torch.randint(0, 30, (P,), device=dev, dtype=torch.int32)
+mr, acc, den = torch.zeros(P, device=dev), torch.zeros(P, 1, device=dev), torch.zeros(P, 1, device=dev)
+DN.update_stats(radii, torch.randn(P, 3, device=dev), mr, acc, den)
+fl, cnt = DN.densify_flags(acc, den, torch.randn(P, 3, device=dev), torch.randn(P, 1, device=dev), mr, max_grad=0.5,
+                           min_opacity=0.3, extent=4.0, max_screen_size=20.0)
 torch.cuda.synchronize()
-print("sanitize pass done", float(l), tuple(y.shape))
+print("sanitize pass done", float(l), tuple(y.shape), tuple(hm.shape), tuple(code.shape), cnt.tolist())

@@ -33,7 +33,6 @@ namespace ols {
 constexpr int HR_THREADS = 192;
 constexpr int HR_BOX_W = 8, HR_BOX_H = 16;  // 128 pixels = one UMMA M tile
 constexpr int HR_MAX_TAPS = 9;
-constexpr int HR_TMEM_COLS = 256;
 constexpr int HR_A_BYTES = 128 * 128;       // one A slab: 128 pixels x 64 bf16
 
 enum { HR_MODE_BF16 = 0, HR_MODE_GATE = 1, HR_MODE_F32 = 2 };

@@ -77,6 +77,23 @@ def test_transposed_conv_parity_classes():
     assert torch.allclose(out, ref, atol=1e-5)
 
 
+def test_batchnorm_folding_matches_torch():
+    """Host-side folding (supervised_net._fold_bn) of eval-mode BatchNorm into Conv2d / ConvTranspose2d weights."""
+    import torch.nn as nn
+    torch.manual_seed(4)
+    for conv in (nn.Conv2d(6, 10, 3, padding=1), nn.ConvTranspose2d(6, 10, 4, stride=2, padding=1)):
+        bn = nn.BatchNorm2d(10).eval()
+        with torch.no_grad():
+            bn.running_mean.normal_(0, 0.3); bn.running_var.uniform_(0.5, 1.5); bn.weight.uniform_(0.7, 1.3); bn.bias.normal_(0, 0.2)
+        x = torch.randn(2, 6, 9, 7)
+        w, b = SN._fold_bn(conv, bn)
+        with torch.no_grad():
+            ref = bn(conv(x))
+            got = (torch.nn.functional.conv_transpose2d(x, w, b, stride=2, padding=1) if isinstance(conv, nn.ConvTranspose2d)
+                   else torch.nn.functional.conv2d(x, w, b, padding=1))
+        assert torch.allclose(got, ref, atol=1e-5)
+
+
 def test_rejects_training_and_cpu():
     net = SN.HighResLanguageFeatureNet()
     fv, f3, f2 = make_inputs(0, 16, 16)

@@ -81,6 +81,12 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
 __device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, float c, float d) {
     asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// Cluster barrier, used twice per thread in a split-K kernel:
+//   #1 "everybody has started": arrive right after the prologue, wait just before the exchange -- distributed shared
+//      memory of a CTA may only be written once that CTA is running (co-scheduling alone does not say it has begun);
+//   #2 "partials have landed": arrive.release after the remote stores / wait.acquire before rank 0 reads them.
+__device__ __forceinline__ void cluster_arrive_started() { asm volatile("barrier.cluster.arrive.relaxed;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_started() { asm volatile("barrier.cluster.wait;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_relacq() {
     asm volatile("barrier.cluster.arrive.release;\nbarrier.cluster.wait.acquire;" ::: "memory");
 }
@@ -120,6 +126,7 @@ __global__ void __launch_bounds__(HR_THREADS, 1) k_hr_conv(const __grid_constant
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_launch_dependents();  // the next layer may start its prologue; it blocks in pdl_wait() until this grid is done
+    if (p.split > 1) cluster_arrive_started();
 
     // split-K: the cluster's CTAs take consecutive ranges of the (tap, source, slab) steps of the same tile
     const uint32_t rank = p.split > 1 ? cluster_ctarank() : 0u;
@@ -155,7 +162,7 @@ __global__ void __launch_bounds__(HR_THREADS, 1) k_hr_conv(const __grid_constant
                 if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
             }
         }
-        if (p.split > 1) cluster_sync_relacq();
+        if (p.split > 1) { cluster_wait_started(); cluster_sync_relacq(); }
     } else if (warp == 1) {
         int stage = 0;
         uint32_t phase = 0;
@@ -176,7 +183,7 @@ __global__ void __launch_bounds__(HR_THREADS, 1) k_hr_conv(const __grid_constant
         }
         if (lane == 0) umma_commit(mma_done);
         __syncwarp();
-        if (p.split > 1) cluster_sync_relacq();
+        if (p.split > 1) { cluster_wait_started(); cluster_sync_relacq(); }
     } else {
         // epilogue: thread = one pixel of the patch = one TMEM lane
         const int quad = warp & 3;
@@ -187,6 +194,7 @@ __global__ void __launch_bounds__(HR_THREADS, 1) k_hr_conv(const __grid_constant
         tcgen05_fence_after();
         if (rank != 0) {
             // ship the partial accumulator into rank 0's shared memory, then meet at the cluster barrier
+            cluster_wait_started();
             const uint32_t remote = map_to_rank(smem_u32(part_smem), 0) + (rank - 1) * (uint32_t)p.bn * 512u;
             for (int c = 0; c < p.bn; c += 32) {
                 uint32_t r[32];
@@ -200,7 +208,7 @@ __global__ void __launch_bounds__(HR_THREADS, 1) k_hr_conv(const __grid_constant
             }
             cluster_sync_relacq();
         } else {
-        if (p.split > 1) cluster_sync_relacq();  // the other ranks' partials have landed in part_smem
+        if (p.split > 1) { cluster_wait_started(); cluster_sync_relacq(); }  // the other ranks' partials have landed in part_smem
         if (p.mode == HR_MODE_GATE) mbar_wait(gate_full, 0);
         if (tracer) p.trace[2] = gtimer();
         for (int c = 0; c < p.bn; c += 32) {

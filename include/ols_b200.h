@@ -356,7 +356,10 @@ int ols_ae_forward_bf16(const ols_ae_plan* plan, const void* d_x_bf16, float* d_
  *   6 upsample2.0           ConvT  512->256 4/2/1
  * Weights are float32 in torch layout (Conv2d [Cout,Cin,kh,kw], ConvTranspose2d [Cin,Cout,4,4]) with the
  * eval-mode BatchNorm that follows a convolution already folded in by the caller (as for the autoencoder).
- * The plan owns bf16 re-laid-out weights and the bf16 NHWC activations between the layers.
+ * The plan owns bf16 re-laid-out weights, the bf16 NHWC activations between the layers, and a side stream on which the
+ * two low_res_align convolutions run next to layers 0-1 (forked from / joined to the caller's stream with events, so
+ * the call is still ordered on `stream` and can be captured into a CUDA graph).  A plan is not re-entrant: calls that
+ * use the same plan must be ordered on one stream; use one plan per concurrent stream.
  * ------------------------------------------------------------------------------------------- */
 #define OLS_HR_N_CONV 13
 typedef struct ols_hr_weights {

@@ -6,6 +6,8 @@ Mirrors what a mapping iteration of the reference computes per view right after 
     loss = get_loss_mapping(config, image, depth, viewpoint, opacity)          # alpha * l1_rgb + (1 - alpha) * l1_depth
          + lamda_lang * l1_loss(language, F.interpolate(gt_lang_feat[None], (H, W), mode="bilinear")[0])
 
+(the colour-only sub-forms ``get_loss_tracking_rgb`` / ``get_loss_mapping_rgb`` of utils/slam_utils.py:96-105,128-137 are the
+same kernels with ``alpha = 1.0``)
 but keeps the low-resolution language target on the device (the reference copies the up-sampled
 15 x H x W map over PCIe every iteration) and produces the three image-space gradients directly.
 There is no torch fallback: without the CUDA library the call raises.

@@ -207,3 +207,30 @@ def test_hr_fused_encode():
     with torch.no_grad():
         again = ae.encode_hr(wrap, fv.to(dev), f3.to(dev), f2.to(dev))
     assert torch.equal(again, fused)
+
+
+@pytest.mark.gpu
+def test_hr_cuda_graph_capture():
+    """The whole HR forward (16 launches, side stream fork/join, programmatic dependent launch, cluster launches) can be
+    captured into a CUDA graph by the caller and replays to the same bits."""
+    dev = torch.device("cuda:0")
+    sd, net = _build(5, dev)
+    fv, f3, f2 = (t.to(dev) for t in make_inputs(1, 16, 24))
+    with torch.no_grad():
+        eager = net(fv, f3, f2).clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            net(fv, f3, f2)  # warm-up on the capture stream
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = net(fv, f3, f2)
+        out.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, eager)
+        fv.mul_(0.5)  # new input, same buffers
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, net(fv, f3, f2))

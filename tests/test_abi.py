@@ -89,3 +89,25 @@ def test_no_cpu_fallback():
     with pytest.raises(RuntimeError):
         r(means3D=x, means2D=x, opacities=torch.zeros(4, 1), shs=torch.zeros(4, 1, 3), scales=x,
           rotations=torch.zeros(4, 4), language_precomp=torch.zeros(4, 15))
+
+
+def test_header_is_plain_c_and_struct_sizes_match_ctypes(tmp_path):
+    """include/ols_b200.h compiles as C99 (it is the drop-in boundary for non-C++ hosts) and every ctypes mirror in
+    _native.py has exactly the size the C compiler gives the struct."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    pairs = [("ols_raster_args", N.RasterArgs), ("ols_fwd_out", N.FwdOut), ("ols_fwd_info", N.FwdInfo), ("ols_bwd_args", N.BwdArgs),
+             ("ols_dis_args", N.DisArgs), ("ols_dis_fwd_out", N.DisFwdOut), ("ols_dis_bwd_args", N.DisBwdArgs),
+             ("ols_loss_args", N.LossArgs), ("ols_adam_group", N.AdamGroup), ("ols_ws_view", N.WsView), ("ols_host_out", N.HostOut),
+             ("ols_ae_chain", N.AEChain), ("ols_hr_weights", N.HRWeights), ("ols_ssim_args", N.SsimArgs),
+             ("ols_densify_params", N.DensifyParams)]
+    src = tmp_path / "sizes.c"
+    body = "\n".join('    printf("%s %%zu\\n", sizeof(%s));' % (c, c) for c, _ in pairs)
+    src.write_text('#include <stdio.h>\n#include "ols_b200.h"\nint main(void) {\n%s\n    return 0;\n}\n' % body)
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, ctype in pairs:
+        assert int(out[cname]) == C.sizeof(ctype), (cname, out[cname], C.sizeof(ctype))

@@ -125,6 +125,7 @@ def cpu_frame_seconds(args, keyframes: int = 1):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _util as U
     from oracle import oracle as O
+    from oracle import torch_oracle as TO
     cores = O.num_threads()
     torch.set_num_threads(max(cores, 1))
     sc = U.make_scene(P=args.gaussians, F=15, W=args.width, H=args.height, seed=0, scale=0.01)
@@ -135,7 +136,7 @@ def cpu_frame_seconds(args, keyframes: int = 1):
     t0 = time.perf_counter()
     for _ in range(keyframes):
         with torch.no_grad():
-            AE.reference_chain(list(ae.encoder), x)
+            TO.reference_chain(list(ae.encoder), x)
         U.run_oracle(sc, tile=args.tile, grads=grads, compat=(args.backward_mode == "compat"))
     dt = (time.perf_counter() - t0) / keyframes
     return dt, cores

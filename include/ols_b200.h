@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define OLS_ABI_VERSION 1
+#define OLS_ABI_VERSION 2
 
 typedef enum ols_status {
     OLS_OK = 0,
@@ -127,7 +127,10 @@ typedef struct ols_bwd_args {
     float* d_dL_dsh;         /* [P,M,3] or NULL when M == 0                                            */
     float* d_dL_dscales;     /* [P,3]                                                                  */
     float* d_dL_drotations;  /* [P,4]                                                                  */
-    float* d_dL_dtau;        /* [P,6]  per-Gaussian pose gradient (rho | theta); caller sums over P      */
+    float* d_dL_dtau;        /* [P,6]  per-Gaussian pose gradient (rho | theta) as the reference returns it
+                                (rasterize_points.cu:452); may be NULL when d_dL_dtau_sum is given        */
+    float* d_dL_dtau_sum;    /* [6]    the same summed over the Gaussians -- what the reference's Python computes
+                                right after the call (diff_gaussian_rasterization/__init__.py:383-385) -- or NULL */
 } ols_bwd_args;
 
 int ols_abi_version(void);
@@ -149,6 +152,26 @@ int ols_lang_read_info(const void* d_workspace, ols_fwd_info* h_info, void* stre
 
 /* replaces _C.rasterize_language_gaussians_backward (ext.cpp:19). */
 int ols_lang_backward(const ols_raster_args* args, const ols_bwd_args* grads, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-view batch: V views of the SAME Gaussians in one set of launches (grid.y = view).  This is the loop over the
+ * window keyframes of a mapping iteration (utils/slam_backend.py:510-662 calls render() 8-12 times on the same
+ * Gaussians, sums the losses and back-propagates once), and the loop over rendered views of any evaluation pass.
+ * views[0..V) must agree in P, F, M, sh_degree, W, H, tile, flags, scale_modifier, R_cap and in every Gaussian
+ * parameter pointer; viewmatrix / projmatrix / projmatrix_raw / campos / tanfov / bg / workspace are per view
+ * (V <= OLS_MAX_BATCH_VIEWS, one workspace of ols_lang_workspace_size() bytes per view).  Each Gaussian is read and
+ * its 3D covariance computed once for all views; the view-independent covariances are kept in views[0]'s workspace.
+ * Backward: grads[v] holds view v's image-space gradients, radii, d_dL_dmeans2D and d_dL_dtau / d_dL_dtau_sum; the
+ * parameter gradients (means3D, colors, language, opacity, cov3D, sh, scales, rotations) are taken from grads[0]
+ * and receive the SUM over the views -- what autograd accumulates across the reference's V render() calls.
+ * ols_lang_forward / ols_lang_backward are the V = 1 case of the same kernels.
+ * ------------------------------------------------------------------------------------------- */
+#define OLS_MAX_BATCH_VIEWS 16
+int ols_lang_forward_batch(const ols_raster_args* views, const ols_fwd_out* outs, int32_t V, void* stream);
+int ols_lang_backward_batch(const ols_raster_args* views, const ols_bwd_args* grads, int32_t V, void* stream);
+/* asynchronous copy of the V info headers into h_info[V] (pinned host memory for a truly asynchronous copy); the
+ * caller orders its read with an event / stream synchronisation of its own */
+int ols_lang_read_info_async(const ols_raster_args* views, int32_t V, ols_fwd_info* h_info, void* stream);
 
 /* replaces _C.mark_visible (ext.cpp:20; checkFrustum, rasterizer_impl.cu:54-66): present[i] = view.z > 0.2 */
 int ols_mark_visible(int32_t P, const float* d_means3D, const float* d_viewmatrix, const float* d_projmatrix,
@@ -273,6 +296,10 @@ typedef struct ols_loss_args {
     /* tracking form, get_loss_tracking_rgbd (utils/slam_utils.py:96-118); both NULL for the mapping form */
     const float* d_opacity;    /* [1,H,W] render()["opacity"]: weights the colour residual, gates depth at > 0.95 */
     const float* d_grad_mask;  /* [1,H,W] viewpoint.grad_mask (0/1 floats) or NULL                     */
+    /* device-resident exposure parameters (viewpoint.exposure_a / _b are nn.Parameters, utils/camera_utils.py:59-64):
+     * when non-NULL they replace the two floats above, so the caller never reads them back to the host */
+    const float* d_exposure_a; /* [1] or NULL                                                          */
+    const float* d_exposure_b; /* [1] or NULL                                                          */
 } ols_loss_args;
 /* d_out6 = [l1_rgb, l1_depth, l1_lang, dloss/dexposure_a, dloss/dexposure_b, loss]; d_scratch8: 8 floats */
 int ols_mapping_loss_forward(const ols_loss_args* args, float* d_out6, float* d_scratch8, void* stream);

@@ -22,6 +22,7 @@ FLAG_BWD_EXACT = 1 << 3
 FLAG_BWD_ACCUMULATE = 1 << 4
 TIMING_TAGS = ("preprocess", "binning", "sort", "blend_fwd", "blend_bwd", "geometry_bwd", "ae", "other")
 AE_MAX_LAYERS = 8
+MAX_BATCH_VIEWS = 16
 
 # every symbol include/ols_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = (
@@ -33,6 +34,7 @@ EXPORTED_SYMBOLS = (
     "ols_hr_plan_create", "ols_hr_plan_destroy", "ols_hr_forward", "ols_hr_read_activation",
     "ols_ssim_loss_forward", "ols_ssim_loss_backward", "ols_densify_stats", "ols_densify_flags",
     "ols_ae_forward_bf16", "ols_hr_forward_features",
+    "ols_lang_forward_batch", "ols_lang_backward_batch", "ols_lang_read_info_async",
 )
 
 
@@ -59,7 +61,7 @@ class BwdArgs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("d_dL_dout_color", "d_dL_dout_language", "d_dL_dout_depth", "d_radii",
                                           "d_dL_dmeans2D", "d_dL_dcolors", "d_dL_dlanguage", "d_dL_dopacity",
                                           "d_dL_dmeans3D", "d_dL_dcov3D", "d_dL_dsh", "d_dL_dscales",
-                                          "d_dL_drotations", "d_dL_dtau")]
+                                          "d_dL_drotations", "d_dL_dtau", "d_dL_dtau_sum")]
 
 
 class DisArgs(C.Structure):
@@ -87,7 +89,7 @@ class LossArgs(C.Structure):
                 ("alpha", C.c_float), ("rgb_boundary_threshold", C.c_float), ("exposure_a", C.c_float),
                 ("exposure_b", C.c_float), ("lambda_lang", C.c_float)] + \
                [(n, C.c_void_p) for n in ("d_image", "d_depth", "d_language", "d_gt_image", "d_gt_depth", "d_gt_lang",
-                                          "d_opacity", "d_grad_mask")]
+                                          "d_opacity", "d_grad_mask", "d_exposure_a", "d_exposure_b")]
 
 
 class AdamGroup(C.Structure):
@@ -151,6 +153,9 @@ def lib() -> C.CDLL:
     L.ols_lang_forward.argtypes = [C.POINTER(RasterArgs), C.POINTER(FwdOut), C.c_void_p]
     L.ols_lang_read_info.argtypes = [C.c_void_p, C.POINTER(FwdInfo), C.c_void_p]
     L.ols_lang_backward.argtypes = [C.POINTER(RasterArgs), C.POINTER(BwdArgs), C.c_void_p]
+    L.ols_lang_forward_batch.argtypes = [C.POINTER(RasterArgs), C.POINTER(FwdOut), C.c_int32, C.c_void_p]
+    L.ols_lang_backward_batch.argtypes = [C.POINTER(RasterArgs), C.POINTER(BwdArgs), C.c_int32, C.c_void_p]
+    L.ols_lang_read_info_async.argtypes = [C.POINTER(RasterArgs), C.c_int32, C.c_void_p, C.c_void_p]
     L.ols_mark_visible.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.ols_lang_workspace_view.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
                                           C.c_void_p, C.POINTER(WsView)]

@@ -205,10 +205,3 @@ class EncoderDecoderOnline(nn.Module, _ChainMixin):
 
     def forward(self, x):
         return self.decode(self.encode(x))
-
-
-def reference_chain(modules: Sequence[nn.Module], x: torch.Tensor) -> torch.Tensor:
-    """The reference's arithmetic in plain torch (used by tests and the CPU baseline only)."""
-    for m in modules:
-        x = m(x)
-    return x / x.norm(dim=-1, keepdim=True)

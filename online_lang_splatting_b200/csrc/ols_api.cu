@@ -106,16 +106,55 @@ size_t ols_lang_workspace_size(int32_t P, int32_t F, int32_t W, int32_t H, int32
     return ws_layout(P, F, W, H, tile, R_cap).total;
 }
 
-int ols_lang_forward(const ols_raster_args* a, const ols_fwd_out* o, void* stream) {
-    WsLayout L;
-    int rc = validate(a, &L);
-    if (rc != OLS_OK) return rc;
-    if (!o || !o->d_color || !o->d_language || !o->d_depth || !o->d_opacity || !o->d_radii || !o->d_n_touched) {
-        ols_set_error("null output pointer");
-        return OLS_ERR_INVALID;
+// the views of a batch share everything but the camera, the background, the outputs and the workspace
+static int validate_batch(const ols_raster_args* views, int V, WsLayout* L) {
+    if (!views || V < 1 || V > OLS_MAX_BATCH_VIEWS) { ols_set_error("bad view count %d (1..%d)", V, OLS_MAX_BATCH_VIEWS); return OLS_ERR_INVALID; }
+    static_assert(OLS_MAX_BATCH_VIEWS == OLS_MAX_VIEWS, "header / kernel batch limits");
+    for (int v = 0; v < V; v++) {
+        WsLayout Lv;
+        int rc = validate(&views[v], &Lv);
+        if (rc != OLS_OK) return rc;
+        if (v == 0) { *L = Lv; continue; }
+        const ols_raster_args &a = views[0], &b = views[v];
+        if (a.P != b.P || a.F != b.F || a.sh_degree != b.sh_degree || a.M != b.M || a.W != b.W || a.H != b.H || a.tile != b.tile ||
+            a.flags != b.flags || a.scale_modifier != b.scale_modifier || a.R_cap != b.R_cap || a.d_means3D != b.d_means3D ||
+            a.d_shs != b.d_shs || a.d_colors_precomp != b.d_colors_precomp || a.d_language != b.d_language ||
+            a.d_opacities != b.d_opacities || a.d_scales != b.d_scales || a.d_rotations != b.d_rotations ||
+            a.d_cov3D_precomp != b.d_cov3D_precomp) {
+            ols_set_error("view %d of the batch differs from view 0 in a size, a flag, R_cap or a Gaussian parameter pointer", v);
+            return OLS_ERR_INVALID;
+        }
+        if (a.d_workspace == b.d_workspace) { ols_set_error("view %d shares its workspace with view 0", v); return OLS_ERR_INVALID; }
     }
-    if (a->P == 0) { ols_set_error("P == 0: nothing to render (reference returns None)"); return OLS_ERR_INVALID; }
-    return ols_launch_forward(a, o, L, (cudaStream_t)stream);
+    return OLS_OK;
+}
+
+int ols_lang_forward_batch(const ols_raster_args* views, const ols_fwd_out* outs, int32_t V, void* stream) {
+    WsLayout L;
+    int rc = validate_batch(views, V, &L);
+    if (rc != OLS_OK) return rc;
+    for (int v = 0; v < V; v++) {
+        const ols_fwd_out* o = outs ? &outs[v] : nullptr;
+        if (!o || !o->d_color || !o->d_language || !o->d_depth || !o->d_opacity || !o->d_radii || !o->d_n_touched) {
+            ols_set_error("null output pointer");
+            return OLS_ERR_INVALID;
+        }
+    }
+    if (views[0].P == 0) { ols_set_error("P == 0: nothing to render (reference returns None)"); return OLS_ERR_INVALID; }
+    return ols_launch_forward(views, outs, V, L, (cudaStream_t)stream);
+}
+
+int ols_lang_forward(const ols_raster_args* a, const ols_fwd_out* o, void* stream) {
+    return ols_lang_forward_batch(a, o, 1, stream);
+}
+
+int ols_lang_read_info_async(const ols_raster_args* views, int32_t V, ols_fwd_info* h_info, void* stream) {
+    if (!views || !h_info || V < 1 || V > OLS_MAX_BATCH_VIEWS) { ols_set_error("bad arguments"); return OLS_ERR_INVALID; }
+    for (int v = 0; v < V; v++) {
+        if (!views[v].d_workspace) { ols_set_error("null workspace"); return OLS_ERR_INVALID; }
+        OLS_CUDA_TRY(cudaMemcpyAsync(&h_info[v], views[v].d_workspace, sizeof(ols_fwd_info), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    }
+    return OLS_OK;
 }
 
 int ols_lang_read_info(const void* d_workspace, ols_fwd_info* h_info, void* stream) {
@@ -126,19 +165,33 @@ int ols_lang_read_info(const void* d_workspace, ols_fwd_info* h_info, void* stre
     return OLS_OK;
 }
 
-int ols_lang_backward(const ols_raster_args* a, const ols_bwd_args* g, void* stream) {
+int ols_lang_backward_batch(const ols_raster_args* views, const ols_bwd_args* grads, int32_t V, void* stream) {
     WsLayout L;
-    int rc = validate(a, &L);
+    int rc = validate_batch(views, V, &L);
     if (rc != OLS_OK) return rc;
-    if (!g || !g->d_dL_dout_color || !g->d_dL_dout_language || !g->d_dL_dout_depth || !g->d_radii ||
-        !g->d_dL_dmeans2D || !g->d_dL_dcolors || !g->d_dL_dlanguage || !g->d_dL_dopacity || !g->d_dL_dmeans3D ||
-        !g->d_dL_dcov3D || !g->d_dL_dscales || !g->d_dL_drotations || !g->d_dL_dtau) {
+    if (!grads) { ols_set_error("null gradient pointer"); return OLS_ERR_INVALID; }
+    const ols_raster_args* a = &views[0];
+    const ols_bwd_args* g = &grads[0];
+    if (!g->d_dL_dcolors || !g->d_dL_dlanguage || !g->d_dL_dopacity || !g->d_dL_dmeans3D || !g->d_dL_dcov3D ||
+        !g->d_dL_dscales || !g->d_dL_drotations) {
         ols_set_error("null gradient pointer");
         return OLS_ERR_INVALID;
     }
+    for (int v = 0; v < V; v++) {
+        const ols_bwd_args* q = &grads[v];
+        if (!q->d_dL_dout_color || !q->d_dL_dout_language || !q->d_dL_dout_depth || !q->d_radii || !q->d_dL_dmeans2D ||
+            (!q->d_dL_dtau && !q->d_dL_dtau_sum)) {
+            ols_set_error("null per-view gradient pointer (view %d)", v);
+            return OLS_ERR_INVALID;
+        }
+        if (!views[v].d_projmatrix_raw) { ols_set_error("projmatrix_raw is required by backward"); return OLS_ERR_INVALID; }
+    }
     if (a->M > 0 && a->d_shs && !g->d_dL_dsh) { ols_set_error("d_dL_dsh is null but SHs were given"); return OLS_ERR_INVALID; }
-    if (!a->d_projmatrix_raw) { ols_set_error("projmatrix_raw is required by backward"); return OLS_ERR_INVALID; }
-    return ols_launch_backward(a, g, L, (cudaStream_t)stream);
+    return ols_launch_backward(views, grads, V, L, (cudaStream_t)stream);
+}
+
+int ols_lang_backward(const ols_raster_args* a, const ols_bwd_args* g, void* stream) {
+    return ols_lang_backward_batch(a, g, 1, stream);
 }
 
 int ols_timing_begin(int32_t max_marks) {

@@ -31,12 +31,10 @@ __host__ __device__ constexpr int grad_floats(int F) { return ((10 + F) + 3) / 4
 //                         6 ddepth | 7..9 dcolor | 10.. dlanguage[F]
 constexpr int GR_MX = 0, GR_MY = 1, GR_CX = 2, GR_CY = 3, GR_CW = 4, GR_OP = 5, GR_DEPTH = 6, GR_RGB = 7, GR_LANG = 10;
 
-struct BwdBlendArgs {
-    int W, H, gx;
+struct BwdView {  // one view of a batch (blockIdx.y)
     const uint2* ranges;
     const uint32_t* point_list;
     const float* records;
-    const float* language;   // [P,F] caller's language rows (joint pass), else unused
     const float* bg;
     const DeviceInfo* info;
     const float* final_T;
@@ -46,9 +44,15 @@ struct BwdBlendArgs {
     const float* dL_ddepth;
     const uint8_t* warp_hits;  // [R] from the forward: which pixel blocks of the tile blended each list entry
     float* gacc;             // [P, grad_floats(F)] zero-initialised
+};
+struct BwdBlendArgs {
+    int W, H, gx;
+    int fast_exp;            // the forward blended with ex2.approx (no OLS_FLAG_BITEXACT_BLEND): use the same alpha here
+    const float* language;   // [P,F] caller's language rows (joint pass), else unused
     uint32_t lane_ok[8];     // Q3 lane mask (compat); all ones otherwise
     uint8_t packed_rank[128];  // packed compat variant: reference thread rank handled by thread t (255 = none)
     uint8_t packed_fmask[4];   // packed variant: forward 8x4 pixel blocks (bit w) that contain a pixel of packed warp k
+    BwdView v[OLS_MAX_VIEWS];
 };
 
 typedef unsigned long long f32x2;  // two floats in one 64-bit register pair
@@ -56,6 +60,11 @@ __device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
     f32x2 r;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
+}
+__device__ __forceinline__ float fast_exp2(float x) {  // same instruction sequence as the forward's fast_exp
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
 }
 __device__ __forceinline__ float hsum2(f32x2 v) {
     float lo, hi;
@@ -120,7 +129,8 @@ __device__ __forceinline__ int multi_reduce_owner(int lane) {
 // dead lanes through every step.  Its warps are 15-pixel-wide strips, so the forward's per-8x4-block hit bits do
 // not apply; a warp decides by a vote after evaluating an entry.
 template <int TILE, int NCOL, int F, bool COMPAT, bool PACKED>
-__global__ void __launch_bounds__(PACKED ? 128 : BWD_THREADS, PACKED ? 8 : 4) k_blend_bwd(const BwdBlendArgs a) {
+__global__ void __launch_bounds__(PACKED ? 128 : BWD_THREADS, PACKED ? 8 : 4) k_blend_bwd(const __grid_constant__ BwdBlendArgs a) {
+    const BwdView& vw = a.v[blockIdx.y];
     static_assert(TILE <= 16 && BWD_BATCH == 32, "8 warps of 8x4 pixels; one ballot per batch");
     static_assert(!PACKED || COMPAT, "packing follows the compat lane mask");
     constexpr int NT = PACKED ? 128 : BWD_THREADS;
@@ -156,17 +166,17 @@ __global__ void __launch_bounds__(PACKED ? 128 : BWD_THREADS, PACKED ? 8 : 4) k_
     const size_t HW = (size_t)a.W * a.H;
     const size_t pix = inside ? (size_t)pyi * a.W + pxi : 0;
 
-    uint2 rg = a.ranges[blockIdx.x];
-    if (a.info->overflow) rg = make_uint2(0u, 0u);
+    uint2 rg = vw.ranges[blockIdx.x];
+    if (vw.info->overflow) rg = make_uint2(0u, 0u);
     // the list is walked as far as ANY pixel of the tile got (also the pixels the packed variant does not carry:
     // the reference's block visits those entries and advances the language recurrence of every pixel, Q2)
-    uint32_t last_contributor = inside ? a.n_contrib[pix] : 0u;
+    uint32_t last_contributor = inside ? vw.n_contrib[pix] : 0u;
     uint32_t warp_maxc = __reduce_max_sync(0xffffffffu, last_contributor);
     if (PACKED) {
         uint32_t other = 0;
         for (int r = tid; r < TILE * TILE; r += NT) {
             const int ox = tile_x * TILE + r % TILE, oy = tile_y * TILE + r / TILE;
-            if (ox < a.W && oy < a.H) other = max(other, a.n_contrib[(size_t)oy * a.W + ox]);
+            if (ox < a.W && oy < a.H) other = max(other, vw.n_contrib[(size_t)oy * a.W + ox]);
         }
         warp_maxc = max(warp_maxc, __reduce_max_sync(0xffffffffu, other));
     }
@@ -179,7 +189,7 @@ __global__ void __launch_bounds__(PACKED ? 128 : BWD_THREADS, PACKED ? 8 : 4) k_
     const int total = min((int)s_maxc, (int)(rg.y - rg.x));
     if (total == 0) return;
 
-    const float T_final = inside ? a.final_T[pix] : 0.0f;
+    const float T_final = inside ? vw.final_T[pix] : 0.0f;
     float T = T_final;
     float g[NCH > 0 ? NCH + 1 : 1];  // dL/dpixel per channel (+1: the zero partner of an odd last channel)
     float gd = 0.0f;
@@ -187,16 +197,16 @@ __global__ void __launch_bounds__(PACKED ? 128 : BWD_THREADS, PACKED ? 8 : 4) k_
     for (int c = 0; c < NCH + 1; c++) g[c] = 0.0f;
     if (inside) {
 #pragma unroll
-        for (int c = 0; c < NCOL; c++) g[c] = a.dL_dcolor[c * HW + pix];
+        for (int c = 0; c < NCOL; c++) g[c] = vw.dL_dcolor[c * HW + pix];
 #pragma unroll
-        for (int c = 0; c < F; c++) g[NCOL + c] = a.dL_dlanguage[c * HW + pix];
-        if (NCOL) gd = a.dL_ddepth[pix];
+        for (int c = 0; c < F; c++) g[NCOL + c] = vw.dL_dlanguage[c * HW + pix];
+        if (NCOL) gd = vw.dL_ddepth[pix];
     }
     f32x2 g2[NPAIR > LP0 ? NPAIR - LP0 : 1];  // language-only pairs of g, packed for FFMA2
 #pragma unroll
     for (int p = LP0; p < NPAIR; p++) asm("mov.b64 %0, {%1, %2};" : "=l"(g2[p - LP0]) : "f"(g[2 * p]), "f"(g[2 * p + 1]));
     float bg_dot = 0.0f;
-    if (NCOL) bg_dot = a.bg[0] * g[0] + a.bg[1] * g[1] + a.bg[2] * g[2];
+    if (NCOL) bg_dot = vw.bg[0] * g[0] + vw.bg[1] * g[1] + vw.bg[2] * g[2];
     const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
     // Q3: the lane mask is indexed by the reference's thread rank ly * TILE + lx
     const int ref_rank = ly * TILE + lx;
@@ -234,14 +244,14 @@ __global__ void __launch_bounds__(PACKED ? 128 : BWD_THREADS, PACKED ? 8 : 4) k_
             constexpr int TPE = NT / BWD_BATCH;
             const int gi = tid / TPE;
             if (gi < cnt) {
-                const uint32_t id = a.point_list[rg.x + base + gi];
+                const uint32_t id = vw.point_list[rg.x + base + gi];
                 if ((tid % TPE) == 0) s_id[gi] = id;
 #pragma unroll
-                for (int q = tid % TPE; q < OPS; q += TPE) Stage::copy(&s_rec[gi * REC], a.records, a.language, id, q);
+                for (int q = tid % TPE; q < OPS; q += TPE) Stage::copy(&s_rec[gi * REC], vw.records, a.language, id, q);
             }
         }
         cp_async_commit();
-        const uint32_t hit = lane < cnt ? (uint32_t)a.warp_hits[rg.x + base + lane] : 0u;
+        const uint32_t hit = lane < cnt ? (uint32_t)vw.warp_hits[rg.x + base + lane] : 0u;
         // entries a pixel of this warp blended (packed variant: not known in advance, decided by a vote below)
         // (packed: entries some forward block overlapping this warp's pixels blended -- a superset, the vote decides)
         const uint32_t mine = PACKED ? __ballot_sync(0xffffffffu, (hit & a.packed_fmask[wid & 3]) != 0u)
@@ -265,7 +275,7 @@ __global__ void __launch_bounds__(PACKED ? 128 : BWD_THREADS, PACKED ? 8 : 4) k_
                 dy = fsub(g0.y, pfy);
                 const float power = ffma(ffma(dx, fmul(dx, g0.z), fmul(dy, fmul(dy, g1.x))), -0.5f, -fmul(dy, fmul(dx, g0.w)));
                 if (inside && (uint32_t)(base + j) < last_contributor && !(power > 0.0f) && !(power < g1.z)) {
-                    G = expf(power);
+                    G = a.fast_exp ? fast_exp2(power) : expf(power);
                     alpha = fminf(0.99f, fmul(g1.y, G));
                     contrib = !(alpha < 1.0f / 255.0f);
                 }
@@ -362,7 +372,7 @@ __global__ void __launch_bounds__(PACKED ? 128 : BWD_THREADS, PACKED ? 8 : 4) k_
             const float val = s_acc[e];
             if (val != 0.0f) {
                 const int gi = e / GR, vi = e - gi * GR;
-                atomicAdd(&a.gacc[(size_t)s_id[gi] * GR + vi], val);
+                atomicAdd(&vw.gacc[(size_t)s_id[gi] * GR + vi], val);
                 s_acc[e] = 0.0f;
             }
         }
@@ -370,21 +380,31 @@ __global__ void __launch_bounds__(PACKED ? 128 : BWD_THREADS, PACKED ? 8 : 4) k_
 }
 
 // ---------------------------------------------------------------------------------------------------
-struct GeomCommon {
-    int P, F, sh_degree, M, W, H, gr;
-    float tanfovx, tanfovy, focal_x, focal_y, scale_modifier;
-    const float *means3D, *shs, *viewmatrix, *projmatrix, *projmatrix_raw, *campos;
+struct GeomView {  // camera + per-view buffers of one view
+    const float *viewmatrix, *projmatrix, *projmatrix_raw, *campos;
     const uint32_t* clamped;
     const float* gacc;
+    const int32_t* radii;
+    float* dL_dmeans2D;   // [P,3] this view's screen-space gradient (viewspace_points.grad)
+    float* dL_dtau;       // [P,6] per-Gaussian pose gradient as the reference returns it, or NULL
+    float* dL_dtau_sum;   // [6]   pose gradient summed over the Gaussians (zeroed by the launcher), or NULL
+    float tanfovx, tanfovy, focal_x, focal_y;
+};
+
+struct GeomCommon {
+    int P, F, sh_degree, M, W, H, gr;
+    float scale_modifier;
+    const float *means3D, *shs;
     bool colors_precomp;
     bool accumulate;  // += into the parameter gradients (means3D, sh, opacity, scales, rotations, language, cov3D)
     float* dL_dsh;
 };
 
 struct GeomBwdArgs : GeomCommon {
+    int V;
     const float *scales, *rotations, *cov3D;
-    const int32_t* radii;
-    float *dL_dmeans2D, *dL_dcolors, *dL_dlanguage, *dL_dopacity, *dL_dmeans3D, *dL_dcov3D, *dL_dscales, *dL_drots, *dL_dtau;
+    float *dL_dcolors, *dL_dlanguage, *dL_dopacity, *dL_dmeans3D, *dL_dcov3D, *dL_dscales, *dL_drots;
+    GeomView v[OLS_MAX_VIEWS];
 };
 
 __constant__ float B_SH_C0 = 0.28209479177387814f;
@@ -397,7 +417,7 @@ __constant__ float B_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.45
 // computeCov2DCUDA (backward.cu:150-346): conic gradient -> dL/dcov3D (written), dL/dmean3D (assigned) and the
 // pose gradient (accumulated).  D/'s computeCov2DCUDA_no_tau (D/backward.cu:354-446) is the same arithmetic
 // keeping only dL/dcov3D: callers simply drop the other two results.
-__device__ __forceinline__ void geom_cov2d_bwd(const GeomCommon& a, const float* V, const float* mp, const float* c3,
+__device__ __forceinline__ void geom_cov2d_bwd(const GeomView& a, const float* V, const float* mp, const float* c3,
                                        float dcx, float dcy, float dcz, float* dcov, float* dmean, float* dtau) {
     const float fx = a.focal_x, fy = a.focal_y;
     // ---- computeCov2DCUDA (backward.cu:150-346)
@@ -525,17 +545,17 @@ __device__ __forceinline__ void geom_proj_bwd(const float* V, const float* Pm, c
 }
 
 // computeColorFromSH backward (backward.cu:21-145)
-__device__ __forceinline__ void geom_sh_bwd(const GeomCommon& a, int i, const float* mp, const float* dcol, float* dsh0,
-                                    float* dmean, float* dtau) {
+__device__ __forceinline__ void geom_sh_bwd(const GeomCommon& a, const GeomView& vw, int i, const float* mp, const float* dcol,
+                                    float* dsh0, float* dmean, float* dtau) {
     const int M = a.M;
     if (a.shs && !a.colors_precomp) {  // computeColorFromSH backward (backward.cu:21-145)
         const float* sh = a.shs + (size_t)i * M * 3;
         float* dsh = a.dL_dsh + (size_t)i * M * 3;  // zeroed above unless accumulating: always add
         const int deg = a.sh_degree;
-        const float dir0[3] = {mp[0] - a.campos[0], mp[1] - a.campos[1], mp[2] - a.campos[2]};
+        const float dir0[3] = {mp[0] - vw.campos[0], mp[1] - vw.campos[1], mp[2] - vw.campos[2]};
         const float len = sqrtf(dir0[0] * dir0[0] + dir0[1] * dir0[1] + dir0[2] * dir0[2]);
         const float x = dir0[0] / len, y = dir0[1] / len, z = dir0[2] / len;
-        const uint32_t cl = a.clamped[i];
+        const uint32_t cl = vw.clamped[i];
         float dRGB[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) dRGB[c] = dcol[c] * (((cl >> (8 * c)) & 0xffu) ? 0.f : 1.f);
@@ -622,56 +642,100 @@ __device__ __forceinline__ void geom_cov3d_bwd(const float* scales, const float*
     }
 }
 
+// One thread per Gaussian, all V views of the batch: each view's packed gradient record is turned into that view's
+// mean / covariance / pose gradients with the view's camera, the results are summed in registers and the parameter
+// gradients are written ONCE (the reference runs its two kernels once per view and lets autograd add the V results).
+// The scale / rotation gradient is linear in dL/dcov3D, so it is evaluated once on the summed covariance gradient.
 template <int F>
-__global__ void __launch_bounds__(256, 4) k_geometry_bwd(const GeomBwdArgs a) {
+__global__ void __launch_bounds__(256, 2) k_geometry_bwd(const __grid_constant__ GeomBwdArgs a) {
+    __shared__ float s_tau[OLS_MAX_VIEWS][6];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.P) return;
+    const int lane = threadIdx.x & 31;
+    const bool valid = i < a.P;
     const int M = a.M;
     constexpr int GRF = grad_floats(F);
-    // the whole packed gradient record in registers: GRF/4 independent 16-byte loads
-    float gr[GRF];
-    {
-        const float4* src = reinterpret_cast<const float4*>(a.gacc + (size_t)i * GRF);
+    if (threadIdx.x < OLS_MAX_VIEWS * 6) (&s_tau[0][0])[threadIdx.x] = 0.0f;
+    __syncthreads();
+    float dmean[3] = {0, 0, 0}, dcov[6] = {0, 0, 0, 0, 0, 0};
+    float dcol[3] = {0, 0, 0}, dsh0[3] = {0, 0, 0}, dlang[F], dop = 0.0f;
 #pragma unroll
-        for (int q = 0; q < GRF / 4; q++) {
-            const float4 v = src[q];
-            gr[4 * q] = v.x; gr[4 * q + 1] = v.y; gr[4 * q + 2] = v.z; gr[4 * q + 3] = v.w;
+    for (int k = 0; k < F; k++) dlang[k] = 0.0f;
+    const bool acc = a.accumulate;
+    if (valid && a.dL_dsh && !acc && M > 1)
+        for (int k = 3; k < 3 * M; k++) a.dL_dsh[(size_t)3 * M * i + k] = 0.0f;
+    float mp[3] = {0, 0, 0};
+    if (valid) { mp[0] = a.means3D[3 * (size_t)i]; mp[1] = a.means3D[3 * (size_t)i + 1]; mp[2] = a.means3D[3 * (size_t)i + 2]; }
+    bool any_total = false;
+    for (int v = 0; v < a.V; v++) {
+        const GeomView& vw = a.v[v];
+        // the whole packed gradient record in registers: GRF/4 independent 16-byte loads
+        float gr[GRF];
+        bool any = false;
+        if (valid) {
+            const float4* src = reinterpret_cast<const float4*>(vw.gacc + (size_t)i * GRF);
+#pragma unroll
+            for (int q = 0; q < GRF / 4; q++) {
+                const float4 t = src[q];
+                gr[4 * q] = t.x; gr[4 * q + 1] = t.y; gr[4 * q + 2] = t.z; gr[4 * q + 3] = t.w;
+            }
+            // Most Gaussians of a view receive no gradient at all (they lie behind the saturation depth of every pixel
+            // they cover).  Everything below is linear in the record, so a zero record yields exactly zero gradients.
+#pragma unroll
+            for (int k = 0; k < GRF; k++) any = any || (gr[k] != 0.0f);
+        }
+        float dtau[6] = {0, 0, 0, 0, 0, 0};
+        float g2x = 0.0f, g2y = 0.0f;
+        bool vis = false;
+        if (any) {
+            any_total = true;
+            g2x = gr[GR_MX]; g2y = gr[GR_MY];
+            const float dcol_v[3] = {gr[GR_RGB], gr[GR_RGB + 1], gr[GR_RGB + 2]};
+            vis = vw.radii[i] > 0;
+            if (vis) {
+                const float* V = vw.viewmatrix;
+                const float* c3 = a.cov3D + 6 * (size_t)i;
+                float dmean_v[3] = {0, 0, 0}, dcov_v[6] = {0, 0, 0, 0, 0, 0}, dsh0_v[3] = {0, 0, 0};
+                geom_cov2d_bwd(vw, V, mp, c3, gr[GR_CX], gr[GR_CY], gr[GR_CW], dcov_v, dmean_v, dtau);
+                geom_proj_bwd(V, vw.projmatrix, vw.projmatrix_raw, mp, g2x, g2y, gr[GR_DEPTH], dmean_v, dtau);
+                geom_sh_bwd(a, vw, i, mp, dcol_v, dsh0_v, dmean_v, dtau);
+#pragma unroll
+                for (int k = 0; k < 3; k++) { dmean[k] += dmean_v[k]; dsh0[k] += dsh0_v[k]; }
+#pragma unroll
+                for (int k = 0; k < 6; k++) dcov[k] += dcov_v[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) dcol[k] += dcol_v[k];
+            dop += gr[GR_OP];
+#pragma unroll
+            for (int k = 0; k < F; k++) dlang[k] += gr[GR_LANG + k];
+        }
+        if (valid) {  // per-view outputs are always written
+            float* m2 = vw.dL_dmeans2D + 3 * (size_t)i;
+            m2[0] = g2x; m2[1] = g2y; m2[2] = 0.0f;
+            if (vw.dL_dtau) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) vw.dL_dtau[6 * (size_t)i + k] = dtau[k];
+            }
+        }
+        if (vw.dL_dtau_sum && __any_sync(0xffffffffu, vis)) {  // reference: torch.sum(dL_dtau, dim=0) (__init__.py:383-385)
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                float t = dtau[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                if (lane == 0 && t != 0.0f) atomicAdd(&s_tau[v][k], t);
+            }
         }
     }
-    float dmean[3] = {0, 0, 0}, dcov[6] = {0, 0, 0, 0, 0, 0}, dtau[6] = {0, 0, 0, 0, 0, 0};
+    __syncthreads();
+    if (threadIdx.x < a.V * 6) {
+        const int v = threadIdx.x / 6, k = threadIdx.x - 6 * v;
+        const float t = s_tau[v][k];
+        if (a.v[v].dL_dtau_sum && t != 0.0f) atomicAdd(&a.v[v].dL_dtau_sum[k], t);
+    }
+    if (!valid || (acc && !any_total)) return;  // accumulating a zero gradient: nothing to read or rewrite
     float dsc[3] = {0, 0, 0}, dq[4] = {0, 0, 0, 0};
-    // Most Gaussians of a view receive no gradient at all (they lie behind the saturation depth of every pixel
-    // they cover).  Everything below is linear in the record, so a zero record yields exactly zero gradients:
-    // nothing has to be recomputed for it, and when accumulating nothing has to be read or rewritten either.
-    bool any = false;
-#pragma unroll
-    for (int k = 0; k < GRF; k++) any = any || (gr[k] != 0.0f);
-    const bool acc = a.accumulate;
-    if (acc && !any) {
-        a.dL_dmeans2D[3 * (size_t)i] = 0.0f;
-        a.dL_dmeans2D[3 * (size_t)i + 1] = 0.0f;
-        a.dL_dmeans2D[3 * (size_t)i + 2] = 0.0f;
-#pragma unroll
-        for (int k = 0; k < 6; k++) a.dL_dtau[6 * (size_t)i + k] = 0.0f;  // per-view outputs are always written
-        return;
-    }
-    const bool vis = any && a.radii[i] > 0;
-    // unpack what the blend pass accumulated (zero for invisible Gaussians); all stores happen at the end
-    const float g2x = gr[GR_MX], g2y = gr[GR_MY];
-    float dcol[3] = {gr[GR_RGB], gr[GR_RGB + 1], gr[GR_RGB + 2]};
-    float dsh0[3] = {0, 0, 0};
-    if (a.dL_dsh && !acc && M > 1)
-        for (int k = 3; k < 3 * M; k++) a.dL_dsh[(size_t)3 * M * i + k] = 0.0f;
-
-    if (vis) {
-        const float* V = a.viewmatrix;
-        const float* c3 = a.cov3D + 6 * (size_t)i;
-        const float mp[3] = {a.means3D[3 * (size_t)i], a.means3D[3 * (size_t)i + 1], a.means3D[3 * (size_t)i + 2]};
-        geom_cov2d_bwd(a, V, mp, c3, gr[GR_CX], gr[GR_CY], gr[GR_CW], dcov, dmean, dtau);
-        geom_proj_bwd(V, a.projmatrix, a.projmatrix_raw, mp, g2x, g2y, gr[GR_DEPTH], dmean, dtau);
-        geom_sh_bwd(a, i, mp, dcol, dsh0, dmean, dtau);
-        geom_cov3d_bwd(a.scales, a.rotations, a.scale_modifier, i, dcov, dsc, dq);
-    }
+    if (any_total) geom_cov3d_bwd(a.scales, a.rotations, a.scale_modifier, i, dcov, dsc, dq);
     // ---- outputs: when accumulating, fetch every old value first (independent loads), then store ----
     float o_mean[3], o_cov[6], o_sc[3], o_q[4], o_op, o_col[3], o_lang[F], o_sh[3];
     float* p_mean = a.dL_dmeans3D + 3 * (size_t)i;
@@ -702,10 +766,7 @@ __global__ void __launch_bounds__(256, 4) k_geometry_bwd(const GeomBwdArgs a) {
         for (int k = 0; k < F; k++) o_lang[k] = 0;
         o_op = 0;
     }
-    a.dL_dmeans2D[3 * (size_t)i] = g2x;
-    a.dL_dmeans2D[3 * (size_t)i + 1] = g2y;
-    a.dL_dmeans2D[3 * (size_t)i + 2] = 0.0f;
-    a.dL_dopacity[i] = o_op + gr[GR_OP];
+    a.dL_dopacity[i] = o_op + dop;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         p_mean[k] = o_mean[k] + dmean[k];
@@ -714,14 +775,11 @@ __global__ void __launch_bounds__(256, 4) k_geometry_bwd(const GeomBwdArgs a) {
         if (p_sh) p_sh[k] = o_sh[k] + dsh0[k];
     }
 #pragma unroll
-    for (int k = 0; k < 6; k++) {
-        p_cov[k] = o_cov[k] + dcov[k];
-        a.dL_dtau[6 * (size_t)i + k] = dtau[k];  // per-view pose gradient: never accumulated
-    }
+    for (int k = 0; k < 6; k++) p_cov[k] = o_cov[k] + dcov[k];
 #pragma unroll
     for (int k = 0; k < 4; k++) p_q[k] = o_q[k] + dq[k];
 #pragma unroll
-    for (int k = 0; k < F; k++) p_lang[k] = o_lang[k] + gr[GR_LANG + k];
+    for (int k = 0; k < F; k++) p_lang[k] = o_lang[k] + dlang[k];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -731,12 +789,13 @@ __global__ void __launch_bounds__(256, 4) k_geometry_bwd(const GeomBwdArgs a) {
 // compat mode the projection / depth / SH / scale / rotation gradients of either footprint only exist for
 // Gaussians visible in both lists.  Exact mode gates every term by the footprint it belongs to.
 struct GeomDisArgs : GeomCommon {
+    GeomView vw;  // the single view (its gacc / radii / dL_dmeans2D / dL_dtau belong to the colour footprint)
     const float *scales, *rotations, *cov3D, *scales_lang, *rotations_lang, *cov3D_lang;
-    const int32_t *radii, *radii_lang;
+    const int32_t* radii_lang;
     const float* gacc_lang;
     bool exact;
-    float *dL_dmeans2D, *dL_dcolors, *dL_dlanguage, *dL_dopacity, *dL_dopacity_lang, *dL_dmeans3D, *dL_dcov3D,
-        *dL_dcov3D_lang, *dL_dscales, *dL_dscales_lang, *dL_drots, *dL_drots_lang, *dL_dtau;
+    float *dL_dcolors, *dL_dlanguage, *dL_dopacity, *dL_dopacity_lang, *dL_dmeans3D, *dL_dcov3D,
+        *dL_dcov3D_lang, *dL_dscales, *dL_dscales_lang, *dL_drots, *dL_drots_lang;
 };
 
 template <int F>
@@ -747,7 +806,7 @@ __global__ void __launch_bounds__(256) k_geometry_bwd_dis(const GeomDisArgs a) {
     constexpr int GRC = grad_floats(0), GRL = grad_floats(F);
     float gc[GRC], gl[GRL];
     {
-        const float4* src = reinterpret_cast<const float4*>(a.gacc + (size_t)i * GRC);
+        const float4* src = reinterpret_cast<const float4*>(a.vw.gacc + (size_t)i * GRC);
 #pragma unroll
         for (int q = 0; q < GRC / 4; q++) {
             const float4 v = src[q];
@@ -764,28 +823,28 @@ __global__ void __launch_bounds__(256) k_geometry_bwd_dis(const GeomDisArgs a) {
     float dsc[3] = {0, 0, 0}, dq[4] = {0, 0, 0, 0}, dscl[3] = {0, 0, 0}, dql[4] = {0, 0, 0, 0};
     float dcol[3] = {gc[GR_RGB], gc[GR_RGB + 1], gc[GR_RGB + 2]};
     float dsh0[3] = {0, 0, 0};
-    const bool vis_c = a.radii[i] > 0, vis_l = a.radii_lang[i] > 0;
+    const bool vis_c = a.vw.radii[i] > 0, vis_l = a.radii_lang[i] > 0;
     const float g2x = gc[GR_MX], g2y = gc[GR_MY];
     if (a.dL_dsh && M > 1)
         for (int k = 3; k < 3 * M; k++) a.dL_dsh[(size_t)3 * M * i + k] = 0.0f;
-    const float* V = a.viewmatrix;
+    const float* V = a.vw.viewmatrix;
     const float mp[3] = {a.means3D[3 * (size_t)i], a.means3D[3 * (size_t)i + 1], a.means3D[3 * (size_t)i + 2]};
-    if (vis_c) geom_cov2d_bwd(a, V, mp, a.cov3D + 6 * (size_t)i, gc[GR_CX], gc[GR_CY], gc[GR_CW], dcov, dmean, dtau);
+    if (vis_c) geom_cov2d_bwd(a.vw, V, mp, a.cov3D + 6 * (size_t)i, gc[GR_CX], gc[GR_CY], gc[GR_CW], dcov, dmean, dtau);
     if (vis_l) {
         float dm_unused[3] = {0, 0, 0}, dt_unused[6] = {0, 0, 0, 0, 0, 0};
-        geom_cov2d_bwd(a, V, mp, a.cov3D_lang + 6 * (size_t)i, gl[GR_CX], gl[GR_CY], gl[GR_CW], dcovl, dm_unused, dt_unused);
+        geom_cov2d_bwd(a.vw, V, mp, a.cov3D_lang + 6 * (size_t)i, gl[GR_CX], gl[GR_CY], gl[GR_CW], dcovl, dm_unused, dt_unused);
     }
     const bool both = vis_c && vis_l;
     if (a.exact ? vis_c : both) {
-        geom_proj_bwd(V, a.projmatrix, a.projmatrix_raw, mp, g2x, g2y, gc[GR_DEPTH], dmean, dtau);
-        geom_sh_bwd(a, i, mp, dcol, dsh0, dmean, dtau);
+        geom_proj_bwd(V, a.vw.projmatrix, a.vw.projmatrix_raw, mp, g2x, g2y, gc[GR_DEPTH], dmean, dtau);
+        geom_sh_bwd(a, a.vw, i, mp, dcol, dsh0, dmean, dtau);
         geom_cov3d_bwd(a.scales, a.rotations, a.scale_modifier, i, dcov, dsc, dq);
     }
     if (a.exact ? vis_l : both) geom_cov3d_bwd(a.scales_lang, a.rotations_lang, a.scale_modifier, i, dcovl, dscl, dql);
 
-    a.dL_dmeans2D[3 * (size_t)i] = g2x;
-    a.dL_dmeans2D[3 * (size_t)i + 1] = g2y;
-    a.dL_dmeans2D[3 * (size_t)i + 2] = 0.0f;
+    a.vw.dL_dmeans2D[3 * (size_t)i] = g2x;
+    a.vw.dL_dmeans2D[3 * (size_t)i + 1] = g2y;
+    a.vw.dL_dmeans2D[3 * (size_t)i + 2] = 0.0f;
     a.dL_dopacity[i] = gc[GR_OP];
     a.dL_dopacity_lang[i] = gl[GR_OP];
 #pragma unroll
@@ -800,7 +859,7 @@ __global__ void __launch_bounds__(256) k_geometry_bwd_dis(const GeomDisArgs a) {
     for (int k = 0; k < 6; k++) {
         a.dL_dcov3D[6 * (size_t)i + k] = dcov[k];
         a.dL_dcov3D_lang[6 * (size_t)i + k] = dcovl[k];
-        a.dL_dtau[6 * (size_t)i + k] = dtau[k];
+        a.vw.dL_dtau[6 * (size_t)i + k] = dtau[k];
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -812,13 +871,14 @@ __global__ void __launch_bounds__(256) k_geometry_bwd_dis(const GeomDisArgs a) {
 }
 
 template <int TILE, int NCOL, int F>
-static void launch_blend_bwd(const BwdBlendArgs& ba, int n_tiles, bool exact, bool packed, cudaStream_t st) {
+static void launch_blend_bwd(const BwdBlendArgs& ba, int n_tiles, int V, bool exact, bool packed, cudaStream_t st) {
+    const dim3 grid(n_tiles, V);
     if (exact)
-        k_blend_bwd<TILE, NCOL, F, false, false><<<n_tiles, BWD_THREADS, 0, st>>>(ba);
+        k_blend_bwd<TILE, NCOL, F, false, false><<<grid, BWD_THREADS, 0, st>>>(ba);
     else if (packed)
-        k_blend_bwd<TILE, NCOL, F, true, true><<<n_tiles, 128, 0, st>>>(ba);
+        k_blend_bwd<TILE, NCOL, F, true, true><<<grid, 128, 0, st>>>(ba);
     else
-        k_blend_bwd<TILE, NCOL, F, true, false><<<n_tiles, BWD_THREADS, 0, st>>>(ba);
+        k_blend_bwd<TILE, NCOL, F, true, false><<<grid, BWD_THREADS, 0, st>>>(ba);
 }
 
 }  // namespace ols
@@ -852,19 +912,28 @@ static void reduce_lane_mask(int n, bool exact, uint32_t* mask8) {
     }
 }
 
-// backward blend of one pass (its own sorted list, records, final_T, n_contrib and gradient scratch)
-static int run_blend_bwd(int W, int H, int tile, int ncol, int F, unsigned flags, char* ws, const WsLayout& L, const float* d_bg,
-                         const float* language, const float* dL_dcolor, const float* dL_dlanguage, const float* dL_ddepth, cudaStream_t st) {
+// One view of a backward blend pass: its workspace (sorted list, records, final_T, n_contrib, gradient scratch) and the
+// image-space gradients it starts from.
+struct BwdPassView { char* ws; const float* bg; const float *dL_dcolor, *dL_dlanguage, *dL_ddepth; };
+
+// backward blend of one pass for the V views of a batch (grid.y = view)
+static int run_blend_bwd(int W, int H, int tile, int ncol, int F, unsigned flags, const BwdPassView* pv, int V, const WsLayout& L,
+                         const float* language, cudaStream_t st) {
     const bool exact = (flags & OLS_FLAG_BWD_EXACT) != 0;
-    float* gacc = (float*)(ws + L.gacc);
     BwdBlendArgs ba;
     ba.W = W; ba.H = H; ba.gx = L.gx;
-    ba.ranges = (const uint2*)(ws + L.ranges); ba.point_list = (const uint32_t*)(ws + L.point_list);
-    ba.records = (const float*)(ws + L.records); ba.language = language; ba.bg = d_bg; ba.info = (const DeviceInfo*)(ws + L.info);
-    ba.final_T = (const float*)(ws + L.final_T); ba.n_contrib = (const uint32_t*)(ws + L.n_contrib);
-    ba.dL_dcolor = dL_dcolor; ba.dL_dlanguage = dL_dlanguage; ba.dL_ddepth = dL_ddepth;
-    ba.gacc = gacc;
-    ba.warp_hits = (const uint8_t*)(ws + L.warp_hits);
+    ba.language = language;
+    ba.fast_exp = (flags & OLS_FLAG_BITEXACT_BLEND) ? 0 : 1;
+    for (int v = 0; v < V; v++) {
+        char* ws = pv[v].ws;
+        BwdView& q = ba.v[v];
+        q.ranges = (const uint2*)(ws + L.ranges); q.point_list = (const uint32_t*)(ws + L.point_list);
+        q.records = (const float*)(ws + L.records); q.bg = pv[v].bg; q.info = (const DeviceInfo*)(ws + L.info);
+        q.final_T = (const float*)(ws + L.final_T); q.n_contrib = (const uint32_t*)(ws + L.n_contrib);
+        q.dL_dcolor = pv[v].dL_dcolor; q.dL_dlanguage = pv[v].dL_dlanguage; q.dL_ddepth = pv[v].dL_ddepth;
+        q.gacc = (float*)(ws + L.gacc);
+        q.warp_hits = (const uint8_t*)(ws + L.warp_hits);
+    }
     reduce_lane_mask(tile * tile, exact, ba.lane_ok);
     // packed compat variant: possible when at most 128 pixels of a tile survive the reference's reduction (15x15: 128)
     bool packed = false;
@@ -889,16 +958,16 @@ static int run_blend_bwd(int W, int H, int tile, int ncol, int F, unsigned flags
     }
     const int key = tile * 10000 + ncol * 100 + F;
     switch (key) {
-        case 150315: launch_blend_bwd<15, 3, 15>(ba, L.n_tiles, exact, packed, st); break;
-        case 160315: launch_blend_bwd<16, 3, 15>(ba, L.n_tiles, exact, packed, st); break;
-        case 150303: launch_blend_bwd<15, 3, 3>(ba, L.n_tiles, exact, packed, st); break;
-        case 160303: launch_blend_bwd<16, 3, 3>(ba, L.n_tiles, exact, packed, st); break;
-        case 150300: launch_blend_bwd<15, 3, 0>(ba, L.n_tiles, exact, packed, st); break;
-        case 160300: launch_blend_bwd<16, 3, 0>(ba, L.n_tiles, exact, packed, st); break;
-        case 150003: launch_blend_bwd<15, 0, 3>(ba, L.n_tiles, exact, packed, st); break;
-        case 160003: launch_blend_bwd<16, 0, 3>(ba, L.n_tiles, exact, packed, st); break;
-        case 150015: launch_blend_bwd<15, 0, 15>(ba, L.n_tiles, exact, packed, st); break;
-        case 160015: launch_blend_bwd<16, 0, 15>(ba, L.n_tiles, exact, packed, st); break;
+        case 150315: launch_blend_bwd<15, 3, 15>(ba, L.n_tiles, V, exact, packed, st); break;
+        case 160315: launch_blend_bwd<16, 3, 15>(ba, L.n_tiles, V, exact, packed, st); break;
+        case 150303: launch_blend_bwd<15, 3, 3>(ba, L.n_tiles, V, exact, packed, st); break;
+        case 160303: launch_blend_bwd<16, 3, 3>(ba, L.n_tiles, V, exact, packed, st); break;
+        case 150300: launch_blend_bwd<15, 3, 0>(ba, L.n_tiles, V, exact, packed, st); break;
+        case 160300: launch_blend_bwd<16, 3, 0>(ba, L.n_tiles, V, exact, packed, st); break;
+        case 150003: launch_blend_bwd<15, 0, 3>(ba, L.n_tiles, V, exact, packed, st); break;
+        case 160003: launch_blend_bwd<16, 0, 3>(ba, L.n_tiles, V, exact, packed, st); break;
+        case 150015: launch_blend_bwd<15, 0, 15>(ba, L.n_tiles, V, exact, packed, st); break;
+        case 160015: launch_blend_bwd<16, 0, 15>(ba, L.n_tiles, V, exact, packed, st); break;
         default: ols_set_error("unsupported (tile=%d, F=%d)", tile, F); return OLS_ERR_UNSUPPORTED;
     }
     OLS_CUDA_TRY(cudaGetLastError());
@@ -909,36 +978,54 @@ static int run_blend_bwd(int W, int H, int tile, int ncol, int F, unsigned flags
     return OLS_OK;
 }
 
-static void fill_geom_common(GeomCommon& ga, const ols_raster_args* a, const char* ws, const WsLayout& L, float* dL_dsh) {
+static void fill_geom_common(GeomCommon& ga, const ols_raster_args* a, float* dL_dsh) {
     ga.accumulate = (a->flags & OLS_FLAG_BWD_ACCUMULATE) != 0;
     ga.P = a->P; ga.F = a->F; ga.sh_degree = a->sh_degree; ga.M = a->M; ga.W = a->W; ga.H = a->H; ga.gr = grad_floats(a->F);
-    ga.tanfovx = a->tanfovx; ga.tanfovy = a->tanfovy;
-    ga.focal_y = a->H / (2.0f * a->tanfovy); ga.focal_x = a->W / (2.0f * a->tanfovx);
     ga.scale_modifier = a->scale_modifier;
     ga.means3D = a->d_means3D; ga.shs = a->d_shs;
-    ga.viewmatrix = a->d_viewmatrix; ga.projmatrix = a->d_projmatrix; ga.projmatrix_raw = a->d_projmatrix_raw;
-    ga.campos = a->d_campos; ga.clamped = (const uint32_t*)(ws + L.clamped); ga.gacc = (const float*)(ws + L.gacc);
     ga.colors_precomp = a->d_colors_precomp != nullptr;
     ga.dL_dsh = (a->d_shs && a->M > 0) ? dL_dsh : nullptr;
 }
 
-int ols_launch_backward(const ols_raster_args* a, const ols_bwd_args* g, const WsLayout& L, cudaStream_t st) {
-    char* ws = (char*)a->d_workspace;
+static void fill_geom_view(GeomView& q, const ols_raster_args* a, const char* ws, const WsLayout& L, const int32_t* radii,
+                           float* dL_dmeans2D, float* dL_dtau, float* dL_dtau_sum) {
+    q.viewmatrix = a->d_viewmatrix; q.projmatrix = a->d_projmatrix; q.projmatrix_raw = a->d_projmatrix_raw;
+    q.campos = a->d_campos; q.clamped = (const uint32_t*)(ws + L.clamped); q.gacc = (const float*)(ws + L.gacc);
+    q.radii = radii; q.dL_dmeans2D = dL_dmeans2D; q.dL_dtau = dL_dtau; q.dL_dtau_sum = dL_dtau_sum;
+    q.tanfovx = a->tanfovx; q.tanfovy = a->tanfovy;
+    q.focal_y = a->H / (2.0f * a->tanfovy); q.focal_x = a->W / (2.0f * a->tanfovx);
+}
+
+// Backward of V views of the same Gaussians.  grads[v] carries the view's image-space gradients, its radii and its
+// per-view outputs (dL_dmeans2D, dL_dtau / dL_dtau_sum); the parameter-gradient pointers are taken from grads[0] and
+// receive the SUM over the views (added to their previous content with OLS_FLAG_BWD_ACCUMULATE).
+int ols_launch_backward(const ols_raster_args* views, const ols_bwd_args* grads, int V, const WsLayout& L, cudaStream_t st) {
+    const ols_raster_args* a = &views[0];
+    const ols_bwd_args* g = &grads[0];
     const bool debug = (a->flags & OLS_FLAG_DEBUG) != 0;
-    OLS_CUDA_TRY(cudaMemsetAsync(ws + L.gacc, 0, ols_bwd_scratch_bytes(a->P, a->F), st));
+    BwdPassView pv[OLS_MAX_VIEWS];
+    for (int v = 0; v < V; v++) {
+        char* ws = (char*)views[v].d_workspace;
+        OLS_CUDA_TRY(cudaMemsetAsync(ws + L.gacc, 0, ols_bwd_scratch_bytes(a->P, a->F), st));
+        if (grads[v].d_dL_dtau_sum) OLS_CUDA_TRY(cudaMemsetAsync(grads[v].d_dL_dtau_sum, 0, 6 * sizeof(float), st));
+        pv[v] = BwdPassView{ws, views[v].d_bg, grads[v].d_dL_dout_color, grads[v].d_dL_dout_language, grads[v].d_dL_dout_depth};
+    }
     ols_timing_mark(-1, st);
-    int rc = run_blend_bwd(a->W, a->H, a->tile, 3, a->F, a->flags, ws, L, a->d_bg, a->d_language, g->d_dL_dout_color, g->d_dL_dout_language,
-                           g->d_dL_dout_depth, st);
+    int rc = run_blend_bwd(a->W, a->H, a->tile, 3, a->F, a->flags, pv, V, L, a->d_language, st);
     if (rc != OLS_OK) return rc;
     ols_timing_mark(OLS_T_BLEND_BWD, st);
     GeomBwdArgs ga;
-    fill_geom_common(ga, a, ws, L, g->d_dL_dsh);
+    fill_geom_common(ga, a, g->d_dL_dsh);
+    ga.V = V;
     ga.scales = a->d_scales; ga.rotations = a->d_rotations;
-    ga.cov3D = a->d_cov3D_precomp ? a->d_cov3D_precomp : (const float*)(ws + L.cov3D);
-    ga.radii = g->d_radii;
-    ga.dL_dmeans2D = g->d_dL_dmeans2D; ga.dL_dcolors = g->d_dL_dcolors; ga.dL_dlanguage = g->d_dL_dlanguage;
+    // the view-independent 3D covariances live in the first view's workspace (k_preprocess)
+    ga.cov3D = a->d_cov3D_precomp ? a->d_cov3D_precomp : (const float*)((char*)views[0].d_workspace + L.cov3D);
+    ga.dL_dcolors = g->d_dL_dcolors; ga.dL_dlanguage = g->d_dL_dlanguage;
     ga.dL_dopacity = g->d_dL_dopacity; ga.dL_dmeans3D = g->d_dL_dmeans3D; ga.dL_dcov3D = g->d_dL_dcov3D;
-    ga.dL_dscales = g->d_dL_dscales; ga.dL_drots = g->d_dL_drotations; ga.dL_dtau = g->d_dL_dtau;
+    ga.dL_dscales = g->d_dL_dscales; ga.dL_drots = g->d_dL_drotations;
+    for (int v = 0; v < V; v++)
+        fill_geom_view(ga.v[v], &views[v], (const char*)views[v].d_workspace, L, grads[v].d_radii, grads[v].d_dL_dmeans2D,
+                       grads[v].d_dL_dtau, grads[v].d_dL_dtau_sum);
     if (a->F == 15) k_geometry_bwd<15><<<(a->P + 255) / 256, 256, 0, st>>>(ga);
     else k_geometry_bwd<3><<<(a->P + 255) / 256, 256, 0, st>>>(ga);
     OLS_CUDA_TRY(cudaGetLastError());
@@ -959,25 +1046,28 @@ int ols_launch_backward_dis(const ols_dis_args* d, const ols_dis_bwd_args* g, co
     OLS_CUDA_TRY(cudaMemsetAsync(wc + Lc.gacc, 0, ols_bwd_scratch_bytes(a->P, 0), st));
     OLS_CUDA_TRY(cudaMemsetAsync(wl + Ll.gacc, 0, ols_bwd_scratch_bytes(a->P, a->F), st));
     ols_timing_mark(-1, st);
-    int rc = run_blend_bwd(a->W, a->H, a->tile, 3, 0, a->flags, wc, Lc, a->d_bg, nullptr, g->d_dL_dout_color, nullptr, g->d_dL_dout_depth, st);
+    const BwdPassView pc{wc, a->d_bg, g->d_dL_dout_color, nullptr, g->d_dL_dout_depth};
+    int rc = run_blend_bwd(a->W, a->H, a->tile, 3, 0, a->flags, &pc, 1, Lc, nullptr, st);
     if (rc != OLS_OK) return rc;
-    rc = run_blend_bwd(a->W, a->H, a->tile, 0, a->F, a->flags, wl, Ll, a->d_bg, nullptr, nullptr, g->d_dL_dout_language, nullptr, st);
+    const BwdPassView pl{wl, a->d_bg, nullptr, g->d_dL_dout_language, nullptr};
+    rc = run_blend_bwd(a->W, a->H, a->tile, 0, a->F, a->flags, &pl, 1, Ll, nullptr, st);
     if (rc != OLS_OK) return rc;
     ols_timing_mark(OLS_T_BLEND_BWD, st);
     GeomDisArgs ga;
-    fill_geom_common(ga, a, wc, Lc, g->d_dL_dsh);
+    fill_geom_common(ga, a, g->d_dL_dsh);
+    fill_geom_view(ga.vw, a, wc, Lc, g->d_radii, g->d_dL_dmeans2D, g->d_dL_dtau, nullptr);
     ga.exact = (a->flags & OLS_FLAG_BWD_EXACT) != 0;
     ga.scales = a->d_scales; ga.rotations = a->d_rotations;
     ga.cov3D = a->d_cov3D_precomp ? a->d_cov3D_precomp : (const float*)(wc + Lc.cov3D);
     ga.scales_lang = d->d_scales_lang; ga.rotations_lang = d->d_rotations_lang;
     ga.cov3D_lang = d->d_cov3D_precomp_lang ? d->d_cov3D_precomp_lang : (const float*)(wl + Ll.cov3D);
-    ga.radii = g->d_radii; ga.radii_lang = g->d_radii_lang;
+    ga.radii_lang = g->d_radii_lang;
     ga.gacc_lang = (const float*)(wl + Ll.gacc);
-    ga.dL_dmeans2D = g->d_dL_dmeans2D; ga.dL_dcolors = g->d_dL_dcolors; ga.dL_dlanguage = g->d_dL_dlanguage;
+    ga.dL_dcolors = g->d_dL_dcolors; ga.dL_dlanguage = g->d_dL_dlanguage;
     ga.dL_dopacity = g->d_dL_dopacity; ga.dL_dopacity_lang = g->d_dL_dopacity_lang; ga.dL_dmeans3D = g->d_dL_dmeans3D;
     ga.dL_dcov3D = g->d_dL_dcov3D; ga.dL_dcov3D_lang = g->d_dL_dcov3D_lang;
     ga.dL_dscales = g->d_dL_dscales; ga.dL_dscales_lang = g->d_dL_dscales_lang;
-    ga.dL_drots = g->d_dL_drotations; ga.dL_drots_lang = g->d_dL_drotations_lang; ga.dL_dtau = g->d_dL_dtau;
+    ga.dL_drots = g->d_dL_drotations; ga.dL_drots_lang = g->d_dL_drotations_lang;
     if (a->F == 15) k_geometry_bwd_dis<15><<<(a->P + 255) / 256, 256, 0, st>>>(ga);
     else k_geometry_bwd_dis<3><<<(a->P + 255) / 256, 256, 0, st>>>(ga);
     OLS_CUDA_TRY(cudaGetLastError());

@@ -72,6 +72,21 @@ inline __host__ WsLayout ws_layout(int P, int F, int W, int H, int tile, int64_t
     return L;
 }
 
+// ---- multi-view batches ----------------------------------------------------------------------------
+// The views of one mapping iteration (utils/slam_backend.py:510-662 renders the 8-12 window keyframes one after the
+// other) are rendered by ONE set of launches: blockIdx.y selects the view, every view owns a workspace with the same
+// layout, and the kernels receive the per-view pointers as a __grid_constant__ array (constant-bank indexed loads).
+constexpr int OLS_MAX_VIEWS = 16;
+
+struct PassView {           // one view of one blending pass (binning + sort + blend)
+    char* ws;               // the view's workspace
+    const float* depths;    // [P] view-space depths (D/ shares them between its two passes)
+    const float* bg;
+    float *color, *language, *depth, *opacity;
+    int32_t* n_touched;
+};
+struct PassBatch { PassView v[OLS_MAX_VIEWS]; };
+
 struct DeviceInfo {  // lives at workspace offset 0; first 32 bytes == ols_fwd_info
     unsigned long long R;
     int overflow;
@@ -149,8 +164,8 @@ void ols_set_error(const char* fmt, ...);
 void ols_timing_mark(int tag, cudaStream_t st);
 
 // kernel launchers implemented in ols_forward.cu / ols_backward.cu
-int ols_launch_forward(const ols_raster_args* a, const ols_fwd_out* o, const ols::WsLayout& L, cudaStream_t st);
-int ols_launch_backward(const ols_raster_args* a, const ols_bwd_args* g, const ols::WsLayout& L, cudaStream_t st);
+int ols_launch_forward(const ols_raster_args* views, const ols_fwd_out* outs, int V, const ols::WsLayout& L, cudaStream_t st);
+int ols_launch_backward(const ols_raster_args* views, const ols_bwd_args* grads, int V, const ols::WsLayout& L, cudaStream_t st);
 int ols_launch_forward_dis(const ols_dis_args* d, const ols_dis_fwd_out* o, const ols::WsLayout& Lc, const ols::WsLayout& Ll,
                            size_t lang_base, cudaStream_t st);
 int ols_launch_backward_dis(const ols_dis_args* d, const ols_dis_bwd_args* g, const ols::WsLayout& Lc, const ols::WsLayout& Ll,

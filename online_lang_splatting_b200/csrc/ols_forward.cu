@@ -26,6 +26,7 @@
 #include <cooperative_groups.h>
 #include <math_constants.h>
 #include <cstdio>
+#include <cstdlib>
 
 namespace ols {
 
@@ -36,22 +37,20 @@ __constant__ float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.3153
 __constant__ float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
                                -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
 
-struct PreArgs {
-    int P, F, sh_degree, M, W, H, tile, gx, gy, rec;
-    unsigned flags;
-    float tanfovx, tanfovy, focal_x, focal_y, scale_modifier;
-    const float *means3D, *shs, *colors_precomp, *opacities, *scales, *rotations, *cov3D_precomp;
+struct PreView {  // what differs between the views of a batch in the preprocess
     const float *viewmatrix, *projmatrix, *campos;
-    float* records;
-    float* depths;
-    float* cov3D;
-    uint32_t* clamped;
-    uint32_t* tiles_touched;
-    uint2* rect;
-    uint32_t* cta_hist;
-    int chunk;
+    float tanfovx, tanfovy, focal_x, focal_y;
+    char* ws;
     int32_t* radii;
-    DeviceInfo* info;
+};
+struct PreBatch { PreView v[OLS_MAX_VIEWS]; };
+
+struct PreArgs {
+    int P, F, sh_degree, M, W, H, tile, gx, gy, rec, V, VG, chunk;
+    unsigned flags;
+    float scale_modifier;
+    const float *means3D, *shs, *colors_precomp, *opacities, *scales, *rotations, *cov3D_precomp;
+    size_t o_records, o_depths, o_cov3D, o_clamped, o_tiles_touched, o_rect, o_cta_hist, o_info;  // workspace offsets
 };
 
 // m[i]*x + m[4+i]*y + m[8+i]*z + m[12+i] in the compiled reference's order
@@ -148,43 +147,7 @@ __device__ void sh_to_rgb(int deg, int M, const float* sh, float dx, float dy, f
 }
 
 constexpr int PRE_THREADS = 256;
-
-// Each CTA owns a contiguous chunk of Gaussians (one thread per Gaussian, 256 at a time).  Inputs with
-// 3-float rows are staged through shared memory so the global loads are contiguous; the instances
-// each Gaussian contributes to every tile are counted in a per-CTA shared-memory histogram that is
-// written out once per CTA (cta_hist[cta][tile]) -- no global atomics on hot tile counters.
-__device__ void preprocess_one(const PreArgs& a, int i, int tid, const float* s_mean, const float* s_scale,
-                               const float* V, const float* Pm, uint32_t* s_hist, int& visible);
-
-__global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreArgs a) {
-    extern __shared__ uint32_t s_hist[];  // [n_tiles]
-    __shared__ float s_mean[PRE_THREADS * 3];
-    __shared__ float s_scale[PRE_THREADS * 3];
-    __shared__ float s_V[16], s_Pm[16];
-    const int tid = threadIdx.x;
-    const int n_tiles = a.gx * a.gy;
-    for (int t = tid; t < n_tiles; t += PRE_THREADS) s_hist[t] = 0;
-    if (tid < 16) { s_V[tid] = a.viewmatrix[tid]; s_Pm[tid] = a.projmatrix[tid]; }
-    const int chunk_begin = min(a.P, (int)blockIdx.x * a.chunk), chunk_end = min(a.P, chunk_begin + a.chunk);
-    int visible = 0;
-    for (int base = chunk_begin; base < chunk_end; base += PRE_THREADS) {
-        const int nloc = min(PRE_THREADS, chunk_end - base);
-        __syncthreads();  // previous iteration's readers of s_mean/s_scale are done (and s_hist zeroed)
-        for (int e = tid; e < nloc * 3; e += PRE_THREADS) {
-            s_mean[e] = a.means3D[(size_t)base * 3 + e];
-            if (a.scales) s_scale[e] = a.scales[(size_t)base * 3 + e];
-        }
-        __syncthreads();
-        if (tid < nloc) preprocess_one(a, base + tid, tid, s_mean, s_scale, s_V, s_Pm, s_hist, visible);
-    }
-    const int nvis = __syncthreads_count(visible);  // also orders the histogram updates before the flush
-    (void)nvis;
-    uint32_t* out = a.cta_hist + (size_t)blockIdx.x * n_tiles;
-    for (int t = tid; t < n_tiles; t += PRE_THREADS) out[t] = s_hist[t];
-    // n_visible: block-reduce the per-thread counts
-    for (int o = 16; o > 0; o >>= 1) visible += __shfl_xor_sync(0xffffffffu, visible, o);
-    if ((tid & 31) == 0 && visible) atomicAdd(&a.info->n_visible, visible);
-}
+constexpr int PRE_CAM = 36;  // floats of per-view camera data staged in shared memory: V[16] Pm[16] campos[3] pad
 
 // ---- pieces of the per-Gaussian preprocess shared by the joint (P/) and the disentangled (D/) kernels ----
 
@@ -266,13 +229,17 @@ __device__ __forceinline__ void write_record_frame(float* rf, int rec, float pix
     rf[rec - 1] = ey;
 }
 
-__device__ void preprocess_one(const PreArgs& a, int i, int tid, const float* s_mean, const float* s_scale,
-                               const float* s_V, const float* s_Pm, uint32_t* s_hist, int& visible) {
-    a.radii[i] = 0;
-    a.tiles_touched[i] = 0;
-    const float px3 = s_mean[3 * tid], py3 = s_mean[3 * tid + 1], pz3 = s_mean[3 * tid + 2];
-    const float* V = s_V;
-    const float* Pm = s_Pm;
+// One view of one Gaussian: cull / project / cov2D / conic / radius / tile rect / colour, the 16-float colour record,
+// per-tile instance counts (forward.cu:262-371 after computeCov3D).  Returns whether the Gaussian is visible.
+__device__ __forceinline__ bool preprocess_view(const PreArgs& a, const PreView& pv, int i, float px3, float py3, float pz3,
+                                                const float* c3, float op, const float* rgb_pre, const float* cam,
+                                                uint32_t* s_hist) {
+    char* ws = pv.ws;
+    uint32_t* tiles_touched = (uint32_t*)(ws + a.o_tiles_touched);
+    pv.radii[i] = 0;
+    tiles_touched[i] = 0;
+    const float* V = cam;
+    const float* Pm = cam + 16;
     // in_frustum (auxiliary.h:139-164)
     const float vz = xform_row(V, 2, px3, py3, pz3);
     if (!(vz > 0.2f)) {
@@ -280,27 +247,17 @@ __device__ void preprocess_one(const PreArgs& a, int i, int tid, const float* s_
             printf("Point is filtered although prefiltered is set. This shouldn't happen!");
             __trap();
         }
-        return;
+        return false;
     }
     const float hx = xform_row(Pm, 0, px3, py3, pz3);
     const float hy = xform_row(Pm, 1, px3, py3, pz3);
     const float hw = xform_row(Pm, 3, px3, py3, pz3);
     const float pw = __frcp_rn(fadd(hw, 0.0000001f));
     const float projx = fmul(hx, pw), projy = fmul(hy, pw);
-    float c3[6];
-    if (a.cov3D_precomp) {
-#pragma unroll
-        for (int k = 0; k < 6; k++) c3[k] = a.cov3D_precomp[(size_t)6 * i + k];
-    } else {
-        const float4 q = reinterpret_cast<const float4*>(a.rotations)[i];
-        cov3d_from_scale_rot(s_scale[3 * tid], s_scale[3 * tid + 1], s_scale[3 * tid + 2], a.scale_modifier, q, c3);
-#pragma unroll
-        for (int k = 0; k < 6; k++) a.cov3D[(size_t)6 * i + k] = c3[k];
-    }
     float ca, cb, cc;
-    cov2d_from_cov3d(V, px3, py3, pz3, vz, a.tanfovx, a.tanfovy, a.focal_x, a.focal_y, c3, ca, cb, cc);
+    cov2d_from_cov3d(V, px3, py3, pz3, vz, pv.tanfovx, pv.tanfovy, pv.focal_x, pv.focal_y, c3, ca, cb, cc);
     const float det = ffma(ca, cc, -fmul(cb, cb));
-    if (det == 0.0f) return;
+    if (det == 0.0f) return false;
     const float det_inv = __frcp_rn(det);
     const float my_radius = splat_radius(ca, cc, det);
     const float pix_x = ndc2pix(projx, a.W), pix_y = ndc2pix(projy, a.H);
@@ -308,29 +265,101 @@ __device__ void preprocess_one(const PreArgs& a, int i, int tid, const float* s_
     const int ri = __float2int_rz(my_radius);
     get_rect(pix_x, pix_y, ri, a.tile, a.gx, a.gy, mn, mx);
     const uint32_t tiles = (uint32_t)(mx[0] - mn[0]) * (uint32_t)(mx[1] - mn[1]);
-    if (tiles == 0) return;
+    if (tiles == 0) return false;
 
     float rgb[3];
-    if (a.colors_precomp) {
+    if (rgb_pre) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) rgb[c] = a.colors_precomp[(size_t)3 * i + c];
+        for (int c = 0; c < 3; c++) rgb[c] = rgb_pre[c];
     } else {
-        a.clamped[i] = rgb_from_sh(a.sh_degree, a.M, a.shs + (size_t)i * a.M * 3, px3 - a.campos[0], py3 - a.campos[1],
-                                   pz3 - a.campos[2], rgb);
+        ((uint32_t*)(ws + a.o_clamped))[i] = rgb_from_sh(a.sh_degree, a.M, a.shs + (size_t)i * a.M * 3, px3 - cam[32],
+                                                          py3 - cam[33], pz3 - cam[34], rgb);
     }
-    float* rf = a.records + (size_t)i * a.rec;
-    rf[REC_CH] = rgb[0];
-    rf[REC_CH + 1] = rgb[1];
-    rf[REC_CH + 2] = rgb[2];
-    for (int c = REC_CH + 3; c < a.rec - 2; c++) rf[c] = 0.0f;  // the language channels are not part of the global record
-    write_record_frame(rf, a.rec, pix_x, pix_y, fmul(cc, det_inv), fmul(cb, -det_inv), fmul(ca, det_inv), a.opacities[i], vz);
-    a.depths[i] = vz;
-    a.radii[i] = ri;
-    a.rect[i] = make_uint2((uint32_t)mn[0] | ((uint32_t)mn[1] << 16), (uint32_t)mx[0] | ((uint32_t)mx[1] << 16));
-    a.tiles_touched[i] = tiles;
-    visible += 1;
+    float* rf = (float*)(ws + a.o_records) + (size_t)i * a.rec;
+    float4* r4 = reinterpret_cast<float4*>(rf);
+    r4[2] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
+    for (int c = REC_CH + 4; c < a.rec - 2; c++) rf[c] = 0.0f;  // the language channels are not part of the global record
+    write_record_frame(rf, a.rec, pix_x, pix_y, fmul(cc, det_inv), fmul(cb, -det_inv), fmul(ca, det_inv), op, vz);
+    ((float*)(ws + a.o_depths))[i] = vz;
+    pv.radii[i] = ri;
+    ((uint2*)(ws + a.o_rect))[i] = make_uint2((uint32_t)mn[0] | ((uint32_t)mn[1] << 16), (uint32_t)mx[0] | ((uint32_t)mx[1] << 16));
+    tiles_touched[i] = tiles;
     for (int y = mn[1]; y < mx[1]; y++)
         for (int x = mn[0]; x < mx[0]; x++) atomicAdd(&s_hist[y * a.gx + x], 1u);
+    return true;
+}
+
+// Each CTA owns a contiguous chunk of Gaussians (one thread per Gaussian, 256 at a time) and a group of up to VG
+// views (blockIdx.y).  A Gaussian's parameters are read and its 3D covariance is computed ONCE for all the views of
+// the group -- the reference runs the whole preprocess once per rendered view (slam_backend.py:510-662: 8-12 views per
+// mapping iteration over the same Gaussians).  Inputs with 3-float rows are staged through shared memory so the
+// global loads are contiguous; the instances a Gaussian contributes to every tile of every view are counted in per-CTA
+// shared-memory histograms written out once per CTA (cta_hist[cta][tile]) -- no global atomics on hot tile counters.
+__global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreArgs a, const __grid_constant__ PreBatch vb) {
+    extern __shared__ uint32_t s_dyn[];  // [VG][n_tiles] histograms, then [VG][PRE_CAM] camera floats
+    __shared__ float s_mean[PRE_THREADS * 3];
+    __shared__ float s_scale[PRE_THREADS * 3];
+    __shared__ int s_nvis[OLS_MAX_VIEWS];
+    const int tid = threadIdx.x;
+    const int n_tiles = a.gx * a.gy;
+    const int v0 = blockIdx.y * a.VG, nv = min(a.VG, a.V - v0);
+    uint32_t* s_hist = s_dyn;
+    float* s_cam = reinterpret_cast<float*>(s_dyn + (size_t)a.VG * n_tiles);
+    for (int t = tid; t < nv * n_tiles; t += PRE_THREADS) s_hist[t] = 0;
+    for (int e = tid; e < nv * PRE_CAM; e += PRE_THREADS) {
+        const int v = e / PRE_CAM, k = e - v * PRE_CAM;
+        const PreView& pv = vb.v[v0 + v];
+        s_cam[e] = k < 16 ? pv.viewmatrix[k] : (k < 32 ? pv.projmatrix[k - 16] : (k < 35 ? pv.campos[k - 32] : 0.0f));
+    }
+    if (tid < OLS_MAX_VIEWS) s_nvis[tid] = 0;
+    const int chunk_begin = min(a.P, (int)blockIdx.x * a.chunk), chunk_end = min(a.P, chunk_begin + a.chunk);
+    for (int base = chunk_begin; base < chunk_end; base += PRE_THREADS) {
+        const int nloc = min(PRE_THREADS, chunk_end - base);
+        __syncthreads();  // previous iteration's readers of s_mean/s_scale are done (and the histograms are zeroed)
+        for (int e = tid; e < nloc * 3; e += PRE_THREADS) {
+            s_mean[e] = a.means3D[(size_t)base * 3 + e];
+            if (a.scales) s_scale[e] = a.scales[(size_t)base * 3 + e];
+        }
+        __syncthreads();
+        const bool valid = tid < nloc;
+        const int i = base + (valid ? tid : 0);
+        const float px3 = s_mean[3 * (valid ? tid : 0)], py3 = s_mean[3 * (valid ? tid : 0) + 1], pz3 = s_mean[3 * (valid ? tid : 0) + 2];
+        float c3[6], rgb_pre[3] = {0.0f, 0.0f, 0.0f};
+        float op = 0.0f;
+        if (valid) {
+            op = a.opacities[i];
+            if (a.cov3D_precomp) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) c3[k] = a.cov3D_precomp[(size_t)6 * i + k];
+            } else {
+                const float4 q = reinterpret_cast<const float4*>(a.rotations)[i];
+                cov3d_from_scale_rot(s_scale[3 * tid], s_scale[3 * tid + 1], s_scale[3 * tid + 2], a.scale_modifier, q, c3);
+                if (blockIdx.y == 0) {  // view-independent: kept once, in the first view's workspace
+                    float2* dst = reinterpret_cast<float2*>((float*)(vb.v[0].ws + a.o_cov3D) + (size_t)6 * i);
+                    dst[0] = make_float2(c3[0], c3[1]); dst[1] = make_float2(c3[2], c3[3]); dst[2] = make_float2(c3[4], c3[5]);
+                }
+            }
+            if (a.colors_precomp) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) rgb_pre[c] = a.colors_precomp[(size_t)3 * i + c];
+            }
+        }
+        for (int v = 0; v < nv; v++) {
+            bool vis = false;
+            if (valid)
+                vis = preprocess_view(a, vb.v[v0 + v], i, px3, py3, pz3, c3, op, a.colors_precomp ? rgb_pre : nullptr,
+                                      s_cam + v * PRE_CAM, s_hist + (size_t)v * n_tiles);
+            const unsigned m = __ballot_sync(0xffffffffu, vis);
+            if ((tid & 31) == 0 && m) atomicAdd(&s_nvis[v], __popc(m));
+        }
+    }
+    __syncthreads();  // orders the histogram updates before the flush
+    for (int v = 0; v < nv; v++) {
+        uint32_t* out = (uint32_t*)(vb.v[v0 + v].ws + a.o_cta_hist) + (size_t)blockIdx.x * n_tiles;
+        const uint32_t* h = s_hist + (size_t)v * n_tiles;
+        for (int t = tid; t < n_tiles; t += PRE_THREADS) out[t] = h[t];
+        if (tid == 0 && s_nvis[v]) atomicAdd(&((DeviceInfo*)(vb.v[v0 + v].ws + a.o_info))->n_visible, s_nvis[v]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -478,10 +507,12 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess_dis(const PreDisArgs
 // tile_count[t] = instances of tile t.  A CTA handles 32 tiles; its 8 warps split the CTA axis, each lane
 // owns one tile (128-byte coalesced rows), partial sums are combined through shared memory.
 constexpr int TO_WARPS = 8;
-__global__ void __launch_bounds__(32 * TO_WARPS) k_tile_offsets(uint32_t* __restrict__ cta_hist,
-                                                               uint32_t* __restrict__ tile_count, int n_tiles,
-                                                               int n_ctas) {
+__global__ void __launch_bounds__(32 * TO_WARPS) k_tile_offsets(const __grid_constant__ PassBatch pb, const WsLayout L) {
     __shared__ uint32_t s_part[TO_WARPS][32];
+    char* ws = pb.v[blockIdx.y].ws;
+    uint32_t* __restrict__ cta_hist = (uint32_t*)(ws + L.cta_hist);
+    uint32_t* __restrict__ tile_count = (uint32_t*)(ws + L.tile_count);
+    const int n_tiles = L.n_tiles, n_ctas = L.n_ctas;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int t = blockIdx.x * 32 + lane;
     const bool ok = t < n_tiles;
@@ -528,11 +559,15 @@ __global__ void __launch_bounds__(32 * TO_WARPS) k_tile_offsets(uint32_t* __rest
 // One CTA: exclusive scan over tiles.  ranges of empty tiles stay (0,0) like the reference's memset
 // (rasterizer_impl.cu:485).
 constexpr int SCAN_THREADS = 1024;
-__global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(const uint32_t* __restrict__ tile_count,
-                                                          uint32_t* __restrict__ tile_cursor,
-                                                          uint2* __restrict__ ranges, int n_tiles,
-                                                          unsigned long long R_cap, DeviceInfo* info) {
+__global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(const __grid_constant__ PassBatch pb, const WsLayout L,
+                                                          unsigned long long R_cap) {
     __shared__ uint32_t s_warp[32];
+    char* ws = pb.v[blockIdx.y].ws;
+    const uint32_t* __restrict__ tile_count = (const uint32_t*)(ws + L.tile_count);
+    uint32_t* __restrict__ tile_cursor = (uint32_t*)(ws + L.tile_cursor);
+    uint2* __restrict__ ranges = (uint2*)(ws + L.ranges);
+    DeviceInfo* info = (DeviceInfo*)(ws + L.info);
+    const int n_tiles = L.n_tiles;
     __shared__ uint32_t s_carry;
     __shared__ uint32_t s_max;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -583,14 +618,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_scan(const uint32_t* __re
 // CTA c handles the same chunk of Gaussians as in k_preprocess; its write cursors (tile start +
 // instances emitted by earlier CTAs) live in shared memory, so slots are handed out by shared-memory
 // atomics only.
-__global__ void __launch_bounds__(PRE_THREADS) k_scatter(int P, int gx, int n_tiles, int chunk,
-                                                         const uint32_t* __restrict__ tiles_touched,
-                                                         const uint2* __restrict__ rect, const float* __restrict__ depths,
-                                                         const uint32_t* __restrict__ cta_hist,
-                                                         const uint32_t* __restrict__ tile_start,
-                                                         unsigned long long* __restrict__ keys,
-                                                         const DeviceInfo* __restrict__ info) {
+__global__ void __launch_bounds__(PRE_THREADS) k_scatter(const __grid_constant__ PassBatch pb, const WsLayout L, int P) {
     extern __shared__ uint32_t s_cur[];  // [n_tiles]
+    char* ws = pb.v[blockIdx.y].ws;
+    const int gx = L.gx, n_tiles = L.n_tiles, chunk = L.chunk;
+    const uint32_t* __restrict__ tiles_touched = (const uint32_t*)(ws + L.tiles_touched);
+    const uint2* __restrict__ rect = (const uint2*)(ws + L.rect);
+    const float* __restrict__ depths = pb.v[blockIdx.y].depths;
+    const uint32_t* __restrict__ cta_hist = (const uint32_t*)(ws + L.cta_hist);
+    const uint32_t* __restrict__ tile_start = (const uint32_t*)(ws + L.tile_cursor);
+    unsigned long long* __restrict__ keys = (unsigned long long*)(ws + L.keys);
+    const DeviceInfo* __restrict__ info = (const DeviceInfo*)(ws + L.info);
     if (info->overflow) return;
     const int tid = threadIdx.x;
     const uint32_t* mine = cta_hist + (size_t)blockIdx.x * n_tiles;
@@ -663,12 +701,14 @@ constexpr int BS_NB = 2048;                      // buckets
 constexpr int BS_LIMIT = 48;                     // largest bucket this path accepts
 constexpr uint32_t BS_DONE = 0xffffffffu;
 
-__global__ void __launch_bounds__(BS_THREADS) k_sort_tiles_bucket(unsigned long long* __restrict__ keys,
-                                                                 uint32_t* __restrict__ point_list,
-                                                                 const uint2* __restrict__ ranges,
-                                                                 uint32_t* __restrict__ tile_count,
-                                                                 const DeviceInfo* __restrict__ info) {
+__global__ void __launch_bounds__(BS_THREADS) k_sort_tiles_bucket(const __grid_constant__ PassBatch pb, const WsLayout L) {
     __shared__ unsigned long long s_key[BS_CAP];  // 32 KB
+    char* ws = pb.v[blockIdx.y].ws;
+    unsigned long long* __restrict__ keys = (unsigned long long*)(ws + L.keys);
+    uint32_t* __restrict__ point_list = (uint32_t*)(ws + L.point_list);
+    const uint2* __restrict__ ranges = (const uint2*)(ws + L.ranges);
+    uint32_t* __restrict__ tile_count = (uint32_t*)(ws + L.tile_count);
+    const DeviceInfo* __restrict__ info = (const DeviceInfo*)(ws + L.info);
     __shared__ uint32_t s_cnt[BS_NB];             // 8 KB: counts -> exclusive starts -> ends
     __shared__ uint32_t s_warp[BS_THREADS / 32];
     __shared__ float s_lohi[2];
@@ -778,12 +818,14 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_CAP = 4096;
 constexpr int RS_ITEMS = RS_CAP / RS_THREADS;  // 16 keys per thread at most
 
-__global__ void __launch_bounds__(RS_THREADS) k_sort_tiles_radix(unsigned long long* __restrict__ keys,
-                                                                uint32_t* __restrict__ point_list,
-                                                                const uint2* __restrict__ ranges,
-                                                                const uint32_t* __restrict__ tile_count,
-                                                                const DeviceInfo* __restrict__ info) {
+__global__ void __launch_bounds__(RS_THREADS) k_sort_tiles_radix(const __grid_constant__ PassBatch pb, const WsLayout L) {
     __shared__ unsigned long long s_key[RS_CAP];       // 32 KB
+    char* ws = pb.v[blockIdx.y].ws;
+    unsigned long long* __restrict__ keys = (unsigned long long*)(ws + L.keys);
+    uint32_t* __restrict__ point_list = (uint32_t*)(ws + L.point_list);
+    const uint2* __restrict__ ranges = (const uint2*)(ws + L.ranges);
+    const uint32_t* __restrict__ tile_count = (const uint32_t*)(ws + L.tile_count);
+    const DeviceInfo* __restrict__ info = (const DeviceInfo*)(ws + L.info);
     __shared__ uint32_t s_cnt[RS_WARPS][256];          // 8 KB  per-warp digit counters / bases
     __shared__ uint32_t s_scan[RS_WARPS];
     if (info->overflow) return;
@@ -953,11 +995,13 @@ __device__ void smem_sort_full(unsigned long long* s, int n) {
     }
 }
 
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(unsigned long long* __restrict__ keys,
-                                                            uint32_t* __restrict__ point_list,
-                                                            const uint2* __restrict__ ranges,
-                                                            const DeviceInfo* __restrict__ info, int min_len) {
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const __grid_constant__ PassBatch pb, const WsLayout L, int min_len) {
     __shared__ unsigned long long s[SORT_CHUNK];
+    char* ws = pb.v[blockIdx.y].ws;
+    unsigned long long* __restrict__ keys = (unsigned long long*)(ws + L.keys);
+    uint32_t* __restrict__ point_list = (uint32_t*)(ws + L.point_list);
+    const uint2* __restrict__ ranges = (const uint2*)(ws + L.ranges);
+    const DeviceInfo* __restrict__ info = (const DeviceInfo*)(ws + L.info);
     if (info->overflow) return;
     const uint2 rg = ranges[blockIdx.x];
     const int n = (int)(rg.y - rg.x);
@@ -1031,6 +1075,8 @@ struct BlendArgs {
     uint8_t* warp_hits;  // [R] per list entry: which of the tile's 8 pixel blocks blended it (read by the backward)
 };
 
+struct BlendBatch { BlendArgs v[OLS_MAX_VIEWS]; };
+
 typedef unsigned long long f32x2;  // two floats in one 64-bit register pair (lo = first)
 __device__ __forceinline__ f32x2 pack2(float lo, float hi) {
     f32x2 r;
@@ -1053,7 +1099,8 @@ __device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {  // per-component mul
 
 // NCOL = 3: the pass blends rgb (+ background) and depth; NCOL = 0: language channels only (second pass of D/).
 template <int TILE, int NCOL, int F, bool BITEXACT>
-__global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend(const BlendArgs a) {
+__global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend(const __grid_constant__ BlendBatch bb) {
+    const BlendArgs& a = bb.v[blockIdx.y];
     static_assert(TILE <= 16, "8 warps of 8x4 pixels cover at most 16x16");
     static_assert(NCOL == 0 || NCOL == 3, "colour channels");
     constexpr int NCH = NCOL + F;               // channels stored from REC_CH on (an odd count is zero-padded)
@@ -1224,12 +1271,249 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend(const BlendArgs a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Forward blend, two pixels per lane (the default).  One CTA of 128 threads per tile; each of the 4 warps owns an
+// 8x8 pixel block -- lane l: column (l & 7), rows (l >> 3) and (l >> 3) + 4 -- so everything of a (block, Gaussian)
+// step that does not depend on the pixel row (list walk, the two header loads and the five channel loads from
+// shared memory, dx, dx*A, dx*B) is paid once per TWO pixels, and each lane carries two independent dependency
+// chains.  Per-pixel arithmetic, thresholds and accumulation order are those of k_blend (and, in BITEXACT mode, of
+// the compiled reference, forward.cu:437-483), so every output bit is unchanged.  The two 8x4 halves of a warp's block
+// are the pixel blocks of k_blend: the hit byte the backward reads (bit w = block w blended the entry) keeps its
+// meaning.  Without BITEXACT alpha uses ex2.approx(power * log2 e) (2 instructions instead of expf's 8; relative
+// error of alpha <= 4e-7, tests/test_forward_gpu.py states the tolerance); the backward then uses the same function
+// so that its blend / skip decisions agree with the forward's.
+// ---------------------------------------------------------------------------------------------------
+constexpr int B2_THREADS = 128;
+__device__ __forceinline__ float fast_exp(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
+
+template <int TILE, int NCOL, int F, bool BITEXACT>
+__global__ void __launch_bounds__(B2_THREADS, 5) k_blend2(const __grid_constant__ BlendBatch bb) {
+    const BlendArgs& a = bb.v[blockIdx.y];
+    static_assert(TILE <= 16, "4 warps of 8x8 pixels cover at most 16x16");
+    static_assert(NCOL == 0 || NCOL == 3, "colour channels");
+    constexpr int NCH = NCOL + F;
+    constexpr int REC = rec_floats_nch(NCH);
+    using Stage = RecordStage<NCOL, F>;
+    constexpr int OPS = Stage::OPS;
+    constexpr int NPAIR = (NCH + 1) / 2;
+    constexpr int EXT = REC - 2;
+    constexpr int NHALF = BLEND_BATCH / 32;
+    __shared__ __align__(16) float s_rec[2][BLEND_BATCH * REC];
+    __shared__ uint32_t s_id[2][BLEND_BATCH];
+    __shared__ uint32_t s_hit[2][8][NHALF];  // per 8x4 pixel block (k_blend's warp index): bit j = the block blended entry j
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tile_x = blockIdx.x % a.gx, tile_y = blockIdx.x / a.gx;
+    const int bx0 = (wid & 1) * 8, by0 = (wid >> 1) * 8;
+    const int lx = bx0 + (lane & 7);
+    const int pxi = tile_x * TILE + lx;
+    int ly[2], pyi[2];
+    bool inside[2], done[2];
+    float pfy[2];
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+        ly[p] = by0 + (lane >> 3) + 4 * p;
+        pyi[p] = tile_y * TILE + ly[p];
+        inside[p] = lx < TILE && ly[p] < TILE && pxi < a.W && pyi[p] < a.H;
+        done[p] = !inside[p];
+        pfy[p] = (float)pyi[p];
+    }
+    const float pfx = (float)pxi;
+    // block ids of the two halves in k_blend's numbering: ((y / 4) * 2 + x / 8)
+    const int blk0 = ((wid >> 1) * 2) * 2 + (wid & 1), blk1 = blk0 + 2;
+    if (tid < 2 * 8 * NHALF) (&s_hit[0][0][0])[tid] = 0u;
+    // this warp's pixel rectangle, clipped to the tile and the image
+    const float fx0 = (float)(tile_x * TILE + bx0), fy0 = (float)(tile_y * TILE + by0);
+    const float fx1 = (float)min(min(tile_x * TILE + bx0 + 7, tile_x * TILE + TILE - 1), a.W - 1);
+    const float fy1 = (float)min(min(tile_y * TILE + by0 + 7, tile_y * TILE + TILE - 1), a.H - 1);
+
+    uint2 rg = a.ranges[blockIdx.x];
+    const bool overflow = a.info->overflow != 0;  // instance capacity exceeded: nothing was binned; the images become NaN
+    if (overflow) rg = make_uint2(0u, 0u);
+    const int total = (int)(rg.y - rg.x);
+    const int n_batches = (total + BLEND_BATCH - 1) / BLEND_BATCH;
+
+    auto flush_hits = [&](int b) {
+        if (tid < BLEND_BATCH) {
+            uint32_t byte = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) byte |= ((s_hit[b & 1][w][tid >> 5] >> (tid & 31)) & 1u) << w;
+            const int e = b * BLEND_BATCH + tid;
+            if (e < total) a.warp_hits[rg.x + e] = (uint8_t)byte;
+        }
+    };
+    auto issue = [&](int b) {
+        const int cnt = min(BLEND_BATCH, total - b * BLEND_BATCH);
+        const int buf = b & 1;
+        constexpr int TPE = B2_THREADS / BLEND_BATCH;
+        const int g = tid / TPE;
+        if (g < cnt) {
+            const uint32_t id = a.point_list[rg.x + b * BLEND_BATCH + g];
+            if ((tid % TPE) == 0) s_id[buf][g] = id;
+#pragma unroll
+            for (int q = tid % TPE; q < OPS; q += TPE) Stage::copy(&s_rec[buf][g * REC], a.records, a.language, id, q);
+        }
+        cp_async_commit();
+    };
+
+    float T[2] = {1.0f, 1.0f};
+    f32x2 acc2[2][NPAIR];
+#pragma unroll
+    for (int p = 0; p < 2; p++)
+#pragma unroll
+        for (int c = 0; c < NPAIR; c++) acc2[p][c] = 0ull;
+    float acc_d[2] = {0.0f, 0.0f};
+    uint32_t last_contributor[2] = {0u, 0u};
+
+    if (n_batches > 0) issue(0);
+    int b = 0;
+    for (; b < n_batches; b++) {
+        cp_async_wait<0>();
+        if (__syncthreads_count(done[0] && done[1]) == B2_THREADS) break;
+        if (b > 0) flush_hits(b - 1);
+        if (b + 1 < n_batches) issue(b + 1);
+        const int cnt = min(BLEND_BATCH, total - b * BLEND_BATCH);
+        const float* rec = s_rec[b & 1];
+        const uint32_t* ids = s_id[b & 1];
+        const uint32_t cbase = (uint32_t)b * BLEND_BATCH;
+#pragma unroll 1
+        for (int half = 0; half < NHALF; half++) {
+            uint32_t myhits[2] = {0u, 0u}, mytouch[2] = {0u, 0u};
+            if (__all_sync(0xffffffffu, done[0] && done[1])) {
+                if (lane == 0) { s_hit[b & 1][blk0][half] = 0u; s_hit[b & 1][blk1][half] = 0u; }
+                continue;
+            }
+            const int e = half * 32 + lane;
+            bool hit = false;
+            if (e < cnt) {
+                const float2 c = *reinterpret_cast<const float2*>(rec + e * REC + REC_X);
+                const float2 h = *reinterpret_cast<const float2*>(rec + e * REC + EXT);
+                hit = (c.x + h.x >= fx0) && (c.x - h.x <= fx1) && (c.y + h.y >= fy0) && (c.y - h.y <= fy1);
+            }
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            while (m) {
+                const int jl = __ffs(m) - 1;
+                const int j = half * 32 + jl;
+                m &= m - 1;
+                const float* rj = rec + j * REC;
+                const uint32_t jbit = 1u << jl;
+                const float4 g0 = *reinterpret_cast<const float4*>(rj);      // x y A B
+                const float4 g1 = *reinterpret_cast<const float4*>(rj + 4);  // C op pth depth
+                const float dx = fsub(g0.x, pfx);
+                const float dxa = fmul(dx, g0.z), dxb = fmul(dx, g0.w);
+                float power[2];
+                bool pass[2];
+#pragma unroll
+                for (int p = 0; p < 2; p++) {
+                    const float dy = fsub(g0.y, pfy[p]);
+                    power[p] = ffma(ffma(dx, dxa, fmul(dy, fmul(dy, g1.x))), -0.5f, -fmul(dy, dxb));
+                    pass[p] = !done[p] && !(power[p] > 0.0f) && !(power[p] < g1.z);
+                }
+                if (pass[0] || pass[1]) {
+                    f32x2 v[NPAIR];
+#pragma unroll
+                    for (int q = 0; q + 1 < NPAIR; q += 2) {
+                        const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(rj + REC_CH + 2 * q);
+                        v[q] = t.x;
+                        v[q + 1] = t.y;
+                    }
+                    if (NPAIR & 1) v[NPAIR - 1] = *reinterpret_cast<const f32x2*>(rj + REC_CH + 2 * (NPAIR - 1));
+#pragma unroll
+                    for (int p = 0; p < 2; p++) {
+                        if (pass[p]) {
+                            const float G = BITEXACT ? expf(power[p]) : fast_exp(power[p]);
+                            const float alpha = fminf(fmul(g1.y, G), 0.99f);
+                            if (!(alpha < 1.0f / 255.0f)) {
+                                const float test_T = fmul(T[p], fsub(1.0f, alpha));
+                                if (test_T < 0.0001f) {
+                                    done[p] = true;
+                                } else {
+                                    if (BITEXACT) {  // acc = fma(T, alpha * c, acc) like the compiled reference
+                                        const f32x2 a2 = pack2(alpha, alpha), T2 = pack2(T[p], T[p]);
+#pragma unroll
+                                        for (int q = 0; q < NPAIR; q++) acc2[p][q] = ffma2(T2, fmul2(a2, v[q]), acc2[p][q]);
+                                        if (NCOL) acc_d[p] = ffma(T[p], fmul(alpha, g1.w), acc_d[p]);
+                                    } else {
+                                        const float w = fmul(alpha, T[p]);
+                                        const f32x2 w2 = pack2(w, w);
+#pragma unroll
+                                        for (int q = 0; q < NPAIR; q++) acc2[p][q] = ffma2(w2, v[q], acc2[p][q]);
+                                        if (NCOL) acc_d[p] = ffma(w, g1.w, acc_d[p]);
+                                    }
+                                    myhits[p] |= jbit;
+                                    if (test_T > 0.5f) mytouch[p] |= jbit;
+                                    T[p] = test_T;
+                                    last_contributor[p] = cbase + (uint32_t)j + 1u;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            // once per 32 entries: which entries did each 8x4 half blend (for the backward), and the n_touched counts
+            const uint32_t h0 = __reduce_or_sync(0xffffffffu, myhits[0]), h1 = __reduce_or_sync(0xffffffffu, myhits[1]);
+            if (lane == 0) { s_hit[b & 1][blk0][half] = h0; s_hit[b & 1][blk1][half] = h1; }
+            for (uint32_t tmask = __reduce_or_sync(0xffffffffu, mytouch[0] | mytouch[1]); tmask; tmask &= tmask - 1) {
+                const int jl = __ffs(tmask) - 1;
+                const int n = __popc(__ballot_sync(0xffffffffu, (mytouch[0] >> jl) & 1u)) +
+                              __popc(__ballot_sync(0xffffffffu, (mytouch[1] >> jl) & 1u));
+                if (lane == 0) atomicAdd(&a.n_touched[ids[half * 32 + jl]], n);
+            }
+        }
+    }
+    cp_async_wait<0>();
+    if (b > 0) {  // the last batch that was worked on (a `break` leaves before flushing it)
+        __syncthreads();
+        flush_hits(b - 1);
+    }
+    const size_t HW = (size_t)a.W * a.H;
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+        if (inside[p]) {
+            const size_t pix = (size_t)pyi[p] * a.W + pxi;
+            float acc[2 * NPAIR];
+#pragma unroll
+            for (int q = 0; q < NPAIR; q++) unpack2(acc2[p][q], acc[2 * q], acc[2 * q + 1]);
+            if (overflow) {  // never hand back a plausible-looking empty image (the wrapper re-renders with the exact capacity)
+#pragma unroll
+                for (int q = 0; q < 2 * NPAIR; q++) acc[q] = CUDART_NAN_F;
+                acc_d[p] = CUDART_NAN_F;
+                T[p] = CUDART_NAN_F;
+            }
+            a.final_T[pix] = T[p];
+            a.n_contrib[pix] = last_contributor[p];
+            if (NCOL) {
+#pragma unroll
+                for (int c = 0; c < NCOL; c++) a.out_color[c * HW + pix] = ffma(a.bg[c], T[p], acc[c]);
+                a.out_depth[pix] = acc_d[p];
+            }
+#pragma unroll
+            for (int c = 0; c < F; c++) a.out_language[c * HW + pix] = acc[NCOL + c];
+            a.out_opacity[pix] = fsub(1.0f, T[p]);
+        }
+    }
+}
+
 template <int TILE, int NCOL, int F>
-static int launch_blend(const BlendArgs& ba, int n_tiles, bool bitexact, cudaStream_t st) {
+static int launch_blend(const BlendBatch& ba, int n_tiles, int V, bool bitexact, cudaStream_t st) {
+    static const bool v1 = getenv("OLS_BLEND_V1") != nullptr;  // A/B aid: the one-pixel-per-lane kernel
+    const dim3 grid(n_tiles, V);
+    if (v1) {
+        if (bitexact)
+            k_blend<TILE, NCOL, F, true><<<grid, BLEND_THREADS, 0, st>>>(ba);
+        else
+            k_blend<TILE, NCOL, F, false><<<grid, BLEND_THREADS, 0, st>>>(ba);
+        return 0;
+    }
     if (bitexact)
-        k_blend<TILE, NCOL, F, true><<<n_tiles, BLEND_THREADS, 0, st>>>(ba);
+        k_blend2<TILE, NCOL, F, true><<<grid, B2_THREADS, 0, st>>>(ba);
     else
-        k_blend<TILE, NCOL, F, false><<<n_tiles, BLEND_THREADS, 0, st>>>(ba);
+        k_blend2<TILE, NCOL, F, false><<<grid, B2_THREADS, 0, st>>>(ba);
     return 0;
 }
 
@@ -1262,62 +1546,55 @@ static int set_hist_smem(size_t hist_smem, int n_tiles) {
     return OLS_OK;
 }
 
-// One footprint's binning + per-tile sort + blend (everything after preprocess).  `ws` / `L` locate the
-// pass' own arrays; `depths` may live in another pass' workspace (D/ shares them between its two lists).
-struct PassOut {
-    float *color, *language, *depth, *opacity;
-    int32_t* n_touched;
-};
-static int run_pass(int P, int W, int H, int tile, int ncol, int F, unsigned flags, int64_t R_cap, char* ws, const WsLayout& L,
-                    const float* depths, const float* language, const float* d_bg, const PassOut& o, cudaStream_t st) {
+// One footprint's binning + per-tile sort + blend (everything after preprocess) for the V views of a batch
+// (grid.y = view).  `L` is the layout every view's workspace shares; `depths` of a view may live in another pass'
+// workspace (D/ shares them between its two lists).
+static int run_pass(int P, int W, int H, int tile, int ncol, int F, unsigned flags, int64_t R_cap, const PassBatch& pb, int V,
+                    const WsLayout& L, const float* language, cudaStream_t st) {
     const bool debug = (flags & OLS_FLAG_DEBUG) != 0;
-    DeviceInfo* info = (DeviceInfo*)(ws + L.info);
-    uint32_t* cta_hist = (uint32_t*)(ws + L.cta_hist);
     const size_t hist_smem = sizeof(uint32_t) * (size_t)L.n_tiles;
-    k_tile_offsets<<<(L.n_tiles + 31) / 32, 32 * TO_WARPS, 0, st>>>(cta_hist, (uint32_t*)(ws + L.tile_count), L.n_tiles, L.n_ctas);
+    k_tile_offsets<<<dim3((L.n_tiles + 31) / 32, V), 32 * TO_WARPS, 0, st>>>(pb, L);
     OLS_DEBUG_SYNC("tile_offsets");
-    k_tile_scan<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)(ws + L.tile_count), (uint32_t*)(ws + L.tile_cursor),
-                                           (uint2*)(ws + L.ranges), L.n_tiles, (unsigned long long)R_cap, info);
+    k_tile_scan<<<dim3(1, V), SCAN_THREADS, 0, st>>>(pb, L, (unsigned long long)R_cap);
     OLS_DEBUG_SYNC("tile_scan");
-    k_scatter<<<L.n_ctas, PRE_THREADS, hist_smem, st>>>(P, L.gx, L.n_tiles, L.chunk, (const uint32_t*)(ws + L.tiles_touched),
-                                                        (const uint2*)(ws + L.rect), depths, cta_hist,
-                                                        (const uint32_t*)(ws + L.tile_cursor),
-                                                        (unsigned long long*)(ws + L.keys), info);
+    k_scatter<<<dim3(L.n_ctas, V), PRE_THREADS, hist_smem, st>>>(pb, L, P);
     OLS_DEBUG_SYNC("scatter");
     ols_timing_mark(OLS_T_BINNING, st);
-    k_sort_tiles_bucket<<<L.n_tiles, BS_THREADS, 0, st>>>((unsigned long long*)(ws + L.keys), (uint32_t*)(ws + L.point_list),
-                                                          (const uint2*)(ws + L.ranges), (uint32_t*)(ws + L.tile_count), info);
+    k_sort_tiles_bucket<<<dim3(L.n_tiles, V), BS_THREADS, 0, st>>>(pb, L);
     OLS_DEBUG_SYNC("sort_tiles_bucket");
-    k_sort_tiles_radix<<<L.n_tiles, RS_THREADS, 0, st>>>((unsigned long long*)(ws + L.keys), (uint32_t*)(ws + L.point_list),
-                                                         (const uint2*)(ws + L.ranges), (const uint32_t*)(ws + L.tile_count), info);
+    k_sort_tiles_radix<<<dim3(L.n_tiles, V), RS_THREADS, 0, st>>>(pb, L);
     OLS_DEBUG_SYNC("sort_tiles_radix");
     // buckets longer than the radix kernel's shared-memory capacity (rare): bitonic fallback
-    k_sort_tiles<<<L.n_tiles, SORT_THREADS, 0, st>>>((unsigned long long*)(ws + L.keys), (uint32_t*)(ws + L.point_list),
-                                                     (const uint2*)(ws + L.ranges), info, RS_CAP);
+    k_sort_tiles<<<dim3(L.n_tiles, V), SORT_THREADS, 0, st>>>(pb, L, RS_CAP);
     OLS_DEBUG_SYNC("sort_tiles");
     ols_timing_mark(OLS_T_SORT, st);
 
-    BlendArgs ba;
-    ba.W = W; ba.H = H; ba.gx = L.gx;
-    ba.ranges = (const uint2*)(ws + L.ranges); ba.point_list = (const uint32_t*)(ws + L.point_list);
-    ba.records = (const float*)(ws + L.records); ba.language = language; ba.bg = d_bg; ba.info = info;
-    ba.final_T = (float*)(ws + L.final_T); ba.n_contrib = (uint32_t*)(ws + L.n_contrib);
-    ba.out_color = o.color; ba.out_language = o.language; ba.out_depth = o.depth;
-    ba.out_opacity = o.opacity; ba.n_touched = o.n_touched;
-    ba.warp_hits = (uint8_t*)(ws + L.warp_hits);
+    BlendBatch bb;
+    for (int v = 0; v < V; v++) {
+        BlendArgs& ba = bb.v[v];
+        char* ws = pb.v[v].ws;
+        ba.W = W; ba.H = H; ba.gx = L.gx;
+        ba.ranges = (const uint2*)(ws + L.ranges); ba.point_list = (const uint32_t*)(ws + L.point_list);
+        ba.records = (const float*)(ws + L.records); ba.language = language; ba.bg = pb.v[v].bg;
+        ba.info = (const DeviceInfo*)(ws + L.info);
+        ba.final_T = (float*)(ws + L.final_T); ba.n_contrib = (uint32_t*)(ws + L.n_contrib);
+        ba.out_color = pb.v[v].color; ba.out_language = pb.v[v].language; ba.out_depth = pb.v[v].depth;
+        ba.out_opacity = pb.v[v].opacity; ba.n_touched = pb.v[v].n_touched;
+        ba.warp_hits = (uint8_t*)(ws + L.warp_hits);
+    }
     const bool bitexact = (flags & OLS_FLAG_BITEXACT_BLEND) != 0;
     const int key = tile * 10000 + ncol * 100 + F;
     switch (key) {
-        case 150315: launch_blend<15, 3, 15>(ba, L.n_tiles, bitexact, st); break;
-        case 160315: launch_blend<16, 3, 15>(ba, L.n_tiles, bitexact, st); break;
-        case 150303: launch_blend<15, 3, 3>(ba, L.n_tiles, bitexact, st); break;
-        case 160303: launch_blend<16, 3, 3>(ba, L.n_tiles, bitexact, st); break;
-        case 150300: launch_blend<15, 3, 0>(ba, L.n_tiles, bitexact, st); break;   // D/ colour pass
-        case 160300: launch_blend<16, 3, 0>(ba, L.n_tiles, bitexact, st); break;
-        case 150003: launch_blend<15, 0, 3>(ba, L.n_tiles, bitexact, st); break;   // D/ language pass
-        case 160003: launch_blend<16, 0, 3>(ba, L.n_tiles, bitexact, st); break;
-        case 150015: launch_blend<15, 0, 15>(ba, L.n_tiles, bitexact, st); break;
-        case 160015: launch_blend<16, 0, 15>(ba, L.n_tiles, bitexact, st); break;
+        case 150315: launch_blend<15, 3, 15>(bb, L.n_tiles, V, bitexact, st); break;
+        case 160315: launch_blend<16, 3, 15>(bb, L.n_tiles, V, bitexact, st); break;
+        case 150303: launch_blend<15, 3, 3>(bb, L.n_tiles, V, bitexact, st); break;
+        case 160303: launch_blend<16, 3, 3>(bb, L.n_tiles, V, bitexact, st); break;
+        case 150300: launch_blend<15, 3, 0>(bb, L.n_tiles, V, bitexact, st); break;   // D/ colour pass
+        case 160300: launch_blend<16, 3, 0>(bb, L.n_tiles, V, bitexact, st); break;
+        case 150003: launch_blend<15, 0, 3>(bb, L.n_tiles, V, bitexact, st); break;   // D/ language pass
+        case 160003: launch_blend<16, 0, 3>(bb, L.n_tiles, V, bitexact, st); break;
+        case 150015: launch_blend<15, 0, 15>(bb, L.n_tiles, V, bitexact, st); break;
+        case 160015: launch_blend<16, 0, 15>(bb, L.n_tiles, V, bitexact, st); break;
         default:
             ols_set_error("unsupported (tile=%d, F=%d): compiled variants are tile in {15,16} x F in {3,15}", tile, F);
             return OLS_ERR_UNSUPPORTED;
@@ -1327,41 +1604,61 @@ static int run_pass(int P, int W, int H, int tile, int ncol, int F, unsigned fla
     return OLS_OK;
 }
 
-int ols_launch_forward(const ols_raster_args* a, const ols_fwd_out* o, const WsLayout& L, cudaStream_t st) {
-    char* ws = (char*)a->d_workspace;
-    DeviceInfo* info = (DeviceInfo*)(ws + L.info);
+// Views per CTA of k_preprocess: as many as fit a 64 KB budget of tile histograms, spread evenly over the groups.
+static int preprocess_view_group(int V, int n_tiles) {
+    const size_t per_view = sizeof(uint32_t) * (size_t)n_tiles + sizeof(float) * PRE_CAM;
+    int vg_max = (int)((64 * 1024) / per_view);
+    if (vg_max < 1) vg_max = 1;
+    const int groups = (V + vg_max - 1) / vg_max;
+    return (V + groups - 1) / groups;
+}
+
+// Forward of V views of the same Gaussians (V = 1: the reference's call).  The views share every size, the flags and
+// the Gaussian parameter pointers (validated by the caller); matrices, field of view, background, outputs and the
+// workspace are per view.
+int ols_launch_forward(const ols_raster_args* views, const ols_fwd_out* outs, int V, const WsLayout& L, cudaStream_t st) {
+    const ols_raster_args* a = &views[0];
     const bool debug = (a->flags & OLS_FLAG_DEBUG) != 0;
     if (a->F != 3 && a->F != 15) {
         ols_set_error("unsupported (tile=%d, F=%d): compiled variants are tile in {15,16} x F in {3,15}", a->tile, a->F);
         return OLS_ERR_UNSUPPORTED;
     }
-    OLS_CUDA_TRY(cudaMemsetAsync(ws + L.info, 0, 256, st));
-    OLS_CUDA_TRY(cudaMemsetAsync(o->d_n_touched, 0, sizeof(int32_t) * (size_t)a->P, st));
-
+    PreBatch vb;
+    PassBatch pb;
+    for (int v = 0; v < V; v++) {
+        char* ws = (char*)views[v].d_workspace;
+        OLS_CUDA_TRY(cudaMemsetAsync(ws + L.info, 0, 256, st));
+        OLS_CUDA_TRY(cudaMemsetAsync(outs[v].d_n_touched, 0, sizeof(int32_t) * (size_t)a->P, st));
+        PreView& pv = vb.v[v];
+        pv.viewmatrix = views[v].d_viewmatrix; pv.projmatrix = views[v].d_projmatrix; pv.campos = views[v].d_campos;
+        pv.tanfovx = views[v].tanfovx; pv.tanfovy = views[v].tanfovy;
+        pv.focal_y = a->H / (2.0f * views[v].tanfovy);  // rasterizer_impl.cu:394-395
+        pv.focal_x = a->W / (2.0f * views[v].tanfovx);
+        pv.ws = ws; pv.radii = outs[v].d_radii;
+        PassView& q = pb.v[v];
+        q.ws = ws; q.depths = (const float*)(ws + L.depths); q.bg = views[v].d_bg;
+        q.color = outs[v].d_color; q.language = outs[v].d_language; q.depth = outs[v].d_depth; q.opacity = outs[v].d_opacity;
+        q.n_touched = outs[v].d_n_touched;
+    }
     PreArgs p;
     p.P = a->P; p.F = a->F; p.sh_degree = a->sh_degree; p.M = a->M; p.W = a->W; p.H = a->H; p.tile = a->tile;
-    p.gx = L.gx; p.gy = L.gy; p.rec = L.rec; p.flags = a->flags;
-    p.tanfovx = a->tanfovx; p.tanfovy = a->tanfovy;
-    p.focal_y = a->H / (2.0f * a->tanfovy);  // rasterizer_impl.cu:394-395
-    p.focal_x = a->W / (2.0f * a->tanfovx);
+    p.gx = L.gx; p.gy = L.gy; p.rec = L.rec; p.V = V; p.chunk = L.chunk; p.flags = a->flags;
     p.scale_modifier = a->scale_modifier;
     p.means3D = a->d_means3D; p.shs = a->d_shs; p.colors_precomp = a->d_colors_precomp;
     p.opacities = a->d_opacities; p.scales = a->d_scales; p.rotations = a->d_rotations;
-    p.cov3D_precomp = a->d_cov3D_precomp; p.viewmatrix = a->d_viewmatrix; p.projmatrix = a->d_projmatrix;
-    p.campos = a->d_campos;
-    p.records = (float*)(ws + L.records); p.depths = (float*)(ws + L.depths); p.cov3D = (float*)(ws + L.cov3D);
-    p.clamped = (uint32_t*)(ws + L.clamped); p.tiles_touched = (uint32_t*)(ws + L.tiles_touched);
-    p.rect = (uint2*)(ws + L.rect); p.cta_hist = (uint32_t*)(ws + L.cta_hist); p.chunk = L.chunk; p.radii = o->d_radii;
-    p.info = info;
+    p.cov3D_precomp = a->d_cov3D_precomp;
+    p.o_records = L.records; p.o_depths = L.depths; p.o_cov3D = L.cov3D; p.o_clamped = L.clamped;
+    p.o_tiles_touched = L.tiles_touched; p.o_rect = L.rect; p.o_cta_hist = L.cta_hist; p.o_info = L.info;
+    p.VG = preprocess_view_group(V, L.n_tiles);
     const size_t hist_smem = sizeof(uint32_t) * (size_t)L.n_tiles;
-    int rc = set_hist_smem(hist_smem, L.n_tiles);
+    const size_t pre_smem = (size_t)p.VG * (hist_smem + sizeof(float) * PRE_CAM);
+    int rc = set_hist_smem(pre_smem, L.n_tiles);
     if (rc != OLS_OK) return rc;
     ols_timing_mark(-1, st);
-    k_preprocess<<<L.n_ctas, PRE_THREADS, hist_smem, st>>>(p);
+    k_preprocess<<<dim3(L.n_ctas, (V + p.VG - 1) / p.VG), PRE_THREADS, pre_smem, st>>>(p, vb);
     OLS_DEBUG_SYNC("preprocess");
     ols_timing_mark(OLS_T_PREPROCESS, st);
-    PassOut po{o->d_color, o->d_language, o->d_depth, o->d_opacity, o->d_n_touched};
-    return run_pass(a->P, a->W, a->H, a->tile, 3, a->F, a->flags, a->R_cap, ws, L, p.depths, a->d_language, a->d_bg, po, st);
+    return run_pass(a->P, a->W, a->H, a->tile, 3, a->F, a->flags, a->R_cap, pb, V, L, a->d_language, st);
 }
 
 // Disentangled forward (D/rasterizer_impl.cu:364-620): one preprocess, then the colour footprint's and
@@ -1408,10 +1705,11 @@ int ols_launch_forward_dis(const ols_dis_args* d, const ols_dis_fwd_out* o, cons
     k_preprocess_dis<<<Lc.n_ctas, PRE_THREADS, 2 * hist_smem, st>>>(p);
     OLS_DEBUG_SYNC("preprocess_dis");
     ols_timing_mark(OLS_T_PREPROCESS, st);
-    PassOut pc{o->d_color, nullptr, o->d_depth, o->d_opacity, o->d_n_touched};
-    rc = run_pass(a->P, a->W, a->H, a->tile, 3, 0, a->flags, a->R_cap, wc, Lc, p.depths, nullptr, a->d_bg, pc, st);
+    PassBatch pc, pl;
+    pc.v[0] = PassView{wc, p.depths, a->d_bg, o->d_color, nullptr, o->d_depth, o->d_opacity, o->d_n_touched};
+    rc = run_pass(a->P, a->W, a->H, a->tile, 3, 0, a->flags, a->R_cap, pc, 1, Lc, nullptr, st);
     if (rc != OLS_OK) return rc;
     ols_timing_mark(-1, st);
-    PassOut pl{nullptr, o->d_language, nullptr, o->d_opacity_lang, o->d_n_touched_lang};
-    return run_pass(a->P, a->W, a->H, a->tile, 0, a->F, a->flags, d->R_cap_lang, wl, Ll, p.depths, nullptr, a->d_bg, pl, st);
+    pl.v[0] = PassView{wl, p.depths, a->d_bg, nullptr, o->d_language, nullptr, o->d_opacity_lang, o->d_n_touched_lang};
+    return run_pass(a->P, a->W, a->H, a->tile, 0, a->F, a->flags, d->R_cap_lang, pl, 1, Ll, nullptr, st);
 }

@@ -26,6 +26,7 @@ struct LossArgs {
     const float* upstream;                  // device scalar dL/dloss (backward)
     float *dimage, *ddepth, *dlanguage;
     float* sums;                            // [8]: |rgb|, |depth|, |lang|, d/d exposure_a, d/d exposure_b
+    const float *d_ea, *d_eb;               // device-resident exposure_a / exposure_b (override ea / eb when non-NULL)
 };
 
 // PyTorch upsample_bilinear2d, align_corners = false (ATen/native/UpSample.h: area_pixel_compute_source_index)
@@ -49,6 +50,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) k_mapping_loss(const LossArgs a)
     const float up = BACKWARD ? a.upstream[0] : 0.0f;
     const float w_rgb = a.alpha / (3.0f * (float)HW), w_d = (1.0f - a.alpha) / (float)HW;
     const float w_l = a.F > 0 ? a.lambda_lang / ((float)a.F * (float)HW) : 0.0f;
+    const float ea = a.d_ea ? expf(a.d_ea[0]) : a.ea, eb = a.d_eb ? a.d_eb[0] : a.eb;
     for (size_t pix = (size_t)blockIdx.x * LOSS_THREADS + threadIdx.x; pix < HW; pix += (size_t)gridDim.x * LOSS_THREADS) {
         const int y = (int)(pix / a.W), x = (int)(pix - (size_t)y * a.W);
         // colour: | (ea * image + eb) * m - gt * m |
@@ -63,14 +65,14 @@ __global__ void __launch_bounds__(LOSS_THREADS) k_mapping_loss(const LossArgs a)
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             const float im = a.image[c * HW + pix];
-            const float diff = (a.ea * im + a.eb) * m - gts[c] * m;
+            const float diff = (ea * im + eb) * m - gts[c] * m;
             abs_sum += fabsf(diff);
             if (BACKWARD) {
-                a.dimage[c * HW + pix] = up * w_rgb * op * sgn(diff) * m * a.ea;
+                a.dimage[c * HW + pix] = up * w_rgb * op * sgn(diff) * m * ea;
             } else {
                 s_rgb += op * fabsf(diff);
                 const float sg = op * sgn(diff) * m;
-                s_ea += sg * a.ea * im;  // d|diff| / d exposure_a
+                s_ea += sg * ea * im;  // d|diff| / d exposure_a
                 s_eb += sg;              // d|diff| / d exposure_b
             }
         }
@@ -153,6 +155,7 @@ static int fill(const ols_loss_args* p, LossArgs* a) {
     a->image = p->d_image; a->depth = p->d_depth; a->language = p->d_language;
     a->gt_image = p->d_gt_image; a->gt_depth = p->d_gt_depth; a->gt_lang = p->d_gt_lang;
     a->opacity = p->d_opacity; a->grad_mask = p->d_grad_mask; a->dopacity = nullptr;
+    a->d_ea = p->d_exposure_a; a->d_eb = p->d_exposure_b;
     a->upstream = nullptr; a->dimage = nullptr; a->ddepth = nullptr; a->dlanguage = nullptr; a->sums = nullptr;
     return OLS_OK;
 }

@@ -72,23 +72,3 @@ def densify_flags(xyz_gradient_accum: torch.Tensor, denom: torch.Tensor, scaling
 
 
 # ---- plain-torch restatements of the reference lines (test references) ----------------------------------------------
-def reference_update_stats(radii, viewspace_grad, max_radii2D, xyz_gradient_accum=None, denom=None):
-    vis = radii > 0
-    max_radii2D[vis] = torch.max(max_radii2D[vis], radii[vis])
-    if viewspace_grad is not None:
-        xyz_gradient_accum[vis] += torch.norm(viewspace_grad[vis, :2], dim=-1, keepdim=True)
-        denom[vis] += 1
-
-
-def reference_densify_flags(xyz_gradient_accum, denom, scaling_raw, opacity_raw, max_radii2D, *, max_grad, min_opacity,
-                            extent, max_screen_size, percent_dense=0.01):
-    grads = xyz_gradient_accum / denom
-    grads[grads.isnan()] = 0.0
-    smax = torch.max(torch.exp(scaling_raw), dim=1).values
-    hot = torch.norm(grads, dim=-1) >= max_grad
-    clone = hot & (smax <= percent_dense * extent)
-    split = (grads.squeeze(-1) >= max_grad) & (smax > percent_dense * extent)
-    prune = (torch.sigmoid(opacity_raw) < min_opacity).squeeze(-1)
-    if max_screen_size:
-        prune = prune | (max_radii2D > max_screen_size) | (smax > 0.1 * extent)
-    return clone.to(torch.uint8) * CLONE + split.to(torch.uint8) * SPLIT + prune.to(torch.uint8) * PRUNE

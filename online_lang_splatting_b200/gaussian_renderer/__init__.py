@@ -11,6 +11,8 @@ Divergences from the reference, all documented in DESIGN.md:
   ``None`` as the reference intended.
 * ``override_color`` is honoured in language mode (the reference tests a local it has just set to
   ``None`` and so silently ignores it, :271-288).
+* ``render_batch(viewpoint_cameras, pc, pipe, bg_color)`` (extension): the window keyframes of a mapping iteration
+  (utils/slam_backend.py:510-662) in one set of launches; returns the list of dictionaries ``render()`` would.
 * Two module-level knobs select the rasterizer build the reference fixes at compile time:
   ``TILE_SIZE`` (15 = reference config.h) and ``BACKWARD_MODE`` ("compat" | "exact").
 """
@@ -24,6 +26,7 @@ from ..diff_gaussian_rasterization import (
     GaussianRasterizationSettings,
     GaussianRasterizer,
     LanguageGaussianRasterizer,
+    rasterize_language_gaussians_batch,
 )
 
 TILE_SIZE = 15
@@ -146,3 +149,76 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
     if language_mode:
         out["language"] = language
     return out
+
+
+def _settings_of(viewpoint_camera, pc, bg_color, scaling_modifier):
+    return GaussianRasterizationSettings(
+        image_height=int(viewpoint_camera.image_height),
+        image_width=int(viewpoint_camera.image_width),
+        tanfovx=math.tan(viewpoint_camera.FoVx * 0.5),
+        tanfovy=math.tan(viewpoint_camera.FoVy * 0.5),
+        bg=bg_color,
+        scale_modifier=scaling_modifier,
+        viewmatrix=viewpoint_camera.world_view_transform,
+        projmatrix=viewpoint_camera.full_proj_transform,
+        projmatrix_raw=viewpoint_camera.projection_matrix,
+        sh_degree=pc.active_sh_degree,
+        campos=viewpoint_camera.camera_center,
+        prefiltered=False,
+        debug=False,
+        tile_size=TILE_SIZE,
+        backward_mode=BACKWARD_MODE,
+        bitexact_blend=BITEXACT_BLEND,
+    )
+
+
+def render_batch(viewpoint_cameras, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None):
+    """``[render(cam, pc, pipe, bg_color, ...) for cam in viewpoint_cameras]`` as ONE batched rasterizer call.
+
+    The reference's mapping iteration renders the current window (8-12 keyframes) and two random older keyframes one
+    after the other over the same Gaussians, sums their losses and back-propagates once
+    (utils/slam_backend.py:510-662).  Here each Gaussian is read and its 3D covariance computed once for all the views,
+    every kernel covers all views (grid.y = view), and the single backward sums the views' parameter gradients inside
+    the kernels.  All cameras must have the same image size.  Each returned dictionary has its own
+    ``viewspace_points`` leaf, so ``viewspace_points.grad`` is that view's screen-space gradient as in the reference.
+    """
+    if pc.get_xyz.shape[0] == 0:
+        return [None for _ in viewpoint_cameras]
+    if not bool(getattr(pc, "is_language", False)):
+        return [render(cam, pc, pipe, bg_color, scaling_modifier, override_color) for cam in viewpoint_cameras]
+    V = len(viewpoint_cameras)
+    means3D = pc.get_xyz
+    screenspace = []
+    for _ in range(V):
+        sp = torch.zeros_like(means3D, dtype=means3D.dtype, requires_grad=True, device="cuda")
+        try:
+            sp.retain_grad()
+        except Exception:
+            pass
+        screenspace.append(sp)
+    scales = rotations = cov3D_precomp = None
+    if pipe.compute_cov3D_python:
+        cov3D_precomp = pc.get_covariance(scaling_modifier)
+    else:
+        scales = pc.get_scaling.repeat(1, 3) if pc.get_scaling.shape[-1] == 1 else pc.get_scaling
+        rotations = pc.get_rotation
+    shs = colors_precomp = None
+    if override_color is not None:
+        colors_precomp = override_color
+    elif pipe.convert_SHs_python:
+        raise NotImplementedError("render_batch: convert_SHs_python produces per-view colours; use render() per view")
+    else:
+        shs = pc.get_features
+    e = torch.Tensor([])
+    nz = lambda t: e if t is None else t
+    rs_list = [_settings_of(cam, pc, bg_color, scaling_modifier) for cam in viewpoint_cameras]
+    res = rasterize_language_gaussians_batch(
+        means3D, screenspace, nz(shs), nz(colors_precomp), pc.get_language_features, pc.get_opacity, nz(scales),
+        nz(rotations), nz(cov3D_precomp), [nz(cam.cam_rot_delta) for cam in viewpoint_cameras],
+        [nz(cam.cam_trans_delta) for cam in viewpoint_cameras], rs_list)
+    outs = []
+    for v, (rendered_image, language, radii, depth, opacity_map, n_touched) in enumerate(res):
+        outs.append({"render": rendered_image, "viewspace_points": screenspace[v], "visibility_filter": radii > 0,
+                     "radii": radii, "depth": depth, "opacity": opacity_map, "n_touched": n_touched,
+                     "language": language})
+    return outs

@@ -39,20 +39,27 @@ class _MappingLoss(torch.autograd.Function):
         opacity_ = f32(opacity) if opacity is not None else None
         grad_mask_ = f32(grad_mask) if grad_mask is not None else None
         F = int(lang_.shape[0]) if has_lang else 0
-        ea = float(exposure_a) if exposure_a is not None else 0.0
-        eb = float(exposure_b) if exposure_b is not None else 0.0
+        # exposure parameters stay on the device (viewpoint.exposure_a / _b are shape-[1] nn.Parameters,
+        # utils/camera_utils.py:59-64): no host read-back, so the call neither synchronises nor breaks graph capture
+        ea_t = exposure_a.detach().to(device=dev, dtype=torch.float32).reshape(-1)[:1].contiguous() if torch.is_tensor(exposure_a) else None
+        eb_t = exposure_b.detach().to(device=dev, dtype=torch.float32).reshape(-1)[:1].contiguous() if torch.is_tensor(exposure_b) else None
+        ea = float(exposure_a) if (exposure_a is not None and ea_t is None) else 0.0
+        eb = float(exposure_b) if (exposure_b is not None and eb_t is None) else 0.0
         args = N.LossArgs(W=W, H=H, F=F, lang_w=int(gt_lang_.shape[2]) if has_lang else 0,
                           lang_h=int(gt_lang_.shape[1]) if has_lang else 0, alpha=float(alpha),
                           rgb_boundary_threshold=float(threshold), exposure_a=ea, exposure_b=eb,
                           lambda_lang=float(lambda_lang), d_image=image_.data_ptr(), d_depth=depth_.data_ptr(),
                           d_language=N.ptr(lang_), d_gt_image=gt_image_.data_ptr(), d_gt_depth=gt_depth_.data_ptr(),
-                          d_gt_lang=N.ptr(gt_lang_), d_opacity=N.ptr(opacity_), d_grad_mask=N.ptr(grad_mask_))
+                          d_gt_lang=N.ptr(gt_lang_), d_opacity=N.ptr(opacity_), d_grad_mask=N.ptr(grad_mask_),
+                          d_exposure_a=N.ptr(ea_t), d_exposure_b=N.ptr(eb_t))
         out = torch.empty(14, dtype=torch.float32, device=dev)  # [0:6] results, [6:14] reduction scratch
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             N.check(N.lib().ols_mapping_loss_forward(C.byref(args), out.data_ptr(), out[6:].data_ptr(), stream))
         ctx.args = args
-        ctx.keep = (image_, depth_, lang_, gt_image_, gt_depth_, gt_lang_, opacity_, grad_mask_)
+        ctx.keep = (image_, depth_, lang_, gt_image_, gt_depth_, gt_lang_, opacity_, grad_mask_, ea_t, eb_t)
+        ctx.exposure_shapes = (tuple(exposure_a.shape) if torch.is_tensor(exposure_a) else None,
+                               tuple(exposure_b.shape) if torch.is_tensor(exposure_b) else None)
         ctx.terms = out
         ctx.exposure_tensors = (torch.is_tensor(exposure_a) and exposure_a.requires_grad,
                                 torch.is_tensor(exposure_b) and exposure_b.requires_grad)
@@ -60,7 +67,7 @@ class _MappingLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_loss):
-        image_, depth_, lang_, _, _, _, opacity_, _ = ctx.keep
+        image_, depth_, lang_, _, _, _, opacity_, _, _, _ = ctx.keep
         dev = image_.device
         up = grad_loss.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
         d_image, d_depth = torch.empty_like(image_), torch.empty_like(depth_)
@@ -70,8 +77,9 @@ class _MappingLoss(torch.autograd.Function):
             stream = torch.cuda.current_stream(dev).cuda_stream
             N.check(N.lib().ols_mapping_loss_backward(C.byref(ctx.args), up.data_ptr(), d_image.data_ptr(),
                                                       d_depth.data_ptr(), N.ptr(d_lang), N.ptr(d_op), stream))
-        ga = ctx.terms[3] * up[0] if ctx.exposure_tensors[0] else None
-        gb = ctx.terms[4] * up[0] if ctx.exposure_tensors[1] else None
+        # gradients take the shape of the parameters they belong to ([1] for the reference's Camera.exposure_a / _b)
+        ga = (ctx.terms[3] * up[0]).reshape(ctx.exposure_shapes[0]) if ctx.exposure_tensors[0] else None
+        gb = (ctx.terms[4] * up[0]).reshape(ctx.exposure_shapes[1]) if ctx.exposure_tensors[1] else None
         return d_image, d_depth, d_lang, None, None, None, ga, gb, None, None, None, d_op, None
 
 
@@ -97,37 +105,6 @@ def tracking_loss(image: torch.Tensor, depth: torch.Tensor, opacity: torch.Tenso
     w.r.t. ``opacity`` is produced, but -- as in the reference -- the rasterizer does not propagate it further."""
     return _MappingLoss.apply(image, depth, None, gt_image, gt_depth, None, exposure_a, exposure_b, alpha,
                               rgb_boundary_threshold, 0.0, opacity, grad_mask)
-
-
-def reference_tracking_loss(image, depth, opacity, gt_image, gt_depth, grad_mask=None, *, alpha=0.95,
-                            rgb_boundary_threshold=0.01, exposure_a=None, exposure_b=None):
-    """Plain-torch restatement of utils/slam_utils.py:91-118 (test reference)."""
-    if exposure_a is not None:
-        image = torch.exp(torch.as_tensor(exposure_a, device=image.device)) * image + torch.as_tensor(exposure_b, device=image.device)
-    rgb_pixel_mask = (gt_image.sum(dim=0) > rgb_boundary_threshold).view(*depth.shape)
-    if grad_mask is not None:
-        rgb_pixel_mask = rgb_pixel_mask * grad_mask
-    l1 = opacity * torch.abs(image * rgb_pixel_mask - gt_image * rgb_pixel_mask)
-    depth_mask = (gt_depth > 0.01).view(*depth.shape) * (opacity > 0.95).view(*depth.shape)
-    l1_depth = torch.abs(depth * depth_mask - gt_depth * depth_mask)
-    return alpha * l1.mean() + (1 - alpha) * l1_depth.mean()
-
-
-def reference_mapping_loss(image, depth, gt_image, gt_depth, language=None, gt_lang_feat=None, *, alpha=0.95,
-                           rgb_boundary_threshold=0.01, exposure_a=None, exposure_b=None, lambda_lang=1.0):
-    """Plain-torch restatement of the reference lines cited above (used by the tests as the fp32 reference)."""
-    if exposure_a is not None:
-        image = torch.exp(torch.as_tensor(exposure_a, device=image.device)) * image + torch.as_tensor(exposure_b, device=image.device)
-    rgb_pixel_mask = (gt_image.sum(dim=0) > rgb_boundary_threshold).view(*depth.shape)
-    depth_pixel_mask = (gt_depth > 0.01).view(*depth.shape)
-    l1_rgb = torch.abs(image * rgb_pixel_mask - gt_image * rgb_pixel_mask)
-    l1_depth = torch.abs(depth * depth_pixel_mask - gt_depth * depth_pixel_mask)
-    loss = alpha * l1_rgb.mean() + (1 - alpha) * l1_depth.mean()
-    if language is not None and gt_lang_feat is not None:
-        up = torch.nn.functional.interpolate(gt_lang_feat.unsqueeze(0), size=tuple(image.shape[1:]), mode="bilinear",
-                                             align_corners=False).squeeze(0)
-        loss = loss + lambda_lang * torch.abs(language - up).mean()
-    return loss
 
 
 # ---- SSIM and the colour-refinement loss (SURVEY 8f N3) -----------------------------------------------------------
@@ -183,24 +160,3 @@ def color_refinement_loss(image: torch.Tensor, gt_image: torch.Tensor, lambda_ds
     """``(1 - lambda_dssim) * l1_loss(image, gt) + lambda_dssim * (1 - ssim(image, gt))`` (utils/slam_backend.py:797-801),
     one forward and one backward kernel."""
     return _SsimLoss.apply(image, gt_image, 1.0 - lambda_dssim, -lambda_dssim) + lambda_dssim
-
-
-def reference_ssim(img1, img2, window_size=11):
-    """Plain-torch restatement of loss_utils.py:41-101 (test reference)."""
-    import math
-    g = torch.tensor([math.exp(-((x - window_size // 2) ** 2) / float(2 * 1.5 ** 2)) for x in range(window_size)])
-    g = (g / g.sum()).unsqueeze(1)
-    channel = img1.size(-3)
-    window = g.mm(g.t()).float().unsqueeze(0).unsqueeze(0).expand(channel, 1, window_size, window_size).contiguous()
-    window = window.to(img1.device).type_as(img1)
-    conv = lambda t: torch.nn.functional.conv2d(t, window, padding=window_size // 2, groups=channel)
-    mu1, mu2 = conv(img1), conv(img2)
-    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
-    sigma1_sq, sigma2_sq, sigma12 = conv(img1 * img1) - mu1_sq, conv(img2 * img2) - mu2_sq, conv(img1 * img2) - mu1_mu2
-    C1, C2 = 0.01 ** 2, 0.03 ** 2
-    ssim_map = ((2 * mu1_mu2 + C1) * (2 * sigma12 + C2)) / ((mu1_sq + mu2_sq + C1) * (sigma1_sq + sigma2_sq + C2))
-    return ssim_map.mean()
-
-
-def reference_color_refinement_loss(image, gt_image, lambda_dssim=0.2):
-    return (1.0 - lambda_dssim) * torch.abs(image - gt_image).mean() + lambda_dssim * (1.0 - reference_ssim(image, gt_image))

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert set(declared) == set(N.EXPORTED_SYMBOLS), (declared, N.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ols_abi_version() == 1
+    assert lib.ols_abi_version() == 2
 
 
 def test_struct_layouts_match_header_sizes():
@@ -31,7 +31,7 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(N.RasterArgs) == 12 * 4 + 14 * 8 + 8 + 8
     assert C.sizeof(N.FwdOut) == 6 * 8
     assert C.sizeof(N.FwdInfo) == 32
-    assert C.sizeof(N.BwdArgs) == 14 * 8
+    assert C.sizeof(N.BwdArgs) == 15 * 8
     assert C.sizeof(N.AEChain) == 4 + 9 * 4 + 4 + 4 + 8 * 8 * 2
 
 

@@ -15,6 +15,7 @@ import torch
 
 import _util as U
 from online_lang_splatting_b200 import autoencoder as AE
+from oracle import torch_oracle as TO  # noqa: E402
 
 CASES = {
     "ae_1stage": (lambda: AE.AutoencoderMLP([384, 192, 96, 48, 24, 15], [24, 48, 96, 192, 384, 384, 768]), 768),
@@ -52,8 +53,8 @@ def test_module_restatement_matches_reference_golden(name):
             assert abs(v.double().sum().item() - cs[0]) < 1e-9 and abs(v.double().abs().sum().item() - cs[1]) < 1e-9, k
     x = torch.from_numpy(z["x"])
     with torch.no_grad():
-        code = AE.reference_chain(list(model.encoder), x)
-        rec = AE.reference_chain(list(model.decoder), code)
+        code = TO.reference_chain(list(model.encoder), x)
+        rec = TO.reference_chain(list(model.decoder), code)
     assert np.abs(code.numpy() - z["code"]).max() < 1e-6
     assert np.abs(rec.numpy() - z["rec"]).max() < 1e-6
 
@@ -69,7 +70,7 @@ def test_bn_folding_is_exact():
             h = torch.relu(h)
     h = h / h.norm(dim=-1, keepdim=True)
     with torch.no_grad():
-        ref = AE.reference_chain(list(model.encoder), x)
+        ref = TO.reference_chain(list(model.encoder), x)
     assert (h - ref).abs().max() < 2e-5
 
 
@@ -118,8 +119,8 @@ def test_fused_autoencoder_matches_torch(cuda, name):
     with torch.no_grad():
         code = model.encode(x)
         rec = model.decode(code)
-        ref_code = AE.reference_chain(list(model.encoder), x)
-        ref_rec_same_code = AE.reference_chain(list(model.decoder), code)
+        ref_code = TO.reference_chain(list(model.encoder), x)
+        ref_rec_same_code = TO.reference_chain(list(model.decoder), code)
     assert code.shape == ref_code.shape and rec.shape == (x.shape[0], din)
     assert torch.allclose(code.norm(dim=-1), torch.ones_like(code[:, 0]), atol=1e-4)
     cos, rel = _metrics(code.cpu(), ref_code.cpu())
@@ -143,7 +144,7 @@ def test_online_autoencoder_train_step_uses_autograd(cuda):
     opt.zero_grad(); loss.backward(); opt.step()
     with torch.no_grad():
         after = model.encode(x)
-        ref_after = AE.reference_chain(list(model.encoder), x)
+        ref_after = TO.reference_chain(list(model.encoder), x)
     assert (after - before).abs().max() > 0
     cos, rel = _metrics(after.cpu(), ref_after.cpu())
     assert cos > 0.9995 and rel < 3e-2
@@ -165,7 +166,7 @@ def test_config4_batch32_full_size(cuda):
         code = model.encode(x)
         rec = model.decode(code)
         idx = torch.randint(0, M, (4096,), device=cuda, generator=g)
-        ref_code = AE.reference_chain(list(model.encoder), x[idx])
+        ref_code = TO.reference_chain(list(model.encoder), x[idx])
         sub_code = model.encode(x[idx].contiguous())
     assert code.shape == (M, 15) and rec.shape == (M, din)
     assert torch.isfinite(code).all() and torch.isfinite(rec).all()

@@ -16,6 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import hr_oracle  # noqa: E402
 from online_lang_splatting_b200 import supervised_net as SN  # noqa: E402
+from oracle import torch_oracle as TO  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden", "hr_small.npz")
 REL_RMS_TOL = 1.5e-2
@@ -195,7 +196,7 @@ def test_hr_fused_encode():
     with torch.no_grad():
         fused = ae.encode_hr(net, fv.to(dev), f3.to(dev), f2.to(dev))
         unfused = ae.encode(net(fv.to(dev), f3.to(dev), f2.to(dev)).permute(0, 2, 3, 1).view(-1, 768))
-        ref = AE.reference_chain(list(ae.encoder), hr_oracle.hr_forward(sd, fv, f3, f2).to(dev).permute(0, 2, 3, 1).reshape(-1, 768))
+        ref = TO.reference_chain(list(ae.encoder), hr_oracle.hr_forward(sd, fv, f3, f2).to(dev).permute(0, 2, 3, 1).reshape(-1, 768))
     assert fused.shape == (192 * 192, 15)
     assert torch.allclose(fused.norm(dim=-1), torch.ones_like(fused[:, 0]), atol=1e-4)
     cos_u = (fused * unfused).sum(-1)

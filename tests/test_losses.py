@@ -4,6 +4,7 @@
 import numpy as np
 import pytest
 import torch
+from oracle import torch_oracle as TO  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -24,7 +25,7 @@ def _case(H, W, F, lh, lw, seed, exposure):
     ea = torch.tensor(0.07, device=dev, requires_grad=True) if exposure else None
     eb = torch.tensor(-0.02, device=dev, requires_grad=True) if exposure else None
     kw = dict(alpha=0.9, rgb_boundary_threshold=0.01, lambda_lang=0.7)
-    ref = LS.reference_mapping_loss(image, depth, gt_image, gt_depth, lang, gt_lang, exposure_a=ea, exposure_b=eb, **kw)
+    ref = TO.reference_mapping_loss(image, depth, gt_image, gt_depth, lang, gt_lang, exposure_a=ea, exposure_b=eb, **kw)
     leaves = [t for t in (image, depth, lang, ea, eb) if t is not None]
     g_ref = torch.autograd.grad(ref * 1.7, leaves)
     ours = LS.mapping_loss(image, depth, gt_image, gt_depth, lang, gt_lang, exposure_a=ea, exposure_b=eb, **kw)
@@ -71,7 +72,7 @@ def test_tracking_loss_matches_reference_lines():
     ea = torch.tensor(-0.05, device=dev, requires_grad=True)
     eb = torch.tensor(0.03, device=dev, requires_grad=True)
     kw = dict(alpha=0.9, rgb_boundary_threshold=0.01, exposure_a=ea, exposure_b=eb)
-    ref = LS.reference_tracking_loss(image, depth, opacity, gt_image, gt_depth, grad_mask, **kw)
+    ref = TO.reference_tracking_loss(image, depth, opacity, gt_image, gt_depth, grad_mask, **kw)
     g_ref = torch.autograd.grad(ref, [image, depth, opacity, ea, eb])
     ours = LS.tracking_loss(image, depth, opacity, gt_image, gt_depth, grad_mask, **kw)
     g_ours = torch.autograd.grad(ours, [image, depth, opacity, ea, eb])

@@ -1,6 +1,6 @@
 """SSIM + colour-refinement loss (gaussian_splatting/utils/loss_utils.py:41-101, utils/slam_backend.py:797-801).
 
-CPU: the torch restatement (losses.reference_ssim) reproduces value and autograd gradient of the REAL reference functions
+CPU: the torch restatement (oracle.torch_oracle.reference_ssim) reproduces value and autograd gradient of the REAL reference functions
 (tests/golden/ssim_small.npz, written by make_golden_ssim.py).  GPU: the fused kernels against the golden and against
 the restatement on larger, ragged images.  fp32; tolerance 2e-6 absolute on the value (the filter taps are summed in a
 different order than cuDNN's), 1e-4 of the largest gradient entry per pixel.
@@ -12,6 +12,7 @@ import pytest
 import torch
 
 from online_lang_splatting_b200 import losses as LS
+from oracle import torch_oracle as TO  # noqa: E402
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ssim_small.npz")
 
@@ -21,8 +22,8 @@ def test_restatement_matches_reference_golden():
     img = torch.from_numpy(z["image"]).requires_grad_(True)
     gt = torch.from_numpy(z["gt"])
     lam = float(z["lambda_dssim"])
-    s = LS.reference_ssim(img, gt)
-    loss = LS.reference_color_refinement_loss(img, gt, lam)
+    s = TO.reference_ssim(img, gt)
+    loss = TO.reference_color_refinement_loss(img, gt, lam)
     loss.backward()
     assert abs(float(s) - float(z["ssim"])) < 1e-6
     assert abs(float(loss) - float(z["loss"])) < 1e-6
@@ -61,14 +62,14 @@ def test_fused_matches_restatement(shape):
     gt = torch.rand(*shape, generator=g).to(dev)
     img = (gt + 0.2 * torch.randn(*shape, generator=g).to(dev)).clamp(0, 1).requires_grad_(True)
     # plain ssim, value and gradient
-    ref = LS.reference_ssim(img, gt)
+    ref = TO.reference_ssim(img, gt)
     (g_ref,) = torch.autograd.grad(ref * 1.3, img)
     ours = LS.ssim(img, gt)
     (g_ours,) = torch.autograd.grad(ours * 1.3, img)
     assert abs(ours.item() - ref.item()) < 2e-6
     assert (g_ours - g_ref).abs().max().item() < 1e-4 * g_ref.abs().max().item()
     # the colour-refinement loss
-    ref = LS.reference_color_refinement_loss(img, gt, 0.2)
+    ref = TO.reference_color_refinement_loss(img, gt, 0.2)
     (g_ref,) = torch.autograd.grad(ref, img)
     ours = LS.color_refinement_loss(img, gt, 0.2)
     (g_ours,) = torch.autograd.grad(ours, img)

@@ -7,6 +7,9 @@ import torch
 from online_lang_splatting_b200 import losses as LS, densification as DN
 from online_lang_splatting_b200.optim import FlatAdam
 from online_lang_splatting_b200.simple_knn._C import distCUDA2
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import torch_oracle as TO  # noqa: E402
 
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
@@ -55,7 +58,7 @@ gti, gtd, gtl = torch.rand(3, H, W, device=dev), torch.rand(1, H, W, device=dev)
 def ours_map():
     LS.mapping_loss(img, dep, gti, gtd, lang, gtl).backward()
 def ref_map():
-    LS.reference_mapping_loss(img, dep, gti, gtd, lang, gtl).backward()
+    TO.reference_mapping_loss(img, dep, gti, gtd, lang, gtl).backward()
 entry("mapping_loss_fwd_bwd", timeit(ours_map), timeit(ref_map), (19 + 4) * 4 * H * W + 19 * 4 * H * W * 2,
       "960x540, 15 language channels, low-resolution target 192x192 resident")
 
@@ -64,7 +67,7 @@ im2 = torch.rand(3, H, W, device=dev, requires_grad=True)
 def ours_ssim():
     LS.color_refinement_loss(im2, gti).backward()
 def ref_ssim():
-    LS.reference_color_refinement_loss(im2, gti).backward()
+    TO.reference_color_refinement_loss(im2, gti).backward()
 entry("color_refinement_loss_fwd_bwd", timeit(ours_ssim), timeit(ref_ssim), (2 + 3 + 3 + 2 + 1) * 3 * 4 * H * W,
       "3x540x960; forward reads 2 images, writes 3 maps; backward reads 3 maps + 2 images, writes 1")
 

@@ -314,16 +314,41 @@ int ols_mapping_loss_backward(const ols_loss_args* args, const float* d_upstream
  * consecutive segments of the flat buffer (sharding.FlatGradBuffer layout), each with its own lr.
  * ------------------------------------------------------------------------------------------- */
 #define OLS_ADAM_MAX_GROUPS 8
+/* The rasterizer's backward produces gradients w.r.t. the ACTIVATED parameters it was given (get_scaling = exp,
+ * get_opacity = sigmoid, get_rotation = F.normalize; gaussian_model.py:67-72,93-130) while Adam updates the raw ones;
+ * in the reference autograd applies the activations' Jacobians in between.  With `activation` set the kernel applies
+ * that chain rule to the flat gradient on the fly (d_param holds the RAW parameters). */
+#define OLS_ACT_NONE       0
+#define OLS_ACT_EXP        1   /* s = exp(p):            dL/dp = dL/ds * s                                  */
+#define OLS_ACT_SIGMOID    2   /* o = sigmoid(p):        dL/dp = dL/do * o (1 - o)                          */
+#define OLS_ACT_NORMALIZE4 3   /* q^ = q / max(|q|,1e-12), rows of 4: dL/dq = (g - q^ (q^ . g)) / |q|          */
 typedef struct ols_adam_group {
     int64_t offset;   /* first element of the group in the flat buffers */
     int64_t count;    /* elements                                        */
     float lr;
+    int32_t activation;   /* OLS_ACT_*                                                                     */
+    int32_t period, head; /* period > 0: elements whose index within the group modulo `period` is >= `head` use
+                             lr_tail -- f_rest at feature_lr / 20 inside the interleaved [P,M,3] SH block
+                             (gaussian_model.py:404-413: f_dc and f_rest are separate groups in the reference) */
+    float lr_tail;
     float _pad;
 } ols_adam_group;
 /* `step` is the 1-based step count after this update (torch's state["step"]). */
 int ols_adam_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n,
                   const ols_adam_group* groups, int32_t n_groups, double beta1, double beta2, double eps, int64_t step,
                   void* stream);
+
+/* The same step with the step count on the device (torch.optim.Adam(capturable=True)): *d_step is the number of steps
+ * taken so far; the kernel uses *d_step + 1 for the bias corrections and a follow-up kernel increments it, so a
+ * captured CUDA graph advances the optimiser state correctly on every replay. */
+int ols_adam_step_dev(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n,
+                      const ols_adam_group* groups, int32_t n_groups, double beta1, double beta2, double eps,
+                      int64_t* d_step, void* stream);
+
+/* Activated parameters from the raw ones (gaussian_model.py:93-130: get_opacity, get_scaling, get_rotation) in one
+ * kernel -- what follows an optimiser step before the next render().  scale_cols = 1 (isotropic) or 3. */
+int ols_activate_params(int32_t P, int32_t scale_cols, const float* d_opacity_raw, const float* d_scaling_raw,
+                        const float* d_rotation_raw, float* d_opacity, float* d_scaling, float* d_rotation, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * distCUDA2 (submodules/simple-knn/spatial.cu + simple_knn.cu:120-220): mean squared distance of every

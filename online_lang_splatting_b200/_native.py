@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = (
     "ols_hr_plan_create", "ols_hr_plan_destroy", "ols_hr_forward", "ols_hr_read_activation",
     "ols_ssim_loss_forward", "ols_ssim_loss_backward", "ols_densify_stats", "ols_densify_flags",
     "ols_ae_forward_bf16", "ols_hr_forward_features",
-    "ols_lang_forward_batch", "ols_lang_backward_batch", "ols_lang_read_info_async",
+    "ols_lang_forward_batch", "ols_lang_backward_batch", "ols_lang_read_info_async", "ols_activate_params", "ols_adam_step_dev",
 )
 
 
@@ -93,7 +93,11 @@ class LossArgs(C.Structure):
 
 
 class AdamGroup(C.Structure):
-    _fields_ = [("offset", C.c_int64), ("count", C.c_int64), ("lr", C.c_float), ("_pad", C.c_float)]
+    _fields_ = [("offset", C.c_int64), ("count", C.c_int64), ("lr", C.c_float), ("activation", C.c_int32),
+                ("period", C.c_int32), ("head", C.c_int32), ("lr_tail", C.c_float), ("_pad", C.c_float)]
+
+
+ACT_NONE, ACT_EXP, ACT_SIGMOID, ACT_NORMALIZE4 = 0, 1, 2, 3
 
 
 class WsView(C.Structure):
@@ -171,6 +175,9 @@ def lib() -> C.CDLL:
                                             C.c_void_p]
     L.ols_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(AdamGroup), C.c_int32,
                                 C.c_double, C.c_double, C.c_double, C.c_int64, C.c_void_p]
+    L.ols_adam_step_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(AdamGroup), C.c_int32,
+                                    C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+    L.ols_activate_params.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 7
     L.ols_knn_workspace_size.restype = C.c_size_t
     L.ols_knn_workspace_size.argtypes = [C.c_int32]
     L.ols_knn_mean_dist2.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]

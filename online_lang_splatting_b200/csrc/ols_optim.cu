@@ -21,11 +21,25 @@ struct AdamArgs {
     int n_groups;
     long long begin[OLS_ADAM_MAX_GROUPS + 1];  // group k covers [begin[k], begin[k+1])
     float step_size[OLS_ADAM_MAX_GROUPS];      // lr_k / (1 - b1^t)
+    float step_tail[OLS_ADAM_MAX_GROUPS];      // lr_tail_k / (1 - b1^t)
+    int activation[OLS_ADAM_MAX_GROUPS], period[OLS_ADAM_MAX_GROUPS], head[OLS_ADAM_MAX_GROUPS];
     float b1, b2, one_m_b1, one_m_b2, eps, inv_sqrt_bc2;  // 1 - beta computed in double on the host, like torch
+    // device-resident step count (capturable form): step_size[] / step_tail[] then hold the bare learning rates and the
+    // bias corrections are computed from *d_step + 1 by every thread (two double pows per thread, once)
+    const long long* d_step;
+    double beta1, beta2;
 };
+
+__global__ void k_adam_inc(long long* d_step) { *d_step += 1; }
 
 __global__ void __launch_bounds__(256) k_adam(const AdamArgs a) {
     const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    float inv_bc1 = 1.0f, inv_sqrt_bc2 = a.inv_sqrt_bc2;
+    if (a.d_step) {
+        const double t = (double)(*a.d_step + 1);
+        inv_bc1 = (float)(1.0 / (1.0 - pow(a.beta1, t)));
+        inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow(a.beta2, t)));
+    }
     for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < a.n; i += stride) {
         float p[4], g[4], m[4], v[4];
         const bool full = i + 4 <= a.n;
@@ -40,16 +54,34 @@ __global__ void __launch_bounds__(256) k_adam(const AdamArgs a) {
                 p[k] = ok ? a.p[i + k] : 0.f; g[k] = ok ? a.g[i + k] : 0.f; m[k] = ok ? a.m[i + k] : 0.f; v[k] = ok ? a.v[i + k] : 0.f;
             }
         }
+        // F.normalize row of 4 (only meaningful inside an OLS_ACT_NORMALIZE4 group): taken before p is updated
+        const float q_old[4] = {p[0], p[1], p[2], p[3]};
+        const float q_inv = 1.0f / fmaxf(sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2] + p[3] * p[3]), 1e-12f);
+        const float q_dot = (p[0] * g[0] + p[1] * g[1] + p[2] * g[2] + p[3] * g[3]) * q_inv;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const long long e = i + k;
             int grp = 0;
 #pragma unroll
             for (int q = 1; q < OLS_ADAM_MAX_GROUPS; q++) grp += (q < a.n_groups && e >= a.begin[q]) ? 1 : 0;
-            m[k] = m[k] + (g[k] - m[k]) * a.one_m_b1;
-            v[k] = v[k] * a.b2 + a.one_m_b2 * g[k] * g[k];
-            const float denom = sqrtf(v[k]) * a.inv_sqrt_bc2 + a.eps;
-            p[k] = p[k] - a.step_size[grp] * (m[k] / denom);
+            float step = a.step_size[grp];
+            if (a.period[grp] > 0 && (int)((e - a.begin[grp]) % a.period[grp]) >= a.head[grp]) step = a.step_tail[grp];
+            step *= inv_bc1;
+            float gk = g[k];
+            const int act = a.activation[grp];
+            if (act == OLS_ACT_EXP) {
+                gk = gk * expf(p[k]);
+            } else if (act == OLS_ACT_SIGMOID) {
+                const float o = 1.0f / (1.0f + expf(-p[k]));
+                gk = gk * o * (1.0f - o);
+            } else if (act == OLS_ACT_NORMALIZE4) {
+                // rows of 4 coincide with this thread's chunk (group offset and count are multiples of 4, validated)
+                gk = (gk - q_old[k] * q_inv * q_dot) * q_inv;
+            }
+            m[k] = m[k] + (gk - m[k]) * a.one_m_b1;
+            v[k] = v[k] * a.b2 + a.one_m_b2 * gk * gk;
+            const float denom = sqrtf(v[k]) * inv_sqrt_bc2 + a.eps;
+            p[k] = p[k] - step * (m[k] / denom);
         }
         if (full) {
             *reinterpret_cast<float4*>(a.p + i) = make_float4(p[0], p[1], p[2], p[3]);
@@ -65,11 +97,11 @@ __global__ void __launch_bounds__(256) k_adam(const AdamArgs a) {
 
 using namespace ols;
 
-extern "C" int ols_adam_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n,
-                             const ols_adam_group* groups, int32_t n_groups, double beta1, double beta2, double eps,
-                             int64_t step, void* stream) {
+static int adam_launch(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n,
+                       const ols_adam_group* groups, int32_t n_groups, double beta1, double beta2, double eps,
+                       int64_t step, int64_t* d_step, void* stream) {
     if (!d_param || !d_grad || !d_exp_avg || !d_exp_avg_sq || n < 0 || !groups || n_groups < 1 || n_groups > OLS_ADAM_MAX_GROUPS ||
-        step < 1) {
+        (step < 1 && !d_step)) {
         ols_set_error("bad Adam arguments");
         return OLS_ERR_INVALID;
     }
@@ -80,20 +112,72 @@ extern "C" int ols_adam_step(float* d_param, const float* d_grad, float* d_exp_a
     if (n == 0) return OLS_OK;
     AdamArgs a;
     a.p = d_param; a.g = d_grad; a.m = d_exp_avg; a.v = d_exp_avg_sq; a.n = n; a.n_groups = n_groups;
-    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    const double bc1 = d_step ? 1.0 : 1.0 - pow(beta1, (double)step), bc2 = d_step ? 1.0 : 1.0 - pow(beta2, (double)step);
+    a.d_step = (const long long*)d_step; a.beta1 = beta1; a.beta2 = beta2;
     long long expect = 0;
     for (int k = 0; k < n_groups; k++) {
         if (groups[k].offset != expect || groups[k].count < 0) { ols_set_error("Adam groups must tile [0, n) in order"); return OLS_ERR_INVALID; }
         a.begin[k] = groups[k].offset;
         a.step_size[k] = (float)((double)groups[k].lr / bc1);
+        a.step_tail[k] = (float)((double)groups[k].lr_tail / bc1);
+        a.activation[k] = groups[k].activation; a.period[k] = groups[k].period; a.head[k] = groups[k].head;
+        if (groups[k].activation < OLS_ACT_NONE || groups[k].activation > OLS_ACT_NORMALIZE4 || groups[k].period < 0 ||
+            (groups[k].activation == OLS_ACT_NORMALIZE4 && (groups[k].count % 4 != 0 || groups[k].offset % 4 != 0))) {
+            ols_set_error("bad Adam group %d (activation / period)", k);
+            return OLS_ERR_INVALID;
+        }
         expect += groups[k].count;
     }
     if (expect != n) { ols_set_error("Adam groups cover %lld of %lld elements", expect, (long long)n); return OLS_ERR_INVALID; }
     for (int k = n_groups; k <= OLS_ADAM_MAX_GROUPS; k++) a.begin[k] = n;
-    for (int k = n_groups; k < OLS_ADAM_MAX_GROUPS; k++) a.step_size[k] = 0.0f;
+    for (int k = n_groups; k < OLS_ADAM_MAX_GROUPS; k++) { a.step_size[k] = a.step_tail[k] = 0.0f; a.activation[k] = a.period[k] = a.head[k] = 0; }
     a.b1 = (float)beta1; a.b2 = (float)beta2; a.one_m_b1 = (float)(1.0 - beta1); a.one_m_b2 = (float)(1.0 - beta2); a.eps = (float)eps; a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
     const long long blocks = (n / 4 + 255) / 256 + 1;
     k_adam<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, (cudaStream_t)stream>>>(a);
+    if (d_step) k_adam_inc<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)d_step);
+    OLS_CUDA_TRY(cudaGetLastError());
+    return OLS_OK;
+}
+
+extern "C" int ols_adam_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n,
+                             const ols_adam_group* groups, int32_t n_groups, double beta1, double beta2, double eps,
+                             int64_t step, void* stream) {
+    return adam_launch(d_param, d_grad, d_exp_avg, d_exp_avg_sq, n, groups, n_groups, beta1, beta2, eps, step, nullptr, stream);
+}
+
+extern "C" int ols_adam_step_dev(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n,
+                                 const ols_adam_group* groups, int32_t n_groups, double beta1, double beta2, double eps,
+                                 int64_t* d_step, void* stream) {
+    if (!d_step) { ols_set_error("null step counter"); return OLS_ERR_INVALID; }
+    return adam_launch(d_param, d_grad, d_exp_avg, d_exp_avg_sq, n, groups, n_groups, beta1, beta2, eps, 0, d_step, stream);
+}
+
+namespace ols {
+// get_opacity / get_scaling / get_rotation (gaussian_model.py:93-130) in one pass over the Gaussians
+__global__ void __launch_bounds__(256) k_activate(int P, int scale_cols, const float* __restrict__ o_raw, const float* __restrict__ s_raw,
+                                                  const float* __restrict__ q_raw, float* __restrict__ o, float* __restrict__ s,
+                                                  float* __restrict__ q) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    o[i] = 1.0f / (1.0f + expf(-o_raw[i]));
+    for (int c = 0; c < scale_cols; c++) s[(size_t)scale_cols * i + c] = expf(s_raw[(size_t)scale_cols * i + c]);
+    const float4 r = reinterpret_cast<const float4*>(q_raw)[i];
+    const float inv = 1.0f / fmaxf(sqrtf(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w), 1e-12f);  // F.normalize
+    reinterpret_cast<float4*>(q)[i] = make_float4(r.x * inv, r.y * inv, r.z * inv, r.w * inv);
+}
+}  // namespace ols
+
+extern "C" int ols_activate_params(int32_t P, int32_t scale_cols, const float* d_opacity_raw, const float* d_scaling_raw,
+                                   const float* d_rotation_raw, float* d_opacity, float* d_scaling, float* d_rotation, void* stream) {
+    if (P < 0 || (scale_cols != 1 && scale_cols != 3) || (P > 0 && (!d_opacity_raw || !d_scaling_raw || !d_rotation_raw || !d_opacity ||
+                                                                      !d_scaling || !d_rotation))) {
+        ols_set_error("bad activation arguments");
+        return OLS_ERR_INVALID;
+    }
+    if ((((uintptr_t)d_rotation_raw | (uintptr_t)d_rotation) & 15) != 0) { ols_set_error("rotation buffers must be 16-byte aligned"); return OLS_ERR_INVALID; }
+    if (P == 0) return OLS_OK;
+    k_activate<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, scale_cols, d_opacity_raw, d_scaling_raw, d_rotation_raw, d_opacity,
+                                                               d_scaling, d_rotation);
     OLS_CUDA_TRY(cudaGetLastError());
     return OLS_OK;
 }

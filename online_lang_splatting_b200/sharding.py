@@ -7,7 +7,14 @@ summed by autograd before a single backward.
 The flat buffer is laid out structure-of-arrays so every parameter group is one contiguous slice
 (a valid output tensor of ols_lang_backward) and the whole thing is a single NCCL call:
 
-    [ xyz 3P | f_dc 3P | f_rest 3(M-1)P | opacity P | scaling 3P | rotation 4P | language F*P ]
+    [ rotation 4P | xyz 3P | sh 3M*P (rows [f_dc 3 | f_rest 3(M-1)] per Gaussian) | opacity P | scaling 3P | language F*P ]
+
+(rotations first so that their rows of 4 are 16-byte aligned for every P).  The buffer holds gradients with respect to
+the ACTIVATED rasterizer inputs -- sigmoid(opacity), exp(scaling), normalised rotation -- exactly as
+``ols_lang_backward`` produces them.  ``FlatParams`` keeps the raw parameters in the same layout and
+``FlatGradBuffer.adam_groups`` describes the buffer to ``optim.FlatAdam`` with the activation of every slice, so the
+optimiser applies the activations' Jacobians itself (the reference leaves that to autograd) and f_dc / f_rest keep
+their separate learning rates (gaussian_model.py:404-413).
 """
 from __future__ import annotations
 
@@ -49,8 +56,9 @@ class FlatGradBuffer:
     def __init__(self, P: int, F: int, M: int = 1, device="cuda"):
         self.P, self.F, self.M = P, F, M
         groups: Sequence[Tuple[str, Tuple[int, ...]]] = (
-            ("means3D", (P, 3)), ("sh", (P, M, 3)), ("opacity", (P, 1)), ("scales", (P, 3)), ("rotations", (P, 4)),
+            ("rotations", (P, 4)), ("means3D", (P, 3)), ("sh", (P, M, 3)), ("opacity", (P, 1)), ("scales", (P, 3)),
             ("language", (P, F)))
+        self.groups = groups
         self.floats_per_gaussian = 3 + 3 * M + 1 + 3 + 4 + F
         self.flat = torch.zeros(self.floats_per_gaussian * P, dtype=torch.float32, device=device)
         self.views: Dict[str, torch.Tensor] = {}
@@ -72,6 +80,18 @@ class FlatGradBuffer:
             out.update(scratch)
         return out
 
+    def adam_groups(self, lr: Dict[str, float]):
+        """Group list for ``optim.FlatAdam`` over this layout.  ``lr`` maps the reference's group names (xyz, f_dc,
+        f_rest, opacity, scaling, rotation, f_language; gaussian_model.py:393-437) to learning rates."""
+        from . import _native as N
+        P, F, M = self.P, self.F, self.M
+        return [("rotation", 4 * P, lr["rotation"], N.ACT_NORMALIZE4),
+                ("xyz", 3 * P, lr["xyz"], N.ACT_NONE),
+                ("f_dc+f_rest", 3 * M * P, lr["f_dc"], N.ACT_NONE, 3 * M if M > 1 else 0, 3, lr.get("f_rest", lr["f_dc"] / 20.0)),
+                ("opacity", P, lr["opacity"], N.ACT_SIGMOID),
+                ("scaling", 3 * P, lr["scaling"], N.ACT_EXP),
+                ("f_language", F * P, lr["f_language"], N.ACT_NONE)]
+
     def all_reduce(self):
         """Sum over ranks (no-op without an initialised process group)."""
         import torch.distributed as dist
@@ -82,3 +102,66 @@ class FlatGradBuffer:
     @property
     def nbytes(self) -> int:
         return self.flat.numel() * 4
+
+
+class FlatParams(FlatGradBuffer):
+    """The raw (pre-activation) Gaussian parameters in the layout of ``FlatGradBuffer`` plus a second buffer with the
+    activated values the rasterizer reads; ``activate()`` refreshes the latter after an optimiser step (one kernel)."""
+
+    def __init__(self, raw: Dict[str, torch.Tensor], F: int, M: int = 1, device="cuda"):
+        P = raw["means3D"].shape[0]
+        super().__init__(P, F, M, device=device)
+        for name, _ in self.groups:
+            self.views[name].copy_(raw[name].reshape(self.views[name].shape))
+        self.act_flat = self.flat.clone()
+        self.act: Dict[str, torch.Tensor] = {}
+        o = 0
+        for name, shape in self.groups:
+            n = math.prod(shape)
+            self.act[name] = self.act_flat[o:o + n].view(shape)
+            o += n
+
+    def activate(self):
+        from .optim import activate_params
+        for name in ("means3D", "sh", "language"):      # identity activations: the rasterizer reads the raw slices
+            self.act[name] = self.views[name]
+        activate_params(self.views["opacity"], self.views["scales"], self.views["rotations"], self.act["opacity"],
+                        self.act["scales"], self.act["rotations"])
+        return self.act
+
+
+class SideStats:
+    """Densification statistics of a sharded mapping iteration: every rank folds its own views into per-step deltas
+    (``densification.update_stats``), the deltas are reduced over the ranks -- SUM for ``xyz_gradient_accum`` and
+    ``denom``, MAX for ``max_radii2D`` (gaussian_model.py:965-969, utils/slam_backend.py:676-680) -- and added to the
+    replicated running state, so all ranks take identical densification decisions."""
+
+    def __init__(self, P: int, device="cuda"):
+        self.P = P
+        self.delta = torch.zeros(2 * P, dtype=torch.float32, device=device)        # [accum P | denom P], one SUM
+        self.delta_max = torch.zeros(P, dtype=torch.float32, device=device)        # one MAX
+        self.xyz_gradient_accum = torch.zeros(P, 1, dtype=torch.float32, device=device)
+        self.denom = torch.zeros(P, 1, dtype=torch.float32, device=device)
+        self.max_radii2D = torch.zeros(P, dtype=torch.float32, device=device)
+
+    def begin_step(self):
+        self.delta.zero_()
+        self.delta_max.zero_()
+
+    def add_view(self, radii: torch.Tensor, viewspace_grad: torch.Tensor):
+        from .densification import update_stats
+        P = self.P
+        update_stats(radii, viewspace_grad, self.delta_max, self.delta[:P].view(P, 1), self.delta[P:].view(P, 1))
+
+    def all_reduce(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.delta)
+            dist.all_reduce(self.delta_max, op=dist.ReduceOp.MAX)
+        return self
+
+    def apply(self):
+        P = self.P
+        self.xyz_gradient_accum += self.delta[:P].view(P, 1)
+        self.denom += self.delta[P:].view(P, 1)
+        torch.maximum(self.max_radii2D, self.delta_max, out=self.max_radii2D)

@@ -117,6 +117,28 @@ def test_dis_side_by_side_with_compiled_reference():
         assert _l2rel(ours["grads"][ok].reshape(r.shape), r) < 1e-3, ok
 
 
+def test_config1_exact_size_three_way():
+    """BASELINE.json configs[0] exactly -- 10k random Gaussians, 3-dim feature, 256x256, one view -- on the variant the
+    north star names (D/): ours == the compiled reference D/ (bit-exact images and lists) == the CPU oracle (lists)."""
+    sc = U.add_lang_footprint(U.make_scene(P=10000, F=3, W=256, H=256, seed=0, scale=0.03), seed=3)
+    grads = U.loss_weights(3, 256, 256, seed=1)
+    ours = U.run_ours_dis(sc, _dev(), tile=16, grads=grads, backward_mode="compat", bitexact=True)
+    ora = U.run_oracle_dis(sc, tile=16, grads=grads, compat=True)
+    assert (ours["R"], ours["R_lang"]) == (ora["R"], ora["R_lang"])
+    assert np.array_equal(ours["ws"]["point_list"].astype(np.uint32), ora["point_list"])
+    assert np.array_equal(ours["ws_lang"]["point_list"].astype(np.uint32), ora["point_list_lang"])
+    for k in ("color", "language", "depth"):
+        assert U.rel_err(ours[k], ora[k]) < 1e-4, k
+    mod = U.ref_module("ref_D_C")
+    if mod is None:
+        pytest.skip("oracle/_ref/ref_D_C.so not present on this box (oracle leg passed)")
+    ref = U.run_ref_dis(mod, sc, _dev(), grads=grads)
+    _check_forward_bitexact(ours, ref, (256 + 15) // 16)
+    for ok, rk in GRAD_PAIRS.items():
+        r = ref["grads"][rk]
+        assert _l2rel(ours["grads"][ok].reshape(r.shape), r) < 1e-3, ok
+
+
 def test_dis_argument_validation():
     from online_lang_splatting_b200 import diff_gaussian_rasterization_disentangle as dd
     sc = U.add_lang_footprint(U.make_scene(P=64, F=3, W=32, H=32, seed=0))

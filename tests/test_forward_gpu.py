@@ -50,14 +50,19 @@ def test_forward_matches_oracle(cuda, tile, F):
 
 
 def test_fast_blend_close_to_bitexact(cuda):
+    """Default blend (alpha from ex2.approx(power * log2 e), channels accumulated as (alpha T) c) against the bit-exact
+    mode.  alpha differs by <= 4e-7 relative, so an alpha >= 1/255 / T < 1e-4 decision can flip only where the
+    value sits within that distance of the threshold: the flipped fraction and the image error are bounded here,
+    two orders of magnitude inside north_star's 1e-4 budget."""
     sc = U.make_scene(P=4000, F=15, W=96, H=64, seed=2, scale=0.05)
     a = U.run_ours(sc, cuda, bitexact=True)
     b = U.run_ours(sc, cuda, bitexact=False)
-    assert np.array_equal(a["ws"]["n_contrib"], b["ws"]["n_contrib"])
-    assert np.array_equal(a["n_touched"], b["n_touched"])
-    assert np.array_equal(a["opacity"], b["opacity"])  # T recurrence is shared
-    for k in ("color", "language", "depth"):
-        assert U.rel_err(b[k], a[k]) < 1e-5, k
+    assert (a["ws"]["n_contrib"] != b["ws"]["n_contrib"]).mean() < 2e-3
+    assert (a["n_touched"] != b["n_touched"]).mean() < 2e-3
+    assert np.array_equal(a["radii"], b["radii"]) and np.array_equal(a["ws"]["point_list"], b["ws"]["point_list"])
+    for k in ("color", "language", "depth", "opacity"):
+        bad = np.abs(b[k] - a[k]) > 5e-6 * max(np.abs(a[k]).max(), 1e-6)
+        assert bad.mean() < 2e-3, (k, bad.mean(), U.rel_err(b[k], a[k]))
 
 
 def test_long_tiles_use_hybrid_sort(cuda):
@@ -105,18 +110,98 @@ def test_edge_cases(cuda):
 
 
 def test_capacity_overflow_regrows(cuda):
+    """CHECK_OVERFLOW = "sync" (the reference's behaviour): an undersized estimate overflows on the device, the wrapper
+    reads the flag and renders again with the exact size."""
     from online_lang_splatting_b200 import diff_gaussian_rasterization as dgr
     sc = U.make_scene(P=3000, F=15, W=96, H=64, seed=0, scale=0.3)
-    key = (cuda.index if cuda.index is not None else 0, sc["P"], sc["W"], sc["H"], 15)
-    dgr._R_HINT[key] = 1  # absurdly small hint -> first attempt overflows on the device, wrapper regrows
-    slack, dgr._SLACK = dgr._SLACK, 0
+    key = (cuda.index if cuda.index is not None else 0, sc["W"], sc["H"], 15)
+    saved = (dgr._SLACK, dgr.CHECK_OVERFLOW, dgr._R_RATIO.get(key))
+    dgr._R_RATIO[key] = 1e-9  # absurdly small estimate -> first attempt overflows on the device, wrapper regrows
+    dgr._SLACK, dgr.CHECK_OVERFLOW = 0, "sync"
     try:
         ours = U.run_ours(sc, cuda)
     finally:
-        dgr._SLACK = slack
+        dgr._SLACK, dgr.CHECK_OVERFLOW = saved[0], saved[1]
     ora = U.run_oracle(sc)
     assert ours["R"] == ora["R"] > 30000
     assert np.array_equal(ours["ws"]["point_list"].astype(np.uint32), ora["point_list"])
+
+
+def test_deferred_overflow_is_loud_and_recovers(cuda):
+    """Default mode: no host synchronisation inside render().  A forward whose estimate was too small hands back NaN
+    images (never a plausible empty frame), its backward raises, and the next render -- whose capacity estimate was
+    raised by the asynchronously delivered header -- is correct."""
+    from online_lang_splatting_b200 import _native as N
+    from online_lang_splatting_b200 import diff_gaussian_rasterization as dgr
+    from online_lang_splatting_b200 import synthetic as S
+    from online_lang_splatting_b200.gaussian_renderer import render
+    W, H = 96, 64
+    g = S.make_gaussians(3000, 15, W, H, seed=0, scale_px_sigma=0.3)
+    pc = S.SyntheticGaussianModel(g, device=cuda, requires_grad=True)
+    cam = S.make_camera(W, H, view=0, seed=0, device="cuda")
+    bg = torch.zeros(3, device=cuda)
+    key = (cuda.index if cuda.index is not None else 0, W, H, 15)
+    assert dgr.CHECK_OVERFLOW == "deferred"
+    good = render(cam, pc, S.PipelineParams(), bg)["render"].detach().clone()   # establishes the estimate (sync, first use)
+    torch.cuda.synchronize()
+    saved = dgr._SLACK
+    dgr._R_RATIO[key] = 1e-9
+    dgr._SLACK = 0
+    calls = {"n": 0}
+    real_sync = torch.cuda.synchronize
+    try:
+        out = render(cam, pc, S.PipelineParams(), bg)        # asynchronous; overflows on the device
+        assert out["render"].grad_fn.state.pending is not None, "the default path must not read the header synchronously"
+        assert torch.isnan(out["render"]).all() and torch.isnan(out["language"]).all()
+        with pytest.raises(N.OlsError, match="capacity"):
+            out["render"].sum().backward()
+    finally:
+        dgr._SLACK = saved
+    again = render(cam, pc, S.PipelineParams(), bg)["render"].detach()
+    assert torch.equal(again, good)
+
+
+def test_forward_host_entry_matches_device_path(cuda):
+    """ols_lang_forward_host: the host-buffer form a non-torch binding (cgo / JNI / ctypes) would call."""
+    import ctypes as C
+    from online_lang_splatting_b200 import _native as N
+    sc = U.make_scene(P=2500, F=15, W=100, H=60, seed=9, view=2, scale=0.06, bg=(0.3, 0.1, 0.2))
+    ours = U.run_ours(sc, cuda, bitexact=True)
+    f = lambda k: np.ascontiguousarray(sc[k].numpy().astype(np.float32))
+    arrs = {k: f(k) for k in ("bg", "means3D", "shs", "language", "opacities", "scales", "rotations", "viewmatrix",
+                              "projmatrix", "projmatrix_raw", "campos")}
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    P, W, H, F = sc["P"], sc["W"], sc["H"], 15
+    args = N.RasterArgs(P=P, F=F, sh_degree=0, M=arrs["shs"].shape[1], W=W, H=H, tile=15, flags=N.FLAG_BITEXACT_BLEND,
+                        tanfovx=sc["tanfovx"], tanfovy=sc["tanfovy"], scale_modifier=1.0, d_bg=p(arrs["bg"]),
+                        d_means3D=p(arrs["means3D"]), d_shs=p(arrs["shs"]), d_colors_precomp=None, d_language=p(arrs["language"]),
+                        d_opacities=p(arrs["opacities"]), d_scales=p(arrs["scales"]), d_rotations=p(arrs["rotations"]),
+                        d_cov3D_precomp=None, d_viewmatrix=p(arrs["viewmatrix"]), d_projmatrix=p(arrs["projmatrix"]),
+                        d_projmatrix_raw=p(arrs["projmatrix_raw"]), d_campos=p(arrs["campos"]), d_workspace=None,
+                        workspace_bytes=0, R_cap=0)
+    o = {"color": np.empty((3, H, W), np.float32), "language": np.empty((F, H, W), np.float32), "depth": np.empty((1, H, W), np.float32),
+         "opacity": np.empty((1, H, W), np.float32), "radii": np.empty(P, np.int32), "n_touched": np.empty(P, np.int32)}
+    ho = N.HostOut(h_color=p(o["color"]), h_language=p(o["language"]), h_depth=p(o["depth"]), h_opacity=p(o["opacity"]),
+                   h_radii=p(o["radii"]), h_n_touched=p(o["n_touched"]))
+    R = C.c_int64(0)
+    N.check(N.lib().ols_lang_forward_host(C.byref(args), C.byref(ho), C.byref(R)))
+    assert R.value == ours["R"]
+    for k in o:
+        assert np.array_equal(o[k], ours[k]), k
+
+
+def test_config1_exact_size_vs_oracle(cuda):
+    """BASELINE.json configs[0] as stated: 10k random Gaussians, 3-dim feature, 256x256, one view."""
+    sc = U.make_scene(P=10000, F=3, W=256, H=256, seed=0, scale=0.03)
+    grads = U.loss_weights(3, 256, 256, seed=1)
+    for tile in (15, 16):
+        ours = U.run_ours(sc, cuda, tile=tile, grads=grads, backward_mode="compat", bitexact=True)
+        ora = U.run_oracle(sc, tile=tile, grads=grads, compat=True)
+        _check_vs_oracle(sc, ours, ora, tile)
+        for k, rk in (("means3D", "dL_dmeans3D"), ("language", "dL_dlang"), ("opacities", "dL_dopacity"), ("scales", "dL_dscales"),
+                      ("rotations", "dL_drots")):
+            a, b = ours["grads"][k].astype(np.float64), ora["grads"][rk].astype(np.float64).reshape(ours["grads"][k].shape)
+            assert np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30) < 2e-3, (tile, k)
 
 
 def test_mark_visible(cuda):

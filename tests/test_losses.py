@@ -82,3 +82,61 @@ def test_tracking_loss_matches_reference_lines():
             assert abs(a.item() - b.item()) <= 1e-4 * max(abs(b.item()), 1e-6)
         else:
             assert (a - b).abs().max().item() <= 1e-5 * b.abs().max().item() + 1e-12
+
+
+# ---- pinned to the REAL reference functions (tests/golden/losses_small.npz, utils/slam_utils.py:91-165) -------------
+def _golden():
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_losses import golden_inputs
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "losses_small.npz"))
+    d = golden_inputs()
+    assert abs(float(sum(v.double().sum() for v in d.values())) - float(z["checksum"][0])) < 1e-6
+    return d, z
+
+
+def _run_golden_case(name, dev, fn_map, fn_track):
+    d, z = _golden()
+    t = {k: v.to(dev) for k, v in d.items()}
+    image, depth, opacity = (t[k].clone().requires_grad_(True) for k in ("image", "depth", "opacity"))
+    ea, eb = (torch.nn.Parameter(t[k].clone()) for k in ("exposure_a", "exposure_b"))   # shape [1], as in Camera
+    gt_depth = t["gt_depth"][None]
+    kw = dict(alpha=0.9, rgb_boundary_threshold=0.01)
+    if name == "mapping":
+        loss = fn_map(image, depth, t["gt_image"], gt_depth, exposure_a=ea, exposure_b=eb, **kw)
+    elif name == "mapping_init":
+        loss = fn_map(image, depth, t["gt_image"], gt_depth, **kw)
+    else:
+        loss = fn_track(image, depth, opacity, t["gt_image"], gt_depth, t["grad_mask"], exposure_a=ea, exposure_b=eb, **kw)
+    (loss * 1.7).backward()
+    assert abs(loss.item() - float(z[name + "_loss"][0])) <= 2e-6 * abs(float(z[name + "_loss"][0]))
+    for key, leaf in (("dimage", image), ("ddepth", depth), ("dopacity", opacity), ("dexposure_a", ea), ("dexposure_b", eb)):
+        if name + "_" + key not in z.files:
+            continue
+        ref = torch.from_numpy(z[name + "_" + key])
+        got = leaf.grad.detach().cpu()
+        assert got.shape == ref.shape, (name, key, got.shape, ref.shape)    # [1] for the exposure parameters
+        if ref.numel() == 1:
+            assert abs(got.item() - ref.item()) <= 1e-4 * max(abs(ref.item()), 1e-6), (name, key)
+        else:
+            assert (got - ref).abs().max().item() <= 1e-5 * ref.abs().max().item() + 1e-12, (name, key)
+
+
+@pytest.mark.parametrize("name", ["mapping", "mapping_init", "tracking"])
+def test_fused_losses_match_real_reference_golden(name):
+    from online_lang_splatting_b200 import losses as LS
+    _run_golden_case(name, torch.device("cuda:0"), LS.mapping_loss, LS.tracking_loss)
+
+
+def test_exposure_parameters_of_shape_1_get_shape_1_gradients():
+    """Camera.exposure_a / _b are nn.Parameter(torch.tensor([0.0])) (utils/camera_utils.py:59-64)."""
+    from online_lang_splatting_b200 import losses as LS
+    dev = torch.device("cuda:0")
+    img = torch.rand(3, 32, 48, device=dev, requires_grad=True)
+    dep = torch.rand(1, 32, 48, device=dev, requires_grad=True)
+    ea = torch.nn.Parameter(torch.tensor([0.0], device=dev))
+    eb = torch.nn.Parameter(torch.tensor([0.0], device=dev))
+    loss = LS.mapping_loss(img, dep, torch.rand(3, 32, 48, device=dev), torch.rand(1, 32, 48, device=dev), exposure_a=ea, exposure_b=eb)
+    loss.backward()
+    assert ea.grad.shape == (1,) and eb.grad.shape == (1,) and torch.isfinite(ea.grad).all()

@@ -419,9 +419,9 @@ def main():
         outs, st = dgr._forward_native_batch(*params_tuple(), rl)
         radii = [o[2] for o in outs]
         V = len(rl)
+        ob = dict(ob)
+        ob["stats"] = stats.fused_outputs()      # densification statistics folded into the backward's geometry kernel
         dgr._backward_native_batch(st, radii, [wc] * V, [wl] * V, [wd] * V, out=ob, accumulate=False)
-        for k in range(V):
-            stats.add_view(radii[k], ob["means2D"][k])
         Rs.extend(r_ for r_ in st.Rs if r_ >= 0)
 
     def phase_update():

@@ -131,6 +131,13 @@ typedef struct ols_bwd_args {
                                 (rasterize_points.cu:452); may be NULL when d_dL_dtau_sum is given        */
     float* d_dL_dtau_sum;    /* [6]    the same summed over the Gaussians -- what the reference's Python computes
                                 right after the call (diff_gaussian_rasterization/__init__.py:383-385) -- or NULL */
+    /* Optional densification statistics, updated in place for the Gaussians with radii > 0 of every view of the call
+     * (all three or none; taken from grads[0] in a batch).  Same arithmetic as ols_densify_stats, i.e. what the mapping
+     * loop does per view right after backward (utils/slam_backend.py:719-728, gaussian_model.py:965-969):
+     *   max_radii2D = max(max_radii2D, radii);  xyz_gradient_accum += |dL_dmeans2D.xy|;  denom += 1 */
+    float* d_stat_max_radii2D;         /* [P] or NULL */
+    float* d_stat_xyz_gradient_accum;  /* [P] or NULL */
+    float* d_stat_denom;               /* [P] or NULL */
 } ols_bwd_args;
 
 int ols_abi_version(void);

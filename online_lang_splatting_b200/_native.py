@@ -61,7 +61,8 @@ class BwdArgs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("d_dL_dout_color", "d_dL_dout_language", "d_dL_dout_depth", "d_radii",
                                           "d_dL_dmeans2D", "d_dL_dcolors", "d_dL_dlanguage", "d_dL_dopacity",
                                           "d_dL_dmeans3D", "d_dL_dcov3D", "d_dL_dsh", "d_dL_dscales",
-                                          "d_dL_drotations", "d_dL_dtau", "d_dL_dtau_sum")]
+                                          "d_dL_drotations", "d_dL_dtau", "d_dL_dtau_sum", "d_stat_max_radii2D",
+                                          "d_stat_xyz_gradient_accum", "d_stat_denom")]
 
 
 class DisArgs(C.Structure):

@@ -35,6 +35,7 @@ constexpr int AE_BLOCK_MAX = 384;     // max rows of a weight slab resident in o
 constexpr int AE_CHUNK_MAX = 256;     // max N of one tcgen05.mma
 constexpr int AE_TMEM_COLS = 512;
 constexpr int AE_MAX_BLOCKS = 4;
+constexpr int AE_STAGING_BYTES = 4 * 32 * 33 * 4 + 128;  // per epilogue warp: a 32 x 32 fp32 chunk, rows padded to 33 (+ pad to 256 B)
 
 struct AeLayer {
     int K, N;            // padded: K multiple of the slab width, N multiple of 16
@@ -72,7 +73,8 @@ __global__ void __launch_bounds__(AE_THREADS, 1) k_ae_chain(const __grid_constan
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* ring = smem;                                          // n_stages * stage_bytes
     uint8_t* act = smem + (size_t)p.n_stages * p.stage_bytes;      // act_bytes: [K-slab][128 rows][128 B]
-    uint64_t* bars = (uint64_t*)(act + p.act_bytes);
+    float* staging = (float*)(act + p.act_bytes);                  // 4 warps x 32 x 33 floats: output transpose buffer
+    uint64_t* bars = (uint64_t*)(act + p.act_bytes + AE_STAGING_BYTES);
     uint64_t* full = bars;                   // [n_stages] TMA -> MMA
     uint64_t* empty = bars + 8;              // [n_stages] MMA -> TMA
     uint64_t* mma_done = bars + 16;          // MMA -> epilogue (accumulator pass complete)
@@ -260,14 +262,25 @@ __global__ void __launch_bounds__(AE_THREADS, 1) k_ae_chain(const __grid_constan
                                 if (q * 8 < nc) *(uint4*)(slab + sw128(row, j0 + q)) = pk;
                             }
                         } else {
+                            // A thread owns a row, so writing its values directly would scatter 4-byte stores one row stride
+                            // apart.  The warp's 32 x 32 chunk is transposed through shared memory instead and leaves as
+                            // one contiguous run of up to 128 bytes per row.
+                            float* stg = staging + quad * (32 * 33);
 #pragma unroll
                             for (int i = 0; i < 32; i++) {
                                 const int col = n0 + c + i;
-                                if (i < nc && col < p.out_real) {
-                                    sumsq = fmaf(v[i], v[i], sumsq);
-                                    if (grow < p.M) p.y[grow * p.out_real + col] = v[i];
-                                }
+                                if (i < nc && col < p.out_real) sumsq = fmaf(v[i], v[i], sumsq);
+                                stg[lane * 33 + i] = v[i];
                             }
+                            __syncwarp();
+                            const long long row0 = (long long)tile * AE_M + quad * 32;
+                            const int col = n0 + c + lane;
+                            if (lane < nc && col < p.out_real) {
+#pragma unroll 4
+                                for (int r = 0; r < 32; r++)
+                                    if (row0 + r < p.M) p.y[(row0 + r) * p.out_real + col] = stg[r * 33 + lane];
+                            }
+                            __syncwarp();
                         }
                     };
                     {
@@ -296,11 +309,29 @@ __global__ void __launch_bounds__(AE_THREADS, 1) k_ae_chain(const __grid_constan
                     mbar_arrive(epi_done);
                     if (tracer && tr_n < 250) p.trace[tr_n++] = gtimer();  // epilogue of (layer l, pass) done
                 }
-                if (last && p.normalize && grow < p.M) {
-                    // x / ||x||_2 (model.py:55,61) -- the un-normalised row was just written by this thread
+                if (last && p.normalize) {
+                    // x / ||x||_2 (model.py:55,61): the warp's 32 un-normalised rows were just written by its own lanes (and
+                    // are still in L2); they are rescaled row by row with coalesced accesses, lane r supplying row r's norm
+                    __syncwarp();
                     const float inv = 1.0f / sqrtf(sumsq);
-                    float* yr = p.y + grow * p.out_real;
-                    for (int col = 0; col < p.out_real; col++) yr[col] *= inv;
+                    const long long row0 = (long long)tile * AE_M + quad * 32;
+                    const bool vec4 = (p.out_real & 3) == 0 && (((uintptr_t)p.y) & 15) == 0;
+                    for (int r = 0; r < 32; r++) {
+                        const float inv_r = __shfl_sync(0xffffffffu, inv, r);
+                        if (row0 + r >= p.M) break;
+                        float* yr = p.y + (row0 + r) * p.out_real;
+                        if (vec4) {
+                            float4* y4 = reinterpret_cast<float4*>(yr);
+                            for (int q = lane; q < (p.out_real >> 2); q += 32) {
+                                float4 t = y4[q];
+                                t.x *= inv_r; t.y *= inv_r; t.z *= inv_r; t.w *= inv_r;
+                                y4[q] = t;
+                            }
+                        } else {
+                            for (int col = lane; col < p.out_real; col += 32) yr[col] *= inv_r;
+                        }
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -446,12 +477,12 @@ int ols_ae_plan_create(const ols_ae_chain* chain, ols_ae_plan** out_plan, void* 
     if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { ols_set_error("weight packing failed"); return fail(OLS_ERR_CUDA); }
     stage_bytes = round_up(stage_bytes, 1024);
     const int act_bytes = round_up(act_cols_bytes > 0 ? act_cols_bytes : 1024, 1024);
-    const int budget = 227 * 1024 - 1024 /*alignment*/ - 256 /*barriers*/ - act_bytes;
+    const int budget = 227 * 1024 - 1024 /*alignment*/ - 256 /*barriers*/ - act_bytes - AE_STAGING_BYTES;
     int n_stages = budget / stage_bytes;
     if (n_stages > 8) n_stages = 8;
     if (n_stages < 2) { ols_set_error("layer chain does not fit shared memory (stage %d B, act %d B)", stage_bytes, act_bytes); return fail(OLS_ERR_UNSUPPORTED); }
     p.n_stages = n_stages; p.stage_bytes = stage_bytes; p.act_bytes = act_bytes;
-    plan->smem_bytes = (size_t)n_stages * stage_bytes + act_bytes + 256 + 1024;
+    plan->smem_bytes = (size_t)n_stages * stage_bytes + act_bytes + AE_STAGING_BYTES + 256 + 1024;
     // the attribute belongs to the kernel, not to the plan: always reserve the opt-in maximum so that plans with
     // different shared-memory needs (encoder / decoder) can be launched in any order
     if (plan->smem_bytes > 227 * 1024 ||

@@ -404,6 +404,7 @@ struct GeomBwdArgs : GeomCommon {
     int V;
     const float *scales, *rotations, *cov3D;
     float *dL_dcolors, *dL_dlanguage, *dL_dopacity, *dL_dmeans3D, *dL_dcov3D, *dL_dscales, *dL_drots;
+    float *stat_max_radii, *stat_accum, *stat_denom;  // optional densification statistics (all or none)
     GeomView v[OLS_MAX_VIEWS];
 };
 
@@ -666,6 +667,9 @@ __global__ void __launch_bounds__(256, 2) k_geometry_bwd(const __grid_constant__
     float mp[3] = {0, 0, 0};
     if (valid) { mp[0] = a.means3D[3 * (size_t)i]; mp[1] = a.means3D[3 * (size_t)i + 1]; mp[2] = a.means3D[3 * (size_t)i + 2]; }
     bool any_total = false;
+    const bool stats = a.stat_denom != nullptr;
+    float st_norm = 0.0f, st_cnt = 0.0f;
+    int st_rad = 0;
     for (int v = 0; v < a.V; v++) {
         const GeomView& vw = a.v[v];
         // the whole packed gradient record in registers: GRF/4 independent 16-byte loads
@@ -686,11 +690,13 @@ __global__ void __launch_bounds__(256, 2) k_geometry_bwd(const __grid_constant__
         float dtau[6] = {0, 0, 0, 0, 0, 0};
         float g2x = 0.0f, g2y = 0.0f;
         bool vis = false;
+        int rad = 0;
+        if (stats && valid) rad = vw.radii[i];
         if (any) {
             any_total = true;
             g2x = gr[GR_MX]; g2y = gr[GR_MY];
             const float dcol_v[3] = {gr[GR_RGB], gr[GR_RGB + 1], gr[GR_RGB + 2]};
-            vis = vw.radii[i] > 0;
+            vis = (stats ? rad : vw.radii[i]) > 0;
             if (vis) {
                 const float* V = vw.viewmatrix;
                 const float* c3 = a.cov3D + 6 * (size_t)i;
@@ -708,6 +714,11 @@ __global__ void __launch_bounds__(256, 2) k_geometry_bwd(const __grid_constant__
             dop += gr[GR_OP];
 #pragma unroll
             for (int k = 0; k < F; k++) dlang[k] += gr[GR_LANG + k];
+        }
+        if (rad > 0) {  // densification statistics of this view (gaussian_model.py:965-969)
+            st_norm += sqrtf(g2x * g2x + g2y * g2y);
+            st_cnt += 1.0f;
+            st_rad = max(st_rad, rad);
         }
         if (valid) {  // per-view outputs are always written
             float* m2 = vw.dL_dmeans2D + 3 * (size_t)i;
@@ -732,6 +743,11 @@ __global__ void __launch_bounds__(256, 2) k_geometry_bwd(const __grid_constant__
         const int v = threadIdx.x / 6, k = threadIdx.x - 6 * v;
         const float t = s_tau[v][k];
         if (a.v[v].dL_dtau_sum && t != 0.0f) atomicAdd(&a.v[v].dL_dtau_sum[k], t);
+    }
+    if (stats && valid && st_cnt > 0.0f) {
+        a.stat_accum[i] += st_norm;
+        a.stat_denom[i] += st_cnt;
+        a.stat_max_radii[i] = fmaxf(a.stat_max_radii[i], (float)st_rad);
     }
     if (!valid || (acc && !any_total)) return;  // accumulating a zero gradient: nothing to read or rewrite
     float dsc[3] = {0, 0, 0}, dq[4] = {0, 0, 0, 0};
@@ -1023,6 +1039,10 @@ int ols_launch_backward(const ols_raster_args* views, const ols_bwd_args* grads,
     ga.dL_dcolors = g->d_dL_dcolors; ga.dL_dlanguage = g->d_dL_dlanguage;
     ga.dL_dopacity = g->d_dL_dopacity; ga.dL_dmeans3D = g->d_dL_dmeans3D; ga.dL_dcov3D = g->d_dL_dcov3D;
     ga.dL_dscales = g->d_dL_dscales; ga.dL_drots = g->d_dL_drotations;
+    const bool stats = g->d_stat_max_radii2D && g->d_stat_xyz_gradient_accum && g->d_stat_denom;
+    ga.stat_max_radii = stats ? g->d_stat_max_radii2D : nullptr;
+    ga.stat_accum = stats ? g->d_stat_xyz_gradient_accum : nullptr;
+    ga.stat_denom = stats ? g->d_stat_denom : nullptr;
     for (int v = 0; v < V; v++)
         fill_geom_view(ga.v[v], &views[v], (const char*)views[v].d_workspace, L, grads[v].d_radii, grads[v].d_dL_dmeans2D,
                        grads[v].d_dL_dtau, grads[v].d_dL_dtau_sum);

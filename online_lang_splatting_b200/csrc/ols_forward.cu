@@ -701,7 +701,8 @@ constexpr int BS_NB = 2048;                      // buckets
 constexpr int BS_LIMIT = 48;                     // largest bucket this path accepts
 constexpr uint32_t BS_DONE = 0xffffffffu;
 
-__global__ void __launch_bounds__(BS_THREADS) k_sort_tiles_bucket(const __grid_constant__ PassBatch pb, const WsLayout L) {
+__global__ void __launch_bounds__(BS_THREADS) k_sort_tiles_bucket(const __grid_constant__ PassBatch pb, const WsLayout L,
+                                                                 const int write_keys) {
     __shared__ unsigned long long s_key[BS_CAP];  // 32 KB
     char* ws = pb.v[blockIdx.y].ws;
     unsigned long long* __restrict__ keys = (unsigned long long*)(ws + L.keys);
@@ -800,7 +801,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_sort_tiles_bucket(const __grid_c
     __syncthreads();
     for (int i = tid; i < n; i += BS_THREADS) {  // coalesced write-out
         const unsigned long long v = s_key[i];
-        g[i] = v;
+        if (write_keys) g[i] = v;  // the sorted keys are only read back by tests / debugging (ols_ws_view.d_keys)
         point_list[rg.x + i] = (uint32_t)v;
     }
     if (tid == 0) tile_count[blockIdx.x] = BS_DONE;
@@ -818,7 +819,8 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_CAP = 4096;
 constexpr int RS_ITEMS = RS_CAP / RS_THREADS;  // 16 keys per thread at most
 
-__global__ void __launch_bounds__(RS_THREADS) k_sort_tiles_radix(const __grid_constant__ PassBatch pb, const WsLayout L) {
+__global__ void __launch_bounds__(RS_THREADS) k_sort_tiles_radix(const __grid_constant__ PassBatch pb, const WsLayout L,
+                                                                const int write_keys) {
     __shared__ unsigned long long s_key[RS_CAP];       // 32 KB
     char* ws = pb.v[blockIdx.y].ws;
     unsigned long long* __restrict__ keys = (unsigned long long*)(ws + L.keys);
@@ -947,7 +949,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_sort_tiles_radix(const __grid_co
     }
     for (int i = tid; i < n; i += RS_THREADS) {
         const unsigned long long v = s_key[i];
-        g[i] = v;
+        if (write_keys) g[i] = v;
         point_list[rg.x + i] = (uint32_t)v;
     }
 }
@@ -1560,9 +1562,10 @@ static int run_pass(int P, int W, int H, int tile, int ncol, int F, unsigned fla
     k_scatter<<<dim3(L.n_ctas, V), PRE_THREADS, hist_smem, st>>>(pb, L, P);
     OLS_DEBUG_SYNC("scatter");
     ols_timing_mark(OLS_T_BINNING, st);
-    k_sort_tiles_bucket<<<dim3(L.n_tiles, V), BS_THREADS, 0, st>>>(pb, L);
+    const int write_keys = debug ? 1 : 0;  // sorted 64-bit keys are a debugging view; the blend passes read point_list
+    k_sort_tiles_bucket<<<dim3(L.n_tiles, V), BS_THREADS, 0, st>>>(pb, L, write_keys);
     OLS_DEBUG_SYNC("sort_tiles_bucket");
-    k_sort_tiles_radix<<<dim3(L.n_tiles, V), RS_THREADS, 0, st>>>(pb, L);
+    k_sort_tiles_radix<<<dim3(L.n_tiles, V), RS_THREADS, 0, st>>>(pb, L, write_keys);
     OLS_DEBUG_SYNC("sort_tiles_radix");
     // buckets longer than the radix kernel's shared-memory capacity (rare): bitonic fallback
     k_sort_tiles<<<dim3(L.n_tiles, V), SORT_THREADS, 0, st>>>(pb, L, RS_CAP);

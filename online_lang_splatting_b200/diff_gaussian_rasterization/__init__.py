@@ -126,7 +126,17 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 class _Ctx:
     """What forward leaves for backward (the reference keeps geomBuffer/binningBuffer/imgBuffer)."""
-    __slots__ = ("args", "args_arr", "keep", "R", "Rs", "info", "V", "pending", "workspaces")
+    __slots__ = ("args", "args_arr", "keep", "_R", "Rs", "info", "V", "pending", "workspaces")
+
+    @property
+    def R(self) -> int:
+        """num_rendered of the first view (reference: the first return of rasterize_language_gaussians).  In the deferred
+        mode it is not known when forward returns; reading it waits for the header (tests / debugging only)."""
+        if self._R < 0 and self.pending is not None:
+            self.pending.poll(block=True)
+            self.Rs = list(self.pending.Rs)
+            self._R = self.Rs[0]
+        return self._R
 
     def resolve(self) -> None:
         """Called by backward: the forward's overflow flag is known by now (waits for it if it is not)."""
@@ -137,7 +147,7 @@ class _Ctx:
         if pend in _PENDING:
             _PENDING.remove(pend)
         self.Rs = list(pend.Rs)
-        self.R = self.Rs[0]
+        self._R = self.Rs[0]
         self.pending = None
         if pend.overflow:
             raise N.OlsError(N.OLS_ERR_OVERFLOW,
@@ -285,7 +295,7 @@ def _forward_native_batch(means3D, sh, colors_precomp, language_precomp, opaciti
     st.args_arr, st.args, st.keep, st.V, st.pending, st.workspaces = args, args[0], keep, V, pend, workspaces
     st.info = infos[0] if infos else None
     st.Rs = [int(i.R) for i in infos] if infos else [-1] * V
-    st.R = st.Rs[0]
+    st._R = st.Rs[0]
     return outs, st
 
 
@@ -295,7 +305,7 @@ def _forward_native(means3D, sh, colors_precomp, language_precomp, opacities, sc
     outs, st = _forward_native_batch(means3D, sh, colors_precomp, language_precomp, opacities, scales, rotations,
                                      cov3Ds_precomp, [rs])
     color, language, radii, depth, opacity, n_touched = outs[0]
-    return (st.R if st is not None else 0), color, language, radii, depth, opacity, n_touched, st
+    return (st._R if st is not None else 0), color, language, radii, depth, opacity, n_touched, st
 
 
 GRAD_SHAPES = lambda P, F, M: {"colors": (P, 3), "language": (P, F), "opacity": (P, 1),
@@ -310,7 +320,8 @@ def _backward_native_batch(st: _Ctx, radii, grad_color, grad_language, grad_dept
     gradient), "tau_sum" [V,6] (each view's pose gradient summed over the Gaussians) and, on request, "tau"
     [V,P,6] (the reference's per-Gaussian form).  ``out`` may hold preallocated contiguous fp32 tensors under
     the same keys -- e.g. views into one flat buffer that is all-reduced across ranks; with ``accumulate=True``
-    the parameter gradients are added to what ``out`` already holds."""
+    the parameter gradients are added to what ``out`` already holds.  ``out["stats"] = (max_radii2D, xyz_gradient_accum,
+    denom)`` (fp32 [P] each) folds the densification statistics of all the views into the same launch."""
     st.resolve()
     k = st.keep
     a = st.args
@@ -347,6 +358,9 @@ def _backward_native_batch(st: _Ctx, radii, grad_color, grad_language, grad_dept
                          d_dL_dsh=N.ptr(g["sh"]), d_dL_dscales=g["scales"].data_ptr(),
                          d_dL_drotations=g["rotations"].data_ptr(),
                          d_dL_dtau=tg[v].data_ptr() if tg is not None else None, d_dL_dtau_sum=ts[v].data_ptr())
+    stats = (out or {}).get("stats")
+    if stats is not None:
+        b[0].d_stat_max_radii2D, b[0].d_stat_xyz_gradient_accum, b[0].d_stat_denom = (t.data_ptr() for t in stats)
     arr = st.args_arr
     flags = arr[0].flags
     try:

@@ -153,6 +153,12 @@ class SideStats:
         P = self.P
         update_stats(radii, viewspace_grad, self.delta_max, self.delta[:P].view(P, 1), self.delta[P:].view(P, 1))
 
+    def fused_outputs(self):
+        """``out["stats"]`` for ``_backward_native_batch``: the backward's geometry kernel folds all views of the call into
+        the per-step deltas itself (no separate launches)."""
+        P = self.P
+        return (self.delta_max, self.delta[:P], self.delta[P:])
+
     def all_reduce(self):
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:

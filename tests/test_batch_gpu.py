@@ -96,3 +96,27 @@ def test_batch_headline_shape_lists_match_single(cuda):
         R, color, language, radii, depth, opacity, n_touched, st1 = dgr._forward_native(*params, rs_list[v])
         assert torch.equal(outs[v][0], color) and torch.equal(outs[v][1], language) and torch.equal(outs[v][2], radii)
         assert torch.equal(outs[v][5], n_touched)
+
+
+def test_fused_densification_stats_equal_per_view_updates(cuda):
+    """out["stats"] of the batched backward == densification.update_stats applied view by view to the same gradients
+    (utils/slam_backend.py:719-728 + gaussian_model.py:965-969)."""
+    from online_lang_splatting_b200 import densification as DN
+    from online_lang_splatting_b200 import diff_gaussian_rasterization as dgr
+    P, W, H, V = 6000, 128, 80, 4
+    scs = [U.make_scene(P=P, F=15, W=W, H=H, seed=2, view=v, scale=0.05) for v in range(V)]
+    d = lambda k: scs[0][k].to(cuda)
+    e = torch.Tensor([])
+    rs_list = [U.settings(sc, cuda, bitexact=True)._replace(debug=False) for sc in scs]
+    params = (d("means3D"), d("shs"), e, d("language"), d("opacities"), d("scales"), d("rotations"), e)
+    w = [t.to(cuda) for t in U.loss_weights(15, W, H, seed=4)]
+    outs, st = dgr._forward_native_batch(*params, rs_list)
+    radii = [o[2] for o in outs]
+    mx = torch.rand(P, device=cuda) * 3
+    acc, den = torch.rand(P, device=cuda), torch.rand(P, device=cuda).round()
+    mx0, acc0, den0 = mx.clone(), acc.clone(), den.clone()
+    g = dgr._backward_native_batch(st, radii, [w[0]] * V, [w[1]] * V, [w[2]] * V, out={"stats": (mx, acc, den)})
+    for v in range(V):
+        DN.update_stats(radii[v], g["means2D"][v].contiguous(), mx0, acc0.view(P, 1), den0.view(P, 1))
+    assert torch.equal(mx, mx0) and torch.equal(den, den0)
+    assert torch.allclose(acc, acc0, rtol=1e-5, atol=1e-7)

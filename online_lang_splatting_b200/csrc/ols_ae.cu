@@ -60,6 +60,7 @@ struct AeParams {
     int out_real;    // real output width
     int normalize;
     int n_stages, stage_bytes, act_bytes;
+    int stage_out;   // 1: the last layer's output is transposed through shared memory (wide outputs; needs AE_STAGING_BYTES)
     const float* x;
     float* y;
     long long M;
@@ -73,8 +74,8 @@ __global__ void __launch_bounds__(AE_THREADS, 1) k_ae_chain(const __grid_constan
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* ring = smem;                                          // n_stages * stage_bytes
     uint8_t* act = smem + (size_t)p.n_stages * p.stage_bytes;      // act_bytes: [K-slab][128 rows][128 B]
-    float* staging = (float*)(act + p.act_bytes);                  // 4 warps x 32 x 33 floats: output transpose buffer
-    uint64_t* bars = (uint64_t*)(act + p.act_bytes + AE_STAGING_BYTES);
+    float* staging = (float*)(act + p.act_bytes);                  // (stage_out) 4 warps x 32 x 33 floats: output transpose buffer
+    uint64_t* bars = (uint64_t*)(act + p.act_bytes + (p.stage_out ? AE_STAGING_BYTES : 0));
     uint64_t* full = bars;                   // [n_stages] TMA -> MMA
     uint64_t* empty = bars + 8;              // [n_stages] MMA -> TMA
     uint64_t* mma_done = bars + 16;          // MMA -> epilogue (accumulator pass complete)
@@ -260,6 +261,16 @@ __global__ void __launch_bounds__(AE_THREADS, 1) k_ae_chain(const __grid_constan
                                 __nv_bfloat162 h3 = __floats2bfloat162_rn(v[q * 8 + 6], v[q * 8 + 7]);
                                 pk.x = *(uint32_t*)&h0; pk.y = *(uint32_t*)&h1; pk.z = *(uint32_t*)&h2; pk.w = *(uint32_t*)&h3;
                                 if (q * 8 < nc) *(uint4*)(slab + sw128(row, j0 + q)) = pk;
+                            }
+                        } else if (!p.stage_out) {
+                            // narrow outputs (the 15-dim code): a warp's 32 rows are one contiguous block of global memory
+#pragma unroll
+                            for (int i = 0; i < 32; i++) {
+                                const int col = n0 + c + i;
+                                if (i < nc && col < p.out_real) {
+                                    sumsq = fmaf(v[i], v[i], sumsq);
+                                    if (grow < p.M) p.y[grow * p.out_real + col] = v[i];
+                                }
                             }
                         } else {
                             // A thread owns a row, so writing its values directly would scatter 4-byte stores one row stride
@@ -477,12 +488,16 @@ int ols_ae_plan_create(const ols_ae_chain* chain, ols_ae_plan** out_plan, void* 
     if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { ols_set_error("weight packing failed"); return fail(OLS_ERR_CUDA); }
     stage_bytes = round_up(stage_bytes, 1024);
     const int act_bytes = round_up(act_cols_bytes > 0 ? act_cols_bytes : 1024, 1024);
-    const int budget = 227 * 1024 - 1024 /*alignment*/ - 256 /*barriers*/ - act_bytes - AE_STAGING_BYTES;
+    const int budget = 227 * 1024 - 1024 /*alignment*/ - 256 /*barriers*/ - act_bytes;
     int n_stages = budget / stage_bytes;
     if (n_stages > 8) n_stages = 8;
+    // wide outputs leave through a shared-memory transpose when it fits beside the ring (it does for every decoder of the
+    // reference; the encoders write 15- / 32-float rows, which are contiguous per warp anyway)
+    p.stage_out = (p.out_real > 32 && n_stages >= 2 && budget - n_stages * stage_bytes >= AE_STAGING_BYTES) ? 1 : 0;
+    if (p.out_real > 32 && !p.stage_out && n_stages > 2) { n_stages--; p.stage_out = 1; }
     if (n_stages < 2) { ols_set_error("layer chain does not fit shared memory (stage %d B, act %d B)", stage_bytes, act_bytes); return fail(OLS_ERR_UNSUPPORTED); }
     p.n_stages = n_stages; p.stage_bytes = stage_bytes; p.act_bytes = act_bytes;
-    plan->smem_bytes = (size_t)n_stages * stage_bytes + act_bytes + AE_STAGING_BYTES + 256 + 1024;
+    plan->smem_bytes = (size_t)n_stages * stage_bytes + act_bytes + (p.stage_out ? AE_STAGING_BYTES : 0) + 256 + 1024;
     // the attribute belongs to the kernel, not to the plan: always reserve the opt-in maximum so that plans with
     // different shared-memory needs (encoder / decoder) can be launched in any order
     if (plan->smem_bytes > 227 * 1024 ||

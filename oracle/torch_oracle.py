@@ -17,6 +17,8 @@ from typing import Sequence
 import torch
 import torch.nn as nn
 
+CLONE, SPLIT, PRUNE = 1, 2, 4   # bits of the densification flags (densification.py)
+
 def reference_tracking_loss(image, depth, opacity, gt_image, gt_depth, grad_mask=None, *, alpha=0.95,
                             rgb_boundary_threshold=0.01, exposure_a=None, exposure_b=None):
     """Plain-torch restatement of utils/slam_utils.py:91-118 (test reference)."""

@@ -142,13 +142,12 @@ def test_deferred_overflow_is_loud_and_recovers(cuda):
     bg = torch.zeros(3, device=cuda)
     key = (cuda.index if cuda.index is not None else 0, W, H, 15)
     assert dgr.CHECK_OVERFLOW == "deferred"
-    good = render(cam, pc, S.PipelineParams(), bg)["render"].detach().clone()   # establishes the estimate (sync, first use)
+    good = render(cam, pc, S.PipelineParams(), bg)["render"].detach().clone()   # establishes the estimate if there was none
     torch.cuda.synchronize()
+    dgr._poll_pending()     # headers of earlier asynchronous renders are consumed (they would restore the estimate)
     saved = dgr._SLACK
     dgr._R_RATIO[key] = 1e-9
     dgr._SLACK = 0
-    calls = {"n": 0}
-    real_sync = torch.cuda.synchronize
     try:
         out = render(cam, pc, S.PipelineParams(), bg)        # asynchronous; overflows on the device
         assert out["render"].grad_fn.state.pending is not None, "the default path must not read the header synchronously"
@@ -236,9 +235,15 @@ def test_forward_bitexact_vs_compiled_reference(cuda):
         assert np.array_equal(ours["ws"]["final_T"].view(np.uint32), ref["final_T"].view(np.uint32))
         for k in ("color", "language", "depth", "opacity"):
             assert np.array_equal(ours[k].view(np.uint32), ref[k].view(np.uint32)), (k, U.rel_err(ours[k], ref[k]))
+        # default blend (ex2.approx alpha): an alpha >= 1/255 or T < 1e-4 decision can flip where the value sits within
+        # ~4e-7 relative of its threshold; such a pixel then differs by up to alpha*T*c ~ 4e-3.  Tolerance: at most 1 pixel
+        # in 10^4 affected, everything else within 5e-6 of the image scale, relative L2 error below 1e-5.
         fast = U.run_ours(sc, cuda, tile=15, bitexact=False)
         for k in ("color", "language", "depth", "opacity"):
-            assert U.rel_err(fast[k], ref[k]) < 1e-5, k
+            a, b = fast[k].astype(np.float64), ref[k].astype(np.float64)
+            bad = np.abs(a - b) > 5e-6 * max(np.abs(b).max(), 1e-6)
+            assert bad.mean() < 1e-4, (k, bad.mean())
+            assert np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30) < 1e-5, k
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(U.GOLDEN_DIR, "p15_*.npz"))) or [None])

@@ -403,6 +403,25 @@ int ols_ae_forward(const ols_ae_plan* plan, const float* d_x, float* d_y, int64_
 int ols_ae_forward_bf16(const ols_ae_plan* plan, const void* d_x_bf16, float* d_y, int64_t M, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * One training step of the online autoencoder, fused (utils/slam_backend.py:266-323 train_online_autoencoder on
+ * language/autoencoder/model.py:314-354 EncoderDecoderOnline, 32 -> 24 -> 15 -> 24 -> 32):
+ *     comp = encode(x); recon = decode(comp);
+ *     loss = l1_loss(recon, x) + 0.6 * (1 - cosine_similarity(recon, x, dim=1).mean());  loss.backward();  Adam.step()
+ * d_params: the 2351 parameters as one flat fp32 vector in nn.Module.parameters() order (encoder.0.weight [24,32],
+ * encoder.0.bias, encoder.2.weight [15,24], encoder.2.bias, decoder.0.weight [24,15], decoder.0.bias, decoder.2.weight
+ * [32,24], decoder.2.bias), updated in place; d_exp_avg / d_exp_avg_sq: Adam moments (same layout, zero at the start);
+ * d_step: device step counter (steps taken so far, incremented by the call).  d_code receives comp [M,15] computed with
+ * the parameters BEFORE the update (what the reference returns, :323); d_loss the scalar loss.  d_scratch:
+ * ols_online_ae_scratch_bytes() bytes, 256-byte aligned, zero-filled before the first call and then left alone.
+ * Forward and backward are fp32 FMAs; the slab reduction order is fixed, so the step is deterministic.
+ * ------------------------------------------------------------------------------------------- */
+size_t ols_online_ae_scratch_bytes(void);
+int32_t ols_online_ae_param_count(void);
+int ols_online_ae_train_step(float* d_params, float* d_exp_avg, float* d_exp_avg_sq, int64_t* d_step, const float* d_x /* [M,32] */,
+                             int64_t M, float lr, float beta1, float beta2, float eps, float* d_code /* [M,15] or NULL */,
+                             float* d_loss /* [1] */, void* d_scratch, size_t scratch_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * HR module (language/supervisedNet.py:45-109 HighResLanguageFeatureNet, called with torch.no_grad() in eval
  * mode at utils/slam_backend.py:381-386,547-552): fv [768,S,S] + res3 [384,h3,w3] + res2 [192,h2,w2] ->
  * [768,8S,8S] dense CLIP map, the autoencoder's input.  13 convolutions in the order

@@ -35,6 +35,7 @@ EXPORTED_SYMBOLS = (
     "ols_ssim_loss_forward", "ols_ssim_loss_backward", "ols_densify_stats", "ols_densify_flags",
     "ols_ae_forward_bf16", "ols_hr_forward_features",
     "ols_lang_forward_batch", "ols_lang_backward_batch", "ols_lang_read_info_async", "ols_activate_params", "ols_adam_step_dev",
+    "ols_online_ae_scratch_bytes", "ols_online_ae_param_count", "ols_online_ae_train_step",
 )
 
 
@@ -178,6 +179,11 @@ def lib() -> C.CDLL:
                                 C.c_double, C.c_double, C.c_double, C.c_int64, C.c_void_p]
     L.ols_adam_step_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(AdamGroup), C.c_int32,
                                     C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+    L.ols_online_ae_scratch_bytes.restype = C.c_size_t
+    L.ols_online_ae_param_count.restype = C.c_int32
+    L.ols_online_ae_train_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
+                                           C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                           C.c_void_p]
     L.ols_activate_params.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 7
     L.ols_knn_workspace_size.restype = C.c_size_t
     L.ols_knn_workspace_size.argtypes = [C.c_int32]

@@ -106,6 +106,7 @@ def _version(modules: Sequence[nn.Module]):
     for m in modules:
         for t in list(m.parameters(recurse=False)) + list(m.buffers(recurse=False)):
             v.append((t.data_ptr(), t._version))
+        v.append(getattr(m, "_ols_updates", 0))   # in-place updates by fused kernels (invisible to the version counters)
     return tuple(v)
 
 
@@ -205,3 +206,50 @@ class EncoderDecoderOnline(nn.Module, _ChainMixin):
 
     def forward(self, x):
         return self.decode(self.encode(x))
+
+    # ---- fused training step (utils/slam_backend.py:266-323) -----------------------------------------------------
+    def _fused_state(self, dev):
+        st = self.__dict__.get("_train_state")
+        params = list(self.parameters())
+        if st is not None and st["flat"].device == dev and all(
+                p.data_ptr() == st["flat"].data_ptr() + 4 * o for p, o in zip(params, st["offsets"])):
+            return st
+        lib = N.lib()
+        n = int(lib.ols_online_ae_param_count())
+        if sum(p.numel() for p in params) != n or tuple(params[0].shape) != (24, 32) or tuple(params[2].shape) != (15, 24):
+            raise RuntimeError("the fused step is built for the reference's EncoderDecoderOnline (32 -> 24 -> 15 -> 24 -> 32)")
+        flat = torch.cat([p.detach().reshape(-1).float() for p in params]).to(dev).contiguous()
+        offsets, o = [], 0
+        for p in params:                      # the module's parameters become views of the flat vector the kernel updates
+            p.data = flat[o:o + p.numel()].view(p.shape)
+            offsets.append(o)
+            o += p.numel()
+        st = {"flat": flat, "offsets": offsets, "m": torch.zeros_like(flat), "v": torch.zeros_like(flat),
+              "step": torch.zeros(1, dtype=torch.int64, device=dev),
+              "scratch": torch.zeros(int(lib.ols_online_ae_scratch_bytes()), dtype=torch.uint8, device=dev),
+              "loss": torch.zeros(1, dtype=torch.float32, device=dev)}
+        self.__dict__["_train_state"] = st
+        return st
+
+    def fused_train_step(self, features: torch.Tensor, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
+        """``train_online_autoencoder`` (utils/slam_backend.py:266-323) -- encode, decode, ``l1_loss + 0.6 (1 - cos)``,
+        backward and ``torch.optim.Adam(lr).step()`` -- as ONE kernel.  Returns ``(loss, comp_15)``: the loss as a
+        0-dim device tensor (no host synchronisation; the reference calls ``.item()``) and the 15-dim codes computed
+        with the parameters before the update, as the reference returns them.  The Adam moments and the step count live
+        in this module; the parameters are updated in place (they are views of one flat vector from the first call on)."""
+        N.require_cuda()
+        if not features.is_cuda:
+            raise RuntimeError("fused_train_step needs a CUDA tensor: there is no CPU path")
+        x = features.detach().to(torch.float32).contiguous().view(-1, 32)
+        dev = x.device
+        st = self._fused_state(dev)
+        code = torch.empty((x.shape[0], 15), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            N.check(N.lib().ols_online_ae_train_step(st["flat"].data_ptr(), st["m"].data_ptr(), st["v"].data_ptr(),
+                                                     st["step"].data_ptr(), x.data_ptr(), x.shape[0], float(lr), float(betas[0]),
+                                                     float(betas[1]), float(eps), code.data_ptr(), st["loss"].data_ptr(),
+                                                     st["scratch"].data_ptr(), st["scratch"].numel(), stream))
+        for m in list(self.encoder) + list(self.decoder):
+            m._ols_updates = getattr(m, "_ols_updates", 0) + 1
+        return st["loss"][0], code

@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libols_b200.so")
-SOURCES = ["ols_api.cu", "ols_forward.cu", "ols_backward.cu", "ols_ae.cu", "ols_loss.cu", "ols_optim.cu", "ols_knn.cu", "ols_hr.cu", "ols_ssim.cu", "ols_densify.cu"]
+SOURCES = ["ols_api.cu", "ols_forward.cu", "ols_backward.cu", "ols_ae.cu", "ols_loss.cu", "ols_optim.cu", "ols_knn.cu", "ols_hr.cu", "ols_ssim.cu", "ols_densify.cu", "ols_online_ae.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 

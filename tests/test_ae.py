@@ -175,3 +175,40 @@ def test_config4_batch32_full_size(cuda):
     cos = torch.nn.functional.cosine_similarity(code[idx], ref_code, dim=-1)
     assert cos.min().item() > 0.9995
     assert torch.equal(code[idx], sub_code)
+
+
+@pytest.mark.gpu
+def test_fused_online_train_step_matches_torch_adam():
+    """train_online_autoencoder (utils/slam_backend.py:266-323) as one kernel.  Five steps against the
+    reference's own sequence -- the module's torch graph, l1_loss + 0.6 (1 - cosine_similarity.mean()), backward,
+    torch.optim.Adam(lr=1e-3) -- on [36864, 32] unit-norm codes: parameters within 1e-5, loss and returned codes too."""
+    import copy
+    from online_lang_splatting_b200 import autoencoder as AE
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    ref = AE.EncoderDecoderOnline().to(dev)
+    ours = copy.deepcopy(ref)
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    g = torch.Generator().manual_seed(4)
+    for it in range(5):
+        x = torch.randn(36864 if it < 4 else 1000, 32, generator=g)      # last step: ragged row count (not a multiple of 128)
+        x = (x / x.norm(dim=-1, keepdim=True)).to(dev)
+        ref.train()
+        opt.zero_grad()
+        comp = ref.encode(x)
+        recon = ref.decode(comp)
+        loss = torch.nn.functional.l1_loss(recon, x) + 0.6 * (1 - torch.nn.functional.cosine_similarity(recon, x, dim=1).mean())
+        loss.backward()
+        opt.step()
+        l2, c2 = ours.fused_train_step(x, lr=1e-3)
+        assert abs(l2.item() - loss.item()) <= 2e-6 * abs(loss.item()) + 1e-7, (it, l2.item(), loss.item())
+        assert (c2 - comp.detach()).abs().max().item() < 2e-6
+    for p, q in zip(ours.parameters(), ref.parameters()):
+        assert (p.detach() - q.detach()).abs().max().item() < 1e-5
+    # the fused inference path sees the updated weights (its cache is keyed on the in-place update counter)
+    ours.eval()
+    with torch.no_grad():
+        x = torch.randn(4096, 32, generator=g).to(dev)
+        a, b = ours.encode(x), ref.eval().encode(x) if False else None
+        want = torch.nn.functional.normalize(ref.encoder(x), dim=-1)
+        assert torch.nn.functional.cosine_similarity(a, want, dim=-1).min().item() > 0.9995

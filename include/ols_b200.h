@@ -358,6 +358,33 @@ int ols_activate_params(int32_t P, int32_t scale_cols, const float* d_opacity_ra
                         const float* d_rotation_raw, float* d_opacity, float* d_scaling, float* d_rotation, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Pose step of the tracking loop (utils/slam_frontend.py:216-262, utils/pose_utils.py:60-95 update_pose): Adam over
+ * (cam_rot_delta, cam_trans_delta, exposure_a, exposure_b), T_w2c <- SE3_exp(tau) T_w2c, deltas back to zero, and the
+ * camera tensors render() reads rebuilt in place -- one kernel, no host synchronisation (the reference needs two per
+ * iteration).  Matrices in the reference's transposed storage; d_R row-major 3x3.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ols_pose_step {
+    const float* d_grad_tau;       /* [6] (rho | theta) = ols_bwd_args.d_dL_dtau_sum                              */
+    const float* d_grad_exposure;  /* [2] dL/d(exposure_a, exposure_b), or NULL                                   */
+    float* d_exposure;             /* [2] exposure_a, exposure_b, updated in place, or NULL                       */
+    float* d_exp_avg;              /* [8] Adam moments, order: rot 3 | trans 3 | exposure 2                       */
+    float* d_exp_avg_sq;           /* [8]                                                                         */
+    int64_t* d_step;               /* Adam step count, incremented                                                */
+    float* d_R;                    /* [9] world->camera rotation, updated                                         */
+    float* d_T;                    /* [3] world->camera translation, updated                                      */
+    const float* d_projection;     /* [16] projection_matrix                                                      */
+    float* d_viewmatrix;           /* [16] out: world_view_transform                                              */
+    float* d_projmatrix;           /* [16] out: full_proj_transform                                               */
+    float* d_campos;               /* [3]  out: camera_center                                                     */
+    int32_t* d_converged;          /* set to 1 when |tau| < converged_threshold (never cleared), or NULL          */
+    float lr_rot, lr_trans, lr_exposure;   /* config Training.lr.cam_rot_delta / cam_trans_delta, 0.01            */
+    float beta1, beta2, eps;               /* torch.optim.Adam defaults: 0.9, 0.999, 1e-8                         */
+    float converged_threshold;             /* 1e-4                                                                */
+    int32_t zero_grads;                    /* 1: clear d_grad_tau / d_grad_exposure after use (optimizer.zero_grad())  */
+} ols_pose_step;
+int ols_pose_adam_step(const ols_pose_step* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * distCUDA2 (submodules/simple-knn/spatial.cu + simple_knn.cu:120-220): mean squared distance of every
  * point to its 3 nearest neighbours; GaussianModel uses it to size new Gaussians
  * (gaussian_splatting/scene/gaussian_model.py:256-262).  Asynchronous, no host round trips.

@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = (
     "ols_ssim_loss_forward", "ols_ssim_loss_backward", "ols_densify_stats", "ols_densify_flags",
     "ols_ae_forward_bf16", "ols_hr_forward_features",
     "ols_lang_forward_batch", "ols_lang_backward_batch", "ols_lang_read_info_async", "ols_activate_params", "ols_adam_step_dev",
-    "ols_online_ae_scratch_bytes", "ols_online_ae_param_count", "ols_online_ae_train_step",
+    "ols_pose_adam_step", "ols_online_ae_scratch_bytes", "ols_online_ae_param_count", "ols_online_ae_train_step",
 )
 
 
@@ -100,6 +100,14 @@ class AdamGroup(C.Structure):
 
 
 ACT_NONE, ACT_EXP, ACT_SIGMOID, ACT_NORMALIZE4 = 0, 1, 2, 3
+
+
+class PoseStep(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("d_grad_tau", "d_grad_exposure", "d_exposure", "d_exp_avg", "d_exp_avg_sq", "d_step",
+                                          "d_R", "d_T", "d_projection", "d_viewmatrix", "d_projmatrix", "d_campos",
+                                          "d_converged")] + \
+               [(n, C.c_float) for n in ("lr_rot", "lr_trans", "lr_exposure", "beta1", "beta2", "eps", "converged_threshold")] + \
+               [("zero_grads", C.c_int32)]
 
 
 class WsView(C.Structure):
@@ -179,6 +187,7 @@ def lib() -> C.CDLL:
                                 C.c_double, C.c_double, C.c_double, C.c_int64, C.c_void_p]
     L.ols_adam_step_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(AdamGroup), C.c_int32,
                                     C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+    L.ols_pose_adam_step.argtypes = [C.POINTER(PoseStep), C.c_void_p]
     L.ols_online_ae_scratch_bytes.restype = C.c_size_t
     L.ols_online_ae_param_count.restype = C.c_int32
     L.ols_online_ae_train_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,

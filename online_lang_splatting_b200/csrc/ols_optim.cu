@@ -181,3 +181,118 @@ extern "C" int ols_activate_params(int32_t P, int32_t scale_cols, const float* d
     OLS_CUDA_TRY(cudaGetLastError());
     return OLS_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Pose step of the tracking loop, fused (utils/slam_frontend.py:216-262 + utils/pose_utils.py:update_pose):
+//   Adam over (cam_rot_delta, cam_trans_delta, exposure_a, exposure_b) with their own learning rates, then
+//   T_w2c <- SE3_exp([cam_trans_delta, cam_rot_delta]) * T_w2c, the deltas return to zero, and the three camera tensors
+//   render() reads (world_view_transform, full_proj_transform, camera_center) are rebuilt in place.
+// The reference does this with ~40 tiny torch kernels and two host synchronisations per tracking iteration (the
+// `angle < 1e-5` tests of SO3_exp / V and the `converged` test); here it is one single-thread kernel and the
+// convergence flag stays on the device until the caller wants it.
+// ---------------------------------------------------------------------------------------------------
+namespace ols {
+struct PoseStepArgs {
+    const float* grad_tau;      // [6] dL/d(rho | theta) = (cam_trans_delta | cam_rot_delta) gradients (ols_bwd_args.d_dL_dtau_sum)
+    const float* grad_exposure; // [2] dL/d(exposure_a, exposure_b) or NULL
+    float* exposure;            // [2] exposure_a, exposure_b (updated in place) or NULL
+    float* m;                   // [8] Adam first moments: rot 3 | trans 3 | exposure 2
+    float* v;                   // [8]
+    long long* step;            // Adam step count (incremented)
+    float* R;                   // [9] row-major world->camera rotation (updated)
+    float* T;                   // [3] world->camera translation (updated)
+    const float* proj;          // [16] projection_matrix as render() receives it (transposed)
+    float *viewmatrix, *projmatrix, *campos;  // [16], [16], [3] outputs
+    int* converged;             // OR-accumulated: |tau| < threshold
+    float lr_rot, lr_trans, lr_exposure, beta1, beta2, eps, threshold;
+    int zero_grads;
+};
+
+__global__ void k_pose_step(const PoseStepArgs a) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double t = (double)(*a.step + 1);
+    const float inv_bc1 = (float)(1.0 / (1.0 - pow((double)a.beta1, t)));
+    const float inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)a.beta2, t)));
+    float delta[8];
+    // parameter order of the reference's optimiser: cam_rot_delta (theta), cam_trans_delta (rho), exposure_a, exposure_b
+    for (int k = 0; k < 8; k++) {
+        float g;
+        if (k < 3) g = a.grad_tau[3 + k];
+        else if (k < 6) g = a.grad_tau[k - 3];
+        else g = a.grad_exposure ? a.grad_exposure[k - 6] : 0.0f;
+        const float lr = k < 3 ? a.lr_rot : (k < 6 ? a.lr_trans : a.lr_exposure);
+        float m = a.m[k], v = a.v[k];
+        m = m + (g - m) * (1.0f - a.beta1);
+        v = v * a.beta2 + (1.0f - a.beta2) * g * g;
+        a.m[k] = m; a.v[k] = v;
+        delta[k] = -lr * inv_bc1 * (m / (sqrtf(v) * inv_sqrt_bc2 + a.eps));   // the deltas start every iteration at zero
+    }
+    if (a.exposure) { a.exposure[0] += delta[6]; a.exposure[1] += delta[7]; }
+    *a.step += 1;
+    if (a.zero_grads) {   // optimizer.zero_grad() of the next iteration (the gradient buffers are accumulated into by autograd)
+        for (int k = 0; k < 6; k++) const_cast<float*>(a.grad_tau)[k] = 0.0f;
+        if (a.grad_exposure) { const_cast<float*>(a.grad_exposure)[0] = 0.0f; const_cast<float*>(a.grad_exposure)[1] = 0.0f; }
+    }
+    const float th[3] = {delta[0], delta[1], delta[2]}, rho[3] = {delta[3], delta[4], delta[5]};
+    // SO3_exp / V (pose_utils.py:24-57)
+    const float W[3][3] = {{0, -th[2], th[1]}, {th[2], 0, -th[0]}, {-th[1], th[0], 0}};
+    float W2[3][3];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) W2[i][j] = W[i][0] * W[0][j] + W[i][1] * W[1][j] + W[i][2] * W[2][j];
+    const float angle = sqrtf(th[0] * th[0] + th[1] * th[1] + th[2] * th[2]);
+    float ca, cb, va, vb;   // R = I + ca W + cb W2;  V = I + va W + vb W2
+    if (angle < 1e-5f) { ca = 1.0f; cb = 0.5f; va = 0.5f; vb = 1.0f / 6.0f; }
+    else {
+        ca = sinf(angle) / angle; cb = (1.0f - cosf(angle)) / (angle * angle);
+        va = cb; vb = (angle - sinf(angle)) / (angle * angle * angle);
+    }
+    float dR[3][3], Vm[3][3], dt[3];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            const float I = i == j ? 1.0f : 0.0f;
+            dR[i][j] = I + ca * W[i][j] + cb * W2[i][j];
+            Vm[i][j] = I + va * W[i][j] + vb * W2[i][j];
+        }
+    for (int i = 0; i < 3; i++) dt[i] = Vm[i][0] * rho[0] + Vm[i][1] * rho[1] + Vm[i][2] * rho[2];
+    // new_w2c = SE3_exp(tau) @ T_w2c
+    float R[3][3], T[3], nR[3][3], nT[3];
+    for (int i = 0; i < 3; i++) { T[i] = a.T[i]; for (int j = 0; j < 3; j++) R[i][j] = a.R[3 * i + j]; }
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) nR[i][j] = dR[i][0] * R[0][j] + dR[i][1] * R[1][j] + dR[i][2] * R[2][j];
+        nT[i] = dR[i][0] * T[0] + dR[i][1] * T[1] + dR[i][2] * T[2] + dt[i];
+    }
+    for (int i = 0; i < 3; i++) { a.T[i] = nT[i]; for (int j = 0; j < 3; j++) a.R[3 * i + j] = nR[i][j]; }
+    const float nrm = sqrtf(rho[0] * rho[0] + rho[1] * rho[1] + rho[2] * rho[2] + angle * angle);
+    if (a.converged && nrm < a.threshold) *a.converged = 1;
+    // world_view_transform = getWorld2View2(R, T).T ; full_proj_transform = world_view_transform @ projection_matrix ;
+    // camera_center = world_view_transform.inverse()[3, :3] = -R^T T      (utils/camera_utils.py:103-117)
+    float Vt[4][4];
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) Vt[j][i] = nR[i][j]; Vt[3][i] = nT[i]; Vt[i][3] = 0.0f; }
+    Vt[3][3] = 1.0f;
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) {
+            a.viewmatrix[4 * i + j] = Vt[i][j];
+            float s = 0.0f;
+            for (int k = 0; k < 4; k++) s += Vt[i][k] * a.proj[4 * k + j];
+            a.projmatrix[4 * i + j] = s;
+        }
+    for (int j = 0; j < 3; j++) a.campos[j] = -(nR[0][j] * nT[0] + nR[1][j] * nT[1] + nR[2][j] * nT[2]);
+}
+}  // namespace ols
+
+extern "C" int ols_pose_adam_step(const ols_pose_step* p, void* stream) {
+    if (!p || !p->d_grad_tau || !p->d_exp_avg || !p->d_exp_avg_sq || !p->d_step || !p->d_R || !p->d_T || !p->d_projection ||
+        !p->d_viewmatrix || !p->d_projmatrix || !p->d_campos) {
+        ols_set_error("bad pose-step arguments");
+        return OLS_ERR_INVALID;
+    }
+    PoseStepArgs a;
+    a.grad_tau = p->d_grad_tau; a.grad_exposure = p->d_grad_exposure; a.exposure = p->d_exposure; a.m = p->d_exp_avg; a.v = p->d_exp_avg_sq;
+    a.step = (long long*)p->d_step; a.R = p->d_R; a.T = p->d_T; a.proj = p->d_projection; a.viewmatrix = p->d_viewmatrix;
+    a.projmatrix = p->d_projmatrix; a.campos = p->d_campos; a.converged = p->d_converged;
+    a.lr_rot = p->lr_rot; a.lr_trans = p->lr_trans; a.lr_exposure = p->lr_exposure; a.beta1 = p->beta1; a.beta2 = p->beta2;
+    a.eps = p->eps; a.threshold = p->converged_threshold; a.zero_grads = p->zero_grads;
+    k_pose_step<<<1, 32, 0, (cudaStream_t)stream>>>(a);
+    OLS_CUDA_TRY(cudaGetLastError());
+    return OLS_OK;
+}

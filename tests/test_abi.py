@@ -102,7 +102,7 @@ def test_header_is_plain_c_and_struct_sizes_match_ctypes(tmp_path):
              ("ols_dis_args", N.DisArgs), ("ols_dis_fwd_out", N.DisFwdOut), ("ols_dis_bwd_args", N.DisBwdArgs),
              ("ols_loss_args", N.LossArgs), ("ols_adam_group", N.AdamGroup), ("ols_ws_view", N.WsView), ("ols_host_out", N.HostOut),
              ("ols_ae_chain", N.AEChain), ("ols_hr_weights", N.HRWeights), ("ols_ssim_args", N.SsimArgs),
-             ("ols_densify_params", N.DensifyParams)]
+             ("ols_densify_params", N.DensifyParams), ("ols_pose_step", N.PoseStep)]
     src = tmp_path / "sizes.c"
     body = "\n".join('    printf("%s %%zu\\n", sizeof(%s));' % (c, c) for c, _ in pairs)
     src.write_text('#include <stdio.h>\n#include "ols_b200.h"\nint main(void) {\n%s\n    return 0;\n}\n' % body)

@@ -290,7 +290,7 @@ def config5(args, emit, peaks, ClockSampler):
             low = general.encode(x)                                             # [36864, 32]
         cam.coco_lang_feat = low
         _, code = online.fused_train_step(low, lr=1e-4)                         # slam_backend.py:481 (lr = 1e-4 while mapping)
-        cam.gt_lang_feat = code.t().reshape(15, 192, 192)
+        cam.gt_lang_feat = code.t().reshape(15, 192, 192).contiguous()
 
     # warm start: a full window of keyframes + older ones already mapped (so that every timed keyframe maps 10 + 2 views)
     older = frames[:N_RANDOM]
@@ -300,55 +300,141 @@ def config5(args, emit, peaks, ClockSampler):
     stream = frames[N_RANDOM + WINDOW:]
     timers = {"tracking": 0.0, "ae": 0.0, "mapping": 0.0}
     counts = {"tracking_iters": 0, "mapping_iters": 0, "keyframes": 0}
+    use_graph = not args.no_graph
 
     def ev():
         e = torch.cuda.Event(enable_timing=True)
         e.record()
         return e
 
+    # ---- the two iteration bodies (identical in the eager and in the captured form) -------------------------------
+    def tracking_iteration(cam, popt, pct):
+        out = render(cam, pct, pipe, bg)
+        loss = tracking_loss(out["render"], out["depth"], out["opacity"], cam.original_image, cam.depth, cam.grad_mask,
+                             alpha=0.95, rgb_boundary_threshold=0.01, exposure_a=cam.exposure_a, exposure_b=cam.exposure_b)
+        loss.backward()
+        popt.step()
+
+    def mapping_render_backward(mine):
+        pc.fg.zero_()
+        stats.begin_step()
+        outs = render_batch(mine, pc, pipe, bg)
+        total = torch.zeros((), device=dev)
+        for cam, o in zip(mine, outs):
+            total = total + mapping_loss(o["render"], o["depth"], cam.original_image, cam.depth, o["language"], cam.gt_lang_feat,
+                                         alpha=0.95, rgb_boundary_threshold=0.01, exposure_a=cam.exposure_a,
+                                         exposure_b=cam.exposure_b, lambda_lang=1.0)
+        if rank == 0:                                                           # the isotropic term is view independent: once per iteration
+            sc = pc.get_scaling
+            total = total + 10.0 * torch.abs(sc - sc.mean(dim=1).view(-1, 1)).mean()       # slam_backend.py:663-666
+        total.backward()
+        for cam, o in zip(mine, outs):                                          # slam_backend.py:719-728
+            update_stats(o["radii"], o["viewspace_points"].grad, stats.delta_max, stats.delta[:P].view(P, 1), stats.delta[P:].view(P, 1))
+
+    def mapping_update(random_cams):
+        stats.apply()
+        opt.step()                                                              # fused Adam incl. activation Jacobians
+        pc.refresh()
+        for cam in random_cams:                                                 # slam_backend.py:640-648: keep the online AE from forgetting
+            online.fused_train_step(cam.coco_lang_feat, lr=1e-4)
+
+    def reduce_all():
+        if world > 1:
+            pc.fg.all_reduce()
+            stats.all_reduce()
+
+    # ---- static camera slots for the captured form ----------------------------------------------------------------
+    def make_slot(uid):
+        c = DeviceCamera(W, H, FX, FY, CX, CY, torch.eye(3), torch.zeros(3), device=dev, uid=uid)
+        c.original_image, c.depth = torch.zeros(3, H, W, device=dev), torch.zeros(1, H, W, device=dev)
+        c.grad_mask = torch.ones(1, H, W, device=dev)
+        c.gt_lang_feat = torch.zeros(15, 192, 192, device=dev)
+        c.coco_lang_feat = torch.zeros(192 * 192, 32, device=dev)
+        return c
+
+    def load_slot(slot, cam, lang=True):
+        with torch.no_grad():
+            slot.R.copy_(cam.R); slot.T.copy_(cam.T)
+            slot.world_view_transform.copy_(cam.world_view_transform); slot.full_proj_transform.copy_(cam.full_proj_transform)
+            slot.camera_center.copy_(cam.camera_center); slot._exposure.copy_(cam._exposure)
+            slot.original_image.copy_(cam.original_image); slot.depth.copy_(cam.depth)
+            if lang:
+                slot.gt_lang_feat.copy_(cam.gt_lang_feat); slot.coco_lang_feat.copy_(cam.coco_lang_feat)
+
+    graphs = {}
+    if use_graph:
+        from bench import make_graph
+        n_views = WINDOW + N_RANDOM
+        my_pos = shard_views(n_views, rank, world) if world > 1 else list(range(n_views))
+        slots = [make_slot(1000 + i) for i in range(n_views)]
+        for i, cam in enumerate(window + older[:N_RANDOM]):
+            load_slot(slots[i], cam)
+        mine_slots = [slots[i] for i in my_pos]
+        rand_slots = slots[WINDOW:]
+        track_slot = make_slot(2000)
+        load_slot(track_slot, window[-1], lang=False)
+        track_opt = PoseOptimizer(track_slot, lr_rot=0.003, lr_trans=0.001)
+        pct = pc.frozen()
+        # eager warm-up of both bodies (establishes the instance-capacity estimates and every lazily built plan)
+        for _ in range(2):
+            tracking_iteration(track_slot, track_opt, pct)
+            mapping_render_backward(mine_slots); reduce_all(); mapping_update(rand_slots)
+        torch.cuda.synchronize()
+        g_t = make_graph()
+        with torch.cuda.graph(g_t):
+            tracking_iteration(track_slot, track_opt, pct)
+        g_a = make_graph()
+        with torch.cuda.graph(g_a):
+            mapping_render_backward(mine_slots)
+        g_b = make_graph()
+        with torch.cuda.graph(g_b):
+            mapping_update(rand_slots)
+        torch.cuda.synchronize()
+        graphs = {"track": g_t, "map_a": g_a, "map_b": g_b}
+
     def track(cam, prev):
+        if use_graph:
+            load_slot(track_slot, cam, lang=False)
+            track_slot.update_RT(prev.R, prev.T)                                # slam_frontend.py:179-180
+            for t_ in (track_opt.m, track_opt.v, track_opt.steps, track_opt.converged, track_slot._exposure, track_slot._grad_tau,
+                       track_slot._grad_exposure):
+                t_.zero_()                                                      # a fresh optimiser per frame (slam_frontend.py:183-213)
+            for it in range(args.tracking_iters):
+                graphs["track"].replay()
+                counts["tracking_iters"] += 1
+                if it % 10 == 9 and track_opt.has_converged():
+                    break
+            with torch.no_grad():
+                cam.R.copy_(track_slot.R); cam.T.copy_(track_slot.T); cam._exposure.copy_(track_slot._exposure)
+            cam.refresh()
+            return
         cam.update_RT(prev.R, prev.T)                                           # slam_frontend.py:179-180
         popt = PoseOptimizer(cam, lr_rot=0.003, lr_trans=0.001)
-        pct = pc.frozen()
+        pct_ = pc.frozen()
         for it in range(args.tracking_iters):
-            out = render(cam, pct, pipe, bg)
-            loss = tracking_loss(out["render"], out["depth"], out["opacity"], cam.original_image, cam.depth, cam.grad_mask,
-                                 alpha=0.95, rgb_boundary_threshold=0.01, exposure_a=cam.exposure_a, exposure_b=cam.exposure_b)
-            loss.backward()
-            popt.step()
+            tracking_iteration(cam, popt, pct_)
             counts["tracking_iters"] += 1
             if it % 10 == 9 and popt.has_converged():                           # the reference tests every iteration (host sync)
                 break
 
     def map_window(window, older):
-        views = list(window)
-        mine = None
+        if use_graph:
+            for i, cam in enumerate(window):
+                load_slot(slots[i], cam)
         for it in range(args.mapping_iters):
             sel = torch.randperm(len(older))[:N_RANDOM].tolist()                # slam_backend.py:606
-            cams = views + [older[i] for i in sel]
-            mine = [cams[i] for i in shard_views(len(cams), rank, world)] if world > 1 else cams
-            pc.fg.zero_()
-            stats.begin_step()
-            outs = render_batch(mine, pc, pipe, bg)
-            total = torch.zeros((), device=dev)
-            for cam, o in zip(mine, outs):
-                total = total + mapping_loss(o["render"], o["depth"], cam.original_image, cam.depth, o["language"], cam.gt_lang_feat,
-                                             alpha=0.95, rgb_boundary_threshold=0.01, exposure_a=cam.exposure_a,
-                                             exposure_b=cam.exposure_b, lambda_lang=1.0)
-            if rank == 0:                                                       # the isotropic term is view independent: once per iteration
-                sc = pc.get_scaling
-                total = total + 10.0 * torch.abs(sc - sc.mean(dim=1).view(-1, 1)).mean()   # slam_backend.py:663-666
-            total.backward()
-            for cam, o in zip(mine, outs):                                      # slam_backend.py:719-728
-                update_stats(o["radii"], o["viewspace_points"].grad, stats.delta_max, stats.delta[:P].view(P, 1), stats.delta[P:].view(P, 1))
-            if world > 1:
-                pc.fg.all_reduce()
-                stats.all_reduce()
-            stats.apply()
-            opt.step()                                                          # fused Adam incl. activation Jacobians
-            pc.refresh()
-            for i in sel:                                                       # slam_backend.py:640-648: keep the online AE from forgetting
-                online.fused_train_step(older[i].coco_lang_feat, lr=1e-4)
+            if use_graph:
+                for j, i in enumerate(sel):
+                    load_slot(slots[WINDOW + j], older[i])
+                graphs["map_a"].replay()
+                reduce_all()
+                graphs["map_b"].replay()
+            else:
+                cams = list(window) + [older[i] for i in sel]
+                mine = [cams[i] for i in shard_views(len(cams), rank, world)] if world > 1 else cams
+                mapping_render_backward(mine)
+                reduce_all()
+                mapping_update([older[i] for i in sel])
             counts["mapping_iters"] += 1
 
     def run(frame_cams, timed):
@@ -396,6 +482,16 @@ def config5(args, emit, peaks, ClockSampler):
         dist.all_reduce(t_, op=dist.ReduceOp.MAX)
         ms = float(t_.item())
     clocks = sampler.stop() if rank == 0 else None
+    if use_graph:
+        from bench import count_graph_kernels as count_k
+        # one eager, checked iteration of each body: proves that no captured launch ran into an instance-capacity overflow
+        from online_lang_splatting_b200 import diff_gaussian_rasterization as dgr
+        dgr.CHECK_OVERFLOW = "sync"
+        tracking_iteration(track_slot, track_opt, pc.frozen())
+        mapping_render_backward(mine_slots)
+        torch.cuda.synchronize()
+        dgr.CHECK_OVERFLOW = "deferred"
+        assert bool(torch.isfinite(pc.fg.flat).all()), "non-finite gradients: a captured render overflowed its capacity"
     if rank == 0:
         nf = args.steps
         line = {"metric": "render+AE FPS of the Replica-room0-shaped tracking+mapping loop (BASELINE configs[4])",
@@ -415,6 +511,10 @@ def config5(args, emit, peaks, ClockSampler):
                 "tracking_ms_per_iteration": timers["tracking"] / max(counts["tracking_iters"], 1),
                 "mapping_ms_per_iteration": timers["mapping"] / max(counts["mapping_iters"], 1),
                 "ae_ms_per_keyframe": timers["ae"] / max(counts["keyframes"], 1),
+                "launch_mode": ("CUDA-graph replay of the tracking iteration and of the two halves of the mapping iteration (captured from the same "
+                                "public-API calls; cameras live in static device slots)") if use_graph else "eager public-API calls",
+                "gpu_launches_per_iteration": ({"tracking": count_k([graphs["track"]]), "mapping": count_k([graphs["map_a"], graphs["map_b"]])}
+                                               if use_graph else None),
                 "wall_s": wall, "cpu_baseline": None,
                 "e2e": {"value": nf / wall, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4 * (args.tracking_iters // 10),
                         "note": "wall-clock frames/s of the same loop (host launch overhead included); frames are generated on the device"},

@@ -197,7 +197,8 @@ typedef struct ols_ws_view {
     const uint32_t* d_tiles_touched; /* [P]                                                            */
     const uint32_t* d_ranges;      /* [n_tiles,2]                                                      */
     const uint32_t* d_point_list;  /* [R] sorted Gaussian ids                                          */
-    const uint64_t* d_keys;        /* [R] per tile segment: (depth_bits << 32 | gaussian id), sorted    */
+    const uint64_t* d_keys;        /* [R] per tile segment: (depth_bits << 32 | gaussian id), sorted -- written only
+                                      with OLS_FLAG_DEBUG (the blend passes read d_point_list; binning writes bare ids) */
     const float* d_final_T;        /* [H*W]                                                            */
     const uint32_t* d_n_contrib;   /* [H*W]                                                            */
 } ols_ws_view;
@@ -410,11 +411,17 @@ int ols_timing_end(float* ms_per_tag /* [OLS_TIMING_TAGS] */, int32_t* count_per
  * Weights are row-major [out,in] float32 as torch.nn.Linear stores them.
  * ------------------------------------------------------------------------------------------- */
 #define OLS_AE_MAX_LAYERS 8
+#define OLS_AE_FAST 0
+#define OLS_AE_FP32 1
 typedef struct ols_ae_chain {
     int32_t n_layers;
     int32_t dims[OLS_AE_MAX_LAYERS + 1];   /* dims[0] = input width, dims[i+1] = output width of layer i */
     int32_t normalize;                     /* 1: y /= ||y||_2 per row after the last layer               */
     int32_t input_bf16;                    /* 1: x is bfloat16 [M, dims[0]] (dims[0] % 64 == 0): ols_ae_forward_bf16      */
+    int32_t precision;                     /* OLS_AE_FAST (0): tensor cores, tf32 first layer + bf16 inner layers, fp32 accumulate;
+                                              OLS_AE_FP32 (1): parity mode -- every layer in fp32 FMAs on the CUDA cores, the
+                                              arithmetic of the reference's fp32 nn.Linear (model.py:52-62); ~10x slower  */
+    int32_t _pad;
     const float* d_weight[OLS_AE_MAX_LAYERS];  /* [dims[i+1], dims[i]]                                  */
     const float* d_bias[OLS_AE_MAX_LAYERS];    /* [dims[i+1]]                                           */
 } ols_ae_chain;

@@ -122,7 +122,8 @@ class HostOut(C.Structure):
 
 class AEChain(C.Structure):
     _fields_ = [("n_layers", C.c_int32), ("dims", C.c_int32 * (AE_MAX_LAYERS + 1)), ("normalize", C.c_int32),
-                ("input_bf16", C.c_int32), ("d_weight", C.c_void_p * AE_MAX_LAYERS), ("d_bias", C.c_void_p * AE_MAX_LAYERS)]
+                ("input_bf16", C.c_int32), ("precision", C.c_int32), ("_pad", C.c_int32),
+                ("d_weight", C.c_void_p * AE_MAX_LAYERS), ("d_bias", C.c_void_p * AE_MAX_LAYERS)]
 
 
 class SsimArgs(C.Structure):

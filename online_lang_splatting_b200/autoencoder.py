@@ -23,6 +23,11 @@ import torch.nn as nn
 from . import _native as N
 
 
+# "fast": tensor cores (tf32 first layer, bf16 inner layers, fp32 accumulate) -- cos >= 0.99999 against torch fp32;
+# "fp32": parity mode, every layer in fp32 FMAs like the reference's nn.Linear (model.py:52-62), ~10x slower.
+PRECISION = "fast"
+
+
 class _FusedChain:
     """Owns an ``ols_ae_plan`` for a list of (weight, bias) pairs and rebuilds it when they change."""
 
@@ -56,7 +61,8 @@ class _FusedChain:
             x2 = x2.float()
         x2 = x2.contiguous()
         dev = x2.device
-        key = (version_key, dev.index, normalize, x_bf16)
+        fp32 = PRECISION == "fp32" and not x_bf16
+        key = (version_key, dev.index, normalize, x_bf16, fp32)
         lib = N.lib()
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
@@ -64,7 +70,7 @@ class _FusedChain:
                 self._destroy()
                 ws = [w.detach().to(dev, torch.float32).contiguous() for w, _ in layers]
                 bs = [None if b is None else b.detach().to(dev, torch.float32).contiguous() for _, b in layers]
-                chain = N.AEChain(n_layers=len(ws), normalize=int(normalize), input_bf16=int(x_bf16))
+                chain = N.AEChain(n_layers=len(ws), normalize=int(normalize), input_bf16=int(x_bf16), precision=int(fp32))
                 chain.dims[0] = ws[0].shape[1]
                 for i, w in enumerate(ws):
                     chain.dims[i + 1] = w.shape[0]

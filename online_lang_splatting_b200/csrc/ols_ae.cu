@@ -355,6 +355,86 @@ __global__ void __launch_bounds__(AE_THREADS, 1) k_ae_chain(const __grid_constan
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Parity mode (OLS_AE_FP32): the same chain in plain fp32 FMAs -- the arithmetic of the reference's fp32 nn.Linear
+// (language/autoencoder/model.py:52-62) up to summation order.  A CTA owns 32 rows; the activations of the current and
+// the next layer live in shared memory ([row][k], padded); thread t produces output column n = t, t + 128, ... for all
+// 32 rows (32 accumulators), reading the transposed weights Wt[k][n] coalesced and the activations as broadcasts.
+// Not a fast path (about 10x the tensor-core kernel): it exists so that a caller can ask for reference-grade numbers.
+// ---------------------------------------------------------------------------------------------------
+constexpr int AF_ROWS = 32, AF_THREADS = 128;
+struct AeFp32Params {
+    int n_layers, normalize;
+    int dims[OLS_AE_MAX_LAYERS + 1];
+    const float* wt[OLS_AE_MAX_LAYERS];    // [K][N] transposed weights
+    const float* bias[OLS_AE_MAX_LAYERS];  // [N] or NULL
+    const float* x;
+    float* y;
+    long long M;
+    int max_width;                          // widest activation (floats per row of the two shared-memory buffers)
+};
+
+__global__ void __launch_bounds__(AF_THREADS) k_ae_chain_fp32(const AeFp32Params p) {
+    extern __shared__ float af_smem[];
+    const int ld = p.max_width + 1;
+    float* bufA = af_smem;
+    float* bufB = af_smem + (size_t)AF_ROWS * ld;
+    __shared__ float s_inv[AF_ROWS];
+    const int tid = threadIdx.x;
+    const long long n_tiles = (p.M + AF_ROWS - 1) / AF_ROWS;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long row0 = tile * AF_ROWS;
+        const int rows = (int)min((long long)AF_ROWS, p.M - row0);
+        const int K0 = p.dims[0];
+        for (int e = tid; e < AF_ROWS * K0; e += AF_THREADS) {
+            const int r = e / K0, k = e - r * K0;
+            bufA[r * ld + k] = r < rows ? p.x[(row0 + r) * K0 + k] : 0.0f;
+        }
+        __syncthreads();
+        float* in = bufA;
+        float* out = bufB;
+        for (int l = 0; l < p.n_layers; l++) {
+            const int K = p.dims[l], N = p.dims[l + 1];
+            const bool last = l == p.n_layers - 1;
+            const float* __restrict__ wt = p.wt[l];
+            for (int n = tid; n < N; n += AF_THREADS) {
+                float acc[AF_ROWS];
+                const float b = p.bias[l] ? p.bias[l][n] : 0.0f;
+#pragma unroll
+                for (int r = 0; r < AF_ROWS; r++) acc[r] = b;
+                for (int k = 0; k < K; k++) {
+                    const float w = __ldg(wt + (size_t)k * N + n);
+#pragma unroll
+                    for (int r = 0; r < AF_ROWS; r++) acc[r] = fmaf(in[r * ld + k], w, acc[r]);
+                }
+#pragma unroll
+                for (int r = 0; r < AF_ROWS; r++) out[r * ld + n] = last ? acc[r] : fmaxf(acc[r], 0.0f);
+            }
+            __syncthreads();
+            float* t = in; in = out; out = t;
+        }
+        const int N = p.dims[p.n_layers];
+        if (tid < AF_ROWS) {
+            float ss = 0.0f;
+            for (int n = 0; n < N; n++) ss = fmaf(in[tid * ld + n], in[tid * ld + n], ss);
+            s_inv[tid] = p.normalize ? 1.0f / sqrtf(ss) : 1.0f;
+        }
+        __syncthreads();
+        for (int e = tid; e < rows * N; e += AF_THREADS) {
+            const int r = e / N, n = e - r * N;
+            p.y[(row0 + r) * N + n] = in[r * ld + n] * s_inv[r];
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_ae_transpose_weight(const float* __restrict__ w, int N, int K, float* __restrict__ wt) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)N * K) return;
+    const int n = (int)(i / K), k = (int)(i % K);
+    wt[(size_t)k * N + n] = w[i];
+}
+
 // weight re-layout: pad [N,K] fp32 -> [N_pad,K_pad] fp32 (layer 0) or bf16 (inner layers), zero filled
 __global__ void k_ae_pack_weight(const float* __restrict__ w, int N, int K, void* __restrict__ out, int N_pad, int K_pad,
                                  int to_bf16) {
@@ -376,6 +456,8 @@ using namespace ols;
 
 struct ols_ae_plan {
     AeParams p;
+    int fp32_mode = 0;
+    AeFp32Params pf;
     std::vector<void*> owned;
     int device;
     int sm_count;
@@ -435,6 +517,40 @@ int ols_ae_plan_create(const ols_ae_chain* chain, ols_ae_plan** out_plan, void* 
     p.out_real = chain->dims[chain->n_layers];
     p.normalize = chain->normalize;
     p.x_bf16 = chain->input_bf16 ? 1 : 0;
+    if (chain->precision == OLS_AE_FP32) {
+        // parity mode: transposed fp32 weights, no tensor-core plan
+        if (chain->input_bf16) { ols_set_error("the fp32 parity mode takes a float32 input"); return fail(OLS_ERR_UNSUPPORTED); }
+        plan->fp32_mode = 1;
+        AeFp32Params& f = plan->pf;
+        memset(&f, 0, sizeof(f));
+        f.n_layers = chain->n_layers; f.normalize = chain->normalize;
+        for (int l = 0; l <= chain->n_layers; l++) { f.dims[l] = chain->dims[l]; if (chain->dims[l] > f.max_width) f.max_width = chain->dims[l]; }
+        for (int l = 0; l < chain->n_layers; l++) {
+            const int K = chain->dims[l], N = chain->dims[l + 1];
+            if (K <= 0 || N <= 0 || !chain->d_weight[l]) { ols_set_error("bad layer %d", l); return fail(OLS_ERR_INVALID); }
+            float* wt = nullptr; float* bb = nullptr;
+            if (cudaMalloc((void**)&wt, sizeof(float) * (size_t)N * K) != cudaSuccess) { ols_set_error("out of device memory"); return fail(OLS_ERR_CUDA); }
+            plan->owned.push_back(wt);
+            k_ae_transpose_weight<<<(unsigned)(((size_t)N * K + 255) / 256), 256, 0, st>>>(chain->d_weight[l], N, K, wt);
+            f.wt[l] = wt;
+            if (chain->d_bias[l]) {
+                if (cudaMalloc((void**)&bb, sizeof(float) * N) != cudaSuccess) { ols_set_error("out of device memory"); return fail(OLS_ERR_CUDA); }
+                plan->owned.push_back(bb);
+                cudaMemcpyAsync(bb, chain->d_bias[l], sizeof(float) * N, cudaMemcpyDeviceToDevice, st);
+            }
+            f.bias[l] = bb;
+        }
+        if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { ols_set_error("weight packing failed"); return fail(OLS_ERR_CUDA); }
+        plan->smem_bytes = sizeof(float) * 2 * (size_t)AF_ROWS * (f.max_width + 1);
+        // (static + dynamic shared memory share the 227 KB opt-in limit: reserve what this kernel can ever need, once)
+        if (plan->smem_bytes > 226 * 1024 ||
+            cudaFuncSetAttribute(k_ae_chain_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess) {
+            cudaGetLastError();
+            ols_set_error("layer too wide for the fp32 parity kernel"); return fail(OLS_ERR_UNSUPPORTED);
+        }
+        *out_plan = plan;
+        return OLS_OK;
+    }
     p.manual_x = (chain->dims[0] % 32 != 0) ? 1 : 0;  // TMA needs 16-byte row strides; keep whole slabs too
     if (p.x_bf16 && chain->dims[0] % 64 != 0) { ols_set_error("bf16 input needs a width that is a multiple of 64"); return fail(OLS_ERR_UNSUPPORTED); }
     int stage_bytes = 0, act_cols_bytes = 0;
@@ -517,12 +633,12 @@ void ols_ae_plan_destroy(ols_ae_plan* plan) {
 static int ae_forward(const ols_ae_plan* plan, const void* d_x, float* d_y, int64_t M, void* stream);
 
 int ols_ae_forward(const ols_ae_plan* plan, const float* d_x, float* d_y, int64_t M, void* stream) {
-    if (plan && plan->p.x_bf16) { ols_set_error("this plan takes a bf16 input: call ols_ae_forward_bf16"); return OLS_ERR_INVALID; }
+    if (plan && !plan->fp32_mode && plan->p.x_bf16) { ols_set_error("this plan takes a bf16 input: call ols_ae_forward_bf16"); return OLS_ERR_INVALID; }
     return ae_forward(plan, d_x, d_y, M, stream);
 }
 
 int ols_ae_forward_bf16(const ols_ae_plan* plan, const void* d_x_bf16, float* d_y, int64_t M, void* stream) {
-    if (plan && !plan->p.x_bf16) { ols_set_error("this plan takes a float32 input: call ols_ae_forward"); return OLS_ERR_INVALID; }
+    if (plan && (plan->fp32_mode || !plan->p.x_bf16)) { ols_set_error("this plan takes a float32 input: call ols_ae_forward"); return OLS_ERR_INVALID; }
     return ae_forward(plan, d_x_bf16, d_y, M, stream);
 }
 
@@ -531,6 +647,17 @@ int ols_ae_forward_bf16(const ols_ae_plan* plan, const void* d_x_bf16, float* d_
 static int ae_forward(const ols_ae_plan* plan, const void* d_x, float* d_y, int64_t M, void* stream) {
     if (!plan || !d_x || !d_y || M < 0) { ols_set_error("bad arguments"); return OLS_ERR_INVALID; }
     if (M == 0) return OLS_OK;
+    if (plan->fp32_mode) {
+        AeFp32Params f = plan->pf;
+        f.x = (const float*)d_x; f.y = d_y; f.M = M;
+        const long long tiles = (M + AF_ROWS - 1) / AF_ROWS;
+        const int grid = (int)(tiles < 2LL * plan->sm_count ? tiles : 2LL * plan->sm_count);
+        ols_timing_mark(-1, (cudaStream_t)stream);
+        k_ae_chain_fp32<<<grid, AF_THREADS, plan->smem_bytes, (cudaStream_t)stream>>>(f);
+        OLS_CUDA_TRY(cudaGetLastError());
+        ols_timing_mark(OLS_T_AE, (cudaStream_t)stream);
+        return OLS_OK;
+    }
     AeParams p = plan->p;
     p.x = (const float*)d_x; p.y = d_y; p.M = M;
     p.n_tiles = (int)((M + AE_M - 1) / AE_M);

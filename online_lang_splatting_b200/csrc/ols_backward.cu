@@ -21,6 +21,8 @@
 // which is algebraically identical and keeps the per-thread state at ~25 registers instead of ~60.
 #include "ols_common.cuh"
 
+#include <cstdlib>
+
 namespace ols {
 
 constexpr int BWD_THREADS = 256;
@@ -44,6 +46,7 @@ struct BwdView {  // one view of a batch (blockIdx.y)
     const float* dL_ddepth;
     const uint8_t* warp_hits;  // [R] from the forward: which pixel blocks of the tile blended each list entry
     float* gacc;             // [P, grad_floats(F)] zero-initialised
+    uint8_t* gtouched;       // [P] zero-initialised: set to 1 for every Gaussian whose record receives a flush
 };
 struct BwdBlendArgs {
     int W, H, gx;
@@ -373,6 +376,305 @@ __global__ void __launch_bounds__(PACKED ? 128 : BWD_THREADS, PACKED ? 8 : 4) k_
             if (val != 0.0f) {
                 const int gi = e / GR, vi = e - gi * GR;
                 atomicAdd(&vw.gacc[(size_t)s_id[gi] * GR + vi], val);
+                vw.gtouched[s_id[gi]] = 1;   // idempotent byte store: the geometry pass skips untouched records unread
+                s_acc[e] = 0.0f;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Backward blend, two pixels per lane (the default).  Same arithmetic, same gradient modes and the same per-entry
+// bookkeeping as k_blend_bwd, but a warp carries 64 pixels, so everything that is paid per (warp, entry) -- the walk
+// over the list, the record loads from shared memory, the warp-wide butterfly reduction of the 10 (compat) or 25 (exact)
+// per-Gaussian sums and the shared-memory atomics -- is paid once per TWO pixels, and every lane runs two independent
+// dependency chains.  Thread -> pixel mapping:
+//   unpacked  128 threads = 4 warps of 8x8 pixels (lane l: column l & 7, rows l >> 3 and (l >> 3) + 4), the forward's
+//             layout, so a warp's entries are those its two 8x4 halves blended (bits 2*(w>>1)*2 + (w&1) and +2);
+//   PACKED    (compat, 15x15) 64 threads = 2 warps; lane l of warp w carries the surviving pixels with packed index
+//             64 w + l and 64 w + 32 + l (reference rank order); a warp decides by a vote after evaluating an entry.
+// ---------------------------------------------------------------------------------------------------
+template <int TILE, int NCOL, int F, bool COMPAT, bool PACKED>
+__global__ void __launch_bounds__(PACKED ? 64 : 128, PACKED ? 10 : 5) k_blend_bwd2(const __grid_constant__ BwdBlendArgs a) {
+    const BwdView& vw = a.v[blockIdx.y];
+    static_assert(TILE <= 16 && BWD_BATCH == 32, "4 warps of 8x8 pixels; one ballot per batch");
+    static_assert(!PACKED || COMPAT, "packing follows the compat lane mask");
+    constexpr int NT = PACKED ? 64 : 128;
+    static_assert(NCOL == 0 || NCOL == 3, "colour channels");
+    constexpr int NCH = NCOL + F;
+    constexpr int REC = rec_floats_nch(NCH);
+    using Stage = RecordStage<NCOL, F>;
+    constexpr int OPS = Stage::OPS;
+    constexpr int GR = grad_floats(F);
+    constexpr int NPAIR = (NCH + 1) / 2;
+    constexpr int LP0 = (NCOL + 1) / 2;
+    constexpr int NLP = NPAIR > LP0 ? NPAIR - LP0 : 1;
+    constexpr int NGEO = NCOL ? 10 : 4;
+    constexpr int NV = COMPAT ? NGEO : NGEO + F;
+    __shared__ __align__(16) float s_rec[BWD_BATCH * REC];
+    __shared__ uint32_t s_id[BWD_BATCH];
+    __shared__ float s_acc[BWD_BATCH * GR];
+    __shared__ uint32_t s_maxc;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tile_x = blockIdx.x % a.gx, tile_y = blockIdx.x / a.gx;
+    int lx[2], ly[2];
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+        if (PACKED) {
+            const int rank = a.packed_rank[wid * 64 + 32 * p + lane];
+            lx[p] = rank == 255 ? TILE : rank % TILE;
+            ly[p] = rank == 255 ? TILE : rank / TILE;
+        } else {
+            lx[p] = (wid & 1) * 8 + (lane & 7);
+            ly[p] = (wid >> 1) * 8 + (lane >> 3) + 4 * p;
+        }
+    }
+    bool inside[2];
+    float pfx[2], pfy[2];
+    size_t pix[2];
+    const size_t HW = (size_t)a.W * a.H;
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+        const int pxi = tile_x * TILE + lx[p], pyi = tile_y * TILE + ly[p];
+        inside[p] = lx[p] < TILE && ly[p] < TILE && pxi < a.W && pyi < a.H;
+        pfx[p] = (float)pxi; pfy[p] = (float)pyi;
+        pix[p] = inside[p] ? (size_t)pyi * a.W + pxi : 0;
+    }
+
+    uint2 rg = vw.ranges[blockIdx.x];
+    if (vw.info->overflow) rg = make_uint2(0u, 0u);
+    uint32_t last_contributor[2];
+#pragma unroll
+    for (int p = 0; p < 2; p++) last_contributor[p] = inside[p] ? vw.n_contrib[pix[p]] : 0u;
+    uint32_t warp_maxc = __reduce_max_sync(0xffffffffu, max(last_contributor[0], last_contributor[1]));
+    if (PACKED) {
+        uint32_t other = 0;
+        for (int r = tid; r < TILE * TILE; r += NT) {
+            const int ox = tile_x * TILE + r % TILE, oy = tile_y * TILE + r / TILE;
+            if (ox < a.W && oy < a.H) other = max(other, vw.n_contrib[(size_t)oy * a.W + ox]);
+        }
+        warp_maxc = max(warp_maxc, __reduce_max_sync(0xffffffffu, other));
+    }
+    if (tid == 0) s_maxc = 0;
+    for (int e = tid; e < BWD_BATCH * GR; e += NT) s_acc[e] = 0.0f;
+    __syncthreads();
+    if (lane == 0 && warp_maxc) atomicMax(&s_maxc, warp_maxc);
+    __syncthreads();
+    const int total = min((int)s_maxc, (int)(rg.y - rg.x));
+    if (total == 0) return;
+
+    float T_final[2], T[2], g[2][NCH > 0 ? NCH + 1 : 1], gd[2], bg_dot[2];
+    f32x2 g2[2][NLP];
+    bool lane_ok[2];
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+        T_final[p] = inside[p] ? vw.final_T[pix[p]] : 0.0f;
+        T[p] = T_final[p];
+        gd[p] = 0.0f;
+#pragma unroll
+        for (int c = 0; c < NCH + 1; c++) g[p][c] = 0.0f;
+        if (inside[p]) {
+#pragma unroll
+            for (int c = 0; c < NCOL; c++) g[p][c] = vw.dL_dcolor[c * HW + pix[p]];
+#pragma unroll
+            for (int c = 0; c < F; c++) g[p][NCOL + c] = vw.dL_dlanguage[c * HW + pix[p]];
+            if (NCOL) gd[p] = vw.dL_ddepth[pix[p]];
+        }
+#pragma unroll
+        for (int q = LP0; q < NPAIR; q++)
+            asm("mov.b64 %0, {%1, %2};" : "=l"(g2[p][q - LP0]) : "f"(g[p][2 * q]), "f"(g[p][2 * q + 1]));
+        bg_dot[p] = NCOL ? vw.bg[0] * g[p][0] + vw.bg[1] * g[p][1] + vw.bg[2] * g[p][2] : 0.0f;
+        const int ref_rank = ly[p] * TILE + lx[p];
+        lane_ok[p] = PACKED ? inside[p]
+                            : (COMPAT ? (inside[p] && ((a.lane_ok[(ref_rank >> 5) & 7] >> (ref_rank & 31)) & 1u) != 0) : true);
+    }
+    const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
+    const int own = multi_reduce_owner<NV>(lane);
+    const int own_dst = own < 0 ? -1 : (NCOL ? own : (own < NGEO ? GR_CX + own : GR_LANG + (own - NGEO)));
+    // forward 8x4 blocks whose pixels this warp carries
+    uint32_t my_blocks;
+    if (PACKED) my_blocks = (uint32_t)a.packed_fmask[(2 * wid) & 3] | (uint32_t)a.packed_fmask[(2 * wid + 1) & 3];
+    else { const int b0 = ((wid >> 1) * 2) * 2 + (wid & 1); my_blocks = (1u << b0) | (1u << (b0 + 2)); }
+
+    float last_alpha[2] = {0.0f, 0.0f};
+    float A_c[2] = {0.0f, 0.0f}, Dl_c[2] = {0.0f, 0.0f}, A_f[2] = {0.0f, 0.0f}, Dl_f[2] = {0.0f, 0.0f};
+    bool fresh = true;  // Q2 bookkeeping (compat): no pixel of this warp has blended anything yet
+
+    // language part of sum_ch c_ch * dL/dpix_ch of the record at rj, for both pixels (the record is loaded once)
+    auto lang_dot2 = [&](const float* rj, float& d0, float& d1) {
+        d0 = d1 = 0.0f;
+        if (F > 0) {
+            if (NCOL & 1) { const float c = rj[REC_CH + NCOL]; d0 = c * g[0][NCOL]; d1 = c * g[1][NCOL]; }
+            f32x2 acc0 = 0ull, acc1 = 0ull;
+#pragma unroll
+            for (int q = LP0; q < NPAIR; q++) {
+                const f32x2 c2 = *reinterpret_cast<const f32x2*>(rj + REC_CH + 2 * q);
+                acc0 = ffma2(c2, g2[0][q - LP0], acc0);
+                acc1 = ffma2(c2, g2[1][q - LP0], acc1);
+            }
+            d0 += hsum2(acc0);
+            d1 += hsum2(acc1);
+        }
+    };
+
+    const int n_batches = (total + BWD_BATCH - 1) / BWD_BATCH;
+    for (int b = n_batches - 1; b >= 0; b--) {
+        const int base = b * BWD_BATCH;
+        const int cnt = min(BWD_BATCH, total - base);
+        __syncthreads();  // previous batch fully consumed / flushed
+        {
+            constexpr int TPE = NT / BWD_BATCH;
+            const int gi = tid / TPE;
+            if (gi < cnt) {
+                const uint32_t id = vw.point_list[rg.x + base + gi];
+                if ((tid % TPE) == 0) s_id[gi] = id;
+#pragma unroll
+                for (int q = tid % TPE; q < OPS; q += TPE) Stage::copy(&s_rec[gi * REC], vw.records, a.language, id, q);
+            }
+        }
+        cp_async_commit();
+        const uint32_t hit = lane < cnt ? (uint32_t)vw.warp_hits[rg.x + base + lane] : 0u;
+        const uint32_t mine = __ballot_sync(0xffffffffu, (hit & my_blocks) != 0u);
+        uint32_t visit = COMPAT ? __ballot_sync(0xffffffffu, hit != 0u) : mine;
+        cp_async_wait<0>();
+        __syncthreads();
+        int pend = -1;
+
+        while (visit) {
+            const int j = 31 - __clz(visit);  // back to front
+            visit &= ~(1u << j);
+            const float* rj = s_rec + j * REC;
+            float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+            float dx[2] = {0.0f, 0.0f}, dy[2] = {0.0f, 0.0f}, G[2] = {0.0f, 0.0f}, alpha[2] = {0.0f, 0.0f};
+            bool contrib[2] = {false, false};
+            auto evaluate = [&]() {
+                g0 = *reinterpret_cast<const float4*>(rj);      // x y A B
+                g1 = *reinterpret_cast<const float4*>(rj + 4);  // C op pth depth
+#pragma unroll
+                for (int p = 0; p < 2; p++) {
+                    dx[p] = fsub(g0.x, pfx[p]);
+                    dy[p] = fsub(g0.y, pfy[p]);
+                    const float power = ffma(ffma(dx[p], fmul(dx[p], g0.z), fmul(dy[p], fmul(dy[p], g1.x))), -0.5f,
+                                             -fmul(dy[p], fmul(dx[p], g0.w)));
+                    if (inside[p] && (uint32_t)(base + j) < last_contributor[p] && !(power > 0.0f) && !(power < g1.z)) {
+                        G[p] = a.fast_exp ? fast_exp2(power) : expf(power);
+                        alpha[p] = fminf(0.99f, fmul(g1.y, G[p]));
+                        contrib[p] = !(alpha[p] < 1.0f / 255.0f);
+                    }
+                }
+            };
+            bool warp_blends = (mine >> j) & 1u;
+            if (PACKED && warp_blends) {
+                evaluate();
+                warp_blends = __any_sync(0xffffffffu, contrib[0] || contrib[1]);
+            }
+            if (!warp_blends) {  // compat only: another pixel block of the tile blends this entry
+                if (F > 0) {
+                    if (fresh) { pend = j; continue; }
+                    float d0, d1;
+                    lang_dot2(rj, d0, d1);
+                    if (inside[0]) { A_f[0] = last_alpha[0] * Dl_f[0] + (1.0f - last_alpha[0]) * A_f[0]; Dl_f[0] = d0; }
+                    if (inside[1]) { A_f[1] = last_alpha[1] * Dl_f[1] + (1.0f - last_alpha[1]) * A_f[1]; Dl_f[1] = d1; }
+                }
+                continue;
+            }
+            if (COMPAT && F > 0) {
+                if (pend >= 0) {
+                    float d0, d1;
+                    lang_dot2(s_rec + pend * REC, d0, d1);
+                    Dl_f[0] = d0; Dl_f[1] = d1;
+                    pend = -1;
+                }
+                fresh = false;
+            }
+            if (!PACKED) evaluate();
+            float v[NV];
+#pragma unroll
+            for (int i = 0; i < NV; i++) v[i] = 0.0f;
+            float D_f[2] = {0.0f, 0.0f};
+            if ((COMPAT && F > 0) || contrib[0] || contrib[1]) {
+                float d0, d1;
+                lang_dot2(rj, d0, d1);
+                const float dd[2] = {d0, d1};
+#pragma unroll
+                for (int p = 0; p < 2; p++) {
+                    if (inside[p] && ((COMPAT && F > 0) || contrib[p])) {
+                        D_f[p] = dd[p];
+                        if (COMPAT && F > 0) {
+                            A_f[p] = last_alpha[p] * Dl_f[p] + (1.0f - last_alpha[p]) * A_f[p];
+                            Dl_f[p] = dd[p];
+                        }
+                    }
+                }
+            }
+            float w[2] = {0.0f, 0.0f};
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                if (contrib[p]) {
+                    const float inv_1ma = __fdividef(1.0f, 1.0f - alpha[p]);
+                    T[p] = T[p] * inv_1ma;
+                    w[p] = alpha[p] * T[p];
+                    float D_c = 0.0f;
+                    if (NCOL) {
+                        D_c = rj[REC_CH] * g[p][0] + rj[REC_CH + 1] * g[p][1] + rj[REC_CH + 2] * g[p][2] + g1.w * gd[p];
+                        A_c[p] = last_alpha[p] * Dl_c[p] + (1.0f - last_alpha[p]) * A_c[p];
+                        Dl_c[p] = D_c;
+                    }
+                    if (!COMPAT && F > 0) {
+                        A_f[p] = last_alpha[p] * Dl_f[p] + (1.0f - last_alpha[p]) * A_f[p];
+                        Dl_f[p] = D_f[p];
+                    }
+                    float dL_dalpha = ((D_c - A_c[p]) + (D_f[p] - A_f[p])) * T[p];
+                    last_alpha[p] = alpha[p];
+                    if (NCOL) dL_dalpha += (-T_final[p] * inv_1ma) * bg_dot[p];
+                    const float dL_dG = g1.y * dL_dalpha;
+                    const float gdx = G[p] * dx[p], gdy = G[p] * dy[p];
+                    if (lane_ok[p]) {
+                        constexpr int C0 = NCOL ? GR_CX : 0;
+                        if (NCOL) {
+                            const float dG_ddelx = -gdx * g0.z - gdy * g0.w;
+                            const float dG_ddely = -gdy * g1.x - gdx * g0.w;
+                            v[GR_MX] += dL_dG * dG_ddelx * ddelx_dx;
+                            v[GR_MY] += dL_dG * dG_ddely * ddely_dy;
+                            v[GR_DEPTH] += w[p] * gd[p];
+                            v[GR_RGB + 0] += w[p] * g[p][0];
+                            v[GR_RGB + 1] += w[p] * g[p][1];
+                            v[GR_RGB + 2] += w[p] * g[p][2];
+                        }
+                        v[C0 + 0] += -0.5f * gdx * dx[p] * dL_dG;
+                        v[C0 + 1] += -0.5f * gdx * dy[p] * dL_dG;
+                        v[C0 + 2] += -0.5f * gdy * dy[p] * dL_dG;
+                        v[C0 + 3] += G[p] * dL_dalpha;
+                        if (!COMPAT) {
+#pragma unroll
+                            for (int c = 0; c < F; c++) v[NGEO + c] += w[p] * g[p][NCOL + c];
+                        }
+                    }
+                }
+            }
+            // Q1 (compat): only the tile's first thread contributes its own (first) pixel's language gradient
+            if (COMPAT && F > 0 && tid == 0 && contrib[0]) {
+#pragma unroll
+                for (int c = 0; c < F; c++) s_acc[j * GR + GR_LANG + c] += w[0] * g[0][NCOL + c];
+            }
+            if (__any_sync(0xffffffffu, (contrib[0] && lane_ok[0]) || (contrib[1] && lane_ok[1]))) {
+                warp_multi_reduce<NV>(v, lane);
+                if (own_dst >= 0 && v[0] != 0.0f) atomicAdd(&s_acc[j * GR + own_dst], v[0]);
+            }
+        }
+        if (COMPAT && F > 0 && pend >= 0) {
+            float d0, d1;
+            lang_dot2(s_rec + pend * REC, d0, d1);
+            Dl_f[0] = d0; Dl_f[1] = d1;
+        }
+        __syncthreads();
+        for (int e = tid; e < cnt * GR; e += NT) {
+            const float val = s_acc[e];
+            if (val != 0.0f) {
+                const int gi = e / GR, vi = e - gi * GR;
+                atomicAdd(&vw.gacc[(size_t)s_id[gi] * GR + vi], val);
+                vw.gtouched[s_id[gi]] = 1;   // idempotent byte store: the geometry pass skips untouched records unread
                 s_acc[e] = 0.0f;
             }
         }
@@ -384,6 +686,7 @@ struct GeomView {  // camera + per-view buffers of one view
     const float *viewmatrix, *projmatrix, *projmatrix_raw, *campos;
     const uint32_t* clamped;
     const float* gacc;
+    const uint8_t* gtouched;  // [P] or NULL: 0 = the gradient record is all zero (not even read)
     const int32_t* radii;
     float* dL_dmeans2D;   // [P,3] this view's screen-space gradient (viewspace_points.grad)
     float* dL_dtau;       // [P,6] per-Gaussian pose gradient as the reference returns it, or NULL
@@ -643,98 +946,144 @@ __device__ __forceinline__ void geom_cov3d_bwd(const float* scales, const float*
     }
 }
 
-// One thread per Gaussian, all V views of the batch: each view's packed gradient record is turned into that view's
-// mean / covariance / pose gradients with the view's camera, the results are summed in registers and the parameter
-// gradients are written ONCE (the reference runs its two kernels once per view and lets autograd add the V results).
-// The scale / rotation gradient is linear in dL/dcov3D, so it is evaluated once on the summed covariance gradient.
+// A warp's 32 Gaussians own 32 * WD consecutive floats of a [P, WD] output.  Letting every thread store its own WD
+// floats issues WD store instructions that each touch 32 different sectors; staged through shared memory the same
+// WD instructions write 128 contiguous bytes each (8x fewer L2 transactions for the 15-float language rows).
+template <int WD>
+__device__ __forceinline__ void warp_store_rows(float* s, const float (&v)[WD], float* gbase, int n_rows, int lane) {
+#pragma unroll
+    for (int k = 0; k < WD; k++) s[lane * WD + k] = v[k];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < WD; k++) {
+        const int t = k * 32 + lane;
+        if (t < n_rows * WD) gbase[t] = s[t];
+    }
+    __syncwarp();
+}
+
+// Geometry backward for all V views of the batch.  A warp owns 32 Gaussians.  Only ~15 % of the (Gaussian, view) pairs
+// carry a gradient (the others lie behind the saturation depth of every pixel they cover), so running the per-view
+// chain rule one view at a time would execute it 8x per warp with ~5 live lanes.  Instead:
+//   pass 1  one lane per Gaussian: which views touched its record (one byte per view) and the view-count / radius part
+//           of the densification statistics; the warp compacts the touched (Gaussian, view) pairs into a queue;
+//   pass 2  the queue is worked off 32 pairs at a time, one pair per lane: the view's packed gradient record is turned
+//           into that view's mean / covariance / pose gradients with the view's camera and added to the Gaussian's
+//           accumulator row in shared memory (the reference runs its two kernels once per view and lets autograd add
+//           the V results); per-view outputs (screen-space gradient, pose gradient) are written from here;
+//   pass 3  one lane per Gaussian again: scale / rotation gradient from the SUMMED covariance gradient (it is linear
+//           in dL/dcov3D) and coalesced stores of the parameter gradients through a staging block.
+constexpr int GA_MEAN = 0, GA_COV = 3, GA_SH0 = 9, GA_COL = 12, GA_OP = 15, GA_NORM = 16, GA_LANG = 17;  // accumulator row
 template <int F>
 __global__ void __launch_bounds__(256, 2) k_geometry_bwd(const __grid_constant__ GeomBwdArgs a) {
+    constexpr int GA = GA_LANG + F;          // floats per accumulator row
+    constexpr int GA_LD = GA | 1;            // odd leading dimension: conflict-free when lane = row
     __shared__ float s_tau[OLS_MAX_VIEWS][6];
+    __shared__ float s_accum[8][32 * GA_LD];             // per warp: per-Gaussian sums over the views (pass 3 reuses it as the
+                                                         // staging block of the coalesced stores)
+    __shared__ uint16_t s_queue[8][32 * OLS_MAX_VIEWS];  // per warp: touched pairs (lane | view << 8)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float* accw = s_accum[wid];
+    float* stg = accw;
+    static_assert(GA_LD >= F && GA_LD >= 6, "staging block fits the accumulator block");
+    uint16_t* queue = s_queue[wid];
+    const int warp_first = i - lane;                                  // first Gaussian of this warp
+    const int n_rows = min(32, a.P - warp_first);                     // <= 0 for warps past the end
     const bool valid = i < a.P;
     const int M = a.M;
     constexpr int GRF = grad_floats(F);
     if (threadIdx.x < OLS_MAX_VIEWS * 6) (&s_tau[0][0])[threadIdx.x] = 0.0f;
+    for (int e = lane; e < 32 * GA_LD; e += 32) accw[e] = 0.0f;
     __syncthreads();
-    float dmean[3] = {0, 0, 0}, dcov[6] = {0, 0, 0, 0, 0, 0};
-    float dcol[3] = {0, 0, 0}, dsh0[3] = {0, 0, 0}, dlang[F], dop = 0.0f;
-#pragma unroll
-    for (int k = 0; k < F; k++) dlang[k] = 0.0f;
     const bool acc = a.accumulate;
+    const bool stats = a.stat_denom != nullptr;
     if (valid && a.dL_dsh && !acc && M > 1)
         for (int k = 3; k < 3 * M; k++) a.dL_dsh[(size_t)3 * M * i + k] = 0.0f;
-    float mp[3] = {0, 0, 0};
-    if (valid) { mp[0] = a.means3D[3 * (size_t)i]; mp[1] = a.means3D[3 * (size_t)i + 1]; mp[2] = a.means3D[3 * (size_t)i + 2]; }
-    bool any_total = false;
-    const bool stats = a.stat_denom != nullptr;
-    float st_norm = 0.0f, st_cnt = 0.0f;
+    // ---- pass 1 ----
+    float st_cnt = 0.0f;
     int st_rad = 0;
+    uint32_t tmask = 0;
+    if (valid) {
+#pragma unroll 4
+        for (int v = 0; v < a.V; v++) {
+            const GeomView& vw = a.v[v];
+            if (vw.gtouched == nullptr || vw.gtouched[i] != 0) tmask |= 1u << v;
+            if (stats) {
+                const int rad = vw.radii[i];
+                if (rad > 0) { st_cnt += 1.0f; st_rad = max(st_rad, rad); }
+            }
+        }
+    }
+    int n_queue = 0;
     for (int v = 0; v < a.V; v++) {
         const GeomView& vw = a.v[v];
-        // the whole packed gradient record in registers: GRF/4 independent 16-byte loads
-        float gr[GRF];
-        bool any = false;
-        if (valid) {
-            const float4* src = reinterpret_cast<const float4*>(vw.gacc + (size_t)i * GRF);
-#pragma unroll
-            for (int q = 0; q < GRF / 4; q++) {
-                const float4 t = src[q];
-                gr[4 * q] = t.x; gr[4 * q + 1] = t.y; gr[4 * q + 2] = t.z; gr[4 * q + 3] = t.w;
+        const bool t = (tmask >> v) & 1u;
+        const unsigned m = __ballot_sync(0xffffffffu, t);
+        if (t) queue[n_queue + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(lane | (v << 8));
+        n_queue += __popc(m);
+        if (n_rows > 0) {  // per-view outputs exist for every Gaussian: zeros now, the touched pairs overwrite theirs in pass 2
+            float* m2 = vw.dL_dmeans2D + 3 * (size_t)warp_first;
+            for (int t_ = lane; t_ < 3 * n_rows; t_ += 32) m2[t_] = 0.0f;
+            if (vw.dL_dtau) {
+                float* dt = vw.dL_dtau + 6 * (size_t)warp_first;
+                for (int t_ = lane; t_ < 6 * n_rows; t_ += 32) dt[t_] = 0.0f;
             }
-            // Most Gaussians of a view receive no gradient at all (they lie behind the saturation depth of every pixel
-            // they cover).  Everything below is linear in the record, so a zero record yields exactly zero gradients.
+        }
+    }
+    __syncwarp();
+    // ---- pass 2: one touched (Gaussian, view) pair per lane ----
+    for (int q0 = 0; q0 < n_queue; q0 += 32) {
+        const int q = q0 + lane;
+        if (q < n_queue) {
+            const int l = queue[q] & 0xff, v = queue[q] >> 8;
+            const int gi = warp_first + l;
+            const GeomView& vw = a.v[v];
+            float gr[GRF];
+            const float4* src = reinterpret_cast<const float4*>(vw.gacc + (size_t)gi * GRF);
+#pragma unroll
+            for (int k4 = 0; k4 < GRF / 4; k4++) {
+                const float4 t = src[k4];
+                gr[4 * k4] = t.x; gr[4 * k4 + 1] = t.y; gr[4 * k4 + 2] = t.z; gr[4 * k4 + 3] = t.w;
+            }
+            bool any = false;
 #pragma unroll
             for (int k = 0; k < GRF; k++) any = any || (gr[k] != 0.0f);
-        }
-        float dtau[6] = {0, 0, 0, 0, 0, 0};
-        float g2x = 0.0f, g2y = 0.0f;
-        bool vis = false;
-        int rad = 0;
-        if (stats && valid) rad = vw.radii[i];
-        if (any) {
-            any_total = true;
-            g2x = gr[GR_MX]; g2y = gr[GR_MY];
-            const float dcol_v[3] = {gr[GR_RGB], gr[GR_RGB + 1], gr[GR_RGB + 2]};
-            vis = (stats ? rad : vw.radii[i]) > 0;
-            if (vis) {
-                const float* V = vw.viewmatrix;
-                const float* c3 = a.cov3D + 6 * (size_t)i;
-                float dmean_v[3] = {0, 0, 0}, dcov_v[6] = {0, 0, 0, 0, 0, 0}, dsh0_v[3] = {0, 0, 0};
-                geom_cov2d_bwd(vw, V, mp, c3, gr[GR_CX], gr[GR_CY], gr[GR_CW], dcov_v, dmean_v, dtau);
-                geom_proj_bwd(V, vw.projmatrix, vw.projmatrix_raw, mp, g2x, g2y, gr[GR_DEPTH], dmean_v, dtau);
-                geom_sh_bwd(a, vw, i, mp, dcol_v, dsh0_v, dmean_v, dtau);
+            if (any) {
+                float* row = accw + l * GA_LD;
+                const float g2x = gr[GR_MX], g2y = gr[GR_MY];
+                const float dcol_v[3] = {gr[GR_RGB], gr[GR_RGB + 1], gr[GR_RGB + 2]};
+                if (vw.radii[gi] > 0) {
+                    const float mp[3] = {a.means3D[3 * (size_t)gi], a.means3D[3 * (size_t)gi + 1], a.means3D[3 * (size_t)gi + 2]};
+                    const float* V = vw.viewmatrix;
+                    const float* c3 = a.cov3D + 6 * (size_t)gi;
+                    float dmean_v[3] = {0, 0, 0}, dcov_v[6] = {0, 0, 0, 0, 0, 0}, dsh0_v[3] = {0, 0, 0}, dtau[6] = {0, 0, 0, 0, 0, 0};
+                    geom_cov2d_bwd(vw, V, mp, c3, gr[GR_CX], gr[GR_CY], gr[GR_CW], dcov_v, dmean_v, dtau);
+                    geom_proj_bwd(V, vw.projmatrix, vw.projmatrix_raw, mp, g2x, g2y, gr[GR_DEPTH], dmean_v, dtau);
+                    geom_sh_bwd(a, vw, gi, mp, dcol_v, dsh0_v, dmean_v, dtau);
 #pragma unroll
-                for (int k = 0; k < 3; k++) { dmean[k] += dmean_v[k]; dsh0[k] += dsh0_v[k]; }
+                    for (int k = 0; k < 3; k++) { atomicAdd(row + GA_MEAN + k, dmean_v[k]); atomicAdd(row + GA_SH0 + k, dsh0_v[k]); }
 #pragma unroll
-                for (int k = 0; k < 6; k++) dcov[k] += dcov_v[k];
-            }
+                    for (int k = 0; k < 6; k++) atomicAdd(row + GA_COV + k, dcov_v[k]);
+                    if (stats) atomicAdd(row + GA_NORM, sqrtf(g2x * g2x + g2y * g2y));   // gaussian_model.py:965-969
+                    if (vw.dL_dtau) {
 #pragma unroll
-            for (int k = 0; k < 3; k++) dcol[k] += dcol_v[k];
-            dop += gr[GR_OP];
+                        for (int k = 0; k < 6; k++) vw.dL_dtau[6 * (size_t)gi + k] = dtau[k];
+                    }
+                    if (vw.dL_dtau_sum) {  // reference: torch.sum(dL_dtau, dim=0) (__init__.py:383-385)
 #pragma unroll
-            for (int k = 0; k < F; k++) dlang[k] += gr[GR_LANG + k];
-        }
-        if (rad > 0) {  // densification statistics of this view (gaussian_model.py:965-969)
-            st_norm += sqrtf(g2x * g2x + g2y * g2y);
-            st_cnt += 1.0f;
-            st_rad = max(st_rad, rad);
-        }
-        if (valid) {  // per-view outputs are always written
-            float* m2 = vw.dL_dmeans2D + 3 * (size_t)i;
-            m2[0] = g2x; m2[1] = g2y; m2[2] = 0.0f;
-            if (vw.dL_dtau) {
+                        for (int k = 0; k < 6; k++)
+                            if (dtau[k] != 0.0f) atomicAdd(&s_tau[v][k], dtau[k]);
+                    }
+                }
 #pragma unroll
-                for (int k = 0; k < 6; k++) vw.dL_dtau[6 * (size_t)i + k] = dtau[k];
-            }
-        }
-        if (vw.dL_dtau_sum && __any_sync(0xffffffffu, vis)) {  // reference: torch.sum(dL_dtau, dim=0) (__init__.py:383-385)
+                for (int k = 0; k < 3; k++) atomicAdd(row + GA_COL + k, dcol_v[k]);
+                atomicAdd(row + GA_OP, gr[GR_OP]);
 #pragma unroll
-            for (int k = 0; k < 6; k++) {
-                float t = dtau[k];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-                if (lane == 0 && t != 0.0f) atomicAdd(&s_tau[v][k], t);
+                for (int k = 0; k < F; k++) atomicAdd(row + GA_LANG + k, gr[GR_LANG + k]);
+                float* m2 = vw.dL_dmeans2D + 3 * (size_t)gi;
+                m2[0] = g2x; m2[1] = g2y;
+                queue[q] = (uint16_t)(queue[q] | 0x8000u);   // this pair really carried a gradient
             }
         }
     }
@@ -744,16 +1093,46 @@ __global__ void __launch_bounds__(256, 2) k_geometry_bwd(const __grid_constant__
         const float t = s_tau[v][k];
         if (a.v[v].dL_dtau_sum && t != 0.0f) atomicAdd(&a.v[v].dL_dtau_sum[k], t);
     }
+    // ---- pass 3: one lane per Gaussian ----
+    bool any_total = false;
+    for (int q = 0; q < n_queue; q++) any_total = any_total || ((queue[q] & 0x80ffu) == (0x8000u | (unsigned)lane));
+    const float* row = accw + lane * GA_LD;
+    float dmean[3], dcov[6], dsh0[3], dcol[3], dlang[F];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { dmean[k] = row[GA_MEAN + k]; dsh0[k] = row[GA_SH0 + k]; dcol[k] = row[GA_COL + k]; }
+#pragma unroll
+    for (int k = 0; k < 6; k++) dcov[k] = row[GA_COV + k];
+#pragma unroll
+    for (int k = 0; k < F; k++) dlang[k] = row[GA_LANG + k];
+    const float dop = row[GA_OP];
+    const float st_norm = row[GA_NORM];
+    __syncwarp();   // every lane has read its accumulator row: the block now serves as the staging area
     if (stats && valid && st_cnt > 0.0f) {
         a.stat_accum[i] += st_norm;
         a.stat_denom[i] += st_cnt;
         a.stat_max_radii[i] = fmaxf(a.stat_max_radii[i], (float)st_rad);
     }
-    if (!valid || (acc && !any_total)) return;  // accumulating a zero gradient: nothing to read or rewrite
     float dsc[3] = {0, 0, 0}, dq[4] = {0, 0, 0, 0};
-    if (any_total) geom_cov3d_bwd(a.scales, a.rotations, a.scale_modifier, i, dcov, dsc, dq);
-    // ---- outputs: when accumulating, fetch every old value first (independent loads), then store ----
-    float o_mean[3], o_cov[6], o_sc[3], o_q[4], o_op, o_col[3], o_lang[F], o_sh[3];
+    if (valid && any_total) geom_cov3d_bwd(a.scales, a.rotations, a.scale_modifier, i, dcov, dsc, dq);
+    if (!acc) {
+        // overwrite mode: every Gaussian's gradients are written (zeros included), warp-cooperatively
+        if (n_rows <= 0) return;
+        const size_t w0 = (size_t)warp_first;
+        warp_store_rows<3>(stg, dmean, a.dL_dmeans3D + 3 * w0, n_rows, lane);
+        warp_store_rows<3>(stg, dsc, a.dL_dscales + 3 * w0, n_rows, lane);
+        warp_store_rows<3>(stg, dcol, a.dL_dcolors + 3 * w0, n_rows, lane);
+        warp_store_rows<6>(stg, dcov, a.dL_dcov3D + 6 * w0, n_rows, lane);
+        warp_store_rows<4>(stg, dq, a.dL_drots + 4 * w0, n_rows, lane);
+        warp_store_rows<F>(stg, dlang, a.dL_dlanguage + (size_t)F * w0, n_rows, lane);
+        if (valid) a.dL_dopacity[i] = dop;
+        if (a.dL_dsh) {
+            if (M == 1) warp_store_rows<3>(stg, dsh0, a.dL_dsh + 3 * w0, n_rows, lane);
+            else if (valid) { float* p_sh = a.dL_dsh + (size_t)3 * M * i; p_sh[0] = dsh0[0]; p_sh[1] = dsh0[1]; p_sh[2] = dsh0[2]; }
+        }
+        return;
+    }
+    if (!valid || !any_total) return;  // accumulating a zero gradient: nothing to read or rewrite
+    a.dL_dopacity[i] += dop;
     float* p_mean = a.dL_dmeans3D + 3 * (size_t)i;
     float* p_cov = a.dL_dcov3D + 6 * (size_t)i;
     float* p_sc = a.dL_dscales + 3 * (size_t)i;
@@ -761,41 +1140,19 @@ __global__ void __launch_bounds__(256, 2) k_geometry_bwd(const __grid_constant__
     float* p_col = a.dL_dcolors + 3 * (size_t)i;
     float* p_lang = a.dL_dlanguage + (size_t)F * i;
     float* p_sh = a.dL_dsh ? a.dL_dsh + (size_t)3 * M * i : nullptr;
-    if (acc) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) { o_mean[k] = p_mean[k]; o_sc[k] = p_sc[k]; o_col[k] = p_col[k]; o_sh[k] = p_sh ? p_sh[k] : 0.0f; }
-#pragma unroll
-        for (int k = 0; k < 6; k++) o_cov[k] = p_cov[k];
-#pragma unroll
-        for (int k = 0; k < 4; k++) o_q[k] = p_q[k];
-#pragma unroll
-        for (int k = 0; k < F; k++) o_lang[k] = p_lang[k];
-        o_op = a.dL_dopacity[i];
-    } else {
-#pragma unroll
-        for (int k = 0; k < 3; k++) { o_mean[k] = 0; o_sc[k] = 0; o_col[k] = 0; o_sh[k] = 0; }
-#pragma unroll
-        for (int k = 0; k < 6; k++) o_cov[k] = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) o_q[k] = 0;
-#pragma unroll
-        for (int k = 0; k < F; k++) o_lang[k] = 0;
-        o_op = 0;
-    }
-    a.dL_dopacity[i] = o_op + dop;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        p_mean[k] = o_mean[k] + dmean[k];
-        p_sc[k] = o_sc[k] + dsc[k];
-        p_col[k] = o_col[k] + dcol[k];
-        if (p_sh) p_sh[k] = o_sh[k] + dsh0[k];
+        p_mean[k] += dmean[k];
+        p_sc[k] += dsc[k];
+        p_col[k] += dcol[k];
+        if (p_sh) p_sh[k] += dsh0[k];
     }
 #pragma unroll
-    for (int k = 0; k < 6; k++) p_cov[k] = o_cov[k] + dcov[k];
+    for (int k = 0; k < 6; k++) p_cov[k] += dcov[k];
 #pragma unroll
-    for (int k = 0; k < 4; k++) p_q[k] = o_q[k] + dq[k];
+    for (int k = 0; k < 4; k++) p_q[k] += dq[k];
 #pragma unroll
-    for (int k = 0; k < F; k++) p_lang[k] = o_lang[k] + dlang[k];
+    for (int k = 0; k < F; k++) p_lang[k] += dlang[k];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -889,6 +1246,16 @@ __global__ void __launch_bounds__(256) k_geometry_bwd_dis(const GeomDisArgs a) {
 template <int TILE, int NCOL, int F>
 static void launch_blend_bwd(const BwdBlendArgs& ba, int n_tiles, int V, bool exact, bool packed, cudaStream_t st) {
     const dim3 grid(n_tiles, V);
+    static const bool v1 = getenv("OLS_BWD_V1") != nullptr;  // A/B aid: the one-pixel-per-lane kernel
+    if (!v1) {
+        if (exact)
+            k_blend_bwd2<TILE, NCOL, F, false, false><<<grid, 128, 0, st>>>(ba);
+        else if (packed)
+            k_blend_bwd2<TILE, NCOL, F, true, true><<<grid, 64, 0, st>>>(ba);
+        else
+            k_blend_bwd2<TILE, NCOL, F, true, false><<<grid, 128, 0, st>>>(ba);
+        return;
+    }
     if (exact)
         k_blend_bwd<TILE, NCOL, F, false, false><<<grid, BWD_THREADS, 0, st>>>(ba);
     else if (packed)
@@ -948,6 +1315,7 @@ static int run_blend_bwd(int W, int H, int tile, int ncol, int F, unsigned flags
         q.final_T = (const float*)(ws + L.final_T); q.n_contrib = (const uint32_t*)(ws + L.n_contrib);
         q.dL_dcolor = pv[v].dL_dcolor; q.dL_dlanguage = pv[v].dL_dlanguage; q.dL_ddepth = pv[v].dL_ddepth;
         q.gacc = (float*)(ws + L.gacc);
+        q.gtouched = (uint8_t*)(ws + L.gtouched);
         q.warp_hits = (const uint8_t*)(ws + L.warp_hits);
     }
     reduce_lane_mask(tile * tile, exact, ba.lane_ok);
@@ -1007,6 +1375,7 @@ static void fill_geom_view(GeomView& q, const ols_raster_args* a, const char* ws
                            float* dL_dmeans2D, float* dL_dtau, float* dL_dtau_sum) {
     q.viewmatrix = a->d_viewmatrix; q.projmatrix = a->d_projmatrix; q.projmatrix_raw = a->d_projmatrix_raw;
     q.campos = a->d_campos; q.clamped = (const uint32_t*)(ws + L.clamped); q.gacc = (const float*)(ws + L.gacc);
+    q.gtouched = (const uint8_t*)(ws + L.gtouched);
     q.radii = radii; q.dL_dmeans2D = dL_dmeans2D; q.dL_dtau = dL_dtau; q.dL_dtau_sum = dL_dtau_sum;
     q.tanfovx = a->tanfovx; q.tanfovy = a->tanfovy;
     q.focal_y = a->H / (2.0f * a->tanfovy); q.focal_x = a->W / (2.0f * a->tanfovx);
@@ -1022,7 +1391,8 @@ int ols_launch_backward(const ols_raster_args* views, const ols_bwd_args* grads,
     BwdPassView pv[OLS_MAX_VIEWS];
     for (int v = 0; v < V; v++) {
         char* ws = (char*)views[v].d_workspace;
-        OLS_CUDA_TRY(cudaMemsetAsync(ws + L.gacc, 0, ols_bwd_scratch_bytes(a->P, a->F), st));
+        // gradient records and their touched bytes are adjacent in the workspace: one memset
+        OLS_CUDA_TRY(cudaMemsetAsync(ws + L.gacc, 0, (L.gtouched - L.gacc) + (size_t)(a->P > 0 ? a->P : 1), st));
         if (grads[v].d_dL_dtau_sum) OLS_CUDA_TRY(cudaMemsetAsync(grads[v].d_dL_dtau_sum, 0, 6 * sizeof(float), st));
         pv[v] = BwdPassView{ws, views[v].d_bg, grads[v].d_dL_dout_color, grads[v].d_dL_dout_language, grads[v].d_dL_dout_depth};
     }
@@ -1063,8 +1433,8 @@ int ols_launch_backward_dis(const ols_dis_args* d, const ols_dis_bwd_args* g, co
     char* wc = (char*)a->d_workspace;
     char* wl = wc + lang_base;
     const bool debug = (a->flags & OLS_FLAG_DEBUG) != 0;
-    OLS_CUDA_TRY(cudaMemsetAsync(wc + Lc.gacc, 0, ols_bwd_scratch_bytes(a->P, 0), st));
-    OLS_CUDA_TRY(cudaMemsetAsync(wl + Ll.gacc, 0, ols_bwd_scratch_bytes(a->P, a->F), st));
+    OLS_CUDA_TRY(cudaMemsetAsync(wc + Lc.gacc, 0, (Lc.gtouched - Lc.gacc) + (size_t)(a->P > 0 ? a->P : 1), st));
+    OLS_CUDA_TRY(cudaMemsetAsync(wl + Ll.gacc, 0, (Ll.gtouched - Ll.gacc) + (size_t)(a->P > 0 ? a->P : 1), st));
     ols_timing_mark(-1, st);
     const BwdPassView pc{wc, a->d_bg, g->d_dL_dout_color, nullptr, g->d_dL_dout_depth};
     int rc = run_blend_bwd(a->W, a->H, a->tile, 3, 0, a->flags, &pc, 1, Lc, nullptr, st);

@@ -28,7 +28,7 @@ __host__ __device__ constexpr int rec_floats_global(int ncol, int F) { return (n
 
 struct WsLayout {
     size_t info, tile_count, tile_cursor, ranges, cta_hist, records, depths, cov3D, clamped, tiles_touched, rect, final_T,
-        n_contrib, keys, point_list, warp_hits, gacc, total;
+        n_contrib, keys, point_list, warp_hits, gacc, gtouched, total;
     int n_tiles, gx, gy, rec;
     int n_ctas, chunk;  // per-Gaussian kernels: n_ctas CTAs, each owning `chunk` consecutive Gaussians
 };
@@ -68,6 +68,7 @@ inline __host__ WsLayout ws_layout(int P, int F, int W, int H, int tile, int64_t
     L.point_list = take(4 * Rz);
     L.warp_hits = take(Rz);  // per list entry: bit w set iff some pixel of the tile's 8x4 block w blended it (forward -> backward)
     L.gacc = take(4 * (size_t)(((10 + F) + 3) / 4 * 4) * Pz);  // packed per-Gaussian gradient records (backward)
+    L.gtouched = take(Pz);  // one byte per Gaussian: the backward blend flushed something into its gradient record
     L.total = o;
     return L;
 }

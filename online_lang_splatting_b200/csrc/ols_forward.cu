@@ -213,17 +213,18 @@ __device__ __forceinline__ void write_record_frame(float* rf, int rec, float pix
     r4[0] = make_float4(pix_x, pix_y, conA, conB);
     r4[1] = make_float4(conC, op, pth, depth);
     // half-extents of {power >= pth_c} for the conic as stored: |dx| <= sqrt(-2 pth_c C / (AC - B^2)), same for y.
-    // pth_c widens pth by more than the rounding error of the float evaluation of `power` when the
-    // form is reasonably conditioned; otherwise (or for NaNs) the extents are infinite = never rejected.
-    const double A = (double)conA, B = (double)conB, Cc = (double)conC;
-    const double detc = A * Cc - B * B, tr = A + Cc;
+    // pth_c widens pth by more than the rounding error of the float evaluation of `power` when the form is
+    // reasonably conditioned (trace^2 < 1000 det, so the fp32 determinant below is good to ~1e-4 relative -- the 1.001
+    // factor covers it); otherwise (or for NaNs) the extents are infinite = never rejected.
+    const float A = conA, B = conB, Cc = conC;
+    const float detc = fmaf(A, Cc, -B * B), tr = A + Cc;
     float ex = CUDART_INF_F, ey = CUDART_INF_F;
     if (pth > 0.0f) {
         ex = ey = -CUDART_INF_F;  // opacity below 1/255: no pixel can pass
-    } else if (pth > -CUDART_INF_F && A > 0.0 && Cc > 0.0 && detc > 0.0 && tr * tr < 1000.0 * detc) {
-        const double k = -2.0 * (1.002 * (double)pth - 0.02) / detc;
-        ex = (float)(sqrt(k * Cc) * 1.0001 + 0.01);
-        ey = (float)(sqrt(k * A) * 1.0001 + 0.01);
+    } else if (pth > -CUDART_INF_F && A > 0.0f && Cc > 0.0f && detc > 0.0f && tr * tr < 1000.0f * detc) {
+        const float k = -2.0f * (1.002f * pth - 0.02f) / detc;
+        ex = sqrtf(k * Cc) * 1.001f + 0.01f;
+        ey = sqrtf(k * A) * 1.001f + 0.01f;
     }
     rf[rec - 2] = ex;
     rf[rec - 1] = ey;
@@ -624,10 +625,9 @@ __global__ void __launch_bounds__(PRE_THREADS) k_scatter(const __grid_constant__
     const int gx = L.gx, n_tiles = L.n_tiles, chunk = L.chunk;
     const uint32_t* __restrict__ tiles_touched = (const uint32_t*)(ws + L.tiles_touched);
     const uint2* __restrict__ rect = (const uint2*)(ws + L.rect);
-    const float* __restrict__ depths = pb.v[blockIdx.y].depths;
     const uint32_t* __restrict__ cta_hist = (const uint32_t*)(ws + L.cta_hist);
     const uint32_t* __restrict__ tile_start = (const uint32_t*)(ws + L.tile_cursor);
-    unsigned long long* __restrict__ keys = (unsigned long long*)(ws + L.keys);
+    uint32_t* __restrict__ bucket = (uint32_t*)(ws + L.point_list);  // unsorted per-tile lists of Gaussian ids (4 B per instance)
     const DeviceInfo* __restrict__ info = (const DeviceInfo*)(ws + L.info);
     if (info->overflow) return;
     const int tid = threadIdx.x;
@@ -640,18 +640,17 @@ __global__ void __launch_bounds__(PRE_THREADS) k_scatter(const __grid_constant__
     // lane L emits instances L, L + 32, ... of the warp's flattened list, so a Gaussian covering many tiles does
     // not serialise one thread, and 32 independent slot requests are in flight per step.
     // the three per-Gaussian loads of the next round are issued before the current round is emitted
-    auto fetch = [&](int i, uint32_t& cnt, uint2& r, float& d) {
-        cnt = 0; r = make_uint2(0u, 0u); d = 0.0f;
-        if (i < chunk_end) { cnt = tiles_touched[i]; r = rect[i]; d = depths[i]; }
+    auto fetch = [&](int i, uint32_t& cnt, uint2& r) {
+        cnt = 0; r = make_uint2(0u, 0u);
+        if (i < chunk_end) { cnt = tiles_touched[i]; r = rect[i]; }
     };
-    uint32_t n_cnt; uint2 n_r; float n_d;
-    fetch(chunk_begin + (tid & ~31) + lane, n_cnt, n_r, n_d);
+    uint32_t n_cnt; uint2 n_r;
+    fetch(chunk_begin + (tid & ~31) + lane, n_cnt, n_r);
     for (int i0 = chunk_begin + (tid & ~31); i0 < chunk_end; i0 += PRE_THREADS) {
         const int i = i0 + lane;
         const uint32_t cnt = n_cnt;
         const uint2 r = n_r;
-        const unsigned long long key = ((unsigned long long)__float_as_uint(n_d) << 32) | (unsigned)i;
-        fetch(i + PRE_THREADS, n_cnt, n_r, n_d);
+        fetch(i + PRE_THREADS, n_cnt, n_r);
         uint32_t incl = cnt;  // inclusive prefix over the lanes
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -671,14 +670,13 @@ __global__ void __launch_bounds__(PRE_THREADS) k_scatter(const __grid_constant__
             const uint32_t o_incl = __shfl_sync(0xffffffffu, incl, owner);
             const uint32_t o_cnt = __shfl_sync(0xffffffffu, cnt, owner);
             const uint32_t rx = __shfl_sync(0xffffffffu, r.x, owner), ry = __shfl_sync(0xffffffffu, r.y, owner);
-            const unsigned long long okey = __shfl_sync(0xffffffffu, key, owner);
             if (k < total) {
                 const uint32_t local = k - (o_incl - o_cnt);
                 const int x0 = rx & 0xffff, y0 = rx >> 16, x1 = ry & 0xffff;
                 const int w = x1 - x0;
                 const int yy = y0 + (int)(local / (uint32_t)w), xx = x0 + (int)(local % (uint32_t)w);
                 const uint32_t slot = atomicAdd(&s_cur[yy * gx + xx], 1u);
-                keys[slot] = okey;
+                bucket[slot] = (uint32_t)(i0 + owner);
             }
         }
     }
@@ -707,6 +705,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_sort_tiles_bucket(const __grid_c
     char* ws = pb.v[blockIdx.y].ws;
     unsigned long long* __restrict__ keys = (unsigned long long*)(ws + L.keys);
     uint32_t* __restrict__ point_list = (uint32_t*)(ws + L.point_list);
+    const float* __restrict__ depths = pb.v[blockIdx.y].depths;
     const uint2* __restrict__ ranges = (const uint2*)(ws + L.ranges);
     uint32_t* __restrict__ tile_count = (uint32_t*)(ws + L.tile_count);
     const DeviceInfo* __restrict__ info = (const DeviceInfo*)(ws + L.info);
@@ -727,7 +726,8 @@ __global__ void __launch_bounds__(BS_THREADS) k_sort_tiles_bucket(const __grid_c
     for (int r = 0; r < BS_ITEMS; r++) {
         const int idx = r * BS_THREADS + tid;
         if (idx < n) {
-            k[r] = g[idx];
+            const uint32_t id = point_list[rg.x + idx];   // the scatter wrote bare ids: the depth half of the key is gathered here
+            k[r] = ((unsigned long long)__float_as_uint(depths[id]) << 32) | id;
             const float d = __uint_as_float((uint32_t)(k[r] >> 32));
             finite = finite && (d >= 0.0f) && (d < CUDART_INF_F);
             lo = fminf(lo, d);
@@ -825,6 +825,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_sort_tiles_radix(const __grid_co
     char* ws = pb.v[blockIdx.y].ws;
     unsigned long long* __restrict__ keys = (unsigned long long*)(ws + L.keys);
     uint32_t* __restrict__ point_list = (uint32_t*)(ws + L.point_list);
+    const float* __restrict__ depths = pb.v[blockIdx.y].depths;
     const uint2* __restrict__ ranges = (const uint2*)(ws + L.ranges);
     const uint32_t* __restrict__ tile_count = (const uint32_t*)(ws + L.tile_count);
     const DeviceInfo* __restrict__ info = (const DeviceInfo*)(ws + L.info);
@@ -847,7 +848,12 @@ __global__ void __launch_bounds__(RS_THREADS) k_sort_tiles_radix(const __grid_co
     for (int r = 0; r < RS_ITEMS; r++) {
         const int idx = wid * seg + r * 32 + lane;
         const bool real = r < items && idx < n;
-        k[r] = real ? g[idx] : ~0ull;  // +inf padding keeps the tail in place
+        if (real) {
+            const uint32_t id = point_list[rg.x + idx];
+            k[r] = ((unsigned long long)__float_as_uint(depths[id]) << 32) | id;
+        } else {
+            k[r] = ~0ull;  // +inf padding keeps the tail in place
+        }
         if (real) { dmin = min(dmin, (uint32_t)(k[r] >> 32)); dmax = max(dmax, (uint32_t)(k[r] >> 32)); }
     }
     // digits are taken from (depth_bits - tile minimum): only the bytes that differ inside the tile are sorted
@@ -1002,6 +1008,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const __grid_consta
     char* ws = pb.v[blockIdx.y].ws;
     unsigned long long* __restrict__ keys = (unsigned long long*)(ws + L.keys);
     uint32_t* __restrict__ point_list = (uint32_t*)(ws + L.point_list);
+    const float* __restrict__ depths = pb.v[blockIdx.y].depths;
     const uint2* __restrict__ ranges = (const uint2*)(ws + L.ranges);
     const DeviceInfo* __restrict__ info = (const DeviceInfo*)(ws + L.info);
     if (info->overflow) return;
@@ -1010,6 +1017,12 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const __grid_consta
     if (n <= min_len) return;
     unsigned long long* g = keys + rg.x;
     const int tid = threadIdx.x;
+    // materialise the 64-bit keys of this (long) tile from the ids the scatter wrote
+    for (int i = tid; i < n; i += SORT_THREADS) {
+        const uint32_t id = point_list[rg.x + i];
+        g[i] = ((unsigned long long)__float_as_uint(depths[id]) << 32) | id;
+    }
+    __syncthreads();
     if (n <= SORT_CHUNK) {
         for (int i = tid; i < n; i += SORT_THREADS) s[i] = g[i];
         __syncthreads();
@@ -1287,14 +1300,17 @@ __global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend(const __grid_constan
 // so that its blend / skip decisions agree with the forward's.
 // ---------------------------------------------------------------------------------------------------
 constexpr int B2_THREADS = 128;
+#ifndef B2_MIN_BLOCKS
+#define B2_MIN_BLOCKS 5
+#endif
 __device__ __forceinline__ float fast_exp(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
     return y;
 }
 
-template <int TILE, int NCOL, int F, bool BITEXACT>
-__global__ void __launch_bounds__(B2_THREADS, 5) k_blend2(const __grid_constant__ BlendBatch bb) {
+template <int TILE, int NCOL, int F, bool BITEXACT, int MINB = B2_MIN_BLOCKS, int BB = BLEND_BATCH>
+__global__ void __launch_bounds__(B2_THREADS, MINB) k_blend2(const __grid_constant__ BlendBatch bb) {
     const BlendArgs& a = bb.v[blockIdx.y];
     static_assert(TILE <= 16, "4 warps of 8x8 pixels cover at most 16x16");
     static_assert(NCOL == 0 || NCOL == 3, "colour channels");
@@ -1304,9 +1320,9 @@ __global__ void __launch_bounds__(B2_THREADS, 5) k_blend2(const __grid_constant_
     constexpr int OPS = Stage::OPS;
     constexpr int NPAIR = (NCH + 1) / 2;
     constexpr int EXT = REC - 2;
-    constexpr int NHALF = BLEND_BATCH / 32;
-    __shared__ __align__(16) float s_rec[2][BLEND_BATCH * REC];
-    __shared__ uint32_t s_id[2][BLEND_BATCH];
+    constexpr int NHALF = BB / 32;
+    __shared__ __align__(16) float s_rec[2][BB * REC];
+    __shared__ uint32_t s_id[2][BB];
     __shared__ uint32_t s_hit[2][8][NHALF];  // per 8x4 pixel block (k_blend's warp index): bit j = the block blended entry j
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -1338,24 +1354,24 @@ __global__ void __launch_bounds__(B2_THREADS, 5) k_blend2(const __grid_constant_
     const bool overflow = a.info->overflow != 0;  // instance capacity exceeded: nothing was binned; the images become NaN
     if (overflow) rg = make_uint2(0u, 0u);
     const int total = (int)(rg.y - rg.x);
-    const int n_batches = (total + BLEND_BATCH - 1) / BLEND_BATCH;
+    const int n_batches = (total + BB - 1) / BB;
 
     auto flush_hits = [&](int b) {
-        if (tid < BLEND_BATCH) {
+        if (tid < BB) {
             uint32_t byte = 0;
 #pragma unroll
             for (int w = 0; w < 8; w++) byte |= ((s_hit[b & 1][w][tid >> 5] >> (tid & 31)) & 1u) << w;
-            const int e = b * BLEND_BATCH + tid;
+            const int e = b * BB + tid;
             if (e < total) a.warp_hits[rg.x + e] = (uint8_t)byte;
         }
     };
     auto issue = [&](int b) {
-        const int cnt = min(BLEND_BATCH, total - b * BLEND_BATCH);
+        const int cnt = min(BB, total - b * BB);
         const int buf = b & 1;
-        constexpr int TPE = B2_THREADS / BLEND_BATCH;
+        constexpr int TPE = B2_THREADS / BB;
         const int g = tid / TPE;
         if (g < cnt) {
-            const uint32_t id = a.point_list[rg.x + b * BLEND_BATCH + g];
+            const uint32_t id = a.point_list[rg.x + b * BB + g];
             if ((tid % TPE) == 0) s_id[buf][g] = id;
 #pragma unroll
             for (int q = tid % TPE; q < OPS; q += TPE) Stage::copy(&s_rec[buf][g * REC], a.records, a.language, id, q);
@@ -1379,10 +1395,10 @@ __global__ void __launch_bounds__(B2_THREADS, 5) k_blend2(const __grid_constant_
         if (__syncthreads_count(done[0] && done[1]) == B2_THREADS) break;
         if (b > 0) flush_hits(b - 1);
         if (b + 1 < n_batches) issue(b + 1);
-        const int cnt = min(BLEND_BATCH, total - b * BLEND_BATCH);
+        const int cnt = min(BB, total - b * BB);
         const float* rec = s_rec[b & 1];
         const uint32_t* ids = s_id[b & 1];
-        const uint32_t cbase = (uint32_t)b * BLEND_BATCH;
+        const uint32_t cbase = (uint32_t)b * BB;
 #pragma unroll 1
         for (int half = 0; half < NHALF; half++) {
             uint32_t myhits[2] = {0u, 0u}, mytouch[2] = {0u, 0u};
@@ -1512,10 +1528,18 @@ static int launch_blend(const BlendBatch& ba, int n_tiles, int V, bool bitexact,
             k_blend<TILE, NCOL, F, false><<<grid, BLEND_THREADS, 0, st>>>(ba);
         return 0;
     }
-    if (bitexact)
+    if (bitexact) {
         k_blend2<TILE, NCOL, F, true><<<grid, B2_THREADS, 0, st>>>(ba);
-    else
+    } else if (TILE == 15 && NCOL == 3 && F == 15) {   // the headline shape: resident CTAs per SM selectable for A/B runs
+        static const int minb = getenv("OLS_B2_MINB") ? atoi(getenv("OLS_B2_MINB")) : B2_MIN_BLOCKS;
+        if (minb == 128) k_blend2<TILE, NCOL, F, false, 5, 128><<<grid, B2_THREADS, 0, st>>>(ba);       // batch of 128 records
+        else if (minb == 1284) k_blend2<TILE, NCOL, F, false, 4, 128><<<grid, B2_THREADS, 0, st>>>(ba);
+        else if (minb == 4) k_blend2<TILE, NCOL, F, false, 4><<<grid, B2_THREADS, 0, st>>>(ba);
+        else if (minb == 32) k_blend2<TILE, NCOL, F, false, 5, 32><<<grid, B2_THREADS, 0, st>>>(ba);
+        else k_blend2<TILE, NCOL, F, false><<<grid, B2_THREADS, 0, st>>>(ba);
+    } else {
         k_blend2<TILE, NCOL, F, false><<<grid, B2_THREADS, 0, st>>>(ba);
+    }
     return 0;
 }
 

@@ -232,9 +232,34 @@ __global__ void __launch_bounds__(OA_THREADS) k_online_ae_step(const OnlineAeArg
     const double t = (double)(*a.step + 1);
     const float inv_bc1 = (float)(1.0 / (1.0 - pow((double)a.beta1, t)));
     const float inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)a.beta2, t)));
-    for (int e = tid; e < OA_NPARAM + 2; e += OA_THREADS) {
-        float g = 0.0f;
-        for (unsigned c = 0; c < gridDim.x; c++) g += __ldcg(a.partial + (size_t)c * (OA_NPARAM + 2) + e);
+    // thread t owns entries e = t + 128 k.  The slabs are summed in CTA order (deterministic); the loop nest keeps
+    // 4 x 19 independent loads in flight per thread instead of one dependent chain per entry.
+    constexpr int NK = (OA_NPARAM + 2 + OA_THREADS - 1) / OA_THREADS;
+    float gsum[NK];
+#pragma unroll
+    for (int k = 0; k < NK; k++) gsum[k] = 0.0f;
+    for (unsigned c0 = 0; c0 < gridDim.x; c0 += 4) {
+        float t4[4][NK];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const bool ok = c0 + u < gridDim.x;
+            const float* sl = a.partial + (size_t)(c0 + u) * (OA_NPARAM + 2);
+#pragma unroll
+            for (int k = 0; k < NK; k++) {
+                const int e = tid + k * OA_THREADS;
+                t4[u][k] = (ok && e < OA_NPARAM + 2) ? __ldcg(sl + e) : 0.0f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int k = 0; k < NK; k++) gsum[k] += t4[u][k];
+    }
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+        const int e = tid + k * OA_THREADS;
+        if (e >= OA_NPARAM + 2) continue;
+        const float g = gsum[k];
         if (e < OA_NPARAM) {
             // torch.optim.Adam defaults (amsgrad=False, weight_decay=0): same update form as ols_optim.cu
             float m = a.m[e], v = a.v[e];

@@ -32,7 +32,7 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(N.FwdOut) == 6 * 8
     assert C.sizeof(N.FwdInfo) == 32
     assert C.sizeof(N.BwdArgs) == 18 * 8
-    assert C.sizeof(N.AEChain) == 4 + 9 * 4 + 4 + 4 + 8 * 8 * 2
+    assert C.sizeof(N.AEChain) == 4 + 9 * 4 + 4 + 4 + 4 + 4 + 8 * 8 * 2
 
 
 def test_workspace_size_monotone_and_invalid():

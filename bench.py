@@ -135,6 +135,8 @@ def cpu_frame_seconds(args, keyframes: int = 1):
     import _util as U
     from oracle import oracle as O
     from oracle import torch_oracle as TO
+    want = os.cpu_count() or 1
+    O.set_num_threads(want)          # explicit: torchrun exports OMP_NUM_THREADS=1 to its workers
     cores = O.num_threads()
     torch.set_num_threads(max(cores, 1))
     sc = U.make_scene(P=args.gaussians, F=15, W=args.width, H=args.height, seed=0, scale=0.01)
@@ -360,17 +362,22 @@ def main():
         for k in range(KF):
             clip_host.append(clip_dev[k].cpu().pin_memory())
             gt_host.append((torch.rand(3, H, W).pin_memory(), (torch.rand(1, H, W) * 5).pin_memory()))
-    wc, wl, wd = (torch.randn(s, device=dev, generator=gen) for s in ((3, H, W), (15, H, W), (1, H, W)))
+    gen_w = torch.Generator(device=dev).manual_seed(4321)   # the same image-space gradients on every rank (reduce_check recomputes other ranks' views)
+    wc, wl, wd = (torch.randn(s, device=dev, generator=gen_w) for s in ((3, H, W), (15, H, W), (1, H, W)))
 
     # resident training state: raw parameters, activated copies, flat gradient buffer (the all-reduced one), Adam, side stats
     op = g["opacities"].clamp(1e-6, 1 - 1e-6)
     raw = {"means3D": g["means3D"], "sh": g["shs"][:, :1, :], "opacity": torch.log(op / (1 - op)), "scales": torch.log(g["scales"]),
            "rotations": g["rotations"], "language": g["language"]}
     fp = FlatParams({k_: v_.to(dev) for k_, v_ in raw.items()}, 15, 1, device=dev)
-    fbuf = FlatGradBuffer(P, 15, 1, device=dev)
+    # gradients [29 P] + the step's densification sums [2 P] in ONE buffer = ONE all-reduce (SUM) per step; max_radii2D is a
+    # running maximum, which commutes with the cross-rank MAX, so it is reduced only when densification reads it
+    fbuf = FlatGradBuffer(P, 15, 1, device=dev, extra=2 * P)
     flat = fbuf.flat
-    opt = FlatAdam(fp.flat, flat, fbuf.adam_groups(LR), capturable=True)   # step counter on the device: graph replays advance it
-    stats = SideStats(P, device=dev)
+    opt = FlatAdam(fp.flat, fbuf.grads, fbuf.adam_groups(LR), capturable=True)   # step counter on the device: graph replays advance it
+    stats = SideStats(P, device=dev, delta=fbuf.extra)
+    if world > 1:
+        os.environ.setdefault("OLS_AE_MAX_CTAS", "132")   # leave SMs for the NCCL kernels that overlap the encodes
     act = fp.activate()
     out_bufs = fbuf.backward_outputs({"colors": torch.empty(P, 3, device=dev), "cov3D": torch.empty(P, 6, device=dev),
                                       "means2D": torch.empty(KF, P, 3, device=dev), "tau_sum": torch.empty(KF, 6, device=dev)})
@@ -430,8 +437,7 @@ def main():
         stats.apply()
 
     def reduce_all():
-        fbuf.all_reduce()
-        stats.all_reduce()
+        fbuf.all_reduce()      # gradients + accum / denom deltas (one NCCL all-reduce)
 
     def step_resident():
         phase_encode()
@@ -590,13 +596,14 @@ def main():
     reduce_check = None
     if world > 1:
         phase_render()
+        torch.cuda.synchronize()
         reduce_all()
         torch.cuda.synchronize()
         ids = [torch.zeros(KF, dtype=torch.int64, device=dev) for _ in range(world)]
         dist.all_gather(ids, torch.tensor(view_ids, dtype=torch.int64, device=dev))
         if rank == 0:
-            reduced = flat.clone()
-            total = torch.zeros_like(flat)
+            reduced = fbuf.grads.clone()
+            total = torch.zeros_like(reduced)
             side = FlatGradBuffer(P, 15, 1, device=dev)
             ob2 = side.backward_outputs({"colors": out_bufs["colors"], "cov3D": out_bufs["cov3D"], "means2D": out_bufs["means2D"],
                                          "tau_sum": out_bufs["tau_sum"]})
@@ -604,7 +611,7 @@ def main():
                 vs = [settings_of(S.make_camera(W, H, view=int(v), seed=0, device=str(dev))) for v in ids[r_].tolist()]
                 outs, st = dgr._forward_native_batch(*params_tuple(), vs)
                 dgr._backward_native_batch(st, [o[2] for o in outs], [wc] * KF, [wl] * KF, [wd] * KF, out=ob2, accumulate=False)
-                total += side.flat
+                total += side.grads
             torch.cuda.synchronize()
             num = float((reduced.double() - total.double()).norm())
             den = float(total.double().norm())

@@ -173,11 +173,11 @@ class FlatGaussianModel:
     loss.backward() accumulates straight into the buffer NCCL reduces and FlatAdam consumes (activation Jacobians are
     applied inside the Adam kernel, gaussian_model.py:93-130,393-437)."""
 
-    def __init__(self, raw, F, device):
+    def __init__(self, raw, F, device, extra=0):
         import torch
         from online_lang_splatting_b200.sharding import FlatGradBuffer, FlatParams
         self.fp = FlatParams(raw, F, 1, device=device)
-        self.fg = FlatGradBuffer(self.fp.P, F, 1, device=device)
+        self.fg = FlatGradBuffer(self.fp.P, F, 1, device=device, extra=extra)
         self.active_sh_degree = self.max_sh_degree = 0
         self.is_language = True
         self.refresh()
@@ -250,9 +250,10 @@ def config5(args, emit, peaks, ClockSampler):
     op = g["opacities"].clamp(1e-6, 1 - 1e-6)
     raw = {"means3D": g["means3D"], "sh": g["shs"][:, :1, :], "opacity": torch.log(op / (1 - op)), "scales": torch.log(g["scales"]),
            "rotations": g["rotations"], "language": g["language"]}
-    pc = FlatGaussianModel({k: v.to(dev) for k, v in raw.items()}, 15, dev)
-    opt = FlatAdam(pc.fp.flat, pc.fg.flat, pc.fg.adam_groups(LR), capturable=True)
-    stats = SideStats(P, device=dev)
+    # gradients + the step's densification sums in one buffer -> one all-reduce per mapping iteration
+    pc = FlatGaussianModel({k: v.to(dev) for k, v in raw.items()}, 15, dev, extra=2 * P)
+    opt = FlatAdam(pc.fp.flat, pc.fg.grads, pc.fg.adam_groups(LR), capturable=True)
+    stats = SideStats(P, device=dev, delta=pc.fg.extra)
     pipe, bg = S.PipelineParams(), torch.zeros(3, device=dev)
     torch.manual_seed(0)
     general = AE.AutoencoderMLP(ENC2, DEC2).eval().to(dev)                     # 2-stage: 768 -> 32 (frozen)
@@ -340,8 +341,7 @@ def config5(args, emit, peaks, ClockSampler):
 
     def reduce_all():
         if world > 1:
-            pc.fg.all_reduce()
-            stats.all_reduce()
+            pc.fg.all_reduce()      # gradients + accum / denom deltas; max_radii2D is reduced when densification reads it
 
     # ---- static camera slots for the captured form ----------------------------------------------------------------
     def make_slot(uid):
@@ -492,6 +492,7 @@ def config5(args, emit, peaks, ClockSampler):
         torch.cuda.synchronize()
         dgr.CHECK_OVERFLOW = "deferred"
         assert bool(torch.isfinite(pc.fg.flat).all()), "non-finite gradients: a captured render overflowed its capacity"
+        stats.reduce_max_radii()
     if rank == 0:
         nf = args.steps
         line = {"metric": "render+AE FPS of the Replica-room0-shaped tracking+mapping loop (BASELINE configs[4])",

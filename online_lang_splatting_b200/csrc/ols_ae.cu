@@ -666,7 +666,10 @@ static int ae_forward(const ols_ae_plan* plan, const void* d_x, float* d_y, int6
         int rc = make_map(&p.tmap_x, d_x, p.x_bf16 != 0, (uint64_t)M, (uint64_t)p.K0_real, AE_M);
         if (rc != OLS_OK) return rc;
     }
-    const int grid = p.n_tiles < plan->sm_count ? p.n_tiles : plan->sm_count;
+    // OLS_AE_MAX_CTAS: cap on the persistent grid, e.g. to leave SMs to a collective that overlaps the encodes
+    static const int max_ctas = getenv("OLS_AE_MAX_CTAS") ? atoi(getenv("OLS_AE_MAX_CTAS")) : 0;
+    int grid = p.n_tiles < plan->sm_count ? p.n_tiles : plan->sm_count;
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
     static const bool trace_on = getenv("OLS_AE_TRACE") != nullptr;  // development aid: phase timeline of CTA 0 on stderr
     p.trace = nullptr;
     if (trace_on) {

@@ -1113,189 +1113,14 @@ __device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {  // per-component mul
 }
 
 // NCOL = 3: the pass blends rgb (+ background) and depth; NCOL = 0: language channels only (second pass of D/).
-template <int TILE, int NCOL, int F, bool BITEXACT>
-__global__ void __launch_bounds__(BLEND_THREADS, 4) k_blend(const __grid_constant__ BlendBatch bb) {
-    const BlendArgs& a = bb.v[blockIdx.y];
-    static_assert(TILE <= 16, "8 warps of 8x4 pixels cover at most 16x16");
-    static_assert(NCOL == 0 || NCOL == 3, "colour channels");
-    constexpr int NCH = NCOL + F;               // channels stored from REC_CH on (an odd count is zero-padded)
-    constexpr int REC = rec_floats_nch(NCH);
-    using Stage = RecordStage<NCOL, F>;
-    constexpr int OPS = Stage::OPS;             // cp.async pieces per record
-    constexpr int NPAIR = (NCH + 1) / 2;        // (r,g) (b,L0) (L1,L2) ... as stored
-    constexpr int EXT = REC - 2;
-    static_assert(REC_CH + 2 * NPAIR <= EXT, "channel pairs must not run into the extents");
-    __shared__ __align__(16) float s_rec[2][BLEND_BATCH * REC];
-    __shared__ uint32_t s_id[2][BLEND_BATCH];
-    __shared__ uint32_t s_hit[2][BLEND_THREADS / 32][BLEND_BATCH / 32];  // per warp: bit j = the warp blended entry j of the batch
-
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int tile_x = blockIdx.x % a.gx, tile_y = blockIdx.x / a.gx;
-    const int bx0 = (wid & 1) * 8, by0 = (wid >> 1) * 4;
-    const int lx = bx0 + (lane & 7), ly = by0 + (lane >> 3);
-    const int pxi = tile_x * TILE + lx, pyi = tile_y * TILE + ly;
-    const bool inside = lx < TILE && ly < TILE && pxi < a.W && pyi < a.H;
-    const float pfx = (float)pxi, pfy = (float)pyi;
-    if (tid < 2 * (BLEND_THREADS / 32) * (BLEND_BATCH / 32)) (&s_hit[0][0][0])[tid] = 0u;
-    // this warp's pixel rectangle, clipped to the tile and the image
-    const float fx0 = (float)(tile_x * TILE + bx0), fy0 = (float)(tile_y * TILE + by0);
-    const float fx1 = (float)min(min(tile_x * TILE + bx0 + 7, tile_x * TILE + TILE - 1), a.W - 1);
-    const float fy1 = (float)min(min(tile_y * TILE + by0 + 3, tile_y * TILE + TILE - 1), a.H - 1);
-
-    uint2 rg = a.ranges[blockIdx.x];
-    if (a.info->overflow) rg = make_uint2(0u, 0u);
-    const int total = (int)(rg.y - rg.x);
-    const int n_batches = (total + BLEND_BATCH - 1) / BLEND_BATCH;
-
-    auto flush_hits = [&](int b) {  // batch b is complete: its hit bytes go to global memory, the buffer is cleared
-        if (tid < BLEND_BATCH) {  // thread t gathers the byte of entry t from the 8 per-warp masks
-            uint32_t byte = 0;
-#pragma unroll
-            for (int w = 0; w < BLEND_THREADS / 32; w++) byte |= ((s_hit[b & 1][w][tid >> 5] >> (tid & 31)) & 1u) << w;
-            const int e = b * BLEND_BATCH + tid;
-            if (e < total) a.warp_hits[rg.x + e] = (uint8_t)byte;
-        }
-    };
-    auto issue = [&](int b) {  // cp.async the records of batch b into buffer b&1
-        const int cnt = min(BLEND_BATCH, total - b * BLEND_BATCH);
-        const int buf = b & 1;
-        // BLEND_THREADS / BLEND_BATCH threads share one record: one list lookup each, pieces dealt round-robin
-        constexpr int TPE = BLEND_THREADS / BLEND_BATCH;
-        const int g = tid / TPE;
-        if (g < cnt) {
-            const uint32_t id = a.point_list[rg.x + b * BLEND_BATCH + g];
-            if ((tid % TPE) == 0) s_id[buf][g] = id;
-#pragma unroll
-            for (int q = tid % TPE; q < OPS; q += TPE) Stage::copy(&s_rec[buf][g * REC], a.records, a.language, id, q);
-        }
-        cp_async_commit();
-    };
-
-    float T = 1.0f;
-    f32x2 acc2[NPAIR];
-#pragma unroll
-    for (int c = 0; c < NPAIR; c++) acc2[c] = 0ull;
-    float acc_d = 0.0f;
-    uint32_t last_contributor = 0;
-    bool done = !inside;
-
-    if (n_batches > 0) issue(0);
-    int b = 0;
-    for (; b < n_batches; b++) {
-        cp_async_wait<0>();
-        // all threads done -> stop (forward.cu:425-427); also publishes batch b and frees buffer (b+1)&1
-        if (__syncthreads_count(done) == BLEND_THREADS) break;
-        if (b > 0) flush_hits(b - 1);
-        if (b + 1 < n_batches) issue(b + 1);
-        const int cnt = min(BLEND_BATCH, total - b * BLEND_BATCH);
-        const float* rec = s_rec[b & 1];
-        const uint32_t* ids = s_id[b & 1];
-        const uint32_t cbase = (uint32_t)b * BLEND_BATCH;
-#pragma unroll 1
-        for (int half = 0; half < BLEND_BATCH / 32; half++) {
-            uint32_t myhits = 0, mytouch = 0;  // per lane: entries of this half this pixel blended / "touched" (T' > 0.5)
-            if (__all_sync(0xffffffffu, done)) { if (lane == 0) s_hit[b & 1][wid][half] = 0u; continue; }
-            const int e = half * 32 + lane;
-            bool hit = false;
-            if (e < cnt) {
-                const float2 c = *reinterpret_cast<const float2*>(rec + e * REC + REC_X);
-                const float2 h = *reinterpret_cast<const float2*>(rec + e * REC + EXT);
-                hit = (c.x + h.x >= fx0) && (c.x - h.x <= fx1) && (c.y + h.y >= fy0) && (c.y - h.y <= fy1);
-            }
-            unsigned m = __ballot_sync(0xffffffffu, hit);
-            while (m) {
-                const int jl = __ffs(m) - 1;
-                const int j = half * 32 + jl;
-                m &= m - 1;
-                const float* rj = rec + j * REC;
-                const uint32_t jbit = 1u << jl;
-                if (!done) {
-                    const float4 g0 = *reinterpret_cast<const float4*>(rj);      // x y A B
-                    const float4 g1 = *reinterpret_cast<const float4*>(rj + 4);  // C op pth depth
-                    const float dx = fsub(g0.x, pfx), dy = fsub(g0.y, pfy);
-                    const float power =
-                        ffma(ffma(dx, fmul(dx, g0.z), fmul(dy, fmul(dy, g1.x))), -0.5f, -fmul(dy, fmul(dx, g0.w)));
-                    if (!(power > 0.0f) && !(power < g1.z)) {
-                        const float alpha = fminf(fmul(g1.y, expf(power)), 0.99f);
-                        if (!(alpha < 1.0f / 255.0f)) {
-                            const float test_T = fmul(T, fsub(1.0f, alpha));
-                            if (test_T < 0.0001f) {
-                                done = true;
-                            } else {
-                                f32x2 v[NPAIR];
-#pragma unroll
-                                for (int p = 0; p + 1 < NPAIR; p += 2) {
-                                    const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(rj + REC_CH + 2 * p);
-                                    v[p] = t.x;
-                                    v[p + 1] = t.y;
-                                }
-                                if (NPAIR & 1)
-                                    v[NPAIR - 1] = *reinterpret_cast<const f32x2*>(rj + REC_CH + 2 * (NPAIR - 1));
-                                if (BITEXACT) {  // acc = fma(T, alpha * c, acc) like the compiled reference
-                                    const f32x2 a2 = pack2(alpha, alpha), T2 = pack2(T, T);
-#pragma unroll
-                                    for (int p = 0; p < NPAIR; p++) acc2[p] = ffma2(T2, fmul2(a2, v[p]), acc2[p]);
-                                    if (NCOL) acc_d = ffma(T, fmul(alpha, g1.w), acc_d);
-                                } else {
-                                    const float w = fmul(alpha, T);
-                                    const f32x2 w2 = pack2(w, w);
-#pragma unroll
-                                    for (int p = 0; p < NPAIR; p++) acc2[p] = ffma2(w2, v[p], acc2[p]);
-                                    if (NCOL) acc_d = ffma(w, g1.w, acc_d);
-                                }
-                                myhits |= jbit;
-                                if (test_T > 0.5f) mytouch |= jbit;
-                                T = test_T;
-                                last_contributor = cbase + (uint32_t)j + 1u;
-                            }
-                        }
-                    }
-                }
-            }
-            // once per 32 entries: which entries did the warp blend (for the backward), and the n_touched counts
-            const uint32_t hitmask = __reduce_or_sync(0xffffffffu, myhits);
-            if (lane == 0) s_hit[b & 1][wid][half] = hitmask;
-            for (uint32_t tmask = __reduce_or_sync(0xffffffffu, mytouch); tmask; tmask &= tmask - 1) {
-                const int jl = __ffs(tmask) - 1;
-                const unsigned tm = __ballot_sync(0xffffffffu, (mytouch >> jl) & 1u);
-                if (lane == 0) atomicAdd(&a.n_touched[ids[half * 32 + jl]], __popc(tm));
-            }
-        }
-    }
-    cp_async_wait<0>();
-    if (b > 0) {  // the last batch that was worked on (a `break` leaves before flushing it)
-        __syncthreads();
-        flush_hits(b - 1);
-    }
-    if (inside) {
-        const size_t HW = (size_t)a.W * a.H;
-        const size_t pix = (size_t)pyi * a.W + pxi;
-        float acc[2 * NPAIR];
-#pragma unroll
-        for (int p = 0; p < NPAIR; p++) unpack2(acc2[p], acc[2 * p], acc[2 * p + 1]);
-        a.final_T[pix] = T;
-        a.n_contrib[pix] = last_contributor;
-        if (NCOL) {
-#pragma unroll
-            for (int c = 0; c < NCOL; c++) a.out_color[c * HW + pix] = ffma(a.bg[c], T, acc[c]);
-            a.out_depth[pix] = acc_d;
-        }
-#pragma unroll
-        for (int c = 0; c < F; c++) a.out_language[c * HW + pix] = acc[NCOL + c];
-        a.out_opacity[pix] = fsub(1.0f, T);
-    }
-}
-
-
 // ---------------------------------------------------------------------------------------------------
-// Forward blend, two pixels per lane (the default).  One CTA of 128 threads per tile; each of the 4 warps owns an
+// Forward blend, two pixels per lane.  One CTA of 128 threads per tile; each of the 4 warps owns an
 // 8x8 pixel block -- lane l: column (l & 7), rows (l >> 3) and (l >> 3) + 4 -- so everything of a (block, Gaussian)
 // step that does not depend on the pixel row (list walk, the two header loads and the five channel loads from
 // shared memory, dx, dx*A, dx*B) is paid once per TWO pixels, and each lane carries two independent dependency
-// chains.  Per-pixel arithmetic, thresholds and accumulation order are those of k_blend (and, in BITEXACT mode, of
-// the compiled reference, forward.cu:437-483), so every output bit is unchanged.  The two 8x4 halves of a warp's block
-// are the pixel blocks of k_blend: the hit byte the backward reads (bit w = block w blended the entry) keeps its
-// meaning.  Without BITEXACT alpha uses ex2.approx(power * log2 e) (2 instructions instead of expf's 8; relative
+// chains.  Per-pixel arithmetic, thresholds and accumulation order are, in BITEXACT mode, those of the compiled
+// reference (forward.cu:437-483), so every output bit is equal to the reference's.  The two 8x4 halves of a warp's block
+// are the eight 8x4 pixel blocks the hit byte is defined over: bit w = block w = ((y / 4) * 2 + x / 8) blended the entry.  Without BITEXACT alpha uses ex2.approx(power * log2 e) (2 instructions instead of expf's 8; relative
 // error of alpha <= 4e-7, tests/test_forward_gpu.py states the tolerance); the backward then uses the same function
 // so that its blend / skip decisions agree with the forward's.
 // ---------------------------------------------------------------------------------------------------
@@ -1309,8 +1134,8 @@ __device__ __forceinline__ float fast_exp(float x) {
     return y;
 }
 
-template <int TILE, int NCOL, int F, bool BITEXACT, int MINB = B2_MIN_BLOCKS, int BB = BLEND_BATCH>
-__global__ void __launch_bounds__(B2_THREADS, MINB) k_blend2(const __grid_constant__ BlendBatch bb) {
+template <int TILE, int NCOL, int F, bool BITEXACT, int BB = BLEND_BATCH>
+__global__ void __launch_bounds__(B2_THREADS, B2_MIN_BLOCKS) k_blend2(const __grid_constant__ BlendBatch bb) {
     const BlendArgs& a = bb.v[blockIdx.y];
     static_assert(TILE <= 16, "4 warps of 8x8 pixels cover at most 16x16");
     static_assert(NCOL == 0 || NCOL == 3, "colour channels");
@@ -1519,27 +1344,11 @@ __global__ void __launch_bounds__(B2_THREADS, MINB) k_blend2(const __grid_consta
 
 template <int TILE, int NCOL, int F>
 static int launch_blend(const BlendBatch& ba, int n_tiles, int V, bool bitexact, cudaStream_t st) {
-    static const bool v1 = getenv("OLS_BLEND_V1") != nullptr;  // A/B aid: the one-pixel-per-lane kernel
     const dim3 grid(n_tiles, V);
-    if (v1) {
-        if (bitexact)
-            k_blend<TILE, NCOL, F, true><<<grid, BLEND_THREADS, 0, st>>>(ba);
-        else
-            k_blend<TILE, NCOL, F, false><<<grid, BLEND_THREADS, 0, st>>>(ba);
-        return 0;
-    }
-    if (bitexact) {
+    if (bitexact)
         k_blend2<TILE, NCOL, F, true><<<grid, B2_THREADS, 0, st>>>(ba);
-    } else if (TILE == 15 && NCOL == 3 && F == 15) {   // the headline shape: resident CTAs per SM selectable for A/B runs
-        static const int minb = getenv("OLS_B2_MINB") ? atoi(getenv("OLS_B2_MINB")) : B2_MIN_BLOCKS;
-        if (minb == 128) k_blend2<TILE, NCOL, F, false, 5, 128><<<grid, B2_THREADS, 0, st>>>(ba);       // batch of 128 records
-        else if (minb == 1284) k_blend2<TILE, NCOL, F, false, 4, 128><<<grid, B2_THREADS, 0, st>>>(ba);
-        else if (minb == 4) k_blend2<TILE, NCOL, F, false, 4><<<grid, B2_THREADS, 0, st>>>(ba);
-        else if (minb == 32) k_blend2<TILE, NCOL, F, false, 5, 32><<<grid, B2_THREADS, 0, st>>>(ba);
-        else k_blend2<TILE, NCOL, F, false><<<grid, B2_THREADS, 0, st>>>(ba);
-    } else {
+    else
         k_blend2<TILE, NCOL, F, false><<<grid, B2_THREADS, 0, st>>>(ba);
-    }
     return 0;
 }
 

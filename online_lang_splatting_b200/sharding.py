@@ -53,21 +53,26 @@ def balanced_views(costs: Sequence[float], world: int) -> List[List[int]]:
 class FlatGradBuffer:
     """One contiguous fp32 buffer holding every per-Gaussian parameter gradient of the rasterizer."""
 
-    def __init__(self, P: int, F: int, M: int = 1, device="cuda"):
+    def __init__(self, P: int, F: int, M: int = 1, device="cuda", extra: int = 0):
+        """``extra`` floats are appended to the buffer (``self.extra``) so that other per-step sums -- the densification
+        statistics -- travel in the same all-reduce; ``self.grads`` is the gradient part alone (what FlatAdam consumes)."""
         self.P, self.F, self.M = P, F, M
         groups: Sequence[Tuple[str, Tuple[int, ...]]] = (
             ("rotations", (P, 4)), ("means3D", (P, 3)), ("sh", (P, M, 3)), ("opacity", (P, 1)), ("scales", (P, 3)),
             ("language", (P, F)))
         self.groups = groups
         self.floats_per_gaussian = 3 + 3 * M + 1 + 3 + 4 + F
-        self.flat = torch.zeros(self.floats_per_gaussian * P, dtype=torch.float32, device=device)
+        n_grad = self.floats_per_gaussian * P
+        self.flat = torch.zeros(n_grad + int(extra), dtype=torch.float32, device=device)
+        self.grads = self.flat[:n_grad]
+        self.extra = self.flat[n_grad:]
         self.views: Dict[str, torch.Tensor] = {}
         o = 0
         for name, shape in groups:
             n = math.prod(shape)
             self.views[name] = self.flat[o:o + n].view(shape)
             o += n
-        assert o == self.flat.numel()
+        assert o == n_grad
 
     def zero_(self):
         self.flat.zero_()
@@ -136,9 +141,12 @@ class SideStats:
     ``denom``, MAX for ``max_radii2D`` (gaussian_model.py:965-969, utils/slam_backend.py:676-680) -- and added to the
     replicated running state, so all ranks take identical densification decisions."""
 
-    def __init__(self, P: int, device="cuda"):
+    def __init__(self, P: int, device="cuda", delta: torch.Tensor = None):
+        """``delta``: optional [2 P] view (e.g. ``FlatGradBuffer.extra``) so that the per-step sums are reduced together with
+        the gradients; the owner of that buffer then does the all-reduce."""
         self.P = P
-        self.delta = torch.zeros(2 * P, dtype=torch.float32, device=device)        # [accum P | denom P], one SUM
+        self.shared_delta = delta is not None
+        self.delta = delta if delta is not None else torch.zeros(2 * P, dtype=torch.float32, device=device)  # [accum P | denom P], one SUM
         self.delta_max = torch.zeros(P, dtype=torch.float32, device=device)        # one MAX
         self.xyz_gradient_accum = torch.zeros(P, 1, dtype=torch.float32, device=device)
         self.denom = torch.zeros(P, 1, dtype=torch.float32, device=device)
@@ -162,8 +170,17 @@ class SideStats:
     def all_reduce(self):
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.delta)
+            if not self.shared_delta:
+                dist.all_reduce(self.delta)
             dist.all_reduce(self.delta_max, op=dist.ReduceOp.MAX)
+        return self
+
+    def reduce_max_radii(self):
+        """Cross-rank MAX of the running ``max_radii2D``.  A running maximum commutes with the reduction, so this is only
+        needed when densification reads the statistic (every ``gaussian_update_every`` iterations), not every step."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.max_radii2D, op=dist.ReduceOp.MAX)
         return self
 
     def apply(self):

@@ -376,8 +376,6 @@ def main():
     flat = fbuf.flat
     opt = FlatAdam(fp.flat, fbuf.grads, fbuf.adam_groups(LR), capturable=True)   # step counter on the device: graph replays advance it
     stats = SideStats(P, device=dev, delta=fbuf.extra)
-    if world > 1:
-        os.environ.setdefault("OLS_AE_MAX_CTAS", "132")   # leave SMs for the NCCL kernels that overlap the encodes
     act = fp.activate()
     out_bufs = fbuf.backward_outputs({"colors": torch.empty(P, 3, device=dev), "cov3D": torch.empty(P, 6, device=dev),
                                       "means2D": torch.empty(KF, P, 3, device=dev), "tau_sum": torch.empty(KF, 6, device=dev)})
@@ -554,6 +552,34 @@ def main():
             ev.record(comm_stream)
         comm_done[0] = ev
 
+    def step_value_traced(tr):
+        """step_value with CUDA events between the phases (diagnostic, N > 1 with graphs only)"""
+        main_s = torch.cuda.current_stream(dev)
+        def mark():
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(main_s)
+            return e
+        t0 = mark()
+        graph_enc.replay()
+        t1 = mark()
+        if comm_done[0] is not None:
+            main_s.wait_event(comm_done[0])
+            t2 = mark()
+            graph_upd.replay()
+        else:
+            t2 = mark()
+        t3 = mark()
+        graph.replay()
+        t4 = mark()
+        with torch.cuda.stream(comm_stream):
+            comm_stream.wait_event(t4)
+            c0 = torch.cuda.Event(enable_timing=True); c0.record(comm_stream)
+            reduce_all()
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(comm_stream)
+        comm_done[0] = ev
+        tr.append((t0, t1, t2, t3, t4, c0, ev))
+
     def drain():
         if comm_done[0] is not None:
             torch.cuda.current_stream(dev).wait_event(comm_done[0])
@@ -581,6 +607,19 @@ def main():
         dist.all_reduce(t_, op=dist.ReduceOp.MAX)
         ms = float(t_.item())
     launches_per_step = count_graph_kernels([graph, graph_enc, graph_upd]) if graph is not None else None
+    phase_trace = None
+    if split and graph is not None and os.environ.get("OLS_BENCH_TRACE"):
+        tr = []
+        for _ in range(6):
+            step_value_traced(tr)
+        drain()
+        torch.cuda.synchronize()
+        rows = []
+        for (t0, t1, t2, t3, t4, c0, ev) in tr[1:]:
+            rows.append({"encode": t0.elapsed_time(t1), "wait_for_reduce": t1.elapsed_time(t2), "adam_stats": t2.elapsed_time(t3),
+                         "render": t3.elapsed_time(t4), "all_reduce": c0.elapsed_time(ev), "reduce_start_after_render": t4.elapsed_time(c0)})
+        phase_trace = {k: sum(r[k] for r in rows) / len(rows) for k in rows[0]}
+        sys.stderr.write(f"[phase trace rank {rank}] {phase_trace}\n")
     # second region, same K steps launched eagerly: CUDA events between the kernels give the per-kernel times
     Rs.clear()
     ms_eager, marks = timed(step_resident, args.steps, with_marks=True)

@@ -665,6 +665,21 @@ def main():
     if not args.no_e2e:
         e2e = run_e2e(args, torch, dist, dev, world, KF, H, W, ae, cams, pc, pipe, bg, clip_host, gt_host, render_batch, mapping_loss,
                       timed, frames, make_graph)
+        e2e["h2d_ceiling"] = h2d_ceiling(torch, dist, dev, world)
+        e2e["transfer_floor_ms_per_step"] = e2e["h2d_bytes_per_step"] / (e2e["h2d_ceiling"]["per_rank_GBps_min"] * 1e9) * 1e3
+        if not args.no_hr:
+            # the same step fed by what the reference's backbone really produces on the GPU side
+            from online_lang_splatting_b200 import supervised_net as SN
+            torch.manual_seed(11)
+            hr_net = SN.HighResLanguageFeatureNet().eval().to(dev)
+            for p_ in hr_net.parameters():
+                p_.requires_grad_(False)
+            hr_host = [(torch.randn(1, 768, 24, 24).pin_memory(), torch.randn(1, 384, 96, 96).pin_memory(),
+                        torch.randn(1, 192, 192, 192).pin_memory()) for _ in range(KF)]
+            for p_ in pc.parameters():
+                p_.grad = None
+            e2e["hr_input_variant"] = run_e2e(args, torch, dist, dev, world, KF, H, W, ae, cams, pc, pipe, bg, clip_host, gt_host,
+                                              render_batch, mapping_loss, timed, frames, make_graph, hr=(hr_net, hr_host))
 
     if rank != 0:
         if world > 1:
@@ -749,8 +764,38 @@ def main():
         dist.destroy_process_group()
 
 
+def h2d_ceiling(torch, dist, dev, world):
+    """Pinned-host -> device copy bandwidth with ALL ranks copying at the same time (the ceiling of the e2e number when the
+    step is transfer bound): 3 x 1 GiB per rank, barrier-bracketed, CUDA events."""
+    n = 1 << 28
+    h = torch.empty(n, dtype=torch.float32).pin_memory()
+    d = torch.empty(n, dtype=torch.float32, device=dev)
+    d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        d.copy_(h, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    gbps = 3 * n * 4 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    t = torch.tensor([gbps], device=dev)
+    lo = t.clone()
+    if world > 1:
+        dist.all_reduce(t)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    del h, d
+    return {"per_rank_GBps_min": float(lo.item()), "aggregate_GBps": float(t.item()), "ranks_copying_concurrently": world}
+
+
 def run_e2e(args, torch, dist, dev, world, KF, H, W, ae, cams, pc, pipe, bg, clip_host, gt_host, render_batch, mapping_loss, timed,
-            frames, make_graph):
+            frames, make_graph, hr=None):
+    """`hr`: None -> the host input of a keyframe is its 192x192x768 CLIP map (what the metric names); otherwise
+    (net, [(fv, f3, f2) pinned host tensors per keyframe]) -> the host input is what the reference's SED backbone hands to
+    the HR module (fv 24x24x768, res3, res2: 44 MB instead of 113 MB) and the map is produced on the device by
+    AutoencoderMLP.encode_hr (HR up-sampler + encoder, final_conv folded into the first Linear)."""
     """One mapping iteration through the public API with host-resident inputs: H2D of every keyframe's CLIP map and
     ground-truth RGB-D from pinned memory, encode, render_batch, mapping_loss per view, ONE backward, all-reduce of the
     parameter gradients (N > 1), D2H of the code maps and the loss."""
@@ -761,14 +806,23 @@ def run_e2e(args, torch, dist, dev, world, KF, H, W, ae, cams, pc, pipe, bg, cli
     # Double-buffered device staging: a step consumes slot s (filled while the previous step computed) and, at its very
     # start, queues the NEXT step's H2D copies into slot 1-s on the copy stream, so the PCIe link never idles and every
     # step still moves exactly one step's worth of inputs inside the timed region.
-    bufs = [[(torch.empty(192 * 192, 768, device=dev), torch.empty(3, H, W, device=dev), torch.empty(1, H, W, device=dev))
-             for _ in range(KF)] for _ in range(2)]
+    if hr is None:
+        bufs = [[(torch.empty(192 * 192, 768, device=dev), torch.empty(3, H, W, device=dev), torch.empty(1, H, W, device=dev))
+                 for _ in range(KF)] for _ in range(2)]
+    else:
+        hr_net, hr_host = hr
+        bufs = [[(tuple(torch.empty_like(t, device=dev) for t in hr_host[k]), torch.empty(3, H, W, device=dev),
+                  torch.empty(1, H, W, device=dev)) for k in range(KF)] for _ in range(2)]
 
     def issue_copies(slot):
         with torch.cuda.stream(copy_stream):
             for k in range(KF):
                 x, rgb, d = bufs[slot][k]
-                x.copy_(clip_host[k], non_blocking=True)
+                if hr is None:
+                    x.copy_(clip_host[k], non_blocking=True)
+                else:
+                    for dst, src in zip(x, hr_host[k]):
+                        dst.copy_(src, non_blocking=True)
                 rgb.copy_(gt_host[k][0], non_blocking=True)
                 d.copy_(gt_host[k][1], non_blocking=True)
 
@@ -781,7 +835,10 @@ def run_e2e(args, torch, dist, dev, world, KF, H, W, ae, cams, pc, pipe, bg, cli
         for k in range(KF):
             x, gt_rgb, gt_d = bufs[slot][k]
             with torch.no_grad():
-                code = ae.encode(x)                                  # [36864, 15] -> gt_lang_feat (slam_backend.py:557-576)
+                if hr is None:
+                    code = ae.encode(x)                              # [36864, 15] -> gt_lang_feat (slam_backend.py:557-576)
+                else:
+                    code = ae.encode_hr(hr_net, *x).view(-1, 15)     # slam_backend.py:381-395: hr_model(...) then encode
             code_host[k].copy_(code, non_blocking=True)              # the reference keeps it on the CPU (:576)
             gt_lang = code.t().reshape(15, 192, 192)
             loss = mapping_loss(outs[k]["render"], outs[k]["depth"], gt_rgb, gt_d, outs[k]["language"], gt_lang, alpha=0.95,
@@ -843,11 +900,15 @@ def run_e2e(args, torch, dist, dev, world, KF, H, W, ae, cams, pc, pipe, bg, cli
     for _ in range(2):
         step_e2e()
     ms_e, _ = timed(step_e2e, args.steps)
-    h2d = KF * (192 * 192 * 768 * 4 + 3 * H * W * 4 + H * W * 4)
+    per_kf = 192 * 192 * 768 * 4 if hr is None else sum(t.numel() * 4 for t in hr_host[0])
+    h2d = KF * (per_kf + 3 * H * W * 4 + H * W * 4)
     d2h = KF * (192 * 192 * 15 * 4) + 4
     return {"value": frames / (ms_e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "ms_per_step": ms_e / args.steps,
-            "api": "gaussian_renderer.render_batch() + AutoencoderMLP.encode() + losses.mapping_loss(), one loss.backward(); default module flags",
+            "api": ("gaussian_renderer.render_batch() + AutoencoderMLP.encode() + losses.mapping_loss(), one loss.backward(); default module flags"
+                    if hr is None else
+                    "gaussian_renderer.render_batch() + AutoencoderMLP.encode_hr(HighResLanguageFeatureNet, fv, res3, res2) + losses.mapping_loss(), one loss.backward()"),
+            "host_input": "192x192x768 fp32 CLIP map per keyframe (113 MB)" if hr is None else "fv 24x24x768 + res3 96x96x384 + res2 192x192x192 per keyframe (44 MB): the HR module runs on the device",
             "h2d_GBps_achieved": h2d / (ms_e / args.steps * 1e-3) / 1e9,
             "pipelining": "the H2D copies of step i+1 run on a copy stream under the kernels of step i (two staging slots); one step's "
                           "inputs cross the link per step inside the timed region",

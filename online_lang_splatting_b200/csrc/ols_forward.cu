@@ -1,22 +1,23 @@
 // ols_forward.cu -- forward pass of the language-feature Gaussian rasterizer for sm_100a.
 //
-// Pipeline (all on the caller's stream, no host synchronisation, fixed launch geometry -> graph capturable):
-//   k_preprocess        one thread per Gaussian: cull / project / covariance / conic / radius / tile rect, packs the
-//                       16-float colour record, counts instances per tile in per-CTA shared-memory histograms
-//                                                                               (reference: forward.cu:262-371)
+// Pipeline (all on the caller's stream, no host synchronisation, fixed launch geometry -> graph capturable).  Every
+// kernel covers the V views of a batch (grid.y = view; V = 1 is the reference's call):
+//   k_preprocess        one thread per Gaussian, ALL views of its group: the parameters are read and the 3D covariance is
+//                       computed once, then per view cull / project / cov2D / conic / radius / tile rect, the 16-float
+//                       colour record, and per-CTA shared-memory tile histograms      (reference: forward.cu:262-371)
 //   k_preprocess_dis    the same for the two footprints of the disentangled variant   (D/forward.cu:262-430)
 //   k_tile_offsets      column scan of the per-CTA histograms -> per-CTA write cursors and per-tile counts
 //   k_tile_scan         one CTA: exclusive scan of per-tile counts -> ranges, R        (replaces the InclusiveSum over
 //                       Gaussians + D2H read of rasterizer_impl.cu:451-455 and identifyTileRanges :116-138)
-//   k_scatter           writes (depth_bits << 32 | id) into the tiles' buckets; a warp spreads its Gaussians'
-//                       (Gaussian, tile) instances evenly over its lanes           (reference: duplicateWithKeys :70-111)
-//   k_sort_tiles_bucket one CTA per tile: distribution into depth buckets + exact in-bucket ranking in shared memory
+//   k_scatter           writes the Gaussian id (4 bytes) of every (Gaussian, tile) instance into the tile's bucket; a warp
+//                       spreads its instances evenly over its lanes                (reference: duplicateWithKeys :70-111)
+//   k_sort_tiles_bucket one CTA per tile: gathers the depths, distribution into depth buckets + exact in-bucket ranking
 //   k_sort_tiles_radix  tiles the bucket path declines (clumped / tied depths): LSD radix sort in shared memory
 //   k_sort_tiles        tiles longer than 4096 entries: bitonic sort, wide strides in global memory
 //                       (together they replace the global 44-bit cub::DeviceRadixSort of :478-483; the result order
 //                       is identical: (tile, depth bits, id) ascending)
-//   k_blend             one CTA per tile, one warp per 8x4 pixel block: front-to-back alpha blend of RGB + depth + F
-//                       language channels with per-warp culling                     (reference: forward.cu:377-513)
+//   k_blend2            one CTA of 4 warps per tile, a warp per 8x8 pixel block, two pixels per lane: front-to-back alpha
+//                       blend of RGB + depth + F language channels with per-warp culling  (reference: forward.cu:377-513)
 //
 // Bit-exactness: the per-Gaussian arithmetic mirrors the compiled reference operation by operation
 // (oracle/REF_ARITHMETIC.md), written with explicit-rounding intrinsics so that radii, tile rects,
@@ -285,8 +286,13 @@ __device__ __forceinline__ bool preprocess_view(const PreArgs& a, const PreView&
     pv.radii[i] = ri;
     ((uint2*)(ws + a.o_rect))[i] = make_uint2((uint32_t)mn[0] | ((uint32_t)mn[1] << 16), (uint32_t)mx[0] | ((uint32_t)mx[1] << 16));
     tiles_touched[i] = tiles;
-    for (int y = mn[1]; y < mx[1]; y++)
-        for (int x = mn[0]; x < mx[0]; x++) atomicAdd(&s_hist[y * a.gx + x], 1u);
+    // one flat loop over the rect (a warp runs max(tiles) rounds; the nested form ran max(height) * max(width))
+    int x = mn[0], t_idx = mn[1] * a.gx + mn[0];
+    for (uint32_t t = 0; t < tiles; t++) {
+        atomicAdd(&s_hist[t_idx], 1u);
+        t_idx++;
+        if (++x == mx[0]) { x = mn[0]; t_idx += a.gx - (mx[0] - mn[0]); }
+    }
     return true;
 }
 
@@ -724,6 +730,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_sort_tiles_bucket(const __grid_c
     bool finite = true;
 #pragma unroll
     for (int r = 0; r < BS_ITEMS; r++) {
+        if (r * BS_THREADS >= n) break;  // uniform: rounds past the tile's length are skipped, not predicated off
         const int idx = r * BS_THREADS + tid;
         if (idx < n) {
             const uint32_t id = point_list[rg.x + idx];   // the scatter wrote bare ids: the depth half of the key is gathered here
@@ -756,7 +763,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_sort_tiles_bucket(const __grid_c
     };
 #pragma unroll
     for (int r = 0; r < BS_ITEMS; r++)
-        if (r * BS_THREADS + tid < n) atomicAdd(&s_cnt[bucket_of(k[r])], 1u);
+        if (r * BS_THREADS >= n) break; else if (r * BS_THREADS + tid < n) atomicAdd(&s_cnt[bucket_of(k[r])], 1u);
     __syncthreads();
     // exclusive scan of the counters (thread t owns BS_NB / BS_THREADS consecutive ones) + largest bucket
     constexpr int PER = BS_NB / BS_THREADS;
@@ -780,12 +787,13 @@ __global__ void __launch_bounds__(BS_THREADS) k_sort_tiles_bucket(const __grid_c
     // distribute: afterwards s_cnt[b] is the END of bucket b (its start is the end of bucket b - 1)
 #pragma unroll
     for (int r = 0; r < BS_ITEMS; r++)
-        if (r * BS_THREADS + tid < n) s_key[atomicAdd(&s_cnt[bucket_of(k[r])], 1u)] = k[r];
+        if (r * BS_THREADS >= n) break; else if (r * BS_THREADS + tid < n) s_key[atomicAdd(&s_cnt[bucket_of(k[r])], 1u)] = k[r];
     __syncthreads();
     // exact position inside the bucket = number of its keys that compare lower
     uint32_t pos[BS_ITEMS];
 #pragma unroll
     for (int r = 0; r < BS_ITEMS; r++) {
+        if (r * BS_THREADS >= n) break;  // uniform: rounds past the tile's length are skipped, not predicated off
         if (r * BS_THREADS + tid < n) {
             const int b = bucket_of(k[r]);
             const uint32_t s0 = b ? s_cnt[b - 1] : 0u, s1 = s_cnt[b];
@@ -797,7 +805,7 @@ __global__ void __launch_bounds__(BS_THREADS) k_sort_tiles_bucket(const __grid_c
     __syncthreads();  // every thread has finished reading the bucketed array: overwrite it in final order
 #pragma unroll
     for (int r = 0; r < BS_ITEMS; r++)
-        if (r * BS_THREADS + tid < n) s_key[pos[r]] = k[r];
+        if (r * BS_THREADS >= n) break; else if (r * BS_THREADS + tid < n) s_key[pos[r]] = k[r];
     __syncthreads();
     for (int i = tid; i < n; i += BS_THREADS) {  // coalesced write-out
         const unsigned long long v = s_key[i];
@@ -1061,13 +1069,11 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_tiles(const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Forward blend (forward.cu:377-513).  One CTA of 256 threads per tile; each of the 8 warps owns an
-// 8x4 pixel block of the tile (2 x 4 blocks cover 16x16; lanes beyond TILE only help fetching).  The
-// tile's Gaussian records are streamed global -> shared with cp.async in double-buffered batches.
-// Every warp first tests 32 records at a time -- one per lane -- against its own pixel block using the
-// record's conservative half-extents (a Gaussian that cannot reach alpha >= 1/255 anywhere in the block
-// is skipped by every pixel of the reference as well), ballots, and then runs the per-pixel evaluation
-// only for the surviving records.  The channel accumulators are updated with packed FFMA2.
+// Forward blend (forward.cu:377-513).  The tile's Gaussian records are streamed global -> shared with cp.async in
+// double-buffered batches.  Every warp first tests 32 records at a time -- one per lane -- against its own pixel block
+// using the record's conservative half-extents (a Gaussian that cannot reach alpha >= 1/255 anywhere in the block is
+// skipped by every pixel of the reference as well), ballots, and then runs the per-pixel evaluation only for the
+// surviving records.  The channel accumulators are updated with packed FFMA2.
 // ---------------------------------------------------------------------------------------------------
 constexpr int BLEND_THREADS = 256;
 constexpr int BLEND_BATCH = 64;

@@ -631,6 +631,35 @@ def main():
     frames = world * KF * args.steps
     value = frames / (ms * 1e-3)
 
+    # ---- the true-gradient configuration (16x16 tiles, exact backward) on the same keyframes: render forward + backward only ----
+    exact16 = None
+    if rank == 0 and not args.per_view and (args.tile, args.backward_mode) != (16, "exact"):
+        try:
+            rs_alt = [r_._replace(tile_size=16, backward_mode="exact") for r_ in rs_list]
+            def step_alt():
+                outs, st = dgr._forward_native_batch(*params_tuple(), rs_alt)
+                dgr._backward_native_batch(st, [o[2] for o in outs], [wc] * KF, [wl] * KF, [wd] * KF, out=out_bufs, accumulate=False)
+            dgr.CHECK_OVERFLOW = "sync"
+            for _ in range(2):
+                step_alt()
+            dgr.CHECK_OVERFLOW = "deferred"
+            torch.cuda.synchronize()
+            n_alt = 5
+            N.timing_begin(n_alt * 16 + 64)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(n_alt):
+                step_alt()
+            a1.record()
+            torch.cuda.synchronize()
+            m_alt = N.timing_end()
+            exact16 = {"config": "tile 16x16, backward_mode exact (mathematically exact gradients, no reference quirks)",
+                       "render_fwd_bwd_ms_per_view": a0.elapsed_time(a1) / n_alt / KF,
+                       "ms_per_view": {t_: tot_ / max(cnt_, 1) / KF for t_, (tot_, cnt_) in m_alt.items() if cnt_}}
+        except Exception as ex:  # pragma: no cover
+            exact16 = {"error": str(ex)[:200]}
+            dgr.CHECK_OVERFLOW = "deferred"
+
     # ---- multi-GPU correctness: the N-rank reduced buffer equals the 1-rank sum over the same world x KF views ----
     reduce_check = None
     if world > 1:
@@ -747,7 +776,7 @@ def main():
             "vs_baseline": None, "dtype": "f32 (rasterizer, loss, Adam); autoencoder: tf32 first layer + bf16 inner layers, fp32 accumulate",
             "data": "synthetic", "config": workload_config(args),
             "roofline": roofline, "kernels": per_kernel, "cpu_baseline": cpu, "e2e": e2e,
-            "hr_module": hr, "fast_exp_blend": fast_exp, "reduce_check": reduce_check,
+            "hr_module": hr, "fast_exp_blend": fast_exp, "reduce_check": reduce_check, "exact_tile16": exact16,
             "gpu_launches": args.steps * launches_per_step,
             "gpu_launches_per_step": launches_per_step,
             "gpu_launches_source": "kernel nodes of the replayed CUDA graphs (cudaGraphGetNodes)" if graph is not None else "launch list of the eager step",

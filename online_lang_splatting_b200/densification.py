@@ -52,7 +52,14 @@ def densify_flags(xyz_gradient_accum: torch.Tensor, denom: torch.Tensor, scaling
                   max_radii2D: torch.Tensor, *, max_grad: float, min_opacity: float, extent: float,
                   max_screen_size: Optional[float], percent_dense: float = 0.01) -> Tuple[torch.Tensor, torch.Tensor]:
     """-> (flags uint8 [P] with bits CLONE | SPLIT | PRUNE, counts int32 [3]).  ``scaling_raw`` / ``opacity_raw`` are the
-    stored parameters (log-scales [P,1|3], opacity logits [P,1])."""
+    stored parameters (log-scales [P,1|3], opacity logits [P,1]).
+
+    All three masks are evaluated on the state BEFORE densification, in one pass.  The reference evaluates them in
+    sequence (gaussian_model.py:948-963): clone, then split on the set that already holds the clones (whose padded
+    gradients are zero, so no clone is split), then prune on the set after clone + split (so the new points are
+    tested and the removed split parents are not).  A caller that reproduces ``densify_and_prune`` must therefore apply
+    CLONE first, SPLIT second (removing the parents), and evaluate the prune criterion again for the appended points;
+    PRUNE as returned here is exact for the points that survive unchanged."""
     N.require_cuda()
     P = int(opacity_raw.shape[0])
     for t, n in ((xyz_gradient_accum, "xyz_gradient_accum"), (denom, "denom"), (scaling_raw, "scaling"),

@@ -215,8 +215,15 @@ class LangSupervisedNet(nn.Module):
         return self.model(fv, f3, f2)
 
     @classmethod
-    def load_from_checkpoint(cls, path: str, map_location="cpu", **kwargs) -> "LangSupervisedNet":
-        ckpt = torch.load(path, map_location=map_location, weights_only=False)
+    def load_from_checkpoint(cls, path: str, map_location="cpu", allow_pickle: bool = False, **kwargs) -> "LangSupervisedNet":
+        """Reads the ``state_dict`` of a reference (Lightning) checkpoint.  Tensors-only loading is tried first; a
+        checkpoint that needs arbitrary unpickling (it can execute code) is only read with ``allow_pickle=True``."""
+        try:
+            ckpt = torch.load(path, map_location=map_location, weights_only=True)
+        except Exception:
+            if not allow_pickle:
+                raise
+            ckpt = torch.load(path, map_location=map_location, weights_only=False)
         net = cls(**kwargs)
         net.load_state_dict(ckpt["state_dict"] if "state_dict" in ckpt else ckpt)
         return net

@@ -4,7 +4,7 @@
 // cpu_baseline / --impl reference legs of bench.py may load this library.  The
 // product path (online_lang_splatting_b200/) never links, imports or calls it.
 //
-// Parity status: PINNED.  This restatement is checked (tests/test_oracle_golden.py)
+// Parity status: PINNED.  This restatement is checked (tests/test_oracle.py)
 // against tests/golden/*.npz, which hold inputs and outputs of the *real*
 // reference CUDA (submodules/diff-gaussian-rasterization compiled unmodified into
 // oracle/_ref/ref_P_C.so by oracle/build_ref.py and executed on a B200 by

@@ -77,11 +77,70 @@ vg = torch.randn(P, 3, device=dev) * 1e-3
 mr, acc, den = torch.zeros(P, device=dev), torch.zeros(P, 1, device=dev), torch.zeros(P, 1, device=dev)
 mr2, acc2, den2 = mr.clone(), acc.clone(), den.clone()
 entry("densify_stats", timeit(lambda: DN.update_stats(radii, vg, mr, acc, den)),
-      timeit(lambda: DN.reference_update_stats(radii, vg, mr2, acc2, den2)), P * (4 + 8 + 3 * 8 * 0.6), "1M Gaussians, 60 % visible")
+      timeit(lambda: TO.reference_update_stats(radii, vg, mr2, acc2, den2)), P * (4 + 8 + 3 * 8 * 0.6), "1M Gaussians, 60 % visible")
 sc, op = torch.randn(P, 3, device=dev) - 3, torch.randn(P, 1, device=dev)
 kw = dict(max_grad=2e-4, min_opacity=0.3, extent=4.0, max_screen_size=20.0)
 entry("densify_flags", timeit(lambda: DN.densify_flags(acc, den, sc, op, mr, **kw)),
-      timeit(lambda: DN.reference_densify_flags(acc.clone(), den, sc, op, mr, **kw)), P * (4 + 4 + 12 + 4 + 4 + 1), "1M Gaussians")
+      timeit(lambda: TO.reference_densify_flags(acc.clone(), den, sc, op, mr, **kw)), P * (4 + 4 + 12 + 4 + 4 + 1), "1M Gaussians")
+
+# ---- online autoencoder training step (a17): fused kernel vs the reference's torch sequence (slam_backend.py:266-323) ----
+import copy
+from online_lang_splatting_b200 import autoencoder as AE
+torch.manual_seed(0)
+on_ref = AE.EncoderDecoderOnline().to(dev)
+on_fused = copy.deepcopy(on_ref)
+feats = torch.randn(192 * 192, 32, device=dev)
+feats = feats / feats.norm(dim=-1, keepdim=True)
+o_opt = torch.optim.Adam(on_ref.parameters(), lr=1e-3)
+def torch_online_step():
+    on_ref.train()
+    o_opt.zero_grad()
+    comp = on_ref.encode(feats)
+    recon = on_ref.decode(comp)
+    loss = torch.nn.functional.l1_loss(recon, feats) + 0.6 * (1 - torch.nn.functional.cosine_similarity(recon, feats, dim=1).mean())
+    loss.backward()
+    o_opt.step()
+entry("online_ae_train_step", timeit(lambda: on_fused.fused_train_step(feats, lr=1e-3)), timeit(torch_online_step),
+      192 * 192 * (32 + 15) * 4, "36,864 rows x 32; forward + L1 + 0.6 (1 - cos) + backward + Adam; reference = the module's torch graph + torch.optim.Adam")
+
+# ---- tracking pose step: fused kernel vs torch Adam + the reference's update_pose arithmetic on the device ----
+from online_lang_splatting_b200.tracking import DeviceCamera, PoseOptimizer
+cam = DeviceCamera(W, H, W / 2.0, W / 2.0, (W - 1) / 2.0, (H - 1) / 2.0, torch.eye(3), torch.zeros(3), device=dev)
+popt = PoseOptimizer(cam)
+def fused_pose():
+    cam._grad_tau.fill_(1e-3)
+    popt.step()
+rot, trans = torch.nn.Parameter(torch.zeros(3, device=dev)), torch.nn.Parameter(torch.zeros(3, device=dev))
+ea, eb = torch.nn.Parameter(torch.zeros(1, device=dev)), torch.nn.Parameter(torch.zeros(1, device=dev))
+t_opt = torch.optim.Adam([{"params": [rot], "lr": 0.003}, {"params": [trans], "lr": 0.001}, {"params": [ea], "lr": 0.01}, {"params": [eb], "lr": 0.01}])
+Rm, Tm = torch.eye(3, device=dev), torch.zeros(3, device=dev)
+def skew(x):
+    m = torch.zeros(3, 3, device=dev)
+    m[0, 1], m[0, 2], m[1, 0], m[1, 2], m[2, 0], m[2, 1] = -x[2], x[1], x[2], -x[0], -x[1], x[0]
+    return m
+def torch_pose():
+    global Rm, Tm
+    for p_ in (rot, trans, ea, eb):
+        p_.grad = torch.full_like(p_, 1e-3)
+    t_opt.step()
+    with torch.no_grad():      # utils/pose_utils.py:24-95 (SO3_exp, V, SE3_exp, update_pose) incl. its host-side branches
+        tau = torch.cat([trans, rot])
+        Wm = skew(tau[3:]); W2 = Wm @ Wm
+        angle = torch.norm(tau[3:])
+        I = torch.eye(3, device=dev)
+        if angle < 1e-5:
+            Rd, Vm = I + Wm + 0.5 * W2, I + 0.5 * Wm + W2 / 6.0
+        else:
+            Rd = I + (torch.sin(angle) / angle) * Wm + ((1 - torch.cos(angle)) / angle ** 2) * W2
+            Vm = I + Wm * ((1.0 - torch.cos(angle)) / angle ** 2) + W2 * ((angle - torch.sin(angle)) / angle ** 3)
+        T4 = torch.eye(4, device=dev); T4[:3, :3] = Rd; T4[:3, 3] = Vm @ tau[:3]
+        Tw = torch.eye(4, device=dev); Tw[:3, :3] = Rm; Tw[:3, 3] = Tm
+        new = T4 @ Tw
+        Rm, Tm = new[:3, :3], new[:3, 3]
+        converged = bool(tau.norm() < 1e-4)
+        rot.data.fill_(0); trans.data.fill_(0)
+        wv = new.t(); fp_ = wv @ cam.projection_matrix; cc = wv.inverse()[3, :3]
+entry("tracking_pose_step", timeit(fused_pose), timeit(torch_pose), 0, "Adam over rot / trans / exposure + SE3_exp + camera matrices; reference = torch.optim.Adam + pose_utils.update_pose + Camera properties")
 
 # ---- distCUDA2 ----
 pts = torch.rand(P, 3, device=dev) * 4

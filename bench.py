@@ -388,6 +388,7 @@ def main():
             tile_size=args.tile, backward_mode=args.backward_mode)
 
     rs_list = [settings_of(cam) for cam in cams]
+    rank_render_ms = None
     empty = torch.Tensor([])
     Rs = []
     view_ids = [rank * KF + k for k in range(KF)]
@@ -491,9 +492,42 @@ def main():
         all_cost = [torch.zeros(KF, device=dev) for _ in range(world)]
         dist.all_gather(all_cost, cost)
         flat_cost = torch.cat(all_cost).tolist()          # index = global view id (rank-major blocks)
-        view_ids = balanced_views(flat_cost, world)[rank]
+        # refinement: the cost of a view inside a batched launch is not exactly its stand-alone cost.  Every rank measures
+        # its BATCHED render time, the per-view costs of each rank are rescaled so that they add up to it, and the views
+        # are dealt again; the assignment with the smallest slowest-rank time is kept (same data on every rank).
+        assign = balanced_views(flat_cost, world)
+        best = None
+        for rnd in range(4):
+            view_ids = assign[rank]
+            cams[:] = [S.make_camera(W, H, view=v, seed=0, device=str(dev)) for v in view_ids]
+            rs_list[:] = [settings_of(cam) for cam in cams]
+            phase_render()
+            torch.cuda.synchronize()
+            t_best = 1e9
+            for _ in range(3):
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                phase_render()
+                a1.record()
+                torch.cuda.synchronize()
+                t_best = min(t_best, a0.elapsed_time(a1))
+            tr = [torch.zeros(1, device=dev) for _ in range(world)]
+            dist.all_gather(tr, torch.tensor([t_best], device=dev))
+            times = [float(t_.item()) for t_ in tr]
+            if best is None or max(times) < best[0]:
+                best = (max(times), [list(a_) for a_ in assign], times)
+            if max(times) <= 1.01 * (sum(times) / world) or rnd == 3:
+                break
+            for r_ in range(world):
+                scale = times[r_] / max(sum(flat_cost[v] for v in assign[r_]), 1e-9)
+                for v in assign[r_]:
+                    flat_cost[v] *= scale
+            assign = balanced_views(flat_cost, world)
+        assign, rank_render_ms = best[1], best[2]
+        view_ids = assign[rank]
         cams[:] = [S.make_camera(W, H, view=v, seed=0, device=str(dev)) for v in view_ids]
         rs_list[:] = [settings_of(cam) for cam in cams]
+        sys.stderr.write(f"[balance rank {rank}] batched render ms per rank: {[round(t_, 3) for t_ in rank_render_ms]}\n")
         for _ in range(2):
             step_resident()
         torch.cuda.synchronize()
@@ -777,6 +811,7 @@ def main():
             "data": "synthetic", "config": workload_config(args),
             "roofline": roofline, "kernels": per_kernel, "cpu_baseline": cpu, "e2e": e2e,
             "hr_module": hr, "fast_exp_blend": fast_exp, "reduce_check": reduce_check, "exact_tile16": exact16,
+            "rank_render_ms_after_balancing": rank_render_ms,
             "gpu_launches": args.steps * launches_per_step,
             "gpu_launches_per_step": launches_per_step,
             "gpu_launches_source": "kernel nodes of the replayed CUDA graphs (cudaGraphGetNodes)" if graph is not None else "launch list of the eager step",

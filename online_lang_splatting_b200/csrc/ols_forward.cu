@@ -1297,14 +1297,17 @@ __global__ void __launch_bounds__(B2_THREADS, B2_MIN_BLOCKS) k_blend2(const __gr
                                     myhits[p] |= jbit;
                                     if (test_T > 0.5f) mytouch[p] |= jbit;
                                     T[p] = test_T;
-                                    last_contributor[p] = cbase + (uint32_t)j + 1u;
                                 }
                             }
                         }
                     }
                 }
             }
-            // once per 32 entries: which entries did each 8x4 half blend (for the backward), and the n_touched counts
+            // once per 32 entries: the pixel's last contributor so far (its highest hit bit), which entries each 8x4 half
+            // blended (for the backward), and the n_touched counts
+#pragma unroll
+            for (int p = 0; p < 2; p++)
+                if (myhits[p]) last_contributor[p] = cbase + (uint32_t)(half * 32) + (32u - (uint32_t)__clz(myhits[p]));
             const uint32_t h0 = __reduce_or_sync(0xffffffffu, myhits[0]), h1 = __reduce_or_sync(0xffffffffu, myhits[1]);
             if (lane == 0) { s_hit[b & 1][blk0][half] = h0; s_hit[b & 1][blk1][half] = h1; }
             for (uint32_t tmask = __reduce_or_sync(0xffffffffu, mytouch[0] | mytouch[1]); tmask; tmask &= tmask - 1) {

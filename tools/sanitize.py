@@ -52,5 +52,45 @@ mr, acc, den = torch.zeros(P, device=dev), torch.zeros(P, 1, device=dev), torch.
 DN.update_stats(radii, torch.randn(P, 3, device=dev), mr, acc, den)
 fl, cnt = DN.densify_flags(acc, den, torch.randn(P, 3, device=dev), torch.randn(P, 1, device=dev), mr, max_grad=0.5,
                            min_opacity=0.3, extent=4.0, max_screen_size=20.0)
+# round 2: multi-view batch (forward + backward, fused statistics), flat Adam with activation Jacobians + device step count,
+# parameter activation, fused online-AE training step, fused pose step, fp32 parity mode of the autoencoder
+from online_lang_splatting_b200 import synthetic as S, diff_gaussian_rasterization as dgr
+import online_lang_splatting_b200.gaussian_renderer as GR
+g_ = S.make_gaussians(1700, 15, 100, 70, seed=6, scale_px_sigma=0.08)
+pc = S.SyntheticGaussianModel(g_, device=dev, requires_grad=True)
+for mode in ("compat", "exact"):
+    GR.BACKWARD_MODE = mode
+    cams = [S.make_camera(100, 70, view=v, seed=6, device="cuda") for v in range(3)]
+    outs = GR.render_batch(cams, pc, S.PipelineParams(), torch.zeros(3, device=dev))
+    sum((o["render"].sum() + o["language"].sum() + o["depth"].sum()) for o in outs).backward()
+GR.BACKWARD_MODE = "compat"
+scs = [U.make_scene(P=900, F=15, W=64, H=48, seed=2, view=v, scale=0.1) for v in range(2)]
+d_ = lambda k: scs[0][k].to(dev)
+e_ = torch.Tensor([])
+rsl = [U.settings(sc_, dev, bitexact=False)._replace(debug=False) for sc_ in scs]
+bo, bst = dgr._forward_native_batch(d_("means3D"), d_("shs"), e_, d_("language"), d_("opacities"), d_("scales"), d_("rotations"), e_, rsl)
+w_ = [t.to(dev) for t in U.loss_weights(15, 64, 48, seed=4)]
+stt = (torch.zeros(900, device=dev), torch.zeros(900, device=dev), torch.zeros(900, device=dev))
+dgr._backward_native_batch(bst, [o[2] for o in bo], [w_[0]] * 2, [w_[1]] * 2, [w_[2]] * 2, out={"stats": stt})
+from online_lang_splatting_b200.sharding import FlatParams, FlatGradBuffer
+raw = {"means3D": torch.randn(333, 3), "sh": torch.randn(333, 4, 3), "opacity": torch.randn(333, 1), "scales": torch.randn(333, 3),
+       "rotations": torch.randn(333, 4), "language": torch.randn(333, 15)}
+fpar = FlatParams({k: v.to(dev) for k, v in raw.items()}, 15, 4, device=dev)
+fgr = FlatGradBuffer(333, 15, 4, device=dev, extra=666)
+fgr.flat.normal_()
+lr = {"xyz": 1e-4, "f_dc": 2.5e-3, "opacity": 0.05, "scaling": 1e-3, "rotation": 1e-3, "f_language": 2.5e-3}
+fa = FlatAdam(fpar.flat, fgr.grads, fgr.adam_groups(lr), capturable=True)
+fa.step(); fpar.activate(); fa.step()
+online = AE.EncoderDecoderOnline().to(dev)
+feats = torch.randn(1000, 32, device=dev)
+online.fused_train_step(feats / feats.norm(dim=-1, keepdim=True)); online.fused_train_step(feats / feats.norm(dim=-1, keepdim=True))
+from online_lang_splatting_b200.tracking import DeviceCamera, PoseOptimizer
+cam = DeviceCamera(100, 70, 50.0, 50.0, 49.5, 34.5, torch.eye(3), torch.zeros(3), device=dev)
+po = PoseOptimizer(cam)
+cam._grad_tau.fill_(0.01); po.step(); po.step()
+AE.PRECISION = "fp32"
+with torch.no_grad():
+    y32 = ae.decode(ae.encode(x))
+AE.PRECISION = "fast"
 torch.cuda.synchronize()
 print("sanitize pass done", float(l), tuple(y.shape), tuple(hm.shape), tuple(code.shape), cnt.tolist())

@@ -21,6 +21,8 @@
 
 #include "ols_tc.cuh"
 
+#include <cuda_fp16.h>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -44,8 +46,11 @@ struct AeLayer {
     int chunk_n;         // N of one MMA instruction (block_n or block_n / 2)
     int n_blocks;        // N / block_n
     int blocks_per_pass; // N-blocks accumulated in TMEM before the epilogue runs (pass width <= 512 columns)
+    int sps;             // K-slabs of this layer's weights that travel in ONE ring stage (inner layers' slabs are small: fewer
+                         // load -> MMA -> release round trips per layer)
     int relu;
-    int tf32;            // 1: A and B are fp32 (kind::tf32, 32 elements per slab); 0: bf16 (64 per slab)
+    int tf32;            // 1: A and B are fp32 (kind::tf32, 32 elements per slab); 0: 16-bit operands (64 per slab)
+    int fmt;             // operand format of the instruction descriptor: 0 = fp16, 1 = bf16, 2 = tf32
     const float* bias;   // [N] zero padded
 };
 
@@ -55,6 +60,8 @@ struct AeParams {
     AeLayer layer[OLS_AE_MAX_LAYERS];
     int n_layers;
     int manual_x;    // 1: layer-0 input is loaded by the epilogue warps (row stride not TMA compatible)
+    int l0_half;     // 1: layer 0 runs kind::f16 on fp16 operands: W0 is stored in fp16 (half the bytes re-streamed per tile)
+                     //    and the fp32 x tile, staged by TMA in the idle activation buffer, is converted by the epilogue warps
     int x_bf16;      // 1: the input matrix is bf16 (the HR module's last activation); layer 0 then runs kind::f16
     int K0_real;     // real input width
     int out_real;    // real output width
@@ -81,12 +88,19 @@ __global__ void __launch_bounds__(AE_THREADS, 1) k_ae_chain(const __grid_constan
     uint64_t* mma_done = bars + 16;          // MMA -> epilogue (accumulator pass complete)
     uint64_t* epi_done = bars + 17;          // epilogue -> MMA (TMEM drained, next A operand in smem)
     uint32_t* tmem_slot = (uint32_t*)(bars + 18);
+    uint64_t* xfull = bars + 20;             // [2] TMA -> converter (fp32 x staging slot landed)          (l0_half)
+    uint64_t* xfree = bars + 22;             // [2] converter -> TMA (staging slot consumed)
+    uint64_t* afull = bars + 24;             // [n_stages <= 4] converter -> MMA (fp16 A slab written into the ring stage)
+    uint64_t* act_free = bars + 28;          // MMA -> TMA: the tile's last MMAs have read the activation buffer
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.n_stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(mma_done, 1);
         mbar_init(epi_done, 128);
+        for (int s = 0; s < 2; s++) { mbar_init(&xfull[s], 1); mbar_init(&xfree[s], 128); }
+        for (int s = 0; s < 4; s++) mbar_init(&afull[s], 128);
+        mbar_init(act_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -105,25 +119,44 @@ __global__ void __launch_bounds__(AE_THREADS, 1) k_ae_chain(const __grid_constan
             asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_x) : "memory");
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            uint32_t xcount = 0, tiles_p = 0;   // l0_half: fp32 x staging slots issued so far; tiles started
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, tiles_p++) {
                 for (int l = 0; l < p.n_layers; l++) {
                     const AeLayer& L = p.layer[l];
                     const int slab_elems = L.tf32 ? 32 : 64;
-                    const bool load_x = (l == 0) && !p.manual_x;
+                    const bool half0 = (l == 0) && p.l0_half;
+                    const bool load_x = (l == 0) && !p.manual_x && !p.l0_half;
                     for (int b = 0; b < L.n_blocks; b++) {
-                        for (int s = 0; s < L.n_slabs; s++) {
+                        for (int s = 0; s < L.n_slabs; s += L.sps) {
+                            const int cnt = min(L.sps, L.n_slabs - s);
                             mbar_wait(&empty[stage], phase ^ 1);
                             uint8_t* st = ring + (size_t)stage * p.stage_bytes;
-                            const uint32_t bytes = (uint32_t)L.block_n * AE_SLAB_BYTES + (load_x ? AE_M * AE_SLAB_BYTES : 0);
+                            const uint32_t bytes = (uint32_t)cnt * L.block_n * AE_SLAB_BYTES + (load_x ? AE_M * AE_SLAB_BYTES : 0);
                             mbar_expect_tx(&full[stage], bytes);
                             uint8_t* bdst = st;
                             if (load_x) {
                                 tma_load_2d(st, &p.tmap_x, &full[stage], s * slab_elems, tile * AE_M);
                                 bdst = st + AE_M * AE_SLAB_BYTES;
                             }
-                            for (int c = 0; c < L.block_n; c += L.chunk_n)
-                                tma_load_2d(bdst + (size_t)c * AE_SLAB_BYTES, &p.tmap_w[l], &full[stage], s * slab_elems,
-                                            b * L.block_n + c);
+                            if (half0) {
+                                // fp32 x slab (64 columns = two 128-byte boxes) into staging slot xs of the activation buffer;
+                                // the buffer is free once the previous tile's last MMAs have read it
+                                bdst = st + AE_M * AE_SLAB_BYTES;   // the stage's first 16 KB take the converted fp16 A slab
+                                {
+                                    const uint32_t xs = xcount & 1u;
+                                    if (b == 0 && s == 0 && tiles_p > 0) mbar_wait(act_free, (tiles_p - 1) & 1u);
+                                    mbar_wait(&xfree[xs], ((xcount >> 1) & 1u) ^ 1u);
+                                    mbar_expect_tx(&xfull[xs], 2 * AE_M * AE_SLAB_BYTES);
+                                    uint8_t* xdst = act + (size_t)xs * (2 * AE_M * AE_SLAB_BYTES);
+                                    tma_load_2d(xdst, &p.tmap_x, &xfull[xs], s * 64, tile * AE_M);
+                                    tma_load_2d(xdst + AE_M * AE_SLAB_BYTES, &p.tmap_x, &xfull[xs], s * 64 + 32, tile * AE_M);
+                                    xcount++;
+                                }
+                            }
+                            for (int q = 0; q < cnt; q++)
+                                for (int c = 0; c < L.block_n; c += L.chunk_n)
+                                    tma_load_2d(bdst + ((size_t)q * L.block_n + c) * AE_SLAB_BYTES, &p.tmap_w[l], &full[stage],
+                                                (s + q) * slab_elems, b * L.block_n + c);
                             if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -135,11 +168,13 @@ __global__ void __launch_bounds__(AE_THREADS, 1) k_ae_chain(const __grid_constan
         int stage = 0;
         uint32_t phase = 0, epi_phase = 0;
         int tiles_done = 0;
+        uint32_t a_uses[4] = {0u, 0u, 0u, 0u};   // l0_half: how often each ring stage has carried a converted A slab
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, tiles_done++) {
             for (int l = 0; l < p.n_layers; l++) {
                 const AeLayer& L = p.layer[l];
                 const bool a_from_ring = (l == 0) && !p.manual_x;
-                const uint32_t idesc = make_idesc(L.tf32 != 0, L.chunk_n);
+                const bool half0 = (l == 0) && p.l0_half;
+                const uint32_t idesc = make_idesc_fmt((uint32_t)L.fmt, L.chunk_n);
                 for (int b = 0; b < L.n_blocks; b++) {
                     const int in_pass = b % L.blocks_per_pass;
                     if (in_pass == 0) {
@@ -153,21 +188,29 @@ __global__ void __launch_bounds__(AE_THREADS, 1) k_ae_chain(const __grid_constan
                         }
                         tcgen05_fence_after();
                     }
-                    for (int s = 0; s < L.n_slabs; s++) {
+                    for (int s = 0; s < L.n_slabs; s += L.sps) {
+                        const int cnt = min(L.sps, L.n_slabs - s);
                         mbar_wait(&full[stage], phase);
+                        if (half0) {   // the fp16 A slab of this stage has been written by the converter warps
+                            mbar_wait(&afull[stage], a_uses[stage] & 1u);
+                            a_uses[stage]++;
+                        }
                         tcgen05_fence_after();
                         if (lane == 0) {
                             uint8_t* st = ring + (size_t)stage * p.stage_bytes;
-                            const uint32_t a_addr = a_from_ring ? smem_u32(st) : smem_u32(act + (size_t)s * AE_M * AE_SLAB_BYTES);
-                            const uint32_t b_addr = smem_u32(st) + (a_from_ring ? AE_M * AE_SLAB_BYTES : 0);
+                            for (int q = 0; q < cnt; q++) {   // the K-slabs this stage carries
+                                const uint32_t a_addr = a_from_ring ? smem_u32(st) : smem_u32(act + (size_t)(s + q) * AE_M * AE_SLAB_BYTES);
+                                const uint32_t b_addr = smem_u32(st) + (a_from_ring ? AE_M * AE_SLAB_BYTES : 0) +
+                                                        (uint32_t)q * L.block_n * AE_SLAB_BYTES;
 #pragma unroll
-                            for (int k = 0; k < 4; k++) {  // 4 x 32 bytes of K per slab
-                                const uint64_t ad = make_sdesc(a_addr + k * 32);
-                                for (int c = 0; c < L.block_n; c += L.chunk_n) {
-                                    const uint64_t bd = make_sdesc(b_addr + (uint32_t)c * AE_SLAB_BYTES + k * 32);
-                                    const uint32_t d = tmem_base + (uint32_t)(in_pass * L.block_n + c);
-                                    if (L.tf32) umma<true>(d, ad, bd, idesc, (s | k) ? 1u : 0u);
-                                    else umma<false>(d, ad, bd, idesc, (s | k) ? 1u : 0u);
+                                for (int k = 0; k < 4; k++) {  // 4 x 32 bytes of K per slab
+                                    const uint64_t ad = make_sdesc(a_addr + k * 32);
+                                    for (int c = 0; c < L.block_n; c += L.chunk_n) {
+                                        const uint64_t bd = make_sdesc(b_addr + (uint32_t)c * AE_SLAB_BYTES + k * 32);
+                                        const uint32_t d = tmem_base + (uint32_t)(in_pass * L.block_n + c);
+                                        if (L.tf32) umma<true>(d, ad, bd, idesc, ((s + q) | k) ? 1u : 0u);
+                                        else umma<false>(d, ad, bd, idesc, ((s + q) | k) ? 1u : 0u);
+                                    }
                                 }
                             }
                             umma_commit(&empty[stage]);  // frees the ring slot when these MMAs have read it
@@ -176,7 +219,11 @@ __global__ void __launch_bounds__(AE_THREADS, 1) k_ae_chain(const __grid_constan
                         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                     }
                     if (in_pass == L.blocks_per_pass - 1 || b == L.n_blocks - 1) {
-                        if (lane == 0) umma_commit(mma_done);
+                        if (lane == 0) {
+                            umma_commit(mma_done);
+                            // the tile's last MMAs: once they complete, the activation buffer may stage the next tile's x
+                            if (p.l0_half && l == p.n_layers - 1 && b == L.n_blocks - 1) umma_commit(act_free);
+                        }
                         __syncwarp();
                     }
                 }
@@ -191,8 +238,53 @@ __global__ void __launch_bounds__(AE_THREADS, 1) k_ae_chain(const __grid_constan
         const bool tracer = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64;
         int tr_n = 1;
         if (tracer) p.trace[tr_n++] = gtimer();
+        uint32_t xcount = 0, ring_slabs = 0;     // l0_half: staging slots consumed; ring slabs seen (to follow the producer's stage / phase)
+        uint32_t a_uses_c[4] = {0u, 0u, 0u, 0u};
+        (void)a_uses_c;
+        int cstage = 0;
+        uint32_t cphase = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             const long long grow = (long long)tile * AE_M + row;
+            if (p.l0_half) {
+                // layer-0 A operand: the fp32 x slab staged by TMA (two SWIZZLE_128B boxes of 32 columns) -> fp16, K-major,
+                // SWIZZLE_128B, into the first 16 KB of the ring stage whose W slab the producer loads in parallel.
+                // The ring stage sequence of layer 0 is followed with the same (stage, phase) arithmetic as the producer's.
+                const AeLayer& L0 = p.layer[0];
+                for (int b = 0; b < L0.n_blocks; b++) {
+                    for (int s = 0; s < L0.n_slabs; s++) {
+                        {
+                            const uint32_t xs = xcount & 1u;
+                            mbar_wait(&xfull[xs], (xcount >> 1) & 1u);           // fp32 slab landed
+                            mbar_wait(&empty[cstage], cphase ^ 1u);              // ring stage free (MMAs of its previous use done)
+                            const uint8_t* xsrc = act + (size_t)xs * (2 * AE_M * AE_SLAB_BYTES);
+                            uint8_t* adst = ring + (size_t)cstage * p.stage_bytes;
+#pragma unroll
+                            for (int c = 0; c < 8; c++) {      // 16-byte chunk c of the fp16 row = columns 8c .. 8c+7
+                                const uint8_t* box = xsrc + (size_t)(c >> 2) * (AE_M * AE_SLAB_BYTES);
+                                const float4 lo = *(const float4*)(box + sw128(row, 2 * (c & 3)));
+                                const float4 hi = *(const float4*)(box + sw128(row, 2 * (c & 3) + 1));
+                                const __half2 h0 = __floats2half2_rn(lo.x, lo.y), h1 = __floats2half2_rn(lo.z, lo.w);
+                                const __half2 h2 = __floats2half2_rn(hi.x, hi.y), h3 = __floats2half2_rn(hi.z, hi.w);
+                                uint4 pk;
+                                pk.x = *(const uint32_t*)&h0; pk.y = *(const uint32_t*)&h1; pk.z = *(const uint32_t*)&h2; pk.w = *(const uint32_t*)&h3;
+                                *(uint4*)(adst + sw128(row, c)) = pk;
+                            }
+                            fence_proxy_async_smem();
+                            mbar_arrive(&afull[cstage]);
+                            mbar_arrive(&xfree[xs]);
+                            xcount++;
+                        }
+                        if (++cstage == p.n_stages) { cstage = 0; cphase ^= 1u; }
+                    }
+                }
+                // the remaining layers' slabs advance the ring too
+                for (int l = 1; l < p.n_layers; l++) {
+                    const int adv = p.layer[l].n_blocks * ((p.layer[l].n_slabs + p.layer[l].sps - 1) / p.layer[l].sps);
+                    for (int q = 0; q < adv; q++)
+                        if (++cstage == p.n_stages) { cstage = 0; cphase ^= 1u; }
+                }
+                (void)ring_slabs;
+            }
             if (p.manual_x) {
                 // layer-0 A operand written by hand: fp32, zero padded to the slab width
                 const AeLayer& L0 = p.layer[0];
@@ -437,12 +529,13 @@ __global__ void k_ae_transpose_weight(const float* __restrict__ w, int N, int K,
 
 // weight re-layout: pad [N,K] fp32 -> [N_pad,K_pad] fp32 (layer 0) or bf16 (inner layers), zero filled
 __global__ void k_ae_pack_weight(const float* __restrict__ w, int N, int K, void* __restrict__ out, int N_pad, int K_pad,
-                                 int to_bf16) {
+                                 int fmt /* 2 = fp32 (tf32 operand), 1 = bf16, 0 = fp16 */) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)N_pad * K_pad) return;
     const int n = (int)(i / K_pad), k = (int)(i % K_pad);
     const float v = (n < N && k < K) ? w[(size_t)n * K + k] : 0.0f;
-    if (to_bf16) ((__nv_bfloat16*)out)[i] = __float2bfloat16_rn(v);
+    if (fmt == 1) ((__nv_bfloat16*)out)[i] = __float2bfloat16_rn(v);
+    else if (fmt == 0) ((__half*)out)[i] = __float2half_rn(v);
     else ((float*)out)[i] = v;
 }
 __global__ void k_ae_pack_bias(const float* __restrict__ b, int N, float* __restrict__ out, int N_pad) {
@@ -481,15 +574,15 @@ static PFN_encodeTiled get_encode() {
 }
 
 // 2-D row-major tensor [rows, cols] with a [box_rows, 128 bytes] box, 128-byte swizzle
-static int make_map(CUtensorMap* map, const void* base, bool bf16, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+static int make_map(CUtensorMap* map, const void* base, bool bf16, uint64_t rows, uint64_t cols, uint32_t box_rows, bool fp16 = false) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) { ols_set_error("cuTensorMapEncodeTiled not available"); return OLS_ERR_CUDA; }
-    const uint32_t esz = bf16 ? 2 : 4;
+    const uint32_t esz = (bf16 || fp16) ? 2 : 4;
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {cols * esz};
     cuuint32_t box[2] = {AE_SLAB_BYTES / esz, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims,
+    CUresult r = enc(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : (bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32), 2, (void*)base, dims,
                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { ols_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return OLS_ERR_CUDA; }
@@ -553,12 +646,19 @@ int ols_ae_plan_create(const ols_ae_chain* chain, ols_ae_plan** out_plan, void* 
     }
     p.manual_x = (chain->dims[0] % 32 != 0) ? 1 : 0;  // TMA needs 16-byte row strides; keep whole slabs too
     if (p.x_bf16 && chain->dims[0] % 64 != 0) { ols_set_error("bf16 input needs a width that is a multiple of 64"); return fail(OLS_ERR_UNSUPPORTED); }
+    // fp16 first layer (same 10-bit mantissa as tf32, half the weight bytes re-streamed per tile, twice the MMA rate): needs
+    // a TMA-loadable fp32 input of whole 64-column slabs and an activation buffer that can stage two fp32 x slabs (64 KB),
+    // i.e. a second layer of at least 256 inputs.  OLS_AE_L0_TF32=1 keeps the tf32 first layer (A/B aid).
+    static const bool force_tf32 = getenv("OLS_AE_L0_TF32") != nullptr;
+    p.l0_half = (!force_tf32 && !p.manual_x && !p.x_bf16 && chain->dims[0] % 64 == 0 && chain->n_layers >= 2 &&
+                 round_up(chain->dims[1], 64) * AE_M * 2 >= 2 * 2 * AE_M * AE_SLAB_BYTES) ? 1 : 0;
     int stage_bytes = 0, act_cols_bytes = 0;
     for (int l = 0; l < chain->n_layers; l++) {
         const int K = chain->dims[l], N = chain->dims[l + 1];
         if (K <= 0 || N <= 0 || !chain->d_weight[l]) { ols_set_error("bad layer %d", l); return fail(OLS_ERR_INVALID); }
         AeLayer& L = p.layer[l];
-        L.tf32 = (l == 0 && !p.x_bf16) ? 1 : 0;
+        L.tf32 = (l == 0 && !p.x_bf16 && !p.l0_half) ? 1 : 0;
+        L.fmt = L.tf32 ? 2 : ((l == 0 && p.l0_half) ? 0 : 1);
         const int slab = L.tf32 ? 32 : 64;
         // K of layer l must equal the padded N of layer l-1 (the activation the epilogue wrote)
         L.K = round_up(K, slab);
@@ -592,10 +692,10 @@ int ols_ae_plan_create(const ols_ae_chain* chain, ols_ae_plan** out_plan, void* 
         }
         plan->owned.push_back(wbuf); plan->owned.push_back(bbuf);
         const size_t tot = (size_t)L.N * L.K;
-        k_ae_pack_weight<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(chain->d_weight[l], N, K, wbuf, L.N, L.K, L.tf32 ? 0 : 1);
+        k_ae_pack_weight<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(chain->d_weight[l], N, K, wbuf, L.N, L.K, L.fmt);
         k_ae_pack_bias<<<(L.N + 255) / 256, 256, 0, st>>>(chain->d_bias[l], N, bbuf, L.N);
         L.bias = bbuf;
-        int rc = make_map(&p.tmap_w[l], wbuf, !L.tf32, (uint64_t)L.N, (uint64_t)L.K, (uint32_t)L.chunk_n);
+        int rc = make_map(&p.tmap_w[l], wbuf, L.fmt == 1, (uint64_t)L.N, (uint64_t)L.K, (uint32_t)L.chunk_n, L.fmt == 0);
         if (rc != OLS_OK) return fail(rc);
     }
     for (int l = 1; l < chain->n_layers; l++) {
@@ -603,10 +703,18 @@ int ols_ae_plan_create(const ols_ae_chain* chain, ols_ae_plan** out_plan, void* 
     }
     if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { ols_set_error("weight packing failed"); return fail(OLS_ERR_CUDA); }
     stage_bytes = round_up(stage_bytes, 1024);
+    for (int l = 0; l < chain->n_layers; l++) {
+        AeLayer& L = p.layer[l];
+        const int slab_bytes = L.block_n * AE_SLAB_BYTES;
+        L.sps = (l == 0 && !p.manual_x) ? 1 : stage_bytes / slab_bytes;   // layer 0's stage also holds the A slab
+        if (L.sps < 1) L.sps = 1;
+        if (L.sps > L.n_slabs) L.sps = L.n_slabs;
+    }
     const int act_bytes = round_up(act_cols_bytes > 0 ? act_cols_bytes : 1024, 1024);
     const int budget = 227 * 1024 - 1024 /*alignment*/ - 256 /*barriers*/ - act_bytes;
     int n_stages = budget / stage_bytes;
     if (n_stages > 8) n_stages = 8;
+    if (p.l0_half && n_stages > 4) n_stages = 4;   // afull[] has four barriers
     // wide outputs leave through a shared-memory transpose when it fits beside the ring (it does for every decoder of the
     // reference; the encoders write 15- / 32-float rows, which are contiguous per warp anyway)
     p.stage_out = (p.out_real > 32 && n_stages >= 2 && budget - n_stages * stage_bytes >= AE_STAGING_BYTES) ? 1 : 0;

@@ -70,10 +70,10 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
     return d;
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, K-major A and B, M = 128
-__device__ __forceinline__ uint32_t make_idesc(bool tf32, int n) {
-    const uint32_t fmt = tf32 ? 2u : 1u;  // 2 = TF32, 1 = BF16
+__device__ __forceinline__ uint32_t make_idesc_fmt(uint32_t fmt, int n) {  // fmt: 0 = F16, 1 = BF16, 2 = TF32 (A and B alike)
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
+__device__ __forceinline__ uint32_t make_idesc(bool tf32, int n) { return make_idesc_fmt(tf32 ? 2u : 1u, n); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "

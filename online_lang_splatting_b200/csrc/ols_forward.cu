@@ -1312,8 +1312,7 @@ __global__ void __launch_bounds__(B2_THREADS, B2_MIN_BLOCKS) k_blend2(const __gr
             if (lane == 0) { s_hit[b & 1][blk0][half] = h0; s_hit[b & 1][blk1][half] = h1; }
             for (uint32_t tmask = __reduce_or_sync(0xffffffffu, mytouch[0] | mytouch[1]); tmask; tmask &= tmask - 1) {
                 const int jl = __ffs(tmask) - 1;
-                const int n = __popc(__ballot_sync(0xffffffffu, (mytouch[0] >> jl) & 1u)) +
-                              __popc(__ballot_sync(0xffffffffu, (mytouch[1] >> jl) & 1u));
+                const int n = (int)__reduce_add_sync(0xffffffffu, ((mytouch[0] >> jl) & 1u) + ((mytouch[1] >> jl) & 1u));
                 if (lane == 0) atomicAdd(&a.n_touched[ids[half * 32 + jl]], n);
             }
         }

@@ -323,6 +323,31 @@ __global__ void __launch_bounds__(AE_THREADS, 1) k_ae_chain(const __grid_constan
                             for (int i = 16; i < 32; i++) r[i] = 0u;
                         }
                     };
+                    // Row normalisation (model.py:55,61) without a read-modify-write of the output: in the LAST pass of the last
+                    // layer the accumulator is swept twice -- first only for the sum of squares (TMEM reads are cheap), then for
+                    // the scaled, final values.  Earlier passes of a wide last layer (the decoder's 768 columns = 2 passes) have
+                    // to leave before the norm is known: they are written raw and rescaled once at the end.
+                    const bool final_pass = last && (n0 + pass_w >= L.N);
+                    float scale = 1.0f;
+                    if (final_pass && p.normalize) {
+                        uint32_t rs[32];
+                        for (int c = 0; c < w; c += 32) {
+                            const int nc = min(32, w - c);
+                            if (w - c >= 32) tmem_ld32(t_lane + (uint32_t)c, rs);
+                            else tmem_ld16(t_lane + (uint32_t)c, rs);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; i++) {
+                                const int col = n0 + c + i;
+                                if (i < nc && col < p.out_real) {
+                                    const float t = __uint_as_float(rs[i]) + __ldg(L.bias + col);
+                                    sumsq = fmaf(t, t, sumsq);
+                                }
+                            }
+                        }
+                        scale = 1.0f / sqrtf(sumsq);
+                    }
+                    const bool acc_sq = last && !final_pass;   // raw passes contribute to the norm as they go
                     auto process = [&](int c, uint32_t (&r)[32]) {
                         const int nc = min(32, w - c);
                         float v[32];
@@ -338,6 +363,13 @@ __global__ void __launch_bounds__(AE_THREADS, 1) k_ae_chain(const __grid_constan
                         if (L.relu) {
 #pragma unroll
                             for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.0f);
+                        }
+                        if (last) {
+#pragma unroll
+                            for (int i = 0; i < 32; i++) {
+                                if (acc_sq && i < nc && n0 + c + i < p.out_real) sumsq = fmaf(v[i], v[i], sumsq);
+                                v[i] *= scale;
+                            }
                         }
                         if (!last) {
                             // next layer's A operand: bf16, K-major, 128-byte swizzle; column col -> slab col/64
@@ -359,10 +391,7 @@ __global__ void __launch_bounds__(AE_THREADS, 1) k_ae_chain(const __grid_constan
 #pragma unroll
                             for (int i = 0; i < 32; i++) {
                                 const int col = n0 + c + i;
-                                if (i < nc && col < p.out_real) {
-                                    sumsq = fmaf(v[i], v[i], sumsq);
-                                    if (grow < p.M) p.y[grow * p.out_real + col] = v[i];
-                                }
+                                if (i < nc && col < p.out_real && grow < p.M) p.y[grow * p.out_real + col] = v[i];
                             }
                         } else {
                             // A thread owns a row, so writing its values directly would scatter 4-byte stores one row stride
@@ -370,11 +399,7 @@ __global__ void __launch_bounds__(AE_THREADS, 1) k_ae_chain(const __grid_constan
                             // one contiguous run of up to 128 bytes per row.
                             float* stg = staging + quad * (32 * 33);
 #pragma unroll
-                            for (int i = 0; i < 32; i++) {
-                                const int col = n0 + c + i;
-                                if (i < nc && col < p.out_real) sumsq = fmaf(v[i], v[i], sumsq);
-                                stg[lane * 33 + i] = v[i];
-                            }
+                            for (int i = 0; i < 32; i++) stg[lane * 33 + i] = v[i];
                             __syncwarp();
                             const long long row0 = (long long)tile * AE_M + quad * 32;
                             const int col = n0 + c + lane;
@@ -412,26 +437,39 @@ __global__ void __launch_bounds__(AE_THREADS, 1) k_ae_chain(const __grid_constan
                     mbar_arrive(epi_done);
                     if (tracer && tr_n < 250) p.trace[tr_n++] = gtimer();  // epilogue of (layer l, pass) done
                 }
-                if (last && p.normalize) {
-                    // x / ||x||_2 (model.py:55,61): the warp's 32 un-normalised rows were just written by its own lanes (and
-                    // are still in L2); they are rescaled row by row with coalesced accesses, lane r supplying row r's norm
+                const int raw_cols = min(p.out_real, ((L.N - 1) / pass_w) * pass_w);   // columns written before the norm was known
+                if (last && p.normalize && raw_cols > 0) {
+                    // the warp's 32 rows x raw_cols raw values were just written by its own lanes (still in L2): rescale them
+                    // with coalesced accesses, four rows of independent loads in flight, lane r supplying row r's 1 / norm
                     __syncwarp();
                     const float inv = 1.0f / sqrtf(sumsq);
                     const long long row0 = (long long)tile * AE_M + quad * 32;
-                    const bool vec4 = (p.out_real & 3) == 0 && (((uintptr_t)p.y) & 15) == 0;
-                    for (int r = 0; r < 32; r++) {
-                        const float inv_r = __shfl_sync(0xffffffffu, inv, r);
-                        if (row0 + r >= p.M) break;
-                        float* yr = p.y + (row0 + r) * p.out_real;
-                        if (vec4) {
-                            float4* y4 = reinterpret_cast<float4*>(yr);
-                            for (int q = lane; q < (p.out_real >> 2); q += 32) {
-                                float4 t = y4[q];
-                                t.x *= inv_r; t.y *= inv_r; t.z *= inv_r; t.w *= inv_r;
-                                y4[q] = t;
+                    const bool vec4 = (p.out_real & 3) == 0 && (raw_cols & 3) == 0 && (((uintptr_t)p.y) & 15) == 0;
+                    if (vec4) {
+                        const int nq = raw_cols >> 2;
+                        for (int r0 = 0; r0 < 32; r0 += 4) {
+                            float invs[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) invs[u] = __shfl_sync(0xffffffffu, inv, r0 + u);
+                            for (int q = lane; q < nq; q += 32) {
+                                float4 t[4];
+#pragma unroll
+                                for (int u = 0; u < 4; u++)
+                                    if (row0 + r0 + u < p.M) t[u] = __ldcg(reinterpret_cast<const float4*>(p.y + (row0 + r0 + u) * p.out_real) + q);
+#pragma unroll
+                                for (int u = 0; u < 4; u++)
+                                    if (row0 + r0 + u < p.M) {
+                                        t[u].x *= invs[u]; t[u].y *= invs[u]; t[u].z *= invs[u]; t[u].w *= invs[u];
+                                        reinterpret_cast<float4*>(p.y + (row0 + r0 + u) * p.out_real)[q] = t[u];
+                                    }
                             }
-                        } else {
-                            for (int col = lane; col < p.out_real; col += 32) yr[col] *= inv_r;
+                        }
+                    } else {
+                        for (int r = 0; r < 32; r++) {
+                            const float inv_r = __shfl_sync(0xffffffffu, inv, r);
+                            if (row0 + r >= p.M) break;
+                            float* yr = p.y + (row0 + r) * p.out_real;
+                            for (int col = lane; col < raw_cols; col += 32) yr[col] *= inv_r;
                         }
                     }
                     __syncwarp();
